@@ -1,0 +1,183 @@
+/* oeh.h -- C ABI of liboeh.so: the B200 (sm_100a) implementation of OutEffHop's
+ * attention + activation fake-quant hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes / a cudaStream_t
+ * (as void*), returns an int status (0 = ok) and never throws or aborts.  All work is
+ * enqueued asynchronously on the given stream, allocates nothing, performs no host
+ * synchronisation and is CUDA-graph capturable; quantizer ranges are read from DEVICE
+ * memory so a range estimated on the stream can be consumed on the same stream.
+ *
+ * Each declaration names the reference interface it replaces (paths relative to
+ * /root/reference/OutEffHop).  The reference is pure PyTorch, so "the FFI" a maintainer
+ * binds is ctypes from the reference's Python modules -- see INTEGRATION.md.
+ */
+#ifndef OEH_H_
+#define OEH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OEH_VERSION 100 /* major*100 + minor */
+
+typedef void* oeh_stream_t; /* cudaStream_t */
+
+enum oeh_status {
+  OEH_OK = 0,
+  OEH_ERR_BAD_ARG = 1,     /* -> ValueError in the Python shim            */
+  OEH_ERR_UNSUPPORTED = 2, /* -> NotImplementedError (shape/dtype/branch) */
+  OEH_ERR_CUDA = 3,        /* -> RuntimeError, see oeh_last_error()       */
+  OEH_ERR_WORKSPACE = 4,   /* workspace missing or too small              */
+  OEH_ERR_NOT_INITIALIZED = 5 /* -> QuantizerNotInitializedError          */
+};
+
+enum oeh_dtype { OEH_F32 = 0, OEH_F16 = 1, OEH_BF16 = 2 };
+
+/* SOFTMAX_MAPPING families (transformers_language/models/softmax.py:22-64). */
+enum oeh_softmax_kind {
+  OEH_SOFTMAX_VANILLA = 0,  /* F.softmax                                      softmax.py:23      */
+  OEH_SOFTMAX_1 = 1,        /* exp(x_i)/(1+sum_j exp(x_j))        vutils/softmax_1.py:4-28      */
+  OEH_SOFTMAX_CLIPPED = 2,  /* clip((eta-gamma)*softmax+gamma,0,1)            softmax.py:10-13   */
+  OEH_SOFTMAX_CLIPPED1 = 3  /* clip((eta-gamma)*softmax_1+gamma,0,1)          softmax.py:16-19   */
+};
+
+/* Device-resident state of one activation quantizer + its running min/max estimator:
+ * 8 consecutive floats.  Mirrors the reference buffers
+ *   RunningMinMaxEstimator.current_xmin/current_xmax   (quantization/range_estimators.py:16-17)
+ *   AsymmetricUniformQuantizer._delta/_zero_float      (quantizers/uniform_quantizers.py:32-33)
+ * plus the derived scale (:72-76) and zero_point (:79-82) the kernels consume. */
+enum oeh_qstate_slot {
+  OEH_QS_CUR_MIN = 0,
+  OEH_QS_CUR_MAX = 1,
+  OEH_QS_DELTA = 2,
+  OEH_QS_ZERO_FLOAT = 3,
+  OEH_QS_SCALE = 4,      /* &state[OEH_QS_SCALE] is the `qparams` pointer ([scale, zero_point]) */
+  OEH_QS_ZERO_POINT = 5,
+  OEH_QS_INITIALIZED = 6, /* 0.0f until the first range update */
+  OEH_QS_RESERVED = 7,
+  OEH_QS_FLOATS = 8
+};
+
+int oeh_version(void);
+/* Thread-local description of the last non-zero status returned on this thread. */
+const char* oeh_last_error(void);
+/* 1 if the current device is compute capability 10.x (the only supported target). */
+int oeh_device_supported(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused attention forward: QK^T -> *scale -> [qdq] -> +mask -> softmax_fn -> [qdq] -> PV
+ *                           -> [qdq before gate] -> *sigmoid(gate_logits)*gate_scale -> [qdq]
+ * Replaces the body of BertSelfAttentionWithExtras.forward (models/bert_attention.py:222-337),
+ * OPTAttentionWithExtras.forward (models/opt_attention.py:204-322) and, with the qdq pointers
+ * set, of QuantizedBertSelfAttentionWithExtras.forward (models/quantized_bert.py:317-434) and
+ * QuantizedOPTAttentionWithExtras.forward (models/quantized_opt.py:151-257) in fix_ranges state.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct OehAttnArgs {
+  /* Q (B,H,Tq,d), K/V (B,H,Tk,d), out (B,H,Tq,d) as strided views: element strides for
+   * (batch, head, token); the head dimension d is contiguous.  BERT passes the permuted views of
+   * the Linear outputs (bert_attention.py:164-167) and a (B,Tq,H*d) output (the permute of
+   * :335-337 folded into the store); OPT passes head-major copies (opt_attention.py:146-147). */
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  int64_t q_strides[3];
+  int64_t k_strides[3];
+  int64_t v_strides[3];
+  int64_t out_strides[3];
+  int32_t B, H, Tq, Tk, d;
+  int32_t dtype;     /* oeh_dtype of q,k,v,out: OEH_F16 or OEH_BF16 (fp32 accumulate) */
+  float scale;       /* 1/sqrt(d) for BERT (:265); 1.0 for OPT when q is pre-scaled (:167) */
+  int32_t kind;      /* oeh_softmax_kind */
+  double gamma, eta; /* clipped variants; (eta-gamma) is rounded to fp32 like the Python scalar */
+  int32_t causal;    /* 1: key j attends iff j <= i + (Tk-Tq) (HF causal mask), no mask tensor read */
+  /* optional additive mask, element strides for (batch, head, query); key dim contiguous; a
+   * stride of 0 broadcasts.  HF-4.31: (B,1,1,Tk) for BERT, (B,1,Tq,Tk) for OPT. */
+  const void* mask;
+  int32_t mask_dtype; /* oeh_dtype */
+  int64_t mask_strides[3];
+  int32_t clamp_min;  /* 1: max(s+mask, finfo(dtype).min) (opt_attention.py:221-223) */
+  /* optional per-token gate LOGITS (B,H,Tq) fp32 contiguous; ctx *= sigmoid(logit)*gate_scale
+   * (bert_attention.py:294-331; opt_attention.py:276-313). */
+  const float* gate_logits;
+  float gate_scale;
+  /* optional fixed-range fake-quant taps: device pointers to [scale, zero_point]
+   * (quantized_bert.py:363,374,434; quantized_opt.py:154,182,210). */
+  const float* qdq_scores;
+  const float* qdq_probs;
+  const float* qdq_ctx;
+  int32_t n_bits;
+  int32_t ctx_qdq_before_gate; /* OPT taps PV before the gate (:210), BERT after it (:434) */
+  void* workspace;             /* oeh_attn_workspace_bytes() bytes, 256-B aligned, may be NULL if 0 */
+  size_t workspace_bytes;
+  oeh_stream_t stream;
+} OehAttnArgs;
+
+size_t oeh_attn_workspace_bytes(const OehAttnArgs* args);
+int oeh_attn_fwd(const OehAttnArgs* args);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row softmax on a materialised score tensor (the unfused / range-estimation path):
+ *   y = softmax_fn(clamp(x*in_scale + mask))   over the last dimension.
+ * Replaces softmax_1 / clipped_softmax / clipped_softmax1 / F.softmax as called at
+ * bert_attention.py:276 and opt_attention.py:226-232 (vutils/softmax_1.py:4-28; softmax.py:10-19).
+ * x,y: (B*H*Tq, Tk) contiguous.  mask as in OehAttnArgs (rows decompose as ((b*H)+h)*Tq+q).
+ * ------------------------------------------------------------------------------------------- */
+int oeh_softmax_rows(const void* x, void* y, int32_t B, int32_t H, int32_t Tq, int32_t Tk, int32_t dtype,
+                     float in_scale, int32_t kind, double gamma, double eta, const void* mask,
+                     int32_t mask_dtype, const int64_t* mask_strides, int32_t causal, int32_t clamp_min,
+                     oeh_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Per-token gate logits on the attention INPUT split by head (bert_attention.py:303-320;
+ * opt_attention.py:285-302): out[b,h,t] = fc_h(x[b,t,h*d:(h+1)*d]).
+ * hidden == 0: fc_h = Linear(d,1): w1 (H,d), b1 (H); w2,b2 ignored.
+ * hidden  > 0: fc_h = Linear(d,hidden) -> ReLU -> Linear(hidden,1) (--attn_gate_mlp / _mlp2,
+ *              bert_attention.py:126-143): w1 (H,hidden,d), b1 (H,hidden), w2 (H,hidden), b2 (H).
+ * x: (B,T,H*d) with row stride x_row_stride elements; weights fp32; out (B,H,T) fp32.
+ * ------------------------------------------------------------------------------------------- */
+int oeh_gate_logits(const void* x, int32_t dtype, int32_t B, int32_t T, int32_t H, int32_t d,
+                    int64_t x_row_stride, const float* w1, const float* b1, const float* w2, const float* b2,
+                    int32_t hidden, float* out, oeh_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Asymmetric uniform fake-quant (AsymmetricUniformQuantizer.forward / to_integer_forward,
+ * quantization/quantizers/uniform_quantizers.py:92-148):
+ *   x_int = clamp(round_half_even(x/scale) + zp, 0, 2^n-1);  y = scale*(x_int - zp)
+ * qparams: DEVICE pointer to [scale, zero_point].  emit_codes=1 writes x_int instead of y.
+ * fp32 tensors are bit-exact with the reference; fp16/bf16 tensors follow ATen-CUDA semantics
+ * (every scalar converted to the tensor dtype, one rounding per op).
+ * ------------------------------------------------------------------------------------------- */
+int oeh_fake_quant_asym(const void* x, void* y, int64_t n, int32_t dtype, const float* qparams,
+                        int32_t n_bits, int32_t emit_codes, oeh_stream_t stream);
+
+/* Global min/max of a tensor (torch.min / torch.max at range_estimators.py:96-97; NaN propagates).
+ * out2: DEVICE [min, max].  Workspace from oeh_minmax_workspace_bytes(n). */
+size_t oeh_minmax_workspace_bytes(int64_t n);
+int oeh_minmax(const void* x, int64_t n, int32_t dtype, float* out2, void* workspace, size_t workspace_bytes,
+               oeh_stream_t stream);
+
+/* RunningMinMaxEstimator.forward EMA (range_estimators.py:99-104) followed by
+ * AsymmetricUniformQuantizer.set_quant_range (uniform_quantizers.py:204-224), entirely on the
+ * device: state (OEH_QS_FLOATS floats) is updated from new_minmax (DEVICE [min,max], e.g. the
+ * output of oeh_minmax after an optional cross-GPU MIN/MAX all-reduce). */
+int oeh_range_update(float* state, const float* new_minmax, double momentum, int32_t n_bits, double eps,
+                     oeh_stream_t stream);
+
+/* set_quant_range from host scalars (QuantizationManager(x_min=,x_max=), quantization_manager.py:54-56):
+ * out4 = [_delta, _zero_float, scale, zero_point], same fp32 op order as the device path. */
+int oeh_set_quant_range_host(float x_min, float x_max, int32_t n_bits, double eps, float* out4);
+
+/* QuantizationManager.forward in estimate_ranges state (quantization_manager.py:94-102) for one
+ * GPU: minmax -> EMA -> set range -> quantize the same tensor, 3 launches, no host sync. */
+int oeh_estimate_and_quantize(const void* x, void* y, int64_t n, int32_t dtype, float* state, double momentum,
+                              int32_t n_bits, double eps, void* workspace, size_t workspace_bytes,
+                              oeh_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OEH_H_ */

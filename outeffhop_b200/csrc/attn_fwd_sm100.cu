@@ -1,0 +1,536 @@
+// Fused attention forward for sm_100a:  QK^T -> softmax_1 / clipped softmax(_1) [-> gate] -> PV
+// (bert_attention.py:222-337, opt_attention.py:204-322, quantized_{bert,opt}.py taps), written
+// directly against tcgen05 / TMEM / TMA with inline PTX (sm100_ptx.cuh).
+//
+// Data flow of one CTA (128 threads, one 128-row Q tile of one (batch, head)):
+//   TMA (SWIZZLE_128B, 4-D tensor maps built from the caller's strides, OOB rows zero-filled)
+//     Q tile [128 x 64]  -> smem once;   K/V tiles [128 x 64] -> 2-stage smem rings
+//   tcgen05.mma  S[128x128] (fp32, TMEM cols 0..127)   = Q (K-major smem) . K^T (K-major smem)
+//   tcgen05.ld   each thread owns one S row (lane == row): scale, qdq, mask, online softmax with the
+//                softmax_1 "+1" carried as exp2(-m) in the running-max frame (vutils/softmax_1.py:18-20)
+//   tcgen05.st   P (fp16/bf16, packed 2 per column) back into TMEM cols 0..63, aliasing S
+//   tcgen05.mma  O[128x64] (fp32, TMEM cols 128..191) += P (A operand from TMEM) . V (MN-major smem)
+//   epilogue     O / (l [+ exp2(-m)]) -> [qdq] -> * sigmoid(gate)*scale -> [qdq] -> 16-byte stores into
+//                the caller's (B,T,H*d) or (B,H,T,d) layout.
+// Clipped variants and the probs fake-quant need the *normalised* probability before PV, so they run
+// a stats pass (QK^T only, running (m,l)) and then a PV pass that recomputes QK^T; with a single K/V
+// tile (Tk <= 128, the BERT eval shape) both passes collapse into one.
+// Two CTAs are co-resident per SM (2 x 256 TMEM columns, 2 x 81 KB smem) so one CTA's softmax
+// overlaps the other's MMAs.  Roofline: tensor pipe, 4*B*H*Tq*Tk*d flop per call (causal: unmasked half).
+#include <cfloat>
+#include <cstdlib>
+#include <cstring>
+
+#include "oeh_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace oeh {
+namespace {
+
+constexpr int BM = 128;                 // query rows per CTA  (== threads per CTA, lane == row)
+constexpr int BN = 128;                 // keys per K/V tile
+constexpr int HD = 64;                  // head dim (BERT-base / OPT-125m..1.3b)
+constexpr int kTileBytes = BN * HD * 2; // 16 KB
+constexpr int kSmemBytes = 5 * kTileBytes + 1024;
+constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kColS = 0, kColP = 0, kColO = 128;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct TmapCoord {      // which logical index (0 = token row, 1 = head, 2 = batch) each tensor-map dim 1..3 takes
+  int8_t perm[3];
+};
+
+struct AttnParams {
+  int B, H, Tq, Tk;
+  float scale;          // natural-domain score scale
+  int kind;
+  float stretch, gamma; // clip((eta-gamma)*p + gamma, 0, 1)
+  int causal;
+  const void* mask;
+  int mask_dtype;
+  int64_t ms0, ms1, ms2;
+  int clamp_min;
+  float fmin;
+  const float* gate_logits;
+  float gate_scale;
+  const float* qdq_scores;
+  const float* qdq_probs;
+  const float* qdq_ctx;
+  float int_max;
+  int ctx_qdq_before_gate;
+  void* out;
+  int64_t os0, os1, os2;
+  TmapCoord cq, ck, cv;
+  float* dbg_s;         // optional: raw S of K tile 0, (B,H,Tq,BN) fp32
+  float* dbg_o;         // optional: raw O accumulator, (B,H,Tq,HD) fp32
+};
+
+__device__ __forceinline__ float qdq_f32(float x, float scale, float zp, float int_max) {
+  float xi = __fadd_rn(rintf(__fdiv_rn(x, scale)), zp);
+  xi = xi < 0.f ? 0.f : (xi > int_max ? int_max : xi);
+  return __fmul_rn(scale, __fsub_rn(xi, zp));
+}
+
+__device__ __forceinline__ float load_mask_elem(const void* mask, int dtype, int64_t off) {
+  if (dtype == OEH_F32) return __ldg(reinterpret_cast<const float*>(mask) + off);
+  if (dtype == OEH_F16) return __half2float(__ldg(reinterpret_cast<const __half*>(mask) + off));
+  return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(mask) + off));
+}
+
+template <bool kBF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (kBF16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+}
+
+__device__ __forceinline__ void tma_tile(uint32_t dst, const CUtensorMap* m, uint32_t bar, const TmapCoord& c, int row,
+                                         int h, int b) {
+  auto pick = [&](int k) { return k == 0 ? row : (k == 1 ? h : b); };
+  ptx::tma_load_4d(dst, m, bar, 0, pick(c.perm[0]), pick(c.perm[1]), pick(c.perm[2]));
+}
+
+template <bool kBF16>
+__global__ void __launch_bounds__(BM, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
+                const __grid_constant__ CUtensorMap tmv, const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[6];      // q, k0, k1, v0, v1, mma
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
+  const int row = q0 + tid;                       // this thread's query row
+
+  const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-B alignment
+  const uint32_t sQ = smem0;
+  const uint32_t sK[2] = {smem0 + 1 * kTileBytes, smem0 + 2 * kTileBytes};
+  const uint32_t sV[2] = {smem0 + 3 * kTileBytes, smem0 + 4 * kTileBytes};
+  const uint32_t bar_q = ptx::smem_u32(&bars[0]);
+  const uint32_t bar_k[2] = {ptx::smem_u32(&bars[1]), ptx::smem_u32(&bars[2])};
+  const uint32_t bar_v[2] = {ptx::smem_u32(&bars[3]), ptx::smem_u32(&bars[4])};
+  const uint32_t bar_mma = ptx::smem_u32(&bars[5]);
+
+  if (tid == 0) {
+    ptx::prefetch_tmap(&tmq);
+    ptx::prefetch_tmap(&tmk);
+    ptx::prefetch_tmap(&tmv);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) ptx::mbar_init(ptx::smem_u32(&bars[i]), 1);
+    ptx::fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 0) ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(&tmem_base_slot));
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32-lane slice
+
+  // ---- iteration plan -----------------------------------------------------------------------------
+  int n_kv = (p.Tk + BN - 1) / BN;
+  if (p.causal) {
+    const int last = q0 + BM - 1 + (p.Tk - p.Tq);               // last key any row of this tile may see
+    const int lim = last / BN + 1;
+    n_kv = lim < n_kv ? lim : n_kv;
+  }
+  const bool softmax1 = (p.kind == OEH_SOFTMAX_1 || p.kind == OEH_SOFTMAX_CLIPPED1);
+  const bool clipped = p.kind >= OEH_SOFTMAX_CLIPPED;
+  const bool normalized = clipped || p.qdq_probs != nullptr;   // P must be normalised before PV
+  const bool one_tile = normalized && n_kv == 1;
+  const int nA = (normalized && !one_tile) ? n_kv : 0;         // stats-pass iterations
+  const int n_iter = nA + n_kv;
+
+  constexpr uint32_t kIdescQK = ptx::make_idesc_f16(kBF16, BM, BN, false, false);
+  constexpr uint32_t kIdescPV = ptx::make_idesc_f16(kBF16, BM, HD, false, true);
+
+  auto issue_loads = [&](int it) {
+    const int tile = it < nA ? it : it - nA;
+    const int ks = it & 1;
+    ptx::mbar_expect_tx(bar_k[ks], kTileBytes);
+    tma_tile(sK[ks], &tmk, bar_k[ks], p.ck, tile * BN, h, b);
+    if (it >= nA) {
+      const int vs = (it - nA) & 1;
+      ptx::mbar_expect_tx(bar_v[vs], kTileBytes);
+      tma_tile(sV[vs], &tmv, bar_v[vs], p.cv, tile * BN, h, b);
+    }
+  };
+  auto issue_qk = [&](int it) {
+    ptx::mbar_wait(bar_k[it & 1], (uint32_t)(it >> 1) & 1u);
+    ptx::tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < HD / 16; ++k) {
+      const uint64_t da = ptx::make_smem_desc_sw128(sQ + k * 32, 16, 1024);
+      const uint64_t db = ptx::make_smem_desc_sw128(sK[it & 1] + k * 32, 16, 1024);
+      ptx::mma_ss(tmem + kColS, da, db, kIdescQK, k > 0);
+    }
+  };
+  auto issue_pv = [&](int it) {
+    const int vi = it - nA;
+    ptx::mbar_wait(bar_v[vi & 1], (uint32_t)(vi >> 1) & 1u);
+    ptx::tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < BN / 16; ++k) {
+      const uint64_t db = ptx::make_smem_desc_sw128(sV[vi & 1] + k * 2048, 1024, 1024);
+      ptx::mma_ts(tmem + kColO, tmem + kColP + k * 8, db, kIdescPV, (vi > 0 || k > 0) ? 1u : 0u);
+    }
+  };
+
+  if (tid == 0) {
+    ptx::mbar_expect_tx(bar_q, kTileBytes);
+    tma_tile(sQ, &tmq, bar_q, p.cq, q0, h, b);
+    issue_loads(0);
+    if (n_iter > 1) issue_loads(1);
+    ptx::mbar_wait(bar_q, 0);
+    issue_qk(0);
+    ptx::mma_commit(bar_mma);
+  }
+  __syncwarp();
+
+  // ---- per-row state ------------------------------------------------------------------------------
+  const float scale = p.scale;
+  float sc_s = 1.f, zp_s = 0.f, sc_p = 1.f, zp_p = 0.f;
+  if (p.qdq_scores) { sc_s = __ldg(p.qdq_scores); zp_s = __ldg(p.qdq_scores + 1); }
+  if (p.qdq_probs) { sc_p = __ldg(p.qdq_probs); zp_p = __ldg(p.qdq_probs + 1); }
+  const int64_t mask_row = p.mask ? ((int64_t)b * p.ms0 + (int64_t)h * p.ms1 + (int64_t)(row < p.Tq ? row : 0) * p.ms2) : 0;
+  const int causal_lim = p.causal ? row + (p.Tk - p.Tq) : 0x7fffffff;   // keys j <= causal_lim are visible
+
+  float m_run = -INFINITY, l_run = 0.f, inv_den = 1.f;
+  uint32_t mma_phase = 0;
+
+  for (int it = 0; it < n_iter; ++it) {
+    ptx::mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1u;
+    ptx::tc_fence_after();
+    // S(it) is complete, and so is every MMA issued before it: the stage used by iteration it-1 is free
+    if (tid == 0 && it >= 1 && it + 1 < n_iter) issue_loads(it + 1);
+    __syncwarp();
+
+    const bool pv_iter = it >= nA;
+    const int tile = pv_iter ? it - nA : it;
+    const int k0 = tile * BN;
+
+    float s[BN];
+    {
+      uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) ptx::tmem_ld32(t_lane + kColS + c * 32, sr + c * 32);
+      ptx::tmem_wait_ld();
+    }
+    if (p.dbg_s && it == 0 && row < p.Tq) {
+      float* d = p.dbg_s + (((int64_t)b * p.H + h) * p.Tq + row) * BN;
+#pragma unroll
+      for (int j = 0; j < BN; ++j) d[j] = s[j];
+    }
+
+    // scores -> log2 domain, with qdq tap / mask / clamp exactly in the reference's order
+    float tile_max = -INFINITY;
+    const bool plain = !p.qdq_scores && !p.mask && !p.clamp_min;
+    const int valid = min(p.Tk - k0, BN);          // columns < valid exist
+    const int vis = min(valid - 1, causal_lim - k0); // columns <= vis are visible
+    if (plain) {
+      const float sl2 = scale * kLog2e;
+#pragma unroll
+      for (int j = 0; j < BN; ++j) {
+        s[j] = j <= vis ? s[j] * sl2 : -INFINITY;
+        tile_max = fmaxf(tile_max, s[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < BN; ++j) {
+        float x = s[j] * scale;
+        if (p.qdq_scores) x = qdq_f32(x, sc_s, zp_s, p.int_max);
+        if (p.mask && j < valid) x = x + load_mask_elem(p.mask, p.mask_dtype, mask_row + k0 + j);
+        if (p.clamp_min) x = fmaxf(x, p.fmin);
+        x = fmaxf(x * kLog2e, -FLT_MAX);            // finfo.min masks stay finite (all-masked rows -> uniform)
+        s[j] = j <= vis ? x : -INFINITY;
+        tile_max = fmaxf(tile_max, s[j]);
+      }
+    }
+
+    if (!pv_iter || one_tile || !normalized) {
+      // running (m, l) update
+      const float m_new = fmaxf(m_run, tile_max);
+      const float m_safe = m_new == -INFINITY ? 0.f : m_new;
+      const float alpha = ptx::ex2(m_run - m_safe);   // m_run = -inf -> 0
+      if (!pv_iter) {
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < BN; ++j) sum += ptx::ex2(s[j] - m_safe);
+        l_run = l_run * alpha + sum;
+        m_run = m_new;
+        ptx::tc_fence_before();
+        __syncthreads();                              // every thread has read S(it)
+        if (tid == 0) {
+          ptx::tc_fence_after();
+          issue_qk(it + 1);                           // a stats iteration is never the last one
+          ptx::mma_commit(bar_mma);
+        }
+        __syncwarp();
+        continue;
+      }
+      // PV iteration with un-normalised P (online) or the single-tile normalised case
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < BN; ++j) {
+        s[j] = ptx::ex2(s[j] - m_safe);
+        sum += s[j];
+      }
+      l_run = l_run * alpha + sum;
+      m_run = m_new;
+      if (one_tile) {
+        const float den = softmax1 ? l_run + ptx::ex2(-m_safe) : l_run;
+        inv_den = __frcp_rn(den);
+      } else if (it > nA && !__all_sync(0xffffffffu, alpha == 1.f)) {
+        // correction: O *= alpha (TMEM round trip; skipped when no row of this warp moved its max)
+        uint32_t o[HD];
+        ptx::tmem_ld32(t_lane + kColO, o);
+        ptx::tmem_ld32(t_lane + kColO + 32, o + 32);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < HD; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+        ptx::tmem_st32(t_lane + kColO, o);
+        ptx::tmem_st32(t_lane + kColO + 32, o + 32);
+      }
+    } else {
+      // PV pass of the two-pass (normalised) mode: m, l are final
+      const float m_safe = m_run == -INFINITY ? 0.f : m_run;
+      if (it == nA) {
+        const float den = softmax1 ? l_run + ptx::ex2(-m_safe) : l_run;
+        inv_den = __frcp_rn(den);
+      }
+#pragma unroll
+      for (int j = 0; j < BN; ++j) s[j] = ptx::ex2(s[j] - m_safe);
+    }
+
+    if (normalized) {
+#pragma unroll
+      for (int j = 0; j < BN; ++j) {
+        float v = s[j] * inv_den;
+        if (clipped) {
+          v = fmaf(v, p.stretch, p.gamma);
+          v = fminf(fmaxf(v, 0.f), 1.f);
+        }
+        if (p.qdq_probs) v = qdq_f32(v, sc_p, zp_p, p.int_max);
+        s[j] = v;
+      }
+    }
+
+    // P -> TMEM (packed 16-bit pairs), aliasing the S columns this thread has already consumed
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = pack2<kBF16>(s[c * 32 + 2 * j], s[c * 32 + 2 * j + 1]);
+      ptx::tmem_st16(t_lane + kColP + c * 16, pk);
+    }
+    ptx::tmem_wait_st();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      ptx::tc_fence_after();
+      issue_pv(it);
+      if (it + 1 < n_iter) issue_qk(it + 1);
+      ptx::mma_commit(bar_mma);
+    }
+    __syncwarp();
+  }
+
+  // ---- epilogue -------------------------------------------------------------------------------------
+  ptx::mbar_wait(bar_mma, mma_phase);
+  ptx::tc_fence_after();
+  float o[HD];
+  {
+    uint32_t* orr = reinterpret_cast<uint32_t*>(o);
+    ptx::tmem_ld32(t_lane + kColO, orr);
+    ptx::tmem_ld32(t_lane + kColO + 32, orr + 32);
+    ptx::tmem_wait_ld();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem);
+
+  if (row >= p.Tq) return;
+  if (p.dbg_o) {
+    float* d = p.dbg_o + (((int64_t)b * p.H + h) * p.Tq + row) * HD;
+#pragma unroll
+    for (int j = 0; j < HD; ++j) d[j] = o[j];
+  }
+  float mul = 1.f;
+  if (!normalized) {
+    const float m_safe = m_run == -INFINITY ? 0.f : m_run;
+    const float den = softmax1 ? l_run + ptx::ex2(-m_safe) : l_run;
+    mul = __frcp_rn(den);
+  }
+  float gate = 1.f;
+  if (p.gate_logits) {
+    const float z = __ldg(p.gate_logits + ((int64_t)b * p.H + h) * p.Tq + row);
+    gate = __frcp_rn(1.f + expf(-z)) * p.gate_scale;
+  }
+  float sc_c = 1.f, zp_c = 0.f;
+  if (p.qdq_ctx) { sc_c = __ldg(p.qdq_ctx); zp_c = __ldg(p.qdq_ctx + 1); }
+#pragma unroll
+  for (int j = 0; j < HD; ++j) {
+    float v = o[j] * mul;
+    if (p.qdq_ctx && p.ctx_qdq_before_gate) v = qdq_f32(v, sc_c, zp_c, p.int_max);
+    v *= gate;
+    if (p.qdq_ctx && !p.ctx_qdq_before_gate) v = qdq_f32(v, sc_c, zp_c, p.int_max);
+    o[j] = v;
+  }
+  uint8_t* optr = reinterpret_cast<uint8_t*>(p.out) + 2 * ((int64_t)b * p.os0 + (int64_t)h * p.os1 + (int64_t)row * p.os2);
+#pragma unroll
+  for (int c = 0; c < HD / 8; ++c) {
+    uint4 v;
+    v.x = pack2<kBF16>(o[c * 8 + 0], o[c * 8 + 1]);
+    v.y = pack2<kBF16>(o[c * 8 + 2], o[c * 8 + 3]);
+    v.z = pack2<kBF16>(o[c * 8 + 4], o[c * 8 + 5]);
+    v.w = pack2<kBF16>(o[c * 8 + 6], o[c * 8 + 7]);
+    reinterpret_cast<uint4*>(optr)[c] = v;
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 4-D tensor map over a (B,H,T,64) strided view whose head dim is contiguous: dim0 = d, dims 1..3 =
+// (token, head, batch) ordered by increasing stride; box = [64, 128 tokens, 1, 1]; 128-byte swizzle.
+int make_tmap(CUtensorMap* tm, TmapCoord* coord, const void* base, int dtype, int B, int H, int T,
+              const int64_t* strides /* (b,h,t) elements */, const char* what) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(OEH_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (reinterpret_cast<uintptr_t>(base) & 15)
+    return set_error(OEH_ERR_UNSUPPORTED, "oeh_attn_fwd: %s base pointer must be 16-byte aligned", what);
+  struct Dim { int64_t size, stride; int logical; } dims[3] = {{T, strides[2], 0}, {H, strides[1], 1}, {B, strides[0], 2}};
+  for (int i = 0; i < 3; ++i) {
+    if (dims[i].size > 1 && (dims[i].stride <= 0 || (dims[i].stride * 2) % 16 != 0))
+      return set_error(OEH_ERR_UNSUPPORTED, "oeh_attn_fwd: %s stride %lld (elements) must be a positive multiple of 8",
+                       what, (long long)dims[i].stride);
+  }
+  // size-1 dims: their stride is irrelevant; give them a harmless large stride so they sort last
+  int64_t span = HD;
+  for (int i = 0; i < 3; ++i)
+    if (dims[i].size > 1) span = span > dims[i].stride * dims[i].size ? span : dims[i].stride * dims[i].size;
+  for (int i = 0; i < 3; ++i)
+    if (dims[i].size <= 1) { dims[i].size = 1; dims[i].stride = (span + 7) / 8 * 8; }
+  for (int i = 0; i < 3; ++i)       // sort by stride, ascending
+    for (int j = i + 1; j < 3; ++j)
+      if (dims[j].stride < dims[i].stride) { Dim t = dims[i]; dims[i] = dims[j]; dims[j] = t; }
+  cuuint64_t gdim[4] = {HD, (cuuint64_t)dims[0].size, (cuuint64_t)dims[1].size, (cuuint64_t)dims[2].size};
+  cuuint64_t gstr[3] = {(cuuint64_t)dims[0].stride * 2, (cuuint64_t)dims[1].stride * 2, (cuuint64_t)dims[2].stride * 2};
+  cuuint32_t box[4] = {HD, 1, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 3; ++i) {
+    coord->perm[i] = (int8_t)dims[i].logical;
+    if (dims[i].logical == 0) box[i + 1] = BN;
+  }
+  CUresult r = enc(tm, dtype == OEH_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                   const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(OEH_ERR_UNSUPPORTED, "oeh_attn_fwd: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return OEH_OK;
+}
+
+int validate(const OehAttnArgs* a) {
+  OEH_CHECK_ARG(a, "oeh_attn_fwd: null args");
+  OEH_CHECK_ARG(a->B >= 0 && a->H >= 0 && a->Tq >= 0 && a->Tk >= 0, "oeh_attn_fwd: negative dimension");
+  OEH_CHECK_ARG(a->kind >= OEH_SOFTMAX_VANILLA && a->kind <= OEH_SOFTMAX_CLIPPED1, "oeh_attn_fwd: unknown softmax kind %d",
+                a->kind);
+  if (a->d != HD) return set_error(OEH_ERR_UNSUPPORTED, "oeh_attn_fwd: head dim %d (only %d is built)", a->d, HD);
+  if (a->dtype != OEH_F16 && a->dtype != OEH_BF16)
+    return set_error(OEH_ERR_UNSUPPORTED, "oeh_attn_fwd: dtype %d (fp16/bf16 inputs only; fp32 uses the unfused path)", a->dtype);
+  if (a->causal && a->Tk < a->Tq)
+    return set_error(OEH_ERR_UNSUPPORTED, "oeh_attn_fwd: causal with Tk < Tq");
+  if ((a->qdq_scores || a->qdq_probs || a->qdq_ctx) && (a->n_bits < 1 || a->n_bits > 16))
+    return set_error(OEH_ERR_BAD_ARG, "oeh_attn_fwd: n_bits=%d outside [1,16]", a->n_bits);
+  return OEH_OK;
+}
+
+}  // namespace
+}  // namespace oeh
+
+using namespace oeh;
+
+extern "C" size_t oeh_attn_workspace_bytes(const OehAttnArgs* args) {
+  (void)args;   // row statistics of the two-pass modes stay in registers: no workspace
+  return 0;
+}
+
+extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg_o) {
+  int rc = validate(a);
+  if (rc) return rc;
+  if (a->B == 0 || a->H == 0 || a->Tq == 0) return OEH_OK;
+  OEH_CHECK_ARG(a->Tk > 0, "oeh_attn_fwd: Tk == 0 (softmax over an empty dimension)");
+  OEH_CHECK_ARG(a->q && a->k && a->v && a->out, "oeh_attn_fwd: null tensor pointer");
+  OEH_CHECK_ARG(a->H <= 65535 && a->B <= 65535, "oeh_attn_fwd: B and H must be <= 65535");
+  if ((reinterpret_cast<uintptr_t>(a->out) & 15) || a->out_strides[0] % 8 || a->out_strides[1] % 8 || a->out_strides[2] % 8)
+    return set_error(OEH_ERR_UNSUPPORTED, "oeh_attn_fwd: out must be 16-byte aligned with strides that are multiples of 8");
+
+  CUtensorMap tmq, tmk, tmv;
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  if ((rc = make_tmap(&tmq, &p.cq, a->q, a->dtype, a->B, a->H, a->Tq, a->q_strides, "q"))) return rc;
+  if ((rc = make_tmap(&tmk, &p.ck, a->k, a->dtype, a->B, a->H, a->Tk, a->k_strides, "k"))) return rc;
+  if ((rc = make_tmap(&tmv, &p.cv, a->v, a->dtype, a->B, a->H, a->Tk, a->v_strides, "v"))) return rc;
+  p.B = a->B; p.H = a->H; p.Tq = a->Tq; p.Tk = a->Tk;
+  p.scale = a->scale;
+  p.kind = a->kind;
+  p.stretch = (float)(a->eta - a->gamma);
+  p.gamma = (float)a->gamma;
+  p.causal = a->causal;
+  p.mask = a->mask;
+  p.mask_dtype = a->mask_dtype;
+  if (a->mask) { p.ms0 = a->mask_strides[0]; p.ms1 = a->mask_strides[1]; p.ms2 = a->mask_strides[2]; }
+  p.clamp_min = a->clamp_min;
+  p.fmin = a->dtype == OEH_F16 ? -65504.f : -3.3895313892515355e38f;
+  p.gate_logits = a->gate_logits;
+  p.gate_scale = a->gate_scale;
+  p.qdq_scores = a->qdq_scores;
+  p.qdq_probs = a->qdq_probs;
+  p.qdq_ctx = a->qdq_ctx;
+  p.int_max = (float)((1 << (a->n_bits > 0 ? a->n_bits : 8)) - 1);
+  p.ctx_qdq_before_gate = a->ctx_qdq_before_gate;
+  p.out = a->out;
+  p.os0 = a->out_strides[0]; p.os1 = a->out_strides[1]; p.os2 = a->out_strides[2];
+  p.dbg_s = dbg_s;
+  p.dbg_o = dbg_o;
+
+  dim3 grid((unsigned)((a->Tq + BM - 1) / BM), (unsigned)a->H, (unsigned)a->B);
+  cudaStream_t st = (cudaStream_t)a->stream;
+  static bool attr_done[2] = {false, false};
+  if (a->dtype == OEH_BF16) {
+    if (!attr_done[1]) {
+      OEH_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      attr_done[1] = true;
+    }
+    attn_fwd_kernel<true><<<grid, BM, kSmemBytes, st>>>(tmq, tmk, tmv, p);
+  } else {
+    if (!attr_done[0]) {
+      OEH_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      attr_done[0] = true;
+    }
+    attn_fwd_kernel<false><<<grid, BM, kSmemBytes, st>>>(tmq, tmk, tmv, p);
+  }
+  return check_launch("attn_fwd_kernel");
+}
+
+extern "C" int oeh_attn_fwd(const OehAttnArgs* args) { return oeh_attn_fwd_debug(args, nullptr, nullptr); }

@@ -1,0 +1,230 @@
+"""Tensor-level wrappers over the C ABI (include/oeh.h).  PyTorch here is plumbing only: device
+memory, the current CUDA stream and strides.  Every function enqueues on
+``torch.cuda.current_stream()`` and performs no host synchronisation."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.OEH_F32, torch.float16: L.OEH_F16, torch.bfloat16: L.OEH_BF16}
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise NotImplementedError(f"dtype {t.dtype} is not supported by liboeh") from None
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("outeffhop_b200 ops run on CUDA tensors only (there is no CPU fallback)")
+
+
+_ws_cache = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Per-(device, stream) scratch buffer, grown on demand (never shrinks, never synchronises)."""
+    key = (device.index, _stream())
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def _bht_strides(t: torch.Tensor):
+    if t.dim() != 4 or t.stride(3) != 1:
+        raise ValueError("expected a (B,H,T,d) view whose last dimension is contiguous")
+    return (C.c_int64 * 3)(t.stride(0), t.stride(1), t.stride(2))
+
+
+def _mask_args(mask: Optional[torch.Tensor], B: int, H: int, Tq: int, Tk: int):
+    if mask is None:
+        return None, 0, None, None
+    m = mask
+    while m.dim() < 4:
+        m = m.unsqueeze(0)
+    m = m.expand(B, H, Tq, Tk)               # broadcast dims get stride 0
+    if Tk > 1 and m.stride(3) != 1:
+        m = m.contiguous()
+    return m, _dtype_code(m), (C.c_int64 * 3)(m.stride(0), m.stride(1), m.stride(2)), m
+
+
+def attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float, kind: int,
+                  gamma: float = 0.0, eta: float = 1.0, causal: bool = False,
+                  mask: Optional[torch.Tensor] = None, clamp_min: bool = False,
+                  gate_logits: Optional[torch.Tensor] = None, gate_scale: float = 1.0,
+                  qdq_scores: Optional[torch.Tensor] = None, qdq_probs: Optional[torch.Tensor] = None,
+                  qdq_ctx: Optional[torch.Tensor] = None, n_bits: int = 8, ctx_qdq_before_gate: bool = False,
+                  out_layout: str = "bthd", _debug=None) -> torch.Tensor:
+    """Fused attention core (oeh_attn_fwd).  q,k,v: (B,H,T,d) strided views, fp16/bf16.
+    Returns (B,Tq,H*d) for out_layout="bthd" (the reference's permute+view folded into the store,
+    bert_attention.py:335-337 / opt_attention.py:318-322) or (B,H,Tq,d) for "bhtd".
+    qdq_* are device tensors [scale, zero_point] (e.g. ``state[4:6]`` of a quantizer state)."""
+    _require_cuda(q, k, v, mask, gate_logits)
+    B, H, Tq, d = q.shape
+    Tk = k.shape[2]
+    if k.shape != (B, H, Tk, d) or v.shape != (B, H, Tk, d):
+        raise ValueError(f"q/k/v shape mismatch: {tuple(q.shape)} {tuple(k.shape)} {tuple(v.shape)}")
+    if not (q.dtype == k.dtype == v.dtype):
+        raise ValueError("q, k, v must share a dtype")
+    if out_layout == "bthd":
+        base = torch.empty((B, Tq, H, d), dtype=q.dtype, device=q.device)
+        out_view = base.permute(0, 2, 1, 3)
+    elif out_layout == "bhtd":
+        base = out_view = torch.empty((B, H, Tq, d), dtype=q.dtype, device=q.device)
+    else:
+        raise ValueError(f"unknown out_layout {out_layout!r}")
+    a = L.OehAttnArgs()
+    a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out_view.data_ptr()
+    a.q_strides, a.k_strides, a.v_strides = _bht_strides(q), _bht_strides(k), _bht_strides(v)
+    a.out_strides = _bht_strides(out_view)
+    a.B, a.H, a.Tq, a.Tk, a.d = B, H, Tq, Tk, d
+    a.dtype = _dtype_code(q)
+    a.scale = float(scale)
+    a.kind, a.gamma, a.eta = int(kind), float(gamma), float(eta)
+    a.causal = int(bool(causal))
+    m, mdt, mstr, _keep = _mask_args(mask, B, H, Tq, Tk)
+    if m is not None:
+        a.mask, a.mask_dtype, a.mask_strides = m.data_ptr(), mdt, mstr
+    a.clamp_min = int(bool(clamp_min))
+    if gate_logits is not None:
+        if gate_logits.dtype != torch.float32 or gate_logits.numel() != B * H * Tq or not gate_logits.is_contiguous():
+            raise ValueError("gate_logits must be a contiguous fp32 (B,H,Tq) tensor")
+        a.gate_logits = gate_logits.data_ptr()
+    a.gate_scale = float(gate_scale)
+    for name, t in (("qdq_scores", qdq_scores), ("qdq_probs", qdq_probs), ("qdq_ctx", qdq_ctx)):
+        if t is not None:
+            if t.dtype != torch.float32 or t.numel() < 2 or not t.is_cuda:
+                raise ValueError(f"{name} must be a CUDA fp32 tensor [scale, zero_point]")
+            setattr(a, name, t.data_ptr())
+    a.n_bits = int(n_bits)
+    a.ctx_qdq_before_gate = int(bool(ctx_qdq_before_gate))
+    a.stream = _stream()
+    lib = L.lib()
+    need = lib.oeh_attn_workspace_bytes(C.byref(a))
+    if need:
+        ws = _workspace(q.device, need)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    if _debug is not None:
+        dbg_s, dbg_o = _debug
+        L.check(lib.oeh_attn_fwd_debug(C.byref(a), dbg_s.data_ptr() if dbg_s is not None else None,
+                                       dbg_o.data_ptr() if dbg_o is not None else None))
+    else:
+        L.check(lib.oeh_attn_fwd(C.byref(a)))
+    return base.view(B, Tq, H * d) if out_layout == "bthd" else base
+
+
+def softmax_rows(x: torch.Tensor, kind: int, gamma: float = 0.0, eta: float = 1.0, *, in_scale: float = 1.0,
+                 mask: Optional[torch.Tensor] = None, causal: bool = False, clamp_min: bool = False,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Row softmax family on a materialised (B,H,Tq,Tk) (or (...,Tk)) score tensor (oeh_softmax_rows)."""
+    _require_cuda(x, mask)
+    if x.dim() == 4:
+        B, H, Tq, Tk = x.shape
+    else:
+        if mask is not None or causal:
+            raise ValueError("mask / causal need a 4-D (B,H,Tq,Tk) input")
+        Tk = x.shape[-1]
+        B, H, Tq = 1, 1, x.numel() // max(Tk, 1)
+    xc = x.contiguous()
+    y = out if out is not None else torch.empty_like(xc)
+    m, mdt, mstr, _keep = _mask_args(mask, B, H, Tq, Tk)
+    L.check(L.lib().oeh_softmax_rows(xc.data_ptr(), y.data_ptr(), B, H, Tq, Tk, _dtype_code(xc), float(in_scale),
+                                     int(kind), float(gamma), float(eta), m.data_ptr() if m is not None else None,
+                                     mdt, mstr, int(bool(causal)), int(bool(clamp_min)), _stream()))
+    return y
+
+
+def gate_logits(x: torch.Tensor, num_heads: int, w1: torch.Tensor, b1: torch.Tensor,
+                w2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-token gate logits (oeh_gate_logits).  x (B,T,H*d); Linear gate: w1 (H,d), b1 (H);
+    MLP gate: w1 (H,m,d), b1 (H,m), w2 (H,m), b2 (H).  Weights fp32 contiguous.  Returns (B,H,T) fp32."""
+    _require_cuda(x, w1, b1, w2, b2)
+    B, T, HD = x.shape
+    d = HD // num_heads
+    if x.stride(2) != 1 or x.stride(0) != T * x.stride(1):
+        x = x.contiguous()
+    hidden = 0 if w1.dim() == 2 else w1.shape[1]
+    for t in (w1, b1, w2, b2):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+            raise ValueError("gate weights must be contiguous fp32 tensors")
+    out = torch.empty((B, num_heads, T), dtype=torch.float32, device=x.device)
+    L.check(L.lib().oeh_gate_logits(x.data_ptr(), _dtype_code(x), B, T, num_heads, d, x.stride(1), w1.data_ptr(),
+                                    b1.data_ptr(), w2.data_ptr() if w2 is not None else None,
+                                    b2.data_ptr() if b2 is not None else None, hidden, out.data_ptr(), _stream()))
+    return out
+
+
+def fake_quant_asym(x: torch.Tensor, qparams: torch.Tensor, n_bits: int = 8, emit_codes: bool = False,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Asymmetric uniform quantize-dequantize (oeh_fake_quant_asym).  qparams: CUDA fp32 [scale, zero_point]."""
+    _require_cuda(x, qparams)
+    xc = x.contiguous()
+    y = out if out is not None else torch.empty_like(xc)
+    if qparams.dtype != torch.float32 or qparams.numel() < 2:
+        raise ValueError("qparams must be a CUDA fp32 tensor [scale, zero_point]")
+    L.check(L.lib().oeh_fake_quant_asym(xc.data_ptr(), y.data_ptr(), xc.numel(), _dtype_code(xc), qparams.data_ptr(),
+                                        int(n_bits), int(bool(emit_codes)), _stream()))
+    return y
+
+
+def minmax(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Global [min, max] of x as a 2-element CUDA fp32 tensor (oeh_minmax); no host sync."""
+    _require_cuda(x)
+    xc = x.contiguous()
+    if xc.numel() == 0:
+        raise RuntimeError("min(): Expected reduction dim to be specified for input.numel() == 0.")
+    res = out if out is not None else torch.empty(2, dtype=torch.float32, device=x.device)
+    lib = L.lib()
+    need = lib.oeh_minmax_workspace_bytes(xc.numel())
+    ws = _workspace(x.device, need)
+    L.check(lib.oeh_minmax(xc.data_ptr(), xc.numel(), _dtype_code(xc), res.data_ptr(), ws.data_ptr(), ws.numel(),
+                           _stream()))
+    return res
+
+
+def new_qstate(device) -> torch.Tensor:
+    """Zeroed device-resident quantizer state (oeh_qstate_slot layout, 8 floats)."""
+    return torch.zeros(L.QS_FLOATS, dtype=torch.float32, device=device)
+
+
+def range_update(state: torch.Tensor, new_minmax: torch.Tensor, momentum: float = 0.9, n_bits: int = 8,
+                 eps: float = 1e-8) -> None:
+    """EMA + set_quant_range on the device (oeh_range_update)."""
+    _require_cuda(state, new_minmax)
+    L.check(L.lib().oeh_range_update(state.data_ptr(), new_minmax.data_ptr(), float(momentum), int(n_bits), float(eps),
+                                     _stream()))
+
+
+def set_quant_range_host(x_min: float, x_max: float, n_bits: int = 8, eps: float = 1e-8):
+    """(_delta, _zero_float, scale, zero_point) from host scalars (oeh_set_quant_range_host)."""
+    out = (C.c_float * 4)()
+    L.check(L.lib().oeh_set_quant_range_host(float(x_min), float(x_max), int(n_bits), float(eps), out))
+    return tuple(out)
+
+
+def estimate_and_quantize(x: torch.Tensor, state: torch.Tensor, momentum: float = 0.9, n_bits: int = 8,
+                          eps: float = 1e-8) -> torch.Tensor:
+    """QuantizationManager.forward in estimate_ranges state on one GPU (oeh_estimate_and_quantize)."""
+    _require_cuda(x, state)
+    xc = x.contiguous()
+    y = torch.empty_like(xc)
+    lib = L.lib()
+    need = lib.oeh_minmax_workspace_bytes(xc.numel()) + 256
+    ws = _workspace(x.device, need)
+    L.check(lib.oeh_estimate_and_quantize(xc.data_ptr(), y.data_ptr(), xc.numel(), _dtype_code(xc), state.data_ptr(),
+                                          float(momentum), int(n_bits), float(eps), ws.data_ptr(), ws.numel(),
+                                          _stream()))
+    return y

@@ -1,0 +1,168 @@
+"""GPU parity of the fused tcgen05 attention kernel, through the C ABI, vs the oracle.
+Tolerance: max-abs 2e-3 on the attention output (fp16/bf16 inputs, fp32 accumulate) -- BASELINE.json."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oeh_oracle as O  # noqa: E402  (checker only)
+
+F32 = np.float32
+TOL = 2e-3
+
+
+def _ops():
+    from outeffhop_b200 import ops
+    return ops
+
+
+def _mk(B, H, Tq, Tk, dtype, seed, layout="bhtd", bias=0.0):
+    g = torch.Generator().manual_seed(seed)
+    def t(T):
+        x = torch.randn(B, H, T, 64, generator=g)
+        return x
+    q, k, v = t(Tq), t(Tk), t(Tk)
+    q = q + bias / 8.0     # shifts the scores: exercises the "+1" term regimes of softmax_1
+    q, k, v = (x.to(dtype) for x in (q, k, v))
+    def place(x):
+        if layout == "bthd":   # BERT: (B,T,H,d) memory viewed as (B,H,T,d)
+            return x.permute(0, 2, 1, 3).contiguous().cuda().permute(0, 2, 1, 3)
+        return x.cuda()
+    return place(q), place(k), place(v)
+
+
+def _oracle(q, k, v, **kw):
+    f = lambda x: x.float().cpu().numpy()
+    return O.attention_core(f(q), f(k), f(v), **kw)
+
+
+KINDS = [(0, 0.0, 1.0), (1, 0.0, 1.0), (2, -0.025, 1.0), (3, -0.025, 1.1), (2, 0.0, 1.03)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("kind,gamma,eta", KINDS)
+@pytest.mark.parametrize("shape", [(2, 3, 128, 128), (1, 2, 64, 64), (2, 2, 50, 77), (1, 2, 256, 384), (1, 1, 130, 1)])
+def test_attention_vs_oracle(dtype, kind, gamma, eta, shape):
+    ops = _ops()
+    B, H, Tq, Tk = shape
+    q, k, v = _mk(B, H, Tq, Tk, dtype, seed=100 + Tq + kind)
+    out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, out_layout="bhtd")
+    ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta)
+    tol = TOL if dtype == torch.float16 else 8e-3   # bf16 output rounding alone is 2^-9 relative
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=tol, rtol=0)
+
+
+@pytest.mark.parametrize("kind,gamma,eta", KINDS)
+@pytest.mark.parametrize("bias", [-8.0, 0.0, 8.0])
+def test_attention_score_regimes_bert_layout(kind, gamma, eta, bias):
+    """C-BERT-like layout ((B,T,H,d) strided views in, (B,T,H*d) out) in the three score regimes."""
+    ops = _ops()
+    B, H, T = 2, 4, 128
+    q, k, v = _mk(B, H, T, T, torch.float16, seed=7 + kind, layout="bthd", bias=bias)
+    k = k * 0 + k.mean(dim=2, keepdim=True) * 0 + k   # keep k as is (view stays strided)
+    out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, out_layout="bthd")
+    assert out.shape == (B, T, H * 64)
+    ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta)
+    ref = ref.transpose(0, 2, 1, 3).reshape(B, T, H * 64)
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=TOL, rtol=0)
+
+
+@pytest.mark.parametrize("kind,gamma,eta", KINDS)
+@pytest.mark.parametrize("T", [72, 128, 300, 512])
+def test_attention_causal(kind, gamma, eta, T):
+    ops = _ops()
+    q, k, v = _mk(2, 2, T, T, torch.float16, seed=T + kind)
+    out = ops.attention_fwd(q, k, v, scale=1.0 / 8, kind=kind, gamma=gamma, eta=eta, causal=True, out_layout="bhtd")
+    ref = _oracle(q, k, v, scale=1.0 / 8, kind=kind, gamma=gamma, eta=eta, causal=True)
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=TOL, rtol=0)
+
+
+@pytest.mark.parametrize("kind,gamma,eta", KINDS[:4])
+def test_attention_dense_masks(kind, gamma, eta):
+    """HF-4.31 additive masks: (B,1,1,Tk) padding mask (BERT) and (B,1,Tq,Tk) causal mask with clamp (OPT)."""
+    ops = _ops()
+    B, H, T = 2, 2, 200
+    q, k, v = _mk(B, H, T, T, torch.float16, seed=31 + kind)
+    fmin = torch.finfo(torch.float16).min
+    pad = torch.zeros(B, 1, 1, T, dtype=torch.float16)
+    pad[1, ..., 150:] = fmin
+    out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, mask=pad.cuda(), out_layout="bhtd")
+    ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, mask=pad.float().numpy())
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=TOL, rtol=0)
+    cm = torch.full((T, T), fmin, dtype=torch.float16).triu(1)[None, None].expand(B, 1, T, T).contiguous()
+    out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, mask=cm.cuda(), clamp_min=True,
+                            out_layout="bhtd")
+    ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=True)
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=TOL, rtol=0)
+
+
+def test_attention_all_masked_rows_match_reference_semantics():
+    """Row masked entirely with finfo.min: vanilla -> uniform probs, softmax_1 -> zeros."""
+    ops = _ops()
+    B, H, T = 1, 1, 128
+    q, k, v = _mk(B, H, T, T, torch.bfloat16, seed=5)
+    m = torch.zeros(B, 1, T, T)
+    m[:, :, 3, :] = torch.finfo(torch.float32).min
+    for kind in (0, 1):
+        out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, mask=m.cuda(), out_layout="bhtd")
+        ref = _oracle(q, k, v, scale=0.125, kind=kind, mask=m.numpy())
+        np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=8e-3, rtol=0)
+
+
+@pytest.mark.parametrize("kind,gamma,eta", KINDS[:4])
+def test_attention_gate_epilogue(kind, gamma, eta):
+    ops = _ops()
+    B, H, T = 2, 3, 160
+    q, k, v = _mk(B, H, T, T, torch.float16, seed=77 + kind)
+    logits = torch.randn(B, H, T) * 2
+    out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, gate_logits=logits.cuda(),
+                            gate_scale=4.0, out_layout="bhtd")
+    gate = O.sigmoid(logits.numpy())
+    ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, gate=gate, gate_scale=4.0)
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=2 * TOL, rtol=0)   # x4 gate scale
+
+
+def test_attention_error_conventions():
+    ops = _ops()
+    from outeffhop_b200._lib import OehUnsupported
+    q = torch.randn(1, 1, 16, 32, device="cuda", dtype=torch.float16)
+    with pytest.raises(OehUnsupported):
+        ops.attention_fwd(q, q, q, scale=1.0, kind=0)           # head dim 32 is not built
+    q = torch.randn(1, 1, 16, 64, device="cuda", dtype=torch.float16)
+    with pytest.raises(ValueError):
+        ops.attention_fwd(q, q, q, scale=1.0, kind=9)
+    with pytest.raises(ValueError):
+        ops.attention_fwd(q, q[:, :, :8], q, scale=1.0, kind=0)
+    e = torch.empty(0, 2, 16, 64, device="cuda", dtype=torch.float16)
+    assert ops.attention_fwd(e, e, e, scale=1.0, kind=1).shape == (0, 16, 128)
+
+
+@pytest.mark.parametrize("T,B", [(2048, 4), (8192, 1)])
+def test_attention_full_size_properties(T, B):
+    """BASELINE config-5 sizes: checked against a torch fp32 restatement on the device for a sample of
+    heads, plus size-independent properties (rows of vanilla sum to 1 via V=ones; softmax_1 rows <= 1;
+    linearity in V)."""
+    ops = _ops()
+    H = 12
+    torch.manual_seed(T)
+    q = torch.randn(B, H, T, 64, device="cuda", dtype=torch.float16)
+    k = torch.randn(B, H, T, 64, device="cuda", dtype=torch.float16)
+    v = torch.randn(B, H, T, 64, device="cuda", dtype=torch.float16)
+    ones = torch.ones_like(v)
+    row_sum = ops.attention_fwd(q, k, ones, scale=0.125, kind=0, out_layout="bhtd").float()
+    assert (row_sum - 1).abs().max().item() < 2e-3
+    row_sum1 = ops.attention_fwd(q, k, ones, scale=0.125, kind=1, out_layout="bhtd").float()
+    assert row_sum1.max().item() <= 1 + 1e-3 and row_sum1.min().item() > 0
+    o1 = ops.attention_fwd(q, k, v, scale=0.125, kind=1, out_layout="bhtd").float()
+    o2 = ops.attention_fwd(q, k, v * 2, scale=0.125, kind=1, out_layout="bhtd").float()
+    assert (o2 - 2 * o1).abs().max().item() < 4e-3
+    for (b, h) in ((0, 0), (B - 1, H - 1)):
+        s = q[b, h].float() @ k[b, h].float().t() * 0.125
+        m = s.max(-1, keepdim=True).values
+        e = torch.exp(s - m)
+        p = e / (e.sum(-1, keepdim=True) + torch.exp(-m))
+        ref = p @ v[b, h].float()
+        assert (o1[b, h] - ref).abs().max().item() < TOL
