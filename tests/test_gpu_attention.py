@@ -62,7 +62,6 @@ def test_attention_score_regimes_bert_layout(kind, gamma, eta, bias):
     ops = _ops()
     B, H, T = 2, 4, 128
     q, k, v = _mk(B, H, T, T, torch.float16, seed=7 + kind, layout="bthd", bias=bias)
-    k = k * 0 + k.mean(dim=2, keepdim=True) * 0 + k   # keep k as is (view stays strided)
     out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, out_layout="bthd")
     assert out.shape == (B, T, H * 64)
     ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta)
