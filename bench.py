@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of BASELINE.json on N GPUs of one node.
+
+Metric: BERT-base eval tokens/s (forward + MLM loss, no data loading) with
+``--attn_softmax "clippedsoftmax1(-.025:1)"``, fp16, seq 128, batch 32 PER GPU (BASELINE config 2), synthetic
+tokens and random-init weights.  One process per GPU (torchrun), batches sharded over ranks, no data-path
+collective; the eval-loss (sum, count) pair is all-reduced once at the end.
+
+    python bench.py --gpus 1 --steps 50 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference path's CPU port on the host cores (rank 0 only)
+
+Prints ONE JSON line (rank 0).  ``value`` = whole-job tokens/s with inputs resident in HBM; ``e2e`` = the same
+through the module API with pinned-host inputs (H2D) and a host read of the loss (D2H) every step;
+``roofline`` = the fused attention kernel (the dominant kernel of THIS code; the rest of the step is library
+GEMMs) timed alone with CUDA events on its launch stream on the model's own Q/K/V shapes;
+``cpu_baseline`` = the oracle port of the reference path on the host cores (rank 0, N=1).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bert_base_eval_tokens_per_s"
+UNIT = "tokens/s"
+ATTN_SOFTMAX = "clippedsoftmax1(-.025:1)"
+BATCH, SEQ, HEADS, HEAD_DIM, LAYERS = 32, 128, 12, 64, 12
+WORKLOAD = "BERT-base fp16 eval, --attn_softmax clippedsoftmax1(-.025:1), seq 128, batch 32 per GPU (BASELINE config 2)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(tensor=d.get("bf16_tflops", 1590.0), tensor_sustained=d.get("bf16_tflops_sustained", 1400.0),
+                    hbm=d.get("hbm_gbs", 6650.0), source="measured (MEASURED_PEAKS.json)")
+    return dict(tensor=1590.0, tensor_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0: float, t1: float):
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.25 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in rows:
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(rows)}
+
+
+def run_reference(args):
+    """The reference path's CPU implementation (oracle port; /root/reference does not exist on the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import c_oracle
+    from oracle.cpu_model import time_bert_eval_cpu
+    c_oracle.build()
+    # bounded sample: the full 32x128 batch per step unless K is so large that the run would take many minutes
+    sample_batch = BATCH if args.steps * 3.0 <= 240 else max(1, int(BATCH * 240 / (args.steps * 3.0)))
+    tps, ms, threads, losses = time_bert_eval_cpu(ATTN_SOFTMAX, sample_batch, SEQ, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic tokens, random-init weights",
+        "config": {"workload": WORKLOAD + " -- CPU fp32 port of the reference path (oracle/cpu_model.py)",
+                   "sample": f"{sample_batch}x{SEQ} tokens per step"},
+        "cpu_baseline": {"value": tps, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps of {sample_batch}x{SEQ} tokens, HF BERT-base shell + C oracle attention"},
+        "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def time_attention_kernel(torch, ops, fn, dtype, reps=20):
+    """Average launch duration of the fused attention kernel on the model's own shapes/strides:
+    (B,T,H,d)-ordered Q/K/V viewed as (B,H,T,d), output (B,T,H*d).  L2 flushed between launches."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    mk = lambda: torch.randn(BATCH, SEQ, HEADS, HEAD_DIM, device="cuda", dtype=dtype, generator=g).permute(0, 2, 1, 3)
+    q, k, v = mk(), mk(), mk()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    run = lambda: ops.attention_fwd(q, k, v, scale=HEAD_DIM ** -0.5, kind=fn.kind, gamma=fn.gamma, eta=fn.eta)
+    for _ in range(5):
+        run()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return sum(ts) / len(ts) * 1e-3     # seconds
+
+
+def attention_sweep(torch, ops, peaks):
+    """Config-5 style points (12 heads, d=64, B*T = 65536 tokens): attention TFLOP/s vs the tensor roofline."""
+    out = {}
+    for T in (2048, 8192):
+        B = 65536 // T
+        q = torch.randn(B, HEADS, T, HEAD_DIM, device="cuda", dtype=torch.float16)
+        k, v = torch.randn_like(q), torch.randn_like(q)
+        for name, kind in (("softmax1", 1), ("clippedsoftmax1", 3)):
+            f = lambda: ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=-0.025, eta=1.1)
+            for _ in range(3):
+                f()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(5):
+                f()
+            b.record()
+            torch.cuda.synchronize()
+            tf = 4.0 * B * HEADS * T * T * HEAD_DIM * 5 / (a.elapsed_time(b) * 1e-3) / 1e12
+            out[f"{name}_T{T}"] = {"tflops": round(tf, 1), "frac_of_measured_peak": round(tf / peaks["tensor"], 4)}
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from outeffhop_b200 import ops
+    from outeffhop_b200._lib import lib
+    from outeffhop_b200.eval_harness import aggregate_perplexity, build_bert_base, make_eval_step, synthetic_mlm_batch
+    from outeffhop_b200.softmax import SOFTMAX_MAPPING
+    lib()                                                 # fail loudly if the CUDA extension is missing
+    peaks = load_peaks()
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    model = build_bert_base(seed=3000, dtype=torch.float16, attn_softmax=ATTN_SOFTMAX)
+    n_pool = 8                                            # distinct synthetic batches per rank, cycled
+    host_pool = [synthetic_mlm_batch(BATCH, SEQ, seed=3000 + 1000 * rank + i) for i in range(n_pool)]
+    dev_pool = [{k: v.cuda() for k, v in hb.items()} for hb in host_pool]
+    step = make_eval_step(model, host_pool[0], use_graph=not args.no_graph)
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(loop_body):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        loop_body()
+        e1.record()
+        barrier()
+        t1 = time.time()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)     # max over ranks
+        return ms.item(), t0, t1
+
+    # ---- device-resident throughput ("value") -------------------------------------------------------------
+    loss_sum = torch.zeros((), dtype=torch.float32, device="cuda")
+
+    def body_resident(n):
+        for i in range(n):
+            for k2, v in dev_pool[i % n_pool].items():    # device-to-device refresh of the static inputs
+                step.static_inputs[k2].copy_(v, non_blocking=True)
+            loss_sum.add_(step.run())
+
+    body_resident(warmup)
+    loss_sum.zero_()
+    ms_res, t0, t1 = timed(lambda: body_resident(steps))
+    ppl = aggregate_perplexity(loss_sum, steps)
+    clocks = sampler.summary(t0, t1) if rank == 0 else None
+
+    # ---- end to end: pinned host -> H2D -> step -> D2H loss, every step --------------------------------------
+    def body_e2e(n):
+        for i in range(n):
+            step.load(host_pool[i % n_pool])
+            loss_host.copy_(step.run(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()     # the caller reads the loss of every step
+            _ = float(loss_host)
+
+    body_e2e(warmup)
+    ms_e2e, _, _ = timed(lambda: body_e2e(steps))
+    if rank == 0:
+        sampler.stop()
+
+    tokens = world * steps * BATCH * SEQ
+    line = None
+    if rank == 0:
+        fn = SOFTMAX_MAPPING[ATTN_SOFTMAX]
+        t_attn = time_attention_kernel(torch, ops, fn, torch.float16)
+        flops = 4.0 * BATCH * HEADS * SEQ * SEQ * HEAD_DIM            # algorithmic: QK^T + PV, per launch
+        achieved = flops / t_attn / 1e12
+        line = {
+            "metric": METRIC, "value": tokens / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_res / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic tokens, random-init weights",
+            "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "seq_len": SEQ, "parallelism": f"dp{world}",
+                       "cuda_graph": not args.no_graph,
+                       "l2": "no flush: 220 MB of fp16 weights + activations per step exceed the 126 MB L2"},
+            "e2e": {"value": tokens / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": step.h2d_bytes(),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps},
+            "gpu_launches": LAYERS * steps,               # one fused attention kernel per layer per step (ungated config)
+            "clocks": clocks,
+            "perplexity": ppl,
+            "roofline": {"kernel": "attn_fwd_kernel<fp16> (fused QK^T->clippedsoftmax1->PV), B=32 H=12 T=128 d=64",
+                         "bound": "tensor", "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["tensor"], "traffic": None, "peak_source": peaks["source"] + ", burst",
+                         "launch_us": t_attn * 1e6, "algorithmic_flops_per_launch": flops,
+                         "note": "T=128 is one K/V tile per CTA: latency-bound; see attn_sweep for T>=2048"},
+        }
+        if not args.no_sweep:
+            line["attn_sweep"] = attention_sweep(torch, ops, peaks)
+        if world == 1 and not args.no_cpu:
+            from oracle import c_oracle
+            from oracle.cpu_model import time_bert_eval_cpu
+            c_oracle.build()
+            tps, ms_cpu, threads, _ = time_bert_eval_cpu(ATTN_SOFTMAX, BATCH, SEQ, steps=4, warmup=1)
+            line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"4 steps of {BATCH}x{SEQ} tokens (+1 warm-up), fp32, HF BERT-base shell "
+                                              "+ C oracle attention (oracle/cpu_model.py)", "ms_per_step": ms_cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="run the eval step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the T=2048/8192 attention sweep")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

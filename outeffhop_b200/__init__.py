@@ -10,17 +10,33 @@ All compute goes through liboeh.so (include/oeh.h); there is no CPU fallback.
 """
 __version__ = "0.1.0"
 
-from . import _lib  # noqa: F401
+import importlib
+
+_SUBMODULES = ("_lib", "ops", "softmax", "quantization", "bert_attention", "opt_attention", "quantized_attention",
+               "build", "eval_harness")
+_EXPORTS = {
+    "SOFTMAX_MAPPING": "softmax", "SoftmaxFn": "softmax", "softmax_1": "softmax", "clipped_softmax": "softmax",
+    "clipped_softmax1": "softmax", "parse_attn_softmax": "softmax",
+    "AttentionGateType": "bert_attention", "logit": "bert_attention",
+    "BertSelfAttentionWithExtras": "bert_attention", "OPTAttentionWithExtras": "opt_attention",
+    "AsymmetricUniformQuantizer": "quantization", "SymmetricUniformQuantizer": "quantization",
+    "RunningMinMaxEstimator": "quantization", "CurrentMinMaxEstimator": "quantization",
+    "QuantizationManager": "quantization", "QuantizedActivation": "quantization", "QuantizedModule": "quantization",
+    "QuantLinear": "quantization", "QMethods": "quantization", "RangeEstimators": "quantization",
+    "Qstates": "quantization", "QuantizerNotInitializedError": "quantization", "set_range_sync": "quantization",
+    "QuantizedBertSelfAttentionWithExtras": "quantized_attention",
+    "QuantizedOPTAttentionWithExtras": "quantized_attention", "QuantizedModel": "quantized_attention",
+}
 
 
 def __getattr__(name):
-    # lazy: importing the package must not import torch-heavy modules before they are needed
-    import importlib
-    for mod in ("softmax", "bert_attention", "opt_attention", "quantization", "quantized_attention", "ops"):
-        try:
-            m = importlib.import_module(f"{__name__}.{mod}")
-        except ModuleNotFoundError:
-            continue
-        if hasattr(m, name):
-            return getattr(m, name)
-    raise AttributeError(name)
+    # lazy: `import outeffhop_b200` must stay cheap (no torch import) until a symbol is used
+    if name in _SUBMODULES:
+        return importlib.import_module(f"{__name__}.{name}")
+    if name in _EXPORTS:
+        return getattr(importlib.import_module(f"{__name__}.{_EXPORTS[name]}"), name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+
+
+def __dir__():
+    return sorted(list(globals()) + list(_SUBMODULES) + list(_EXPORTS))

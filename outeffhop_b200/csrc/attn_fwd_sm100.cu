@@ -65,11 +65,27 @@ struct AttnParams {
   float* dbg_o;         // optional: raw O accumulator, (B,H,Tq,HD) fp32
 };
 
-__device__ __forceinline__ float qdq_f32(float x, float scale, float zp, float int_max) {
-  float xi = __fadd_rn(rintf(__fdiv_rn(x, scale)), zp);
-  xi = xi < 0.f ? 0.f : (xi > int_max ? int_max : xi);
-  return __fmul_rn(scale, __fsub_rn(xi, zp));
+// Fixed-range fake-quant tap inside the fused kernel.  x/scale is evaluated as x*(1/scale): the tap's input
+// already differs from the unfused reference in the last bits (tensor-core accumulation order), so codes can
+// flip at bin edges either way; the bit-exact contract belongs to the standalone quantizer (quant.cu).
+struct Qdq {
+  float scale, inv_scale, zp, int_max;
+  __device__ __forceinline__ float operator()(float x) const {
+    float xi = rintf(x * inv_scale) + zp;
+    xi = fminf(fmaxf(xi, 0.f), int_max);
+    return scale * (xi - zp);
+  }
+};
+__device__ __forceinline__ Qdq load_qdq(const float* qparams, float int_max) {
+  Qdq q;
+  q.scale = __ldg(qparams);
+  q.zp = __ldg(qparams + 1);
+  q.inv_scale = __frcp_rn(q.scale);
+  q.int_max = int_max;
+  return q;
 }
+
+__device__ __forceinline__ float max4(float a, float b, float c, float d) { return fmaxf(fmaxf(a, b), fmaxf(c, d)); }
 
 __device__ __forceinline__ float load_mask_elem(const void* mask, int dtype, int64_t off) {
   if (dtype == OEH_F32) return __ldg(reinterpret_cast<const float*>(mask) + off);
@@ -94,7 +110,11 @@ __device__ __forceinline__ void tma_tile(uint32_t dst, const CUtensorMap* m, uin
   ptx::tma_load_4d(dst, m, bar, 0, pick(c.perm[0]), pick(c.perm[1]), pick(c.perm[2]));
 }
 
-template <bool kBF16>
+// kGeneric = false: no fake-quant taps, no mask tensor, no clamp, no debug dumps -- the tight hot loop.
+// kGeneric = true : everything; each optional feature is its own loop behind one uniform branch so the
+//                   instruction stream actually executed stays small (a per-element branch version of this
+//                   kernel was 310 KB of SASS and ran 3-4x slower from instruction-cache misses).
+template <bool kBF16, bool kGeneric>
 __global__ void __launch_bounds__(BM, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                 const __grid_constant__ CUtensorMap tmv, const __grid_constant__ AttnParams p) {
@@ -193,9 +213,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
 
   // ---- per-row state ------------------------------------------------------------------------------
   const float scale = p.scale;
-  float sc_s = 1.f, zp_s = 0.f, sc_p = 1.f, zp_p = 0.f;
-  if (p.qdq_scores) { sc_s = __ldg(p.qdq_scores); zp_s = __ldg(p.qdq_scores + 1); }
-  if (p.qdq_probs) { sc_p = __ldg(p.qdq_probs); zp_p = __ldg(p.qdq_probs + 1); }
+  const float sl2 = scale * kLog2e;
+  const bool has_qs = kGeneric && p.qdq_scores != nullptr;
+  const bool has_qp = kGeneric && p.qdq_probs != nullptr;
+  const bool has_mask = kGeneric && p.mask != nullptr;
+  Qdq qd_s{1.f, 1.f, 0.f, p.int_max}, qd_p{1.f, 1.f, 0.f, p.int_max};
+  if (has_qs) qd_s = load_qdq(p.qdq_scores, p.int_max);
+  if (has_qp) qd_p = load_qdq(p.qdq_probs, p.int_max);
   const int64_t mask_row = p.mask ? ((int64_t)b * p.ms0 + (int64_t)h * p.ms1 + (int64_t)(row < p.Tq ? row : 0) * p.ms2) : 0;
   const int causal_lim = p.causal ? row + (p.Tk - p.Tq) : 0x7fffffff;   // keys j <= causal_lim are visible
 
@@ -221,48 +245,92 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       for (int c = 0; c < BN / 32; ++c) ptx::tmem_ld32(t_lane + kColS + c * 32, sr + c * 32);
       ptx::tmem_wait_ld();
     }
-    if (p.dbg_s && it == 0 && row < p.Tq) {
+    if (kGeneric && p.dbg_s && it == 0 && row < p.Tq) {
       float* d = p.dbg_s + (((int64_t)b * p.H + h) * p.Tq + row) * BN;
 #pragma unroll
       for (int j = 0; j < BN; ++j) d[j] = s[j];
     }
 
-    // scores -> log2 domain, with qdq tap / mask / clamp exactly in the reference's order
-    float tile_max = -INFINITY;
-    const bool plain = !p.qdq_scores && !p.mask && !p.clamp_min;
-    const int valid = min(p.Tk - k0, BN);          // columns < valid exist
-    const int vis = min(valid - 1, causal_lim - k0); // columns <= vis are visible
-    if (plain) {
-      const float sl2 = scale * kLog2e;
+    const int valid = min(p.Tk - k0, BN);            // columns < valid exist
+    const int vis = min(valid - 1, causal_lim - k0); // columns <= vis are visible to this row
+    // After this block: s[j] holds the score in "raw" units and (mul, tile_max) are such that the log2-domain
+    // score is s[j]*mul and its tile maximum is tile_max.  Plain path: raw MMA output, mul = scale*log2e (the
+    // scale multiply and the max subtraction fold into one FFMA per element).  Generic path: the reference's
+    // op order scale -> qdq -> +mask -> clamp in natural units, then * log2e, mul = 1.
+    float mul = sl2;
+    if (kGeneric && (has_qs || has_mask || p.clamp_min)) {
+      // log2e is applied explicitly (mul = 1): with finfo.min-sized masked scores the rounding error of the
+      // folded multiply (exact product inside the FFMA vs the rounded tile maximum) would be ~1e31
+      mul = 1.f;
 #pragma unroll
-      for (int j = 0; j < BN; ++j) {
-        s[j] = j <= vis ? s[j] * sl2 : -INFINITY;
-        tile_max = fmaxf(tile_max, s[j]);
-      }
-    } else {
+      for (int j = 0; j < BN; ++j) s[j] *= scale;
+      if (has_qs) {
 #pragma unroll
-      for (int j = 0; j < BN; ++j) {
-        float x = s[j] * scale;
-        if (p.qdq_scores) x = qdq_f32(x, sc_s, zp_s, p.int_max);
-        if (p.mask && j < valid) x = x + load_mask_elem(p.mask, p.mask_dtype, mask_row + k0 + j);
-        if (p.clamp_min) x = fmaxf(x, p.fmin);
-        x = fmaxf(x * kLog2e, -FLT_MAX);            // finfo.min masks stay finite (all-masked rows -> uniform)
-        s[j] = j <= vis ? x : -INFINITY;
-        tile_max = fmaxf(tile_max, s[j]);
+        for (int j = 0; j < BN; ++j) s[j] = qd_s(s[j]);
       }
+      if (has_mask) {
+        if (p.mask_dtype == OEH_F32) {
+          const float* mp = reinterpret_cast<const float*>(p.mask) + mask_row + k0;
+#pragma unroll
+          for (int j = 0; j < BN; ++j)
+            if (j < valid) s[j] += __ldg(mp + j);
+        } else if (p.mask_dtype == OEH_F16) {
+          const __half* mp = reinterpret_cast<const __half*>(p.mask) + mask_row + k0;
+#pragma unroll
+          for (int j = 0; j < BN; ++j)
+            if (j < valid) s[j] += __half2float(__ldg(mp + j));
+        } else {
+          const __nv_bfloat16* mp = reinterpret_cast<const __nv_bfloat16*>(p.mask) + mask_row + k0;
+#pragma unroll
+          for (int j = 0; j < BN; ++j)
+            if (j < valid) s[j] += __bfloat162float(__ldg(mp + j));
+        }
+      }
+      // clamp (opt_attention.py:221-223); the lower bound also keeps finfo.min-masked scores finite after
+      // the log2e multiply, so a row masked entirely with finfo.min stays uniform like the reference's
+      const float lo = p.clamp_min ? fmaxf(p.fmin, -FLT_MAX / 2.f) : -FLT_MAX / 2.f;
+#pragma unroll
+      for (int j = 0; j < BN; ++j) s[j] = fmaxf(s[j], lo) * kLog2e;
+    }
+    if (vis < BN - 1) {                               // ragged last tile / causal diagonal tile
+#pragma unroll
+      for (int j = 0; j < BN; ++j)
+        if (j > vis) s[j] = -INFINITY;
+    }
+    float tile_max;
+    {
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // 4 independent chains
+#pragma unroll
+      for (int j = 0; j < BN; j += 4) {
+        m0 = fmaxf(m0, s[j]);
+        m1 = fmaxf(m1, s[j + 1]);
+        m2 = fmaxf(m2, s[j + 2]);
+        m3 = fmaxf(m3, s[j + 3]);
+      }
+      tile_max = max4(m0, m1, m2, m3) * mul;          // mul > 0
     }
 
-    if (!pv_iter || one_tile || !normalized) {
+    const bool online = !normalized;
+    if (!pv_iter || one_tile || online) {
       // running (m, l) update
       const float m_new = fmaxf(m_run, tile_max);
       const float m_safe = m_new == -INFINITY ? 0.f : m_new;
       const float alpha = ptx::ex2(m_run - m_safe);   // m_run = -inf -> 0
-      if (!pv_iter) {
-        float sum = 0.f;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-        for (int j = 0; j < BN; ++j) sum += ptx::ex2(s[j] - m_safe);
-        l_run = l_run * alpha + sum;
-        m_run = m_new;
+      for (int j = 0; j < BN; j += 4) {
+        s[j] = ptx::ex2(fmaf(s[j], mul, -m_safe));
+        s[j + 1] = ptx::ex2(fmaf(s[j + 1], mul, -m_safe));
+        s[j + 2] = ptx::ex2(fmaf(s[j + 2], mul, -m_safe));
+        s[j + 3] = ptx::ex2(fmaf(s[j + 3], mul, -m_safe));
+        a0 += s[j];
+        a1 += s[j + 1];
+        a2 += s[j + 2];
+        a3 += s[j + 3];
+      }
+      l_run = fmaf(l_run, alpha, (a0 + a1) + (a2 + a3));
+      m_run = m_new;
+      if (!pv_iter) {
         ptx::tc_fence_before();
         __syncthreads();                              // every thread has read S(it)
         if (tid == 0) {
@@ -273,15 +341,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
         __syncwarp();
         continue;
       }
-      // PV iteration with un-normalised P (online) or the single-tile normalised case
-      float sum = 0.f;
-#pragma unroll
-      for (int j = 0; j < BN; ++j) {
-        s[j] = ptx::ex2(s[j] - m_safe);
-        sum += s[j];
-      }
-      l_run = l_run * alpha + sum;
-      m_run = m_new;
       if (one_tile) {
         const float den = softmax1 ? l_run + ptx::ex2(-m_safe) : l_run;
         inv_den = __frcp_rn(den);
@@ -304,19 +363,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
         inv_den = __frcp_rn(den);
       }
 #pragma unroll
-      for (int j = 0; j < BN; ++j) s[j] = ptx::ex2(s[j] - m_safe);
+      for (int j = 0; j < BN; ++j) s[j] = ptx::ex2(fmaf(s[j], mul, -m_safe));
     }
 
     if (normalized) {
+      if (clipped) {
+        const float st = p.stretch * inv_den, gm = p.gamma;   // clip((eta-gamma)*p + gamma, 0, 1)
 #pragma unroll
-      for (int j = 0; j < BN; ++j) {
-        float v = s[j] * inv_den;
-        if (clipped) {
-          v = fmaf(v, p.stretch, p.gamma);
-          v = fminf(fmaxf(v, 0.f), 1.f);
-        }
-        if (p.qdq_probs) v = qdq_f32(v, sc_p, zp_p, p.int_max);
-        s[j] = v;
+        for (int j = 0; j < BN; ++j) s[j] = __saturatef(fmaf(s[j], st, gm));
+      } else {
+#pragma unroll
+        for (int j = 0; j < BN; ++j) s[j] *= inv_den;
+      }
+      if (has_qp) {
+#pragma unroll
+        for (int j = 0; j < BN; ++j) s[j] = qd_p(s[j]);
       }
     }
 
@@ -355,7 +416,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
   if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem);
 
   if (row >= p.Tq) return;
-  if (p.dbg_o) {
+  if (kGeneric && p.dbg_o) {
     float* d = p.dbg_o + (((int64_t)b * p.H + h) * p.Tq + row) * HD;
 #pragma unroll
     for (int j = 0; j < HD; ++j) d[j] = o[j];
@@ -371,15 +432,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
     const float z = __ldg(p.gate_logits + ((int64_t)b * p.H + h) * p.Tq + row);
     gate = __frcp_rn(1.f + expf(-z)) * p.gate_scale;
   }
-  float sc_c = 1.f, zp_c = 0.f;
-  if (p.qdq_ctx) { sc_c = __ldg(p.qdq_ctx); zp_c = __ldg(p.qdq_ctx + 1); }
+  if (kGeneric && p.qdq_ctx) {
+    const Qdq qd_c = load_qdq(p.qdq_ctx, p.int_max);
+    if (p.ctx_qdq_before_gate) {                       // OPT: tap on PV, then gate (quantized_opt.py:210)
 #pragma unroll
-  for (int j = 0; j < HD; ++j) {
-    float v = o[j] * mul;
-    if (p.qdq_ctx && p.ctx_qdq_before_gate) v = qdq_f32(v, sc_c, zp_c, p.int_max);
-    v *= gate;
-    if (p.qdq_ctx && !p.ctx_qdq_before_gate) v = qdq_f32(v, sc_c, zp_c, p.int_max);
-    o[j] = v;
+      for (int j = 0; j < HD; ++j) o[j] = qd_c(o[j] * mul) * gate;
+    } else {                                           // BERT: gate, then tap (quantized_bert.py:434)
+#pragma unroll
+      for (int j = 0; j < HD; ++j) o[j] = qd_c(o[j] * mul * gate);
+    }
+  } else {
+    mul *= gate;
+#pragma unroll
+    for (int j = 0; j < HD; ++j) o[j] *= mul;
   }
   uint8_t* optr = reinterpret_cast<uint8_t*>(p.out) + 2 * ((int64_t)b * p.os0 + (int64_t)h * p.os1 + (int64_t)row * p.os2);
 #pragma unroll
@@ -516,20 +581,18 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
 
   dim3 grid((unsigned)((a->Tq + BM - 1) / BM), (unsigned)a->H, (unsigned)a->B);
   cudaStream_t st = (cudaStream_t)a->stream;
-  static bool attr_done[2] = {false, false};
-  if (a->dtype == OEH_BF16) {
-    if (!attr_done[1]) {
-      OEH_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      attr_done[1] = true;
-    }
-    attn_fwd_kernel<true><<<grid, BM, kSmemBytes, st>>>(tmq, tmk, tmv, p);
-  } else {
-    if (!attr_done[0]) {
-      OEH_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      attr_done[0] = true;
-    }
-    attn_fwd_kernel<false><<<grid, BM, kSmemBytes, st>>>(tmq, tmk, tmv, p);
+  const bool generic = a->qdq_scores || a->qdq_probs || a->qdq_ctx || a->mask || a->clamp_min || dbg_s || dbg_o ||
+                       !(a->scale > 0.f);
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
+  static const KernelFn kernels[4] = {attn_fwd_kernel<false, false>, attn_fwd_kernel<false, true>,
+                                      attn_fwd_kernel<true, false>, attn_fwd_kernel<true, true>};
+  static bool attr_done[4] = {false, false, false, false};
+  const int ki = (a->dtype == OEH_BF16 ? 2 : 0) + (generic ? 1 : 0);
+  if (!attr_done[ki]) {
+    OEH_CUDA_OK(cudaFuncSetAttribute(kernels[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_done[ki] = true;
   }
+  kernels[ki]<<<grid, BM, kSmemBytes, st>>>(tmq, tmk, tmv, p);
   return check_launch("attn_fwd_kernel");
 }
 

@@ -1,0 +1,135 @@
+"""Synthetic evaluation harness: the eval loops of validate_mlm_config.py:489-548 and validate_clm.py:555-594
+re-stated without datasets / Accelerate: random-init HF model of the named architecture,
+attention modules swapped for the drop-ins, synthetic token batches, forward + loss per batch, perplexity =
+exp(mean of per-batch mean losses).
+
+One process per GPU.  Batches are sharded round-robin over ranks (rank r evaluates batches r, r+N, ...), there is no
+data-path collective; the per-rank (sum of batch losses, #batches) pair is all-reduced once at the end
+(replaces the per-step ``gather_for_metrics``, validate_mlm_config.py:496-498).  The eval step is captured in a
+CUDA graph: at B=32,T=128 a BERT-base forward is ~1 ms of GPU work and Python launch overhead would dominate.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from .hf_compat import swap_bert_attention, swap_opt_attention
+
+
+# ---- model / data builders ---------------------------------------------------------------------------------
+
+def build_bert_base(seed: int = 3000, dtype=torch.float16, device="cuda", attn_softmax="clippedsoftmax1(-.025:1)",
+                    num_hidden_layers: int = 12, **attn_kw):
+    """BertConfig() defaults = BERT-base (12L/768/12H/3072, vocab 30522), random init (Cfg1/Cfg2)."""
+    from transformers import BertConfig, BertForMaskedLM
+    cfg = BertConfig(num_hidden_layers=num_hidden_layers)
+    cfg._attn_implementation = "eager"
+    torch.manual_seed(seed)
+    model = BertForMaskedLM(cfg)
+    model = model.to(device=device, dtype=dtype).eval()
+    return swap_bert_attention(model, attn_softmax=attn_softmax, max_seq_length=128, **attn_kw)
+
+
+def build_opt_125m(seed: int = 5678, dtype=torch.float16, device="cuda", attn_softmax="vanilla",
+                   num_hidden_layers: int = 12, causal_hint: bool = True, **attn_kw):
+    """OPT-125m shape (Cfg3/Cfg4), random init."""
+    from transformers import OPTConfig, OPTForCausalLM
+    cfg = OPTConfig(hidden_size=768, num_hidden_layers=num_hidden_layers, ffn_dim=3072, num_attention_heads=12,
+                    word_embed_proj_dim=768, max_position_embeddings=2048, do_layer_norm_before=True,
+                    vocab_size=50272)
+    cfg._attn_implementation = "eager"
+    torch.manual_seed(seed)
+    model = OPTForCausalLM(cfg)
+    model = model.to(device=device, dtype=dtype).eval()
+    return swap_opt_attention(model, attn_softmax=attn_softmax, max_seq_length=512, causal_hint=causal_hint, **attn_kw)
+
+
+def synthetic_mlm_batch(batch: int, seq: int, vocab: int = 30522, seed: int = 0, mlm_probability: float = 0.15,
+                        pin: bool = True) -> Dict[str, torch.Tensor]:
+    """ids ~ U{0..vocab-1}; labels = ids on a Bernoulli(0.15) mask else -100 (DataCollatorForLanguageModeling)."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, vocab, (batch, seq), generator=g)
+    masked = torch.rand(batch, seq, generator=g) < mlm_probability
+    masked[:, 0] = True                                   # never an empty label set
+    labels = torch.where(masked, ids, torch.full_like(ids, -100))
+    out = {"input_ids": ids, "labels": labels}
+    return {k: (v.pin_memory() if pin and torch.cuda.is_available() else v) for k, v in out.items()}
+
+
+def synthetic_clm_batch(batch: int, seq: int, vocab: int = 50272, seed: int = 0, pin: bool = True):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, vocab, (batch, seq), generator=g)
+    out = {"input_ids": ids, "labels": ids.clone()}
+    return {k: (v.pin_memory() if pin and torch.cuda.is_available() else v) for k, v in out.items()}
+
+
+# ---- eval step ----------------------------------------------------------------------------------------------
+
+@dataclass
+class EvalStep:
+    """One captured eval step: static device inputs -> static loss (fp32 scalar on the device)."""
+    model: torch.nn.Module
+    static_inputs: Dict[str, torch.Tensor]
+    loss: torch.Tensor
+    graph: Optional[torch.cuda.CUDAGraph]
+    extra_kwargs: dict
+
+    def load(self, host_batch: Dict[str, torch.Tensor]):
+        """H2D of one batch into the static buffers (async on the current stream; pinned host memory)."""
+        for k, v in host_batch.items():
+            self.static_inputs[k].copy_(v, non_blocking=True)
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            with torch.no_grad():
+                self.loss.copy_(self.model(**self.static_inputs, **self.extra_kwargs).loss.float())
+        return self.loss
+
+    def h2d_bytes(self) -> int:
+        return sum(v.numel() * v.element_size() for v in self.static_inputs.values())
+
+
+def make_eval_step(model, example_batch: Dict[str, torch.Tensor], use_graph: bool = True, warmup: int = 3,
+                   **extra_kwargs) -> EvalStep:
+    dev = next(model.parameters()).device
+    static = {k: v.to(dev) for k, v in example_batch.items()}
+    loss = torch.zeros((), dtype=torch.float32, device=dev)
+    step = EvalStep(model, static, loss, None, extra_kwargs)
+    with torch.no_grad():
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                       # warm every lazy init (cuBLAS handles, gate packs, attrs)
+                loss.copy_(model(**static, **extra_kwargs).loss.float())
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        if use_graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                loss.copy_(model(**static, **extra_kwargs).loss.float())
+            step.graph = g
+    return step
+
+
+def aggregate_perplexity(loss_sum: torch.Tensor, n_batches: int) -> float:
+    """exp(mean over per-batch mean losses), every batch weighted equally (validate_mlm_config.py:542-548);
+    with torch.distributed initialised the (sum, count) pair is all-reduced once."""
+    import torch.distributed as dist
+    buf = torch.stack((loss_sum.double(), torch.tensor(float(n_batches), dtype=torch.float64, device=loss_sum.device)))
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    mean = (buf[0] / buf[1]).item()
+    try:
+        return math.exp(mean)
+    except OverflowError:
+        return float("inf")
+
+
+def shard_indices(n_batches: int, rank: int, world: int):
+    """Round-robin batch sharding: rank r takes batches r, r+N, ...."""
+    return list(range(rank, n_batches, world))

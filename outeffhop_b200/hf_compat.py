@@ -1,0 +1,102 @@
+"""Glue between the drop-in attention modules and the HuggingFace model shells they are swapped into.
+
+The reference targets transformers 4.31 (requirement.txt:47): ``BertAttention`` calls
+``self.self(hidden_states, attention_mask, head_mask, encoder_hidden_states, encoder_attention_mask,
+past_key_value, output_attentions)`` and expects the reference's variable-length tuple.  transformers >= 4.48
+calls ``self.self(hidden_states, attention_mask=..., past_key_values=..., **kw)`` and unpacks exactly
+``(attn_output, attn_weights)``; ``OPTDecoderLayer`` likewise unpacks two values.  The ``*HF`` subclasses
+below keep the reference constructors / state_dict keys and only adapt the call convention, so the
+module-swap loops of validate_mlm_config.py:174-191 and validate_clm.py:147-168 work on either version:
+
+    swap_bert_attention(model, attn_softmax="softmax1", attn_gate_type="conditional_per_token", ...)
+    swap_opt_attention(model, attn_softmax="vanilla", ...)
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import transformers
+from packaging import version
+
+from .bert_attention import AttentionGateType, BertSelfAttentionWithExtras
+from .opt_attention import OPTAttentionWithExtras
+from .softmax import parse_attn_softmax
+
+NEW_STYLE = version.parse(transformers.__version__) >= version.parse("4.48.0")
+
+
+class BertSelfAttentionWithExtrasHF(BertSelfAttentionWithExtras):
+    """Call-convention adapter for transformers >= 4.48 BertAttention."""
+
+    def forward(self, hidden_states, attention_mask=None, head_mask=None, encoder_hidden_states=None,
+                encoder_attention_mask=None, past_key_value=None, output_attentions=False, **kw):
+        if kw.get("past_key_values") is not None:
+            raise NotImplementedError("KV caches are not used on the evaluation path")
+        out = super().forward(hidden_states, attention_mask, head_mask, encoder_hidden_states,
+                              encoder_attention_mask, past_key_value, bool(output_attentions))
+        if not NEW_STYLE:
+            return out
+        return out[0], (out[1] if output_attentions and len(out) > 1 else None)
+
+
+class OPTAttentionWithExtrasHF(OPTAttentionWithExtras):
+    """Call-convention adapter for transformers >= 4.48 OPTDecoderLayer."""
+
+    def forward(self, hidden_states, key_value_states=None, past_key_value=None, attention_mask=None,
+                layer_head_mask=None, output_attentions=False, **kw):
+        if kw.get("past_key_values") is not None:
+            raise NotImplementedError("KV caches are not used on the evaluation path (pass use_cache=False)")
+        out, weights, past = super().forward(hidden_states, key_value_states, past_key_value, attention_mask,
+                                             layer_head_mask, bool(output_attentions))
+        if not NEW_STYLE:
+            return out, weights, past
+        return out, weights
+
+
+def _gate_type(attn_gate_type):
+    return AttentionGateType[attn_gate_type] if isinstance(attn_gate_type, str) else attn_gate_type
+
+
+def swap_bert_attention(model, attn_softmax: str = "vanilla", alpha: Optional[float] = None,
+                        max_seq_length: Optional[int] = None, skip_attn: bool = False,
+                        attn_gate_type="none", attn_gate_init: Optional[float] = None, attn_gate_mlp: bool = False,
+                        attn_gate_mlp2: bool = False, attn_gate_linear_all_features: bool = False,
+                        fine_tuning: bool = False):
+    """validate_mlm_config.py:174-191: replace every ``layer.attention.self`` and copy its weights."""
+    softmax_fn = parse_attn_softmax(attn_softmax)
+    bert = getattr(model, "bert", model)
+    for layer in bert.encoder.layer:
+        old = layer.attention.self
+        new = BertSelfAttentionWithExtrasHF(
+            model.config, softmax_fn=softmax_fn, alpha=alpha, max_seq_length=max_seq_length, skip_attn=skip_attn,
+            attn_gate_type=_gate_type(attn_gate_type), attn_gate_init=attn_gate_init, attn_gate_mlp=attn_gate_mlp,
+            attn_gate_mlp2=attn_gate_mlp2, attn_gate_linear_all_features=attn_gate_linear_all_features,
+            fine_tuning=fine_tuning)
+        new.load_state_dict(old.state_dict(), strict=False)
+        p = next(old.parameters())
+        layer.attention.self = new.to(device=p.device, dtype=p.dtype)
+    return model
+
+
+def swap_opt_attention(model, attn_softmax: str = "vanilla", alpha: Optional[float] = None,
+                       max_seq_length: Optional[int] = None, skip_attn: bool = False, attn_gate_type="none",
+                       attn_gate_init: Optional[float] = None, attn_gate_mlp: bool = False,
+                       attn_gate_mlp2: bool = False, attn_gate_linear_all_features: bool = False,
+                       fine_tuning: bool = False, causal_hint: bool = False):
+    """validate_clm.py:147-168: replace every ``layer.self_attn`` and copy its weights."""
+    softmax_fn = parse_attn_softmax(attn_softmax)
+    cfg = model.config
+    for layer in model.model.decoder.layers:
+        old = layer.self_attn
+        new = OPTAttentionWithExtrasHF(
+            embed_dim=cfg.hidden_size, num_heads=cfg.num_attention_heads, dropout=cfg.attention_dropout,
+            is_decoder=True, bias=cfg.enable_bias, softmax_fn=softmax_fn, alpha=alpha, max_seq_length=max_seq_length,
+            skip_attn=skip_attn, attn_gate_type=_gate_type(attn_gate_type), attn_gate_init=attn_gate_init,
+            attn_gate_mlp=attn_gate_mlp, attn_gate_mlp2=attn_gate_mlp2,
+            attn_gate_linear_all_features=attn_gate_linear_all_features, fine_tuning=fine_tuning)
+        new.load_state_dict(old.state_dict(), strict=False)
+        new.causal_hint = causal_hint
+        p = next(old.parameters())
+        layer.self_attn = new.to(device=p.device, dtype=p.dtype)
+    return model

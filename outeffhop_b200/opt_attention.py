@@ -1,0 +1,188 @@
+"""``OPTAttentionWithExtras`` -- drop-in for the reference module
+(transformers_language/models/opt_attention.py:17-326).  The core ``bmm(q,k^T) -> +mask -> clamp ->
+softmax_fn -> bmm(P,V) -> gate -> transpose`` (:204-322) runs as one fused tcgen05 kernel on strided
+views of the projection outputs (no ``_shape`` head-major copies, no (B*H,T,T) tensors).
+
+Differences from BERT that are kept: q is scaled by d^-0.5 *before* the product (:167;
+folded into the kernel's score scale, exact for power-of-two scalings); the mask is (B,1,T,S) and the sum
+is clamped at finfo.min (:215-224); ``out_proj`` is applied inside the module (:324); the return value is
+the 3-tuple ``(attn_output, attn_weights_reshaped, past_key_value)``.
+
+``causal_hint``: HF passes a dense (B,1,T,T) 0/finfo.min mask.  When the caller knows it is the plain causal
+mask (un-padded evaluation batches, validate_clm.py), setting ``module.causal_hint = True`` lets the kernel
+skip reading it and skip fully masked K/V tiles; the default (False) reads whatever mask is given.
+Reference quirks handled: OPT fp16 + softmax1 raises TypeError in the reference (softmax_1 has no ``dtype``
+kwarg, opt_attention.py:228) -- here it works; ``attn_softmax is "softmax1"`` (:73) is an identity test that
+is never true when called from the scripts -- ``==`` is used, so ``alpha`` + ``attn_softmax="softmax1"``
+selects clipped softmax_1 as the code evidently intended.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import ops
+from .bert_attention import FUSED_HEAD_DIM, AttentionGateType, GateMixin, _check_no_grad
+from .softmax import KIND_CLIPPED, KIND_CLIPPED1, SoftmaxFn, as_softmax_fn
+
+
+class OPTAttentionWithExtras(GateMixin, nn.Module):
+    """Multi-headed attention from 'Attention Is All You Need' paper"""
+
+    def __init__(self, embed_dim: int, num_heads: int, dropout: float = 0.0, is_decoder: bool = False,
+                 bias: bool = True, softmax_fn=torch.nn.functional.softmax, alpha=None, max_seq_length=None,
+                 ssm_eps=None, tau=None, skip_attn=False, attn_gate_type=AttentionGateType.none,
+                 attn_gate_init=None, attn_gate_mlp=False, attn_gate_mlp2=False,
+                 attn_gate_linear_all_features=False, fine_tuning=False, attn_softmax=None):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.dropout = dropout
+        self.head_dim = embed_dim // num_heads
+        if (self.head_dim * num_heads) != self.embed_dim:
+            raise ValueError(f"embed_dim must be divisible by num_heads (got `embed_dim`: {self.embed_dim}"
+                             f" and `num_heads`: {num_heads}).")
+        self.scaling = self.head_dim ** -0.5
+        self.is_decoder = is_decoder
+
+        self.k_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
+        self.v_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
+        self.q_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
+        self.out_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
+
+        self.attn_scores = nn.Identity()
+        self.attn_probs_before_dropout = nn.Identity()
+        self.attn_probs_after_dropout = nn.Identity()
+
+        self.alpha = alpha
+        self.max_seq_length = max_seq_length
+        self.ssm_eps = ssm_eps
+        self.tau = tau
+        self.attn_softmax = attn_softmax
+        if self.alpha is not None:                                       # :69-79
+            assert self.max_seq_length is not None
+            gamma = -self.alpha / self.max_seq_length
+            kind = KIND_CLIPPED1 if self.attn_softmax == "softmax1" else KIND_CLIPPED
+            self.softmax_fn = SoftmaxFn(kind, gamma, 1.0)
+        else:
+            self.softmax_fn = softmax_fn
+        self.skip_attn = skip_attn
+        self.materialize_probs = False
+        self.causal_hint = False
+        self._init_gate(self.num_heads, self.head_dim, self.embed_dim, attn_gate_type, attn_gate_init, attn_gate_mlp,
+                        attn_gate_mlp2, attn_gate_linear_all_features, fine_tuning, fine_tuning_std=0.001)
+
+    def _taps(self):   # overridden by the quantized wrapper (quantized_attention.py)
+        return None
+
+    def _shape(self, tensor: torch.Tensor, seq_len: int, bsz: int):
+        return tensor.view(bsz, seq_len, self.num_heads, self.head_dim).transpose(1, 2).contiguous()
+
+    def _heads(self, tensor: torch.Tensor, bsz: int):
+        """(B,T,E) -> (B,H,T,d) strided view (what ``_shape`` copies in the reference)."""
+        return tensor.view(bsz, -1, self.num_heads, self.head_dim).permute(0, 2, 1, 3)
+
+    def _core(self, q, k, v, attention_mask, gate_logits, layer_head_mask, output_attentions, bsz, tgt_len, taps=None):
+        """(attn_output (B,T,E) before out_proj, attn_weights_reshaped-or-None).  q is NOT pre-scaled."""
+        fn = as_softmax_fn(self.softmax_fn)
+        src_len = k.shape[2]
+        training_dropout = self.training and self.dropout > 0
+        active = [t for t in (taps or ()) if t is not None and t.active]
+        fused = (fn is not None and q.dtype in (torch.float16, torch.bfloat16) and self.head_dim == FUSED_HEAD_DIM
+                 and layer_head_mask is None and not output_attentions and not self.materialize_probs
+                 and not training_dropout and all(t.fixed for t in active))
+        if attention_mask is not None and attention_mask.size() != (bsz, 1, tgt_len, src_len):
+            raise ValueError(
+                f"Attention mask should be of size {(bsz, 1, tgt_len, src_len)}, but is {attention_mask.size()}")
+        if fused:
+            kw = {}
+            if active:
+                ts, tp, tc = taps
+                kw = dict(qdq_scores=ts.kernel_qparams() if ts.active else None,
+                          qdq_probs=tp.kernel_qparams() if tp.active else None,
+                          qdq_ctx=tc.kernel_qparams() if tc.active else None,
+                          n_bits=active[0].activation_quantizer.n_bits, ctx_qdq_before_gate=True)
+            use_causal = bool(self.causal_hint) and attention_mask is not None and tgt_len <= src_len
+            out = ops.attention_fwd(q, k, v, scale=self.scaling, kind=fn.kind, gamma=fn.gamma, eta=fn.eta,
+                                    causal=use_causal, mask=None if use_causal else attention_mask,
+                                    clamp_min=attention_mask is not None and not use_causal,
+                                    gate_logits=gate_logits, gate_scale=self.gate_scaling_factor,
+                                    out_layout="bthd", **kw)
+            return out, None
+        return self._core_unfused(q, k, v, attention_mask, gate_logits, layer_head_mask, output_attentions, bsz,
+                                  tgt_len, taps)
+
+    def _core_unfused(self, q, k, v, attention_mask, gate_logits, layer_head_mask, output_attentions, bsz, tgt_len, taps):
+        ts, tp, tc = taps if taps is not None else (None, None, None)
+        fn = as_softmax_fn(self.softmax_fn)
+        src_len = k.shape[2]
+        q = q * self.scaling                                                                  # :167
+        attn_weights = torch.matmul(q, k.transpose(-1, -2))                                   # :204 (B,H,T,S)
+        attn_weights = self.attn_scores(attn_weights)                                         # :207
+        if ts is not None:
+            attn_weights = ts(attn_weights)                                                   # quantized_opt.py:154
+        if fn is not None:
+            # +mask, max(., finfo.min), softmax in fp32 (:215-232) in one kernel
+            probs = ops.softmax_rows(attn_weights, fn.kind, fn.gamma, fn.eta, mask=attention_mask,
+                                     clamp_min=attention_mask is not None)
+        else:
+            if attention_mask is not None:
+                attn_weights = attn_weights + attention_mask
+                attn_weights = torch.max(attn_weights, torch.tensor(torch.finfo(attn_weights.dtype).min,
+                                                                    device=attn_weights.device))
+            probs = self.softmax_fn(attn_weights, dim=-1)
+        if tp is not None:
+            probs = tp(probs)                                                                 # quantized_opt.py:182
+        if layer_head_mask is not None:                                                       # :234-243
+            if layer_head_mask.size() != (self.num_heads,):
+                raise ValueError(f"Head mask for a single layer should be of size {(self.num_heads,)}, but is"
+                                 f" {layer_head_mask.size()}")
+            probs = layer_head_mask.view(1, -1, 1, 1) * probs
+        attn_weights_reshaped = probs if output_attentions else None                          # :245-253
+        probs = self.attn_probs_before_dropout(probs)
+        probs = nn.functional.dropout(probs, p=self.dropout, training=self.training)         # :258
+        probs = self.attn_probs_after_dropout(probs)
+        attn_output = torch.matmul(probs, v)                                                  # :263 (B,H,T,d)
+        if tc is not None:
+            attn_output = tc(attn_output)                                                     # quantized_opt.py:210
+        if gate_logits is not None:                                                           # :276-313
+            attn_output = attn_output * (torch.sigmoid(gate_logits).to(attn_output.dtype).unsqueeze(-1)
+                                         * self.gate_scaling_factor)
+        attn_output = attn_output.transpose(1, 2).reshape(bsz, tgt_len, self.embed_dim)       # :318-322
+        return attn_output, attn_weights_reshaped
+
+    def forward(self, hidden_states: torch.Tensor, key_value_states: Optional[torch.Tensor] = None,
+                past_key_value: Optional[Tuple[torch.Tensor]] = None, attention_mask: Optional[torch.Tensor] = None,
+                layer_head_mask: Optional[torch.Tensor] = None, output_attentions: bool = False,
+                **hf_kwargs) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[Tuple[torch.Tensor]]]:
+        """Input shape: Batch x Time x Channel"""
+        if hf_kwargs.get("past_key_values") is not None:
+            raise NotImplementedError("HF>=4.36 Cache objects are not supported; pass past_key_value tuples")
+        if not hidden_states.is_cuda:
+            raise RuntimeError("outeffhop_b200.OPTAttentionWithExtras runs on CUDA only (no CPU fallback)")
+        _check_no_grad(hidden_states, self.q_proj.weight)
+        is_cross_attention = key_value_states is not None
+        bsz, tgt_len, _ = hidden_states.size()
+
+        q = self._heads(self.q_proj(hidden_states), bsz)
+        if is_cross_attention and past_key_value is not None:                                 # :169-172
+            k, v = past_key_value[0], past_key_value[1]
+        elif is_cross_attention:                                                              # :173-176
+            k = self._heads(self.k_proj(key_value_states), bsz)
+            v = self._heads(self.v_proj(key_value_states), bsz)
+        elif past_key_value is not None:                                                      # :177-182
+            k = torch.cat([past_key_value[0], self._heads(self.k_proj(hidden_states), bsz)], dim=2)
+            v = torch.cat([past_key_value[1], self._heads(self.v_proj(hidden_states), bsz)], dim=2)
+        else:                                                                                 # :183-186
+            k = self._heads(self.k_proj(hidden_states), bsz)
+            v = self._heads(self.v_proj(hidden_states), bsz)
+        if self.is_decoder:
+            past_key_value = (k, v)                                                           # :196
+
+        gate_logits = self._gate_logits(hidden_states, self.num_heads, self.head_dim)
+        attn_output, attn_weights_reshaped = self._core(q, k, v, attention_mask, gate_logits, layer_head_mask,
+                                                        output_attentions, bsz, tgt_len, taps=self._taps())
+        attn_output = self.out_proj(attn_output)                                              # :324
+        return attn_output, attn_weights_reshaped, past_key_value

@@ -1,0 +1,268 @@
+"""GPU parity of the drop-in modules against fixtures produced by the LIVE reference modules
+(tests/golden/make_golden.py): BertSelfAttentionWithExtras, OPTAttentionWithExtras and their quantized
+wrappers.  Weights and inputs in the fixtures are fp16-representable, so the fp16 fused path and the fp32
+reference start from identical numbers."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+F32 = np.float32
+
+
+def _mods():
+    import outeffhop_b200 as o
+    return o
+
+
+def _bert_cfg():
+    from transformers import BertConfig
+    return BertConfig(hidden_size=128, num_attention_heads=2, attention_probs_dropout_prob=0.0)
+
+
+def _load_sd(module, g, tag, base, prefix="::sd::"):
+    sd = {}
+    for k in g.files:
+        for pre in (base + "::sd::", tag + prefix):
+            if k.startswith(pre):
+                sd[k[len(pre):]] = torch.from_numpy(g[k].astype(F32))
+    missing, unexpected = module.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    return module
+
+
+def _t(a, dtype):
+    return torch.from_numpy(np.ascontiguousarray(a).astype(F32)).cuda().to(dtype)
+
+
+def _make_bert(o, key, gated, **kw):
+    gt = o.AttentionGateType.conditional_per_token if gated else o.AttentionGateType.none
+    return o.BertSelfAttentionWithExtras(_bert_cfg(), softmax_fn=o.SOFTMAX_MAPPING[key], attn_gate_type=gt,
+                                         attn_gate_init=0.25 if gated else None, **kw)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 3e-3), (torch.bfloat16, 2.5e-2), (torch.float32, 2e-4)])
+def test_bert_module_vs_reference_golden(golden, dtype, tol):
+    """fp16/bf16 -> fused tcgen05 kernel; fp32 -> unfused path (cuBLAS + oeh_softmax_rows)."""
+    o = _mods()
+    g = golden("attention_modules.npz")
+    for tag, key, gated, masked in g["bert_cases"]:
+        m = _load_sd(_make_bert(o, str(key), int(gated)), g, tag, "bert_base").cuda().to(dtype).eval()
+        hidden = _t(g[f"{tag}::hidden"], dtype)
+        mask = _t(g[f"{tag}::mask"], torch.float32).clamp(min=torch.finfo(dtype).min).to(dtype) if int(masked) else None
+        with torch.no_grad():
+            out = m(hidden, attention_mask=mask)
+        assert isinstance(out, tuple) and len(out) == 1
+        np.testing.assert_allclose(out[0].float().cpu().numpy(), g[f"{tag}::out"], atol=tol, rtol=0,
+                                   err_msg=f"{tag} {key} {dtype}")
+
+
+def test_bert_alpha_override_and_mlp_gates(golden):
+    o = _mods()
+    g = golden("attention_modules.npz")
+    m = o.BertSelfAttentionWithExtras(_bert_cfg(), alpha=4.0, max_seq_length=64)
+    assert m.softmax_fn.kind == 2 and m.softmax_fn.gamma == -4.0 / 64 and m.softmax_fn.eta == 1.0
+    m = _load_sd(m, g, "bert_alpha", "bert_base").cuda().half().eval()
+    with torch.no_grad():
+        out = m(_t(g["bert_alpha::hidden"], torch.float16))[0]
+    np.testing.assert_allclose(out.float().cpu().numpy(), g["bert_alpha::out"], atol=3e-3, rtol=0)
+    for tag, kw in (("bert_mlp", dict(attn_gate_mlp=True)), ("bert_mlp2", dict(attn_gate_mlp2=True))):
+        m = _load_sd(_make_bert(o, "softmax1", True, **kw), g, tag, "bert_base").cuda().half().eval()
+        with torch.no_grad():
+            out = m(_t(g[f"{tag}::hidden"], torch.float16))[0]
+        np.testing.assert_allclose(out.float().cpu().numpy(), g[f"{tag}::out"], atol=3e-3, rtol=0, err_msg=tag)
+        assert m.last_gate_all_probs.shape == (2, 2, 64, 1) and m.last_gate_avg_prob.shape == (2,)
+
+
+def test_bert_module_interface_details():
+    o = _mods()
+    m = _make_bert(o, "softmax1", True).cuda().half().eval()
+    names = dict(m.named_modules())
+    for n in ("attn_scores", "attn_probs_before_dropout", "attn_probs_after_dropout", "query", "key", "value",
+              "alpha.0", "alpha.1"):
+        assert n in names
+    x = torch.randn(2, 16, 128, device="cuda", dtype=torch.float16)
+    with torch.no_grad():
+        ctx, probs = m(x, output_attentions=True)                  # unfused path, probs materialised
+        ctx2 = m(x)[0]                                             # fused path
+    assert probs.shape == (2, 2, 16, 16)
+    assert (ctx.float() - ctx2.float()).abs().max().item() < 3e-3
+    m.skip_attn = True
+    assert torch.count_nonzero(m(x)[0]) == 0
+    m.skip_attn = False
+    with pytest.raises(NotImplementedError):                       # training / backward is out of scope
+        m(x.requires_grad_(True))
+    with pytest.raises(RuntimeError):
+        m.cpu()(torch.randn(2, 16, 128))                           # no CPU fallback
+    from transformers import BertConfig
+    with pytest.raises(ValueError):
+        o.BertSelfAttentionWithExtras(BertConfig(hidden_size=100, num_attention_heads=3))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 4e-3), (torch.float32, 2e-4)])
+@pytest.mark.parametrize("causal_hint", [False, True])
+def test_opt_module_vs_reference_golden(golden, dtype, tol, causal_hint):
+    o = _mods()
+    g = golden("attention_modules.npz")
+    for tag, key, gated in g["opt_cases"]:
+        gt = o.AttentionGateType.conditional_per_token if int(gated) else o.AttentionGateType.none
+        m = o.OPTAttentionWithExtras(128, 2, is_decoder=True, softmax_fn=o.SOFTMAX_MAPPING[str(key)], attn_gate_type=gt,
+                                     attn_gate_init=0.25 if int(gated) else None)
+        m = _load_sd(m, g, tag, "opt_base").cuda().to(dtype).eval()
+        m.causal_hint = causal_hint
+        hidden = _t(g[f"{tag}::hidden"], dtype)
+        T = hidden.shape[1]
+        mask = torch.full((T, T), torch.finfo(dtype).min, device="cuda", dtype=dtype).triu(1)[None, None].expand(2, 1, T, T)
+        with torch.no_grad():
+            out, w, past = m(hidden, attention_mask=mask.contiguous())
+        assert w is None and past[0].shape == (2, 2, T, 64)
+        np.testing.assert_allclose(out.float().cpu().numpy(), g[f"{tag}::out"], atol=tol, rtol=0,
+                                   err_msg=f"{tag} {key} {dtype}")
+
+
+def test_opt_module_error_conventions():
+    o = _mods()
+    with pytest.raises(ValueError):
+        o.OPTAttentionWithExtras(100, 3)
+    m = o.OPTAttentionWithExtras(128, 2, is_decoder=True).cuda().half().eval()
+    x = torch.randn(2, 8, 128, device="cuda", dtype=torch.float16)
+    with pytest.raises(ValueError), torch.no_grad():
+        m(x, attention_mask=torch.zeros(2, 1, 8, 9, device="cuda", dtype=torch.float16))
+    with pytest.raises(ValueError), torch.no_grad():
+        m(x, layer_head_mask=torch.ones(3, device="cuda", dtype=torch.float16))
+
+
+# ------------------------------------------------------------------------------------------------ quantized
+def _qparams(o):
+    return dict(method=o.QMethods.symmetric_uniform.cls, n_bits=8, n_bits_act=8,
+                act_method=o.QMethods.asymmetric_uniform.cls, per_channel_weights=False, percentile=None,
+                quant_setup="all", weight_range_method=o.RangeEstimators.current_minmax.cls, weight_range_options={},
+                act_range_method=o.RangeEstimators.running_minmax.cls, act_range_options={})
+
+
+def _check_quant_out(got, ref, delta, tag):
+    """Ranges/inputs agree to ~1e-6 but not bitwise (GEMM accumulation order), so a few codes flip at bin
+    edges: nearly all elements must agree closely and no element may be off by more than ~2 grid steps."""
+    diff = np.abs(got - ref)
+    assert diff.max() <= 2.05 * delta + 1e-5, f"{tag}: max diff {diff.max()} vs delta {delta}"
+    assert (diff > 0.25 * delta).mean() < 0.02, f"{tag}: {(diff > 0.25 * delta).mean():.4f} of outputs off by >delta/4"
+
+
+def _golden_quant_state(g, tag, name):
+    return {k.split("::sd::")[1]: g[k] for k in g.files if k.startswith(tag + "::sd::") and name in k}
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_quantized_bert_attention_estimate_then_fixed(golden, ci):
+    o = _mods()
+    g = golden("quantized_attention.npz")
+    tag = f"qbert{ci}"
+    key, gated = str(g[f"{tag}::key"]), int(g[f"{tag}::gated"])
+    fp = _make_bert(o, key, gated)
+    ga = golden("attention_modules.npz")
+    sd = {k[len("bert_base::sd::"):]: torch.from_numpy(ga[k].astype(F32)) for k in ga.files if k.startswith("bert_base::sd::")}
+    sd.update({k[len(tag + "::fp::"):]: torch.from_numpy(g[k].astype(F32)) for k in g.files if k.startswith(tag + "::fp::")})
+    fp.load_state_dict(sd)
+    qm = o.QuantizedBertSelfAttentionWithExtras(fp.cuda(), quant_dict={}, **_qparams(o)).cuda().eval()
+    qm.set_quant_state(weight_quant=True, act_quant=True)
+    ref_sd = {k.split("::sd::")[1]: g[k] for k in g.files if k.startswith(tag + "::sd::")}
+    with torch.no_grad():
+        for step in range(3):                                       # estimate_ranges: unfused, fp32
+            y = qm(_t(g[f"{tag}::x_est"][step], torch.float32))[0]
+            if step == 2:
+                d = float(ref_sd["context_act_quantizer.activation_quantizer.quantizer._delta"])
+                _check_quant_out(y.cpu().numpy(), g[f"{tag}::y_est"][step], d, f"{tag} est{step}")
+        # running ranges equal the reference's to fp32 rounding of the GEMM inputs
+        mine = qm.state_dict()
+        for k, v in ref_sd.items():
+            if k.endswith(("_delta", "_zero_float", "current_xmin", "current_xmax")) and "weight_quantizer" not in k:
+                np.testing.assert_allclose(mine[k].cpu().numpy(), v, rtol=2e-5, atol=1e-6, err_msg=k)
+        for k in ("query", "key", "value"):                         # weight grid: exact (same fp32 op chain)
+            np.testing.assert_array_equal(mine[f"{k}.weight_quantizer.quantizer._delta"].cpu().numpy(),
+                                          ref_sd[f"{k}.weight_quantizer.quantizer._delta"])
+        qm.fix_ranges()
+        d = float(ref_sd["context_act_quantizer.activation_quantizer.quantizer._delta"])
+        xf = g[f"{tag}::x_fixed"]
+        y32 = qm(_t(xf, torch.float32))[0]                          # fix_ranges, fp32: unfused
+        _check_quant_out(y32.cpu().numpy(), g[f"{tag}::y_fixed"], d, f"{tag} fixed fp32")
+        qh = qm.half()
+        y16 = qh(_t(xf, torch.float16))[0]                          # fix_ranges, fp16: ONE fused kernel with 3 taps
+        diff = np.abs(y16.float().cpu().numpy() - g[f"{tag}::y_fixed"])
+        assert diff.max() <= 3.05 * d and (diff > 0.6 * d).mean() < 0.05, (diff.max(), d, (diff > 0.6 * d).mean())
+
+
+@pytest.mark.parametrize("ci", [0, 1])
+def test_quantized_opt_attention_estimate_then_fixed(golden, ci):
+    o = _mods()
+    g = golden("quantized_attention.npz")
+    tag = f"qopt{ci}"
+    key, gated = str(g[f"{tag}::key"]), int(g[f"{tag}::gated"])
+    gt = o.AttentionGateType.conditional_per_token if gated else o.AttentionGateType.none
+    fp = o.OPTAttentionWithExtras(128, 2, is_decoder=True, softmax_fn=o.SOFTMAX_MAPPING[key], attn_gate_type=gt,
+                                  attn_gate_init=0.25 if gated else None)
+    ga = golden("attention_modules.npz")
+    sd = {k[len("opt_base::sd::"):]: torch.from_numpy(ga[k].astype(F32)) for k in ga.files if k.startswith("opt_base::sd::")}
+    sd.update({k[len(tag + "::fp::"):]: torch.from_numpy(g[k].astype(F32)) for k in g.files if k.startswith(tag + "::fp::")})
+    fp.load_state_dict(sd)
+    qm = o.QuantizedOPTAttentionWithExtras(fp.cuda(), **_qparams(o)).cuda().eval()
+    qm.set_quant_state(weight_quant=True, act_quant=True)
+    ref_sd = {k.split("::sd::")[1]: g[k] for k in g.files if k.startswith(tag + "::sd::")}
+    T = 40
+    fmin = torch.finfo(torch.float32).min
+    mask = torch.full((T, T), fmin, device="cuda").triu(1)[None, None].expand(2, 1, T, T).contiguous()
+    d_out = float(ref_sd["out_proj.activation_quantizer.quantizer._delta"])
+    with torch.no_grad():
+        for step in range(3):
+            y = qm(_t(g[f"{tag}::x_est"][step], torch.float32), attention_mask=mask)[0]
+        _check_quant_out(y.cpu().numpy(), g[f"{tag}::y_est"][2], d_out, f"{tag} est2")
+        mine = qm.state_dict()
+        for k, v in ref_sd.items():
+            if k.endswith(("_delta", "_zero_float", "current_xmin", "current_xmax")) and "weight_quantizer" not in k:
+                np.testing.assert_allclose(mine[k].cpu().numpy(), v, rtol=5e-5, atol=2e-6, err_msg=k)
+        qm.fix_ranges()
+        y32 = qm(_t(g[f"{tag}::x_fixed"], torch.float32), attention_mask=mask)[0]
+        _check_quant_out(y32.cpu().numpy(), g[f"{tag}::y_fixed"], d_out, f"{tag} fixed fp32")
+        qh = qm.half()
+        qh.causal_hint = True
+        y16 = qh(_t(g[f"{tag}::x_fixed"], torch.float16), attention_mask=mask.half())[0]
+        diff = np.abs(y16.float().cpu().numpy() - g[f"{tag}::y_fixed"])
+        assert diff.max() <= 3.05 * d_out and (diff > 0.6 * d_out).mean() < 0.05, (diff.max(), d_out)
+
+
+def test_quantizer_module_surface_and_state_dict_roundtrip(golden):
+    o = _mods()
+    AQ = o.AsymmetricUniformQuantizer
+    q = AQ(n_bits=8)
+    assert not q.is_initialized and q._delta is None
+    with pytest.raises(o.QuantizerNotInitializedError):
+        q.delta
+    q.set_quant_range(-1.0, 3.0)
+    assert abs(q.delta.item() - 0.015686275) < 1e-9 and q.zero_point.item() == 64
+    assert abs(q.x_min.item() + 1.003921628) < 1e-6 and abs(q.x_max.item() - 2.996078491) < 1e-6
+    x = torch.tensor([0.5, -2, 5, 0.015686275 / 2, 1.5 * 0.015686275, -1, 3], device="cuda")
+    assert q.to_integer_forward(x).tolist() == [96, 0, 255, 64, 66, 0, 255]
+    qm = o.QuantizationManager(qmethod=AQ, init=o.RunningMinMaxEstimator, qparams=dict(n_bits=8, act_quant=True))
+    with pytest.raises(o.QuantizerNotInitializedError):
+        qm.fix_ranges()
+    g = golden("quantizer.npz")
+    xs = g["rm0::x"]
+    for i in range(xs.shape[0]):
+        y = qm(torch.from_numpy(xs[i]).cuda())
+        assert np.array_equal(y.cpu().numpy(), g["rm0::y"][i])
+    sd = qm.state_dict()
+    assert set(sd) == {"quantizer._delta", "quantizer._zero_float", "range_estimator.current_xmin",
+                       "range_estimator.current_xmax"}
+    assert sd["range_estimator.current_xmin"].item() == g["rm0::cur_min"][-1]
+    qm2 = o.QuantizationManager(qmethod=AQ, init=o.RunningMinMaxEstimator, qparams=dict(n_bits=8, act_quant=True))
+    qm2.load_state_dict(sd)
+    qm2.fix_ranges()
+    xf = torch.from_numpy(g["rm0::x_fixed"]).cuda()
+    assert np.array_equal(qm2(xf).cpu().numpy(), g["rm0::y_fixed"])
+    qa = o.QuantizedActivation(method=AQ, act_method=AQ, n_bits=8, n_bits_act=8)
+    x = torch.from_numpy(g["qa::x"]).cuda()
+    assert torch.equal(qa(x), x)                                   # act quant off: passthrough
+    qa.quantized_acts()
+    assert np.array_equal(qa(x).cpu().numpy(), g["qa::y_q"])
+    qm.reset_ranges()
+    assert not qm.quantizer.is_initialized and qm.range_estimator.current_xmin is None
