@@ -186,7 +186,7 @@ def run_ours(args):
 
     from outeffhop_b200 import ops
     from outeffhop_b200._lib import lib
-    from outeffhop_b200.eval_harness import aggregate_perplexity, build_bert_base, make_eval_step, synthetic_mlm_batch
+    from outeffhop_b200.eval_harness import aggregate_perplexity, build_bert_base, make_bert_eval_step, synthetic_mlm_batch
     from outeffhop_b200.softmax import SOFTMAX_MAPPING
     lib()                                                 # fail loudly if the CUDA extension is missing
     peaks = load_peaks()
@@ -196,7 +196,7 @@ def run_ours(args):
     n_pool = 8                                            # distinct synthetic batches per rank, cycled
     host_pool = [synthetic_mlm_batch(BATCH, SEQ, seed=3000 + 1000 * rank + i) for i in range(n_pool)]
     dev_pool = [{k: v.cuda() for k, v in hb.items()} for hb in host_pool]
-    step = make_eval_step(model, host_pool[0], use_graph=not args.no_graph)
+    step = make_bert_eval_step(model, host_pool[0], use_graph=not args.no_graph)
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
     sampler = ClockSampler(local_rank)
     if rank == 0:

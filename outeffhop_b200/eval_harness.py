@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass
-from typing import Dict, Optional
+from typing import Callable, Dict, Optional
 
 import torch
 
@@ -66,16 +66,61 @@ def synthetic_clm_batch(batch: int, seq: int, vocab: int = 50272, seed: int = 0,
     return {k: (v.pin_memory() if pin and torch.cuda.is_available() else v) for k, v in out.items()}
 
 
+# ---- graph-capturable forwards ---------------------------------------------------------------------------------
+# HF's top-level forward() builds its attention masks with host-side tensor constructions that cannot be captured in
+# a CUDA graph, and (for all-ones masks) with data-dependent checks.  The eval data of the reference is chunked and
+# un-padded (validate_mlm_config.py:344-357), so the BERT mask is all zeros and the OPT mask is the plain causal one:
+# these forwards call the same HF submodules in the same order with that knowledge baked in.
+
+def bert_mlm_loss(model, input_ids: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """BertForMaskedLM.forward for un-padded batches: embeddings -> 12 x BertLayer (attention_mask=None) -> MLM head ->
+    mean CE over the labelled tokens, evaluated in fp32 (a fp16 mean would round the loss to 3 decimal digits)."""
+    bert = model.bert
+    h = bert.embeddings(input_ids=input_ids)
+    for layer in bert.encoder.layer:
+        out = layer(h, attention_mask=None)
+        h = out[0] if isinstance(out, tuple) else out
+    logits = model.cls(h)
+    return torch.nn.functional.cross_entropy(logits.view(-1, logits.shape[-1]).float(), labels.view(-1))
+
+
+def opt_clm_loss(model, input_ids: torch.Tensor, labels: torch.Tensor, causal_mask: torch.Tensor,
+                 position_ids: torch.Tensor) -> torch.Tensor:
+    """OPTForCausalLM.forward for un-padded blocks: token + learned position embeddings -> 12 x OPTDecoderLayer with the
+    (B,1,T,T) causal mask -> final LayerNorm -> lm_head -> shifted mean CE in fp32."""
+    dec = model.model.decoder
+    h = dec.embed_tokens(input_ids)
+    pos = dec.embed_positions(None, 0, position_ids=position_ids)
+    if dec.project_in is not None:
+        h = dec.project_in(h)
+    h = h + pos
+    for layer in dec.layers:
+        out = layer(h, attention_mask=causal_mask, position_ids=position_ids, past_key_values=None, use_cache=False)
+        h = out[0] if isinstance(out, tuple) else out
+    if dec.final_layer_norm is not None:
+        h = dec.final_layer_norm(h)
+    if dec.project_out is not None:
+        h = dec.project_out(h)
+    logits = model.lm_head(h)
+    V = logits.shape[-1]
+    return torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, V).float(), labels[:, 1:].reshape(-1))
+
+
+def make_causal_mask(batch: int, seq: int, dtype, device) -> torch.Tensor:
+    """HF-4.31 ``_make_causal_mask``: (B,1,T,T), 0 on/below the diagonal, finfo(dtype).min above."""
+    m = torch.full((seq, seq), torch.finfo(dtype).min, dtype=dtype, device=device).triu(1)
+    return m[None, None].expand(batch, 1, seq, seq).contiguous()
+
+
 # ---- eval step ----------------------------------------------------------------------------------------------
 
 @dataclass
 class EvalStep:
     """One captured eval step: static device inputs -> static loss (fp32 scalar on the device)."""
-    model: torch.nn.Module
+    loss_fn: Callable[..., torch.Tensor]
     static_inputs: Dict[str, torch.Tensor]
     loss: torch.Tensor
     graph: Optional[torch.cuda.CUDAGraph]
-    extra_kwargs: dict
 
     def load(self, host_batch: Dict[str, torch.Tensor]):
         """H2D of one batch into the static buffers (async on the current stream; pinned host memory)."""
@@ -87,33 +132,47 @@ class EvalStep:
             self.graph.replay()
         else:
             with torch.no_grad():
-                self.loss.copy_(self.model(**self.static_inputs, **self.extra_kwargs).loss.float())
+                self.loss.copy_(self.loss_fn(**self.static_inputs))
         return self.loss
 
     def h2d_bytes(self) -> int:
         return sum(v.numel() * v.element_size() for v in self.static_inputs.values())
 
 
-def make_eval_step(model, example_batch: Dict[str, torch.Tensor], use_graph: bool = True, warmup: int = 3,
-                   **extra_kwargs) -> EvalStep:
-    dev = next(model.parameters()).device
-    static = {k: v.to(dev) for k, v in example_batch.items()}
-    loss = torch.zeros((), dtype=torch.float32, device=dev)
-    step = EvalStep(model, static, loss, None, extra_kwargs)
+def make_eval_step(loss_fn: Callable[..., torch.Tensor], example_batch: Dict[str, torch.Tensor], device="cuda",
+                   use_graph: bool = True, warmup: int = 3) -> EvalStep:
+    """``loss_fn(**batch) -> scalar loss`` is warmed up on a side stream, then captured into one CUDA graph."""
+    static = {k: v.to(device) for k, v in example_batch.items()}
+    loss = torch.zeros((), dtype=torch.float32, device=device)
+    step = EvalStep(loss_fn, static, loss, None)
     with torch.no_grad():
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):                       # warm every lazy init (cuBLAS handles, gate packs, attrs)
-                loss.copy_(model(**static, **extra_kwargs).loss.float())
+                loss.copy_(loss_fn(**static))
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         if use_graph:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                loss.copy_(model(**static, **extra_kwargs).loss.float())
+                loss.copy_(loss_fn(**static))
             step.graph = g
     return step
+
+
+def make_bert_eval_step(model, example_batch, use_graph: bool = True) -> EvalStep:
+    return make_eval_step(lambda input_ids, labels: bert_mlm_loss(model, input_ids, labels), example_batch,
+                          device=next(model.parameters()).device, use_graph=use_graph)
+
+
+def make_opt_eval_step(model, example_batch, use_graph: bool = True) -> EvalStep:
+    p = next(model.parameters())
+    B, T = example_batch["input_ids"].shape
+    mask = make_causal_mask(B, T, p.dtype, p.device)
+    pos = torch.arange(T, device=p.device).unsqueeze(0).expand(B, T).contiguous()
+    return make_eval_step(lambda input_ids, labels: opt_clm_loss(model, input_ids, labels, mask, pos), example_batch,
+                          device=p.device, use_graph=use_graph)
 
 
 def aggregate_perplexity(loss_sum: torch.Tensor, n_batches: int) -> float:

@@ -404,9 +404,16 @@ class RangeEstimatorBase(_StateHolder):
         if self._host_init:
             destination[prefix + "current_xmin"] = self._qstate[L.QS_CUR_MIN].clone()
             destination[prefix + "current_xmax"] = self._qstate[L.QS_CUR_MAX].clone()
+        # the reference registers the quantizer as a submodule of its estimator (range_estimators.py:18), so its
+        # checkpoints carry the quantizer buffers a second time under "<estimator>.quantizer.*": emit them too
+        q = self.quantizer
+        if q is not None and q.is_initialized:
+            q._save_to_state_dict(destination, prefix + "quantizer.", keep_vars)
 
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                               error_msgs):
+        for k in [k for k in state_dict if k.startswith(prefix + "quantizer.")]:
+            state_dict.pop(k)              # duplicate of "<manager>.quantizer.*" (see _save_to_state_dict)
         ka, kb = prefix + "current_xmin", prefix + "current_xmax"
         if ka in state_dict and kb in state_dict:
             lo, hi = state_dict.pop(ka).reshape(()).float(), state_dict.pop(kb).reshape(()).float()

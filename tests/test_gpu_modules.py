@@ -252,7 +252,8 @@ def test_quantizer_module_surface_and_state_dict_roundtrip(golden):
         assert np.array_equal(y.cpu().numpy(), g["rm0::y"][i])
     sd = qm.state_dict()
     assert set(sd) == {"quantizer._delta", "quantizer._zero_float", "range_estimator.current_xmin",
-                       "range_estimator.current_xmax"}
+                       "range_estimator.current_xmax", "range_estimator.quantizer._delta",
+                       "range_estimator.quantizer._zero_float"}      # same key set as the reference's manager
     assert sd["range_estimator.current_xmin"].item() == g["rm0::cur_min"][-1]
     qm2 = o.QuantizationManager(qmethod=AQ, init=o.RunningMinMaxEstimator, qparams=dict(n_bits=8, act_quant=True))
     qm2.load_state_dict(sd)
