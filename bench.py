@@ -231,6 +231,12 @@ def run_ours(args):
             loss_sum.add_(step.run())
 
     body_resident(warmup)
+    if args.profile_one_step:                             # ncu --profile-from-start off: exactly one warm step
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        body_resident(1)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     loss_sum.zero_()
     ms_res, t0, t1 = timed(lambda: body_resident(steps))
     ppl = aggregate_perplexity(loss_sum, steps)
@@ -300,6 +306,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="run the eval step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-sweep", action="store_true", help="skip the T=2048/8192 attention sweep")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile-one-step", action="store_true",
+                    help="bracket one warm eval step with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -75,7 +75,7 @@ def swap_bert_attention(model, attn_softmax: str = "vanilla", alpha: Optional[fl
             fine_tuning=fine_tuning)
         new.load_state_dict(old.state_dict(), strict=False)
         p = next(old.parameters())
-        layer.attention.self = new.to(device=p.device, dtype=p.dtype)
+        layer.attention.self = new.to(device=p.device, dtype=p.dtype).train(old.training)
     return model
 
 
@@ -98,5 +98,5 @@ def swap_opt_attention(model, attn_softmax: str = "vanilla", alpha: Optional[flo
         new.load_state_dict(old.state_dict(), strict=False)
         new.causal_hint = causal_hint
         p = next(old.parameters())
-        layer.self_attn = new.to(device=p.device, dtype=p.dtype)
+        layer.self_attn = new.to(device=p.device, dtype=p.dtype).train(old.training)
     return model

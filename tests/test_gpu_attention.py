@@ -165,3 +165,32 @@ def test_attention_full_size_properties(T, B):
         p = e / (e.sum(-1, keepdim=True) + torch.exp(-m))
         ref = p @ v[b, h].float()
         assert (o1[b, h] - ref).abs().max().item() < TOL
+
+
+@pytest.mark.parametrize("kind,gamma,eta", KINDS[:4])
+@pytest.mark.parametrize("before_gate", [False, True])
+@pytest.mark.parametrize("T", [96, 300])
+def test_attention_fused_int8_taps_vs_oracle(kind, gamma, eta, before_gate, T):
+    """Fixed-range fake-quant taps folded into the kernel (scores before the mask, probs, context before/after the
+    gate: quantized_bert.py:363,374,434 / quantized_opt.py:154,182,210) against the oracle's tap chain on IDENTICAL
+    q,k,v.  Only tensor-core accumulation order differs, so at most a handful of codes may flip at bin edges."""
+    ops = _ops()
+    B, H = 2, 2
+    q, k, v = _mk(B, H, T, T, torch.float16, seed=900 + kind + T)
+    logits = torch.randn(B, H, T)
+    gate = O.sigmoid(logits.numpy())
+    rng = {"s": (-6.0, 7.0), "p": (0.0, 1.0), "c": (-0.9, 1.1)}
+    qs = {n: O.asym_set_quant_range(lo, hi) for n, (lo, hi) in rng.items()}
+    dev = {n: torch.tensor([float(x) for x in O.asym_scale_zero_point(*qs[n])], device="cuda") for n in qs}
+    fq = {n: (lambda x, n=n: O.asym_quantize(x, *qs[n])) for n in qs}
+    pad = torch.zeros(B, 1, 1, T, dtype=torch.float16)
+    pad[1, ..., T - 20:] = torch.finfo(torch.float16).min
+    out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, mask=pad.cuda(),
+                            gate_logits=logits.cuda(), qdq_scores=dev["s"], qdq_probs=dev["p"], qdq_ctx=dev["c"],
+                            n_bits=8, ctx_qdq_before_gate=before_gate, out_layout="bhtd")
+    ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, mask=pad.float().numpy(), gate=gate,
+                  qdq_scores=fq["s"], qdq_probs=fq["p"], qdq_ctx=fq["c"], ctx_qdq_before_gate=before_gate)
+    diff = np.abs(out.float().cpu().numpy() - ref)
+    step = float(qs["c"][0])
+    assert diff.max() <= 1.05 * step + 1e-3, (diff.max(), step)           # never more than one context code
+    assert (diff > 2e-3).mean() < 0.02, (diff > 2e-3).mean()              # and rarely even that
