@@ -1,0 +1,233 @@
+// Definitions shared by the two fused attention kernels (attn_fwd_sm100.cu: one 128-row Q tile per CTA, two CTAs per
+// SM; attn_fwd_ws.cuh: warp-specialised, two Q tiles per CTA): launch parameters, the in-kernel fake-quant tap, the
+// per-row score transform (scale -> qdq -> +mask -> clamp -> visibility) and the output epilogue.
+#pragma once
+
+#include <cfloat>
+
+#include "oeh_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace oeh {
+namespace attn {
+
+constexpr int BN = 128;                 // keys per K/V tile
+constexpr int HD = 64;                  // head dim (BERT-base / OPT-125m..1.3b)
+constexpr int kTileBytes = BN * HD * 2; // 16 KB
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct TmapCoord {      // which logical index (0 = token row, 1 = head, 2 = batch) each tensor-map dim 1..3 takes
+  int8_t perm[3];
+};
+
+struct AttnParams {
+  int B, H, Tq, Tk;
+  float scale;          // natural-domain score scale
+  int kind;
+  float stretch, gamma; // clip((eta-gamma)*p + gamma, 0, 1)
+  int causal;
+  const void* mask;
+  int mask_dtype;
+  int64_t ms0, ms1, ms2;
+  int clamp_min;
+  float fmin;
+  const float* gate_logits;
+  float gate_scale;
+  const float* qdq_scores;
+  const float* qdq_probs;
+  const float* qdq_ctx;
+  float int_max;
+  int ctx_qdq_before_gate;
+  void* out;
+  int64_t os0, os1, os2;
+  TmapCoord cq, ck, cv;
+  float* dbg_s;         // optional: raw S of K tile 0, (B,H,Tq,BN) fp32
+  float* dbg_o;         // optional: raw O accumulator, (B,H,Tq,HD) fp32
+};
+
+// Fixed-range fake-quant tap inside the fused kernel.  x/scale is evaluated as x*(1/scale): the tap's input
+// already differs from the unfused reference in the last bits (tensor-core accumulation order), so codes can
+// flip at bin edges either way; the bit-exact contract belongs to the standalone quantizer (quant.cu).
+struct Qdq {
+  float scale, inv_scale, zp, int_max;
+  __device__ __forceinline__ float operator()(float x) const {
+    float xi = rintf(x * inv_scale) + zp;
+    xi = fminf(fmaxf(xi, 0.f), int_max);
+    return scale * (xi - zp);
+  }
+};
+__device__ __forceinline__ Qdq load_qdq(const float* qparams, float int_max) {
+  Qdq q;
+  q.scale = __ldg(qparams);
+  q.zp = __ldg(qparams + 1);
+  q.inv_scale = __frcp_rn(q.scale);
+  q.int_max = int_max;
+  return q;
+}
+
+__device__ __forceinline__ float max4(float a, float b, float c, float d) { return fmaxf(fmaxf(a, b), fmaxf(c, d)); }
+
+__device__ __forceinline__ float load_mask_elem(const void* mask, int dtype, int64_t off) {
+  if (dtype == OEH_F32) return __ldg(reinterpret_cast<const float*>(mask) + off);
+  if (dtype == OEH_F16) return __half2float(__ldg(reinterpret_cast<const __half*>(mask) + off));
+  return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(mask) + off));
+}
+
+template <bool kBF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (kBF16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+}
+
+__device__ __forceinline__ void tma_tile(uint32_t dst, const CUtensorMap* m, uint32_t bar, const TmapCoord& c, int row,
+                                         int h, int b) {
+  auto pick = [&](int k) { return k == 0 ? row : (k == 1 ? h : b); };
+  ptx::tma_load_4d(dst, m, bar, 0, pick(c.perm[0]), pick(c.perm[1]), pick(c.perm[2]));
+}
+
+
+// Per-row score transform of one 128-key tile, in the reference's op order.  On return s[j]*mul is the log2-domain
+// score of key k0+j (-inf where the key is out of range / causally hidden) and the function returns mul.
+//   plain   : s stays the raw MMA output, mul = scale*log2e (scale multiply and max subtraction fold into one FFMA)
+//   generic : scale -> fake-quant tap -> + additive mask -> clamp(finfo.min) in natural units, then * log2e, mul = 1
+//             (log2e is applied explicitly: with finfo.min-sized masked scores the rounding error of a folded multiply
+//             -- exact product inside the FFMA vs the rounded tile maximum -- would be ~1e31).
+template <bool kGeneric>
+__device__ __forceinline__ float transform_scores(float (&s)[BN], const AttnParams& p, const Qdq& qd_s, bool has_qs,
+                                                  bool has_mask, int64_t mask_row, int k0, int valid, int vis) {
+  float mul = p.scale * kLog2e;
+  if (kGeneric && (has_qs || has_mask || p.clamp_min)) {
+    mul = 1.f;
+    const float scale = p.scale;
+#pragma unroll
+    for (int j = 0; j < BN; ++j) s[j] *= scale;
+    if (has_qs) {
+#pragma unroll
+      for (int j = 0; j < BN; ++j) s[j] = qd_s(s[j]);
+    }
+    if (has_mask) {
+      if (p.mask_dtype == OEH_F32) {
+        const float* mp = reinterpret_cast<const float*>(p.mask) + mask_row + k0;
+#pragma unroll
+        for (int j = 0; j < BN; ++j)
+          if (j < valid) s[j] += __ldg(mp + j);
+      } else if (p.mask_dtype == OEH_F16) {
+        const __half* mp = reinterpret_cast<const __half*>(p.mask) + mask_row + k0;
+#pragma unroll
+        for (int j = 0; j < BN; ++j)
+          if (j < valid) s[j] += __half2float(__ldg(mp + j));
+      } else {
+        const __nv_bfloat16* mp = reinterpret_cast<const __nv_bfloat16*>(p.mask) + mask_row + k0;
+#pragma unroll
+        for (int j = 0; j < BN; ++j)
+          if (j < valid) s[j] += __bfloat162float(__ldg(mp + j));
+      }
+    }
+    // clamp (opt_attention.py:221-223); the lower bound also keeps finfo.min-masked scores finite after the log2e
+    // multiply, so a row masked entirely with finfo.min stays uniform like the reference's
+    const float lo = p.clamp_min ? fmaxf(p.fmin, -FLT_MAX / 2.f) : -FLT_MAX / 2.f;
+#pragma unroll
+    for (int j = 0; j < BN; ++j) s[j] = fmaxf(s[j], lo) * kLog2e;
+  }
+  if (vis < BN - 1) {                               // ragged last tile / causal diagonal tile
+#pragma unroll
+    for (int j = 0; j < BN; ++j)
+      if (j > vis) s[j] = -INFINITY;
+  }
+  return mul;
+}
+
+__device__ __forceinline__ float row_max(const float (&s)[BN]) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // 4 independent chains
+#pragma unroll
+  for (int j = 0; j < BN; j += 4) {
+    m0 = fmaxf(m0, s[j]);
+    m1 = fmaxf(m1, s[j + 1]);
+    m2 = fmaxf(m2, s[j + 2]);
+    m3 = fmaxf(m3, s[j + 3]);
+  }
+  return max4(m0, m1, m2, m3);
+}
+
+// s[j] <- exp2(s[j]*mul - m); returns the row sum (4 independent accumulators)
+__device__ __forceinline__ float exp2_and_sum(float (&s)[BN], float mul, float m) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < BN; j += 4) {
+    s[j] = ptx::ex2(fmaf(s[j], mul, -m));
+    s[j + 1] = ptx::ex2(fmaf(s[j + 1], mul, -m));
+    s[j + 2] = ptx::ex2(fmaf(s[j + 2], mul, -m));
+    s[j + 3] = ptx::ex2(fmaf(s[j + 3], mul, -m));
+    a0 += s[j];
+    a1 += s[j + 1];
+    a2 += s[j + 2];
+    a3 += s[j + 3];
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
+// normalised modes: p = e * inv_den, then clip((eta-gamma)*p + gamma, 0, 1) and / or the probs fake-quant tap
+template <bool kGeneric>
+__device__ __forceinline__ void normalize_probs(float (&s)[BN], const AttnParams& p, float inv_den, bool clipped,
+                                                bool has_qp, const Qdq& qd_p) {
+  if (clipped) {
+    const float st = p.stretch * inv_den, gm = p.gamma;
+#pragma unroll
+    for (int j = 0; j < BN; ++j) s[j] = __saturatef(fmaf(s[j], st, gm));
+  } else {
+#pragma unroll
+    for (int j = 0; j < BN; ++j) s[j] *= inv_den;
+  }
+  if (kGeneric && has_qp) {
+#pragma unroll
+    for (int j = 0; j < BN; ++j) s[j] = qd_p(s[j]);
+  }
+}
+
+// Epilogue of one query row: o[] holds the PV accumulator; mul = 1/denominator (1 in the normalised modes).
+// ctx -> [qdq before gate] -> * sigmoid(gate logit)*gate_scale -> [qdq after gate] -> 8 x 16-byte stores.
+template <bool kBF16, bool kGeneric>
+__device__ __forceinline__ void store_row(float (&o)[HD], const AttnParams& p, float mul, int b, int h, int row) {
+  if (kGeneric && p.dbg_o) {
+    float* d = p.dbg_o + (((int64_t)b * p.H + h) * p.Tq + row) * HD;
+#pragma unroll
+    for (int j = 0; j < HD; ++j) d[j] = o[j];
+  }
+  float gate = 1.f;
+  if (p.gate_logits) {
+    const float z = __ldg(p.gate_logits + ((int64_t)b * p.H + h) * p.Tq + row);
+    gate = __frcp_rn(1.f + expf(-z)) * p.gate_scale;
+  }
+  if (kGeneric && p.qdq_ctx) {
+    const Qdq qd_c = load_qdq(p.qdq_ctx, p.int_max);
+    if (p.ctx_qdq_before_gate) {                       // OPT: tap on PV, then gate (quantized_opt.py:210)
+#pragma unroll
+      for (int j = 0; j < HD; ++j) o[j] = qd_c(o[j] * mul) * gate;
+    } else {                                           // BERT: gate, then tap (quantized_bert.py:434)
+#pragma unroll
+      for (int j = 0; j < HD; ++j) o[j] = qd_c(o[j] * mul * gate);
+    }
+  } else {
+    mul *= gate;
+#pragma unroll
+    for (int j = 0; j < HD; ++j) o[j] *= mul;
+  }
+  uint8_t* optr = reinterpret_cast<uint8_t*>(p.out) + 2 * ((int64_t)b * p.os0 + (int64_t)h * p.os1 + (int64_t)row * p.os2);
+#pragma unroll
+  for (int c = 0; c < HD / 8; ++c) {
+    uint4 v;
+    v.x = pack2<kBF16>(o[c * 8 + 0], o[c * 8 + 1]);
+    v.y = pack2<kBF16>(o[c * 8 + 2], o[c * 8 + 3]);
+    v.z = pack2<kBF16>(o[c * 8 + 4], o[c * 8 + 5]);
+    v.w = pack2<kBF16>(o[c * 8 + 6], o[c * 8 + 7]);
+    reinterpret_cast<uint4*>(optr)[c] = v;
+  }
+}
+
+}  // namespace attn
+}  // namespace oeh

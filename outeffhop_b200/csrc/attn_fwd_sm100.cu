@@ -17,98 +17,21 @@
 // tile (Tk <= 128, the BERT eval shape) both passes collapse into one.
 // Two CTAs are co-resident per SM (2 x 256 TMEM columns, 2 x 81 KB smem) so one CTA's softmax
 // overlaps the other's MMAs.  Roofline: tensor pipe, 4*B*H*Tq*Tk*d flop per call (causal: unmasked half).
-#include <cfloat>
 #include <cstdlib>
 #include <cstring>
 
-#include "oeh_common.cuh"
-#include "sm100_ptx.cuh"
+#include "attn_common.cuh"
+#include "attn_fwd_ws.cuh"
 
 namespace oeh {
 namespace {
 
+using namespace attn;
+
 constexpr int BM = 128;                 // query rows per CTA  (== threads per CTA, lane == row)
-constexpr int BN = 128;                 // keys per K/V tile
-constexpr int HD = 64;                  // head dim (BERT-base / OPT-125m..1.3b)
-constexpr int kTileBytes = BN * HD * 2; // 16 KB
 constexpr int kSmemBytes = 5 * kTileBytes + 1024;
 constexpr uint32_t kTmemCols = 256;
 constexpr uint32_t kColS = 0, kColP = 0, kColO = 128;
-constexpr float kLog2e = 1.4426950408889634f;
-
-struct TmapCoord {      // which logical index (0 = token row, 1 = head, 2 = batch) each tensor-map dim 1..3 takes
-  int8_t perm[3];
-};
-
-struct AttnParams {
-  int B, H, Tq, Tk;
-  float scale;          // natural-domain score scale
-  int kind;
-  float stretch, gamma; // clip((eta-gamma)*p + gamma, 0, 1)
-  int causal;
-  const void* mask;
-  int mask_dtype;
-  int64_t ms0, ms1, ms2;
-  int clamp_min;
-  float fmin;
-  const float* gate_logits;
-  float gate_scale;
-  const float* qdq_scores;
-  const float* qdq_probs;
-  const float* qdq_ctx;
-  float int_max;
-  int ctx_qdq_before_gate;
-  void* out;
-  int64_t os0, os1, os2;
-  TmapCoord cq, ck, cv;
-  float* dbg_s;         // optional: raw S of K tile 0, (B,H,Tq,BN) fp32
-  float* dbg_o;         // optional: raw O accumulator, (B,H,Tq,HD) fp32
-};
-
-// Fixed-range fake-quant tap inside the fused kernel.  x/scale is evaluated as x*(1/scale): the tap's input
-// already differs from the unfused reference in the last bits (tensor-core accumulation order), so codes can
-// flip at bin edges either way; the bit-exact contract belongs to the standalone quantizer (quant.cu).
-struct Qdq {
-  float scale, inv_scale, zp, int_max;
-  __device__ __forceinline__ float operator()(float x) const {
-    float xi = rintf(x * inv_scale) + zp;
-    xi = fminf(fmaxf(xi, 0.f), int_max);
-    return scale * (xi - zp);
-  }
-};
-__device__ __forceinline__ Qdq load_qdq(const float* qparams, float int_max) {
-  Qdq q;
-  q.scale = __ldg(qparams);
-  q.zp = __ldg(qparams + 1);
-  q.inv_scale = __frcp_rn(q.scale);
-  q.int_max = int_max;
-  return q;
-}
-
-__device__ __forceinline__ float max4(float a, float b, float c, float d) { return fmaxf(fmaxf(a, b), fmaxf(c, d)); }
-
-__device__ __forceinline__ float load_mask_elem(const void* mask, int dtype, int64_t off) {
-  if (dtype == OEH_F32) return __ldg(reinterpret_cast<const float*>(mask) + off);
-  if (dtype == OEH_F16) return __half2float(__ldg(reinterpret_cast<const __half*>(mask) + off));
-  return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(mask) + off));
-}
-
-template <bool kBF16>
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  if constexpr (kBF16) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
-  } else {
-    __half2 v = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
-  }
-}
-
-__device__ __forceinline__ void tma_tile(uint32_t dst, const CUtensorMap* m, uint32_t bar, const TmapCoord& c, int row,
-                                         int h, int b) {
-  auto pick = [&](int k) { return k == 0 ? row : (k == 1 ? h : b); };
-  ptx::tma_load_4d(dst, m, bar, 0, pick(c.perm[0]), pick(c.perm[1]), pick(c.perm[2]));
-}
 
 // kGeneric = false: no fake-quant taps, no mask tensor, no clamp, no debug dumps -- the tight hot loop.
 // kGeneric = true : everything; each optional feature is its own loop behind one uniform branch so the
@@ -212,8 +135,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
   __syncwarp();
 
   // ---- per-row state ------------------------------------------------------------------------------
-  const float scale = p.scale;
-  const float sl2 = scale * kLog2e;
   const bool has_qs = kGeneric && p.qdq_scores != nullptr;
   const bool has_qp = kGeneric && p.qdq_probs != nullptr;
   const bool has_mask = kGeneric && p.mask != nullptr;
@@ -253,62 +174,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
 
     const int valid = min(p.Tk - k0, BN);            // columns < valid exist
     const int vis = min(valid - 1, causal_lim - k0); // columns <= vis are visible to this row
-    // After this block: s[j] holds the score in "raw" units and (mul, tile_max) are such that the log2-domain
-    // score is s[j]*mul and its tile maximum is tile_max.  Plain path: raw MMA output, mul = scale*log2e (the
-    // scale multiply and the max subtraction fold into one FFMA per element).  Generic path: the reference's
-    // op order scale -> qdq -> +mask -> clamp in natural units, then * log2e, mul = 1.
-    float mul = sl2;
-    if (kGeneric && (has_qs || has_mask || p.clamp_min)) {
-      // log2e is applied explicitly (mul = 1): with finfo.min-sized masked scores the rounding error of the
-      // folded multiply (exact product inside the FFMA vs the rounded tile maximum) would be ~1e31
-      mul = 1.f;
-#pragma unroll
-      for (int j = 0; j < BN; ++j) s[j] *= scale;
-      if (has_qs) {
-#pragma unroll
-        for (int j = 0; j < BN; ++j) s[j] = qd_s(s[j]);
-      }
-      if (has_mask) {
-        if (p.mask_dtype == OEH_F32) {
-          const float* mp = reinterpret_cast<const float*>(p.mask) + mask_row + k0;
-#pragma unroll
-          for (int j = 0; j < BN; ++j)
-            if (j < valid) s[j] += __ldg(mp + j);
-        } else if (p.mask_dtype == OEH_F16) {
-          const __half* mp = reinterpret_cast<const __half*>(p.mask) + mask_row + k0;
-#pragma unroll
-          for (int j = 0; j < BN; ++j)
-            if (j < valid) s[j] += __half2float(__ldg(mp + j));
-        } else {
-          const __nv_bfloat16* mp = reinterpret_cast<const __nv_bfloat16*>(p.mask) + mask_row + k0;
-#pragma unroll
-          for (int j = 0; j < BN; ++j)
-            if (j < valid) s[j] += __bfloat162float(__ldg(mp + j));
-        }
-      }
-      // clamp (opt_attention.py:221-223); the lower bound also keeps finfo.min-masked scores finite after
-      // the log2e multiply, so a row masked entirely with finfo.min stays uniform like the reference's
-      const float lo = p.clamp_min ? fmaxf(p.fmin, -FLT_MAX / 2.f) : -FLT_MAX / 2.f;
-#pragma unroll
-      for (int j = 0; j < BN; ++j) s[j] = fmaxf(s[j], lo) * kLog2e;
-    }
-    if (vis < BN - 1) {                               // ragged last tile / causal diagonal tile
-#pragma unroll
-      for (int j = 0; j < BN; ++j)
-        if (j > vis) s[j] = -INFINITY;
-    }
-    float tile_max;
-    {
-      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // 4 independent chains
-#pragma unroll
-      for (int j = 0; j < BN; j += 4) {
-        m0 = fmaxf(m0, s[j]);
-        m1 = fmaxf(m1, s[j + 1]);
-        m2 = fmaxf(m2, s[j + 2]);
-        m3 = fmaxf(m3, s[j + 3]);
-      }
-      tile_max = max4(m0, m1, m2, m3) * mul;          // mul > 0
-    }
+    const float mul = transform_scores<kGeneric>(s, p, qd_s, has_qs, has_mask, mask_row, k0, valid, vis);
+    const float tile_max = row_max(s) * mul;         // mul > 0
 
     const bool online = !normalized;
     if (!pv_iter || one_tile || online) {
@@ -316,19 +183,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       const float m_new = fmaxf(m_run, tile_max);
       const float m_safe = m_new == -INFINITY ? 0.f : m_new;
       const float alpha = ptx::ex2(m_run - m_safe);   // m_run = -inf -> 0
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-      for (int j = 0; j < BN; j += 4) {
-        s[j] = ptx::ex2(fmaf(s[j], mul, -m_safe));
-        s[j + 1] = ptx::ex2(fmaf(s[j + 1], mul, -m_safe));
-        s[j + 2] = ptx::ex2(fmaf(s[j + 2], mul, -m_safe));
-        s[j + 3] = ptx::ex2(fmaf(s[j + 3], mul, -m_safe));
-        a0 += s[j];
-        a1 += s[j + 1];
-        a2 += s[j + 2];
-        a3 += s[j + 3];
-      }
-      l_run = fmaf(l_run, alpha, (a0 + a1) + (a2 + a3));
+      l_run = fmaf(l_run, alpha, exp2_and_sum(s, mul, m_safe));
       m_run = m_new;
       if (!pv_iter) {
         ptx::tc_fence_before();
@@ -366,20 +221,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       for (int j = 0; j < BN; ++j) s[j] = ptx::ex2(fmaf(s[j], mul, -m_safe));
     }
 
-    if (normalized) {
-      if (clipped) {
-        const float st = p.stretch * inv_den, gm = p.gamma;   // clip((eta-gamma)*p + gamma, 0, 1)
-#pragma unroll
-        for (int j = 0; j < BN; ++j) s[j] = __saturatef(fmaf(s[j], st, gm));
-      } else {
-#pragma unroll
-        for (int j = 0; j < BN; ++j) s[j] *= inv_den;
-      }
-      if (has_qp) {
-#pragma unroll
-        for (int j = 0; j < BN; ++j) s[j] = qd_p(s[j]);
-      }
-    }
+    if (normalized) normalize_probs<kGeneric>(s, p, inv_den, clipped, has_qp, qd_p);
 
     // P -> TMEM (packed 16-bit pairs), aliasing the S columns this thread has already consumed
 #pragma unroll
@@ -416,46 +258,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
   if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem);
 
   if (row >= p.Tq) return;
-  if (kGeneric && p.dbg_o) {
-    float* d = p.dbg_o + (((int64_t)b * p.H + h) * p.Tq + row) * HD;
-#pragma unroll
-    for (int j = 0; j < HD; ++j) d[j] = o[j];
-  }
   float mul = 1.f;
   if (!normalized) {
     const float m_safe = m_run == -INFINITY ? 0.f : m_run;
     const float den = softmax1 ? l_run + ptx::ex2(-m_safe) : l_run;
     mul = __frcp_rn(den);
   }
-  float gate = 1.f;
-  if (p.gate_logits) {
-    const float z = __ldg(p.gate_logits + ((int64_t)b * p.H + h) * p.Tq + row);
-    gate = __frcp_rn(1.f + expf(-z)) * p.gate_scale;
-  }
-  if (kGeneric && p.qdq_ctx) {
-    const Qdq qd_c = load_qdq(p.qdq_ctx, p.int_max);
-    if (p.ctx_qdq_before_gate) {                       // OPT: tap on PV, then gate (quantized_opt.py:210)
-#pragma unroll
-      for (int j = 0; j < HD; ++j) o[j] = qd_c(o[j] * mul) * gate;
-    } else {                                           // BERT: gate, then tap (quantized_bert.py:434)
-#pragma unroll
-      for (int j = 0; j < HD; ++j) o[j] = qd_c(o[j] * mul * gate);
-    }
-  } else {
-    mul *= gate;
-#pragma unroll
-    for (int j = 0; j < HD; ++j) o[j] *= mul;
-  }
-  uint8_t* optr = reinterpret_cast<uint8_t*>(p.out) + 2 * ((int64_t)b * p.os0 + (int64_t)h * p.os1 + (int64_t)row * p.os2);
-#pragma unroll
-  for (int c = 0; c < HD / 8; ++c) {
-    uint4 v;
-    v.x = pack2<kBF16>(o[c * 8 + 0], o[c * 8 + 1]);
-    v.y = pack2<kBF16>(o[c * 8 + 2], o[c * 8 + 3]);
-    v.z = pack2<kBF16>(o[c * 8 + 4], o[c * 8 + 5]);
-    v.w = pack2<kBF16>(o[c * 8 + 6], o[c * 8 + 7]);
-    reinterpret_cast<uint4*>(optr)[c] = v;
-  }
+  store_row<kBF16, kGeneric>(o, p, mul, b, h, row);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
@@ -579,19 +388,39 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
   p.dbg_s = dbg_s;
   p.dbg_o = dbg_o;
 
-  dim3 grid((unsigned)((a->Tq + BM - 1) / BM), (unsigned)a->H, (unsigned)a->B);
   cudaStream_t st = (cudaStream_t)a->stream;
   const bool generic = a->qdq_scores || a->qdq_probs || a->qdq_ctx || a->mask || a->clamp_min || dbg_s || dbg_o ||
                        !(a->scale > 0.f);
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
+  // Kernel choice: sequences longer than one Q tile use the warp-specialised two-tile kernel; up to 128 query
+  // rows there is nothing to ping-pong with, and the single-tile kernel (2 CTAs / SM) has the lower latency.
+  // OEH_ATTN_KERNEL=tile|ws overrides (tests exercise both on the same shapes).
+  bool use_ws = a->Tq > BM;
+  if (const char* f = getenv("OEH_ATTN_KERNEL")) {
+    if (!strcmp(f, "tile")) use_ws = false;
+    if (!strcmp(f, "ws")) use_ws = true;
+  }
+  const int ki = (a->dtype == OEH_BF16 ? 2 : 0) + (generic ? 1 : 0);
+  if (use_ws) {
+    static const KernelFn kernels[4] = {attn_ws::attn_fwd_ws_kernel<false, false>, attn_ws::attn_fwd_ws_kernel<false, true>,
+                                        attn_ws::attn_fwd_ws_kernel<true, false>, attn_ws::attn_fwd_ws_kernel<true, true>};
+    static bool attr_done[4] = {false, false, false, false};
+    if (!attr_done[ki]) {
+      OEH_CUDA_OK(cudaFuncSetAttribute(kernels[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, attn_ws::kSmemBytes));
+      attr_done[ki] = true;
+    }
+    dim3 grid((unsigned)((a->Tq + attn_ws::kQRows - 1) / attn_ws::kQRows), (unsigned)a->H, (unsigned)a->B);
+    kernels[ki]<<<grid, attn_ws::kThreads, attn_ws::kSmemBytes, st>>>(tmq, tmk, tmv, p);
+    return check_launch("attn_fwd_ws_kernel");
+  }
   static const KernelFn kernels[4] = {attn_fwd_kernel<false, false>, attn_fwd_kernel<false, true>,
                                       attn_fwd_kernel<true, false>, attn_fwd_kernel<true, true>};
   static bool attr_done[4] = {false, false, false, false};
-  const int ki = (a->dtype == OEH_BF16 ? 2 : 0) + (generic ? 1 : 0);
   if (!attr_done[ki]) {
     OEH_CUDA_OK(cudaFuncSetAttribute(kernels[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_done[ki] = true;
   }
+  dim3 grid((unsigned)((a->Tq + BM - 1) / BM), (unsigned)a->H, (unsigned)a->B);
   kernels[ki]<<<grid, BM, kSmemBytes, st>>>(tmq, tmk, tmv, p);
   return check_launch("attn_fwd_kernel");
 }
