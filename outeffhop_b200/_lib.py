@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liboeh.so")
+# OEH_LIB_PATH: developer override used by kernel experiments (tools/); the product always loads lib/liboeh.so
+LIB_PATH = os.environ.get("OEH_LIB_PATH") or os.path.join(_HERE, "lib", "liboeh.so")
 
 OEH_OK, OEH_ERR_BAD_ARG, OEH_ERR_UNSUPPORTED, OEH_ERR_CUDA, OEH_ERR_WORKSPACE, OEH_ERR_NOT_INITIALIZED = range(6)
 OEH_F32, OEH_F16, OEH_BF16 = 0, 1, 2

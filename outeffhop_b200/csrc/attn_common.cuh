@@ -97,34 +97,34 @@ __device__ __forceinline__ void tma_tile(uint32_t dst, const CUtensorMap* m, uin
 //   generic : scale -> fake-quant tap -> + additive mask -> clamp(finfo.min) in natural units, then * log2e, mul = 1
 //             (log2e is applied explicitly: with finfo.min-sized masked scores the rounding error of a folded multiply
 //             -- exact product inside the FFMA vs the rounded tile maximum -- would be ~1e31).
-template <bool kGeneric>
-__device__ __forceinline__ float transform_scores(float (&s)[BN], const AttnParams& p, const Qdq& qd_s, bool has_qs,
+template <int N, bool kGeneric>
+__device__ __forceinline__ float transform_scores(float (&s)[N], const AttnParams& p, const Qdq& qd_s, bool has_qs,
                                                   bool has_mask, int64_t mask_row, int k0, int valid, int vis) {
   float mul = p.scale * kLog2e;
   if (kGeneric && (has_qs || has_mask || p.clamp_min)) {
     mul = 1.f;
     const float scale = p.scale;
 #pragma unroll
-    for (int j = 0; j < BN; ++j) s[j] *= scale;
+    for (int j = 0; j < N; ++j) s[j] *= scale;
     if (has_qs) {
 #pragma unroll
-      for (int j = 0; j < BN; ++j) s[j] = qd_s(s[j]);
+      for (int j = 0; j < N; ++j) s[j] = qd_s(s[j]);
     }
     if (has_mask) {
       if (p.mask_dtype == OEH_F32) {
         const float* mp = reinterpret_cast<const float*>(p.mask) + mask_row + k0;
 #pragma unroll
-        for (int j = 0; j < BN; ++j)
+        for (int j = 0; j < N; ++j)
           if (j < valid) s[j] += __ldg(mp + j);
       } else if (p.mask_dtype == OEH_F16) {
         const __half* mp = reinterpret_cast<const __half*>(p.mask) + mask_row + k0;
 #pragma unroll
-        for (int j = 0; j < BN; ++j)
+        for (int j = 0; j < N; ++j)
           if (j < valid) s[j] += __half2float(__ldg(mp + j));
       } else {
         const __nv_bfloat16* mp = reinterpret_cast<const __nv_bfloat16*>(p.mask) + mask_row + k0;
 #pragma unroll
-        for (int j = 0; j < BN; ++j)
+        for (int j = 0; j < N; ++j)
           if (j < valid) s[j] += __bfloat162float(__ldg(mp + j));
       }
     }
@@ -132,20 +132,21 @@ __device__ __forceinline__ float transform_scores(float (&s)[BN], const AttnPara
     // multiply, so a row masked entirely with finfo.min stays uniform like the reference's
     const float lo = p.clamp_min ? fmaxf(p.fmin, -FLT_MAX / 2.f) : -FLT_MAX / 2.f;
 #pragma unroll
-    for (int j = 0; j < BN; ++j) s[j] = fmaxf(s[j], lo) * kLog2e;
+    for (int j = 0; j < N; ++j) s[j] = fmaxf(s[j], lo) * kLog2e;
   }
-  if (vis < BN - 1) {                               // ragged last tile / causal diagonal tile
+  if (vis < N - 1) {                               // ragged last tile / causal diagonal tile
 #pragma unroll
-    for (int j = 0; j < BN; ++j)
+    for (int j = 0; j < N; ++j)
       if (j > vis) s[j] = -INFINITY;
   }
   return mul;
 }
 
-__device__ __forceinline__ float row_max(const float (&s)[BN]) {
+template <int N>
+__device__ __forceinline__ float row_max(const float (&s)[N]) {
   float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // 4 independent chains
 #pragma unroll
-  for (int j = 0; j < BN; j += 4) {
+  for (int j = 0; j < N; j += 4) {
     m0 = fmaxf(m0, s[j]);
     m1 = fmaxf(m1, s[j + 1]);
     m2 = fmaxf(m2, s[j + 2]);
@@ -155,10 +156,11 @@ __device__ __forceinline__ float row_max(const float (&s)[BN]) {
 }
 
 // s[j] <- exp2(s[j]*mul - m); returns the row sum (4 independent accumulators)
-__device__ __forceinline__ float exp2_and_sum(float (&s)[BN], float mul, float m) {
+template <int N>
+__device__ __forceinline__ float exp2_and_sum(float (&s)[N], float mul, float m) {
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-  for (int j = 0; j < BN; j += 4) {
+  for (int j = 0; j < N; j += 4) {
     s[j] = ptx::ex2(fmaf(s[j], mul, -m));
     s[j + 1] = ptx::ex2(fmaf(s[j + 1], mul, -m));
     s[j + 2] = ptx::ex2(fmaf(s[j + 2], mul, -m));
@@ -172,20 +174,20 @@ __device__ __forceinline__ float exp2_and_sum(float (&s)[BN], float mul, float m
 }
 
 // normalised modes: p = e * inv_den, then clip((eta-gamma)*p + gamma, 0, 1) and / or the probs fake-quant tap
-template <bool kGeneric>
-__device__ __forceinline__ void normalize_probs(float (&s)[BN], const AttnParams& p, float inv_den, bool clipped,
+template <int N, bool kGeneric>
+__device__ __forceinline__ void normalize_probs(float (&s)[N], const AttnParams& p, float inv_den, bool clipped,
                                                 bool has_qp, const Qdq& qd_p) {
   if (clipped) {
     const float st = p.stretch * inv_den, gm = p.gamma;
 #pragma unroll
-    for (int j = 0; j < BN; ++j) s[j] = __saturatef(fmaf(s[j], st, gm));
+    for (int j = 0; j < N; ++j) s[j] = __saturatef(fmaf(s[j], st, gm));
   } else {
 #pragma unroll
-    for (int j = 0; j < BN; ++j) s[j] *= inv_den;
+    for (int j = 0; j < N; ++j) s[j] *= inv_den;
   }
   if (kGeneric && has_qp) {
 #pragma unroll
-    for (int j = 0; j < BN; ++j) s[j] = qd_p(s[j]);
+    for (int j = 0; j < N; ++j) s[j] = qd_p(s[j]);
   }
 }
 

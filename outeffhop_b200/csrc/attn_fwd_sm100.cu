@@ -123,7 +123,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
     }
   };
 
-  if (tid == 0) {
+  // one ELECTED lane of warp 0 issues TMA / tcgen05 (see ptx::elect_one)
+  if (warp == 0 && ptx::elect_one()) {
     ptx::mbar_expect_tx(bar_q, kTileBytes);
     tma_tile(sQ, &tmq, bar_q, p.cq, q0, h, b);
     issue_loads(0);
@@ -152,7 +153,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
     mma_phase ^= 1u;
     ptx::tc_fence_after();
     // S(it) is complete, and so is every MMA issued before it: the stage used by iteration it-1 is free
-    if (tid == 0 && it >= 1 && it + 1 < n_iter) issue_loads(it + 1);
+    if (warp == 0 && it >= 1 && it + 1 < n_iter && ptx::elect_one()) issue_loads(it + 1);
     __syncwarp();
 
     const bool pv_iter = it >= nA;
@@ -174,7 +175,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
 
     const int valid = min(p.Tk - k0, BN);            // columns < valid exist
     const int vis = min(valid - 1, causal_lim - k0); // columns <= vis are visible to this row
-    const float mul = transform_scores<kGeneric>(s, p, qd_s, has_qs, has_mask, mask_row, k0, valid, vis);
+    const float mul = transform_scores<BN, kGeneric>(s, p, qd_s, has_qs, has_mask, mask_row, k0, valid, vis);
     const float tile_max = row_max(s) * mul;         // mul > 0
 
     const bool online = !normalized;
@@ -188,7 +189,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       if (!pv_iter) {
         ptx::tc_fence_before();
         __syncthreads();                              // every thread has read S(it)
-        if (tid == 0) {
+        if (warp == 0 && ptx::elect_one()) {
           ptx::tc_fence_after();
           issue_qk(it + 1);                           // a stats iteration is never the last one
           ptx::mma_commit(bar_mma);
@@ -221,7 +222,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       for (int j = 0; j < BN; ++j) s[j] = ptx::ex2(fmaf(s[j], mul, -m_safe));
     }
 
-    if (normalized) normalize_probs<kGeneric>(s, p, inv_den, clipped, has_qp, qd_p);
+    if (normalized) normalize_probs<BN, kGeneric>(s, p, inv_den, clipped, has_qp, qd_p);
 
     // P -> TMEM (packed 16-bit pairs), aliasing the S columns this thread has already consumed
 #pragma unroll
@@ -234,7 +235,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
     ptx::tmem_wait_st();
     ptx::tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && ptx::elect_one()) {
       ptx::tc_fence_after();
       issue_pv(it);
       if (it + 1 < n_iter) issue_qk(it + 1);
@@ -286,9 +287,9 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // 4-D tensor map over a (B,H,T,64) strided view whose head dim is contiguous: dim0 = d, dims 1..3 =
-// (token, head, batch) ordered by increasing stride; box = [64, 128 tokens, 1, 1]; 128-byte swizzle.
+// (token, head, batch) ordered by increasing stride; box = [64, box_rows tokens, 1, 1]; 128-byte swizzle.
 int make_tmap(CUtensorMap* tm, TmapCoord* coord, const void* base, int dtype, int B, int H, int T,
-              const int64_t* strides /* (b,h,t) elements */, const char* what) {
+              const int64_t* strides /* (b,h,t) elements */, int box_rows, const char* what) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return set_error(OEH_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if (reinterpret_cast<uintptr_t>(base) & 15)
@@ -314,7 +315,7 @@ int make_tmap(CUtensorMap* tm, TmapCoord* coord, const void* base, int dtype, in
   cuuint32_t estr[4] = {1, 1, 1, 1};
   for (int i = 0; i < 3; ++i) {
     coord->perm[i] = (int8_t)dims[i].logical;
-    if (dims[i].logical == 0) box[i + 1] = BN;
+    if (dims[i].logical == 0) box[i + 1] = (cuuint32_t)box_rows;
   }
   CUresult r = enc(tm, dtype == OEH_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
                    const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -359,12 +360,22 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
   if ((reinterpret_cast<uintptr_t>(a->out) & 15) || a->out_strides[0] % 8 || a->out_strides[1] % 8 || a->out_strides[2] % 8)
     return set_error(OEH_ERR_UNSUPPORTED, "oeh_attn_fwd: out must be 16-byte aligned with strides that are multiples of 8");
 
+  // Kernel choice: sequences longer than one Q tile use the warp-specialised two-tile kernel (64-key sub-tiles);
+  // up to 128 query rows there is nothing to ping-pong with, and the single-tile kernel (2 CTAs / SM) has the
+  // lower latency.  OEH_ATTN_KERNEL=tile|ws overrides (tests exercise both on the same shapes).
+  bool use_ws = a->Tq > BM;
+  if (const char* f = getenv("OEH_ATTN_KERNEL")) {
+    if (!strcmp(f, "tile")) use_ws = false;
+    if (!strcmp(f, "ws")) use_ws = true;
+  }
+  const int kv_box = use_ws ? attn_ws::BNW : BN;
+
   CUtensorMap tmq, tmk, tmv;
   AttnParams p;
   memset(&p, 0, sizeof(p));
-  if ((rc = make_tmap(&tmq, &p.cq, a->q, a->dtype, a->B, a->H, a->Tq, a->q_strides, "q"))) return rc;
-  if ((rc = make_tmap(&tmk, &p.ck, a->k, a->dtype, a->B, a->H, a->Tk, a->k_strides, "k"))) return rc;
-  if ((rc = make_tmap(&tmv, &p.cv, a->v, a->dtype, a->B, a->H, a->Tk, a->v_strides, "v"))) return rc;
+  if ((rc = make_tmap(&tmq, &p.cq, a->q, a->dtype, a->B, a->H, a->Tq, a->q_strides, BM, "q"))) return rc;
+  if ((rc = make_tmap(&tmk, &p.ck, a->k, a->dtype, a->B, a->H, a->Tk, a->k_strides, kv_box, "k"))) return rc;
+  if ((rc = make_tmap(&tmv, &p.cv, a->v, a->dtype, a->B, a->H, a->Tk, a->v_strides, kv_box, "v"))) return rc;
   p.B = a->B; p.H = a->H; p.Tq = a->Tq; p.Tk = a->Tk;
   p.scale = a->scale;
   p.kind = a->kind;
@@ -392,14 +403,6 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
   const bool generic = a->qdq_scores || a->qdq_probs || a->qdq_ctx || a->mask || a->clamp_min || dbg_s || dbg_o ||
                        !(a->scale > 0.f);
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
-  // Kernel choice: sequences longer than one Q tile use the warp-specialised two-tile kernel; up to 128 query
-  // rows there is nothing to ping-pong with, and the single-tile kernel (2 CTAs / SM) has the lower latency.
-  // OEH_ATTN_KERNEL=tile|ws overrides (tests exercise both on the same shapes).
-  bool use_ws = a->Tq > BM;
-  if (const char* f = getenv("OEH_ATTN_KERNEL")) {
-    if (!strcmp(f, "tile")) use_ws = false;
-    if (!strcmp(f, "ws")) use_ws = true;
-  }
   const int ki = (a->dtype == OEH_BF16 ? 2 : 0) + (generic ? 1 : 0);
   if (use_ws) {
     static const KernelFn kernels[4] = {attn_ws::attn_fwd_ws_kernel<false, false>, attn_ws::attn_fwd_ws_kernel<false, true>,

@@ -13,6 +13,19 @@ namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of the (converged) warp is elected.  Unlike `lane == 0`, the compiler knows exactly one thread is
+// active inside `if (elect_one())`, so tcgen05 / TMA instructions are emitted straight on the uniform datapath
+// instead of being wrapped in a per-instruction ELECT / BRA.U.ANY loop (~70 cycles per MMA issue, measured).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -41,6 +54,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > 4000000u) __trap();
   }
+}
+
+// ---- named barriers (bar.sync / bar.arrive on ids 1..15; id 0 is __syncthreads) ------------------------------
+// The float operand ties the barrier into the data flow of the surrounding arithmetic (`dep` is returned
+// unchanged): plain arithmetic / non-volatile asm that consumes it cannot be hoisted above a sync, and an arrive that
+// takes a sum cannot be issued before the instructions producing that sum.
+__device__ __forceinline__ void nbar_sync(int id, int nthreads, float& dep) {
+  asm volatile("bar.sync %1, %2;" : "+f"(dep) : "r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void nbar_arrive(int id, int nthreads, float& dep) {
+  asm volatile("bar.arrive %1, %2;" : "+f"(dep) : "r"(id), "r"(nthreads) : "memory");
 }
 
 // ---- TMA --------------------------------------------------------------------------------------
@@ -154,9 +178,13 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(bool bf16, int m, int n, b
 }
 
 __device__ __forceinline__ float ex2(float x) {
+#if defined(OEH_EXP) && (OEH_EXP == 1 || OEH_EXP == 5)   // timing experiment: no MUFU
+  return x * 0.001f;
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 
 }  // namespace ptx
