@@ -191,14 +191,16 @@ __device__ __forceinline__ void normalize_probs(float (&s)[N], const AttnParams&
   }
 }
 
-// Epilogue of one query row: o[] holds the PV accumulator; mul = 1/denominator (1 in the normalised modes).
-// ctx -> [qdq before gate] -> * sigmoid(gate logit)*gate_scale -> [qdq after gate] -> 8 x 16-byte stores.
-template <bool kBF16, bool kGeneric>
-__device__ __forceinline__ void store_row(float (&o)[HD], const AttnParams& p, float mul, int b, int h, int row) {
+// Epilogue of one query row (ND = 64: the whole row; ND = 32: the half starting at head-dim column d0):
+// o[] holds the PV accumulator; mul = 1/denominator (1 in the normalised modes).
+// ctx -> [qdq before gate] -> * sigmoid(gate logit)*gate_scale -> [qdq after gate] -> ND/8 x 16-byte stores.
+template <bool kBF16, bool kGeneric, int ND = HD>
+__device__ __forceinline__ void store_row(float (&o)[ND], const AttnParams& p, float mul, int b, int h, int row,
+                                          int d0 = 0) {
   if (kGeneric && p.dbg_o) {
-    float* d = p.dbg_o + (((int64_t)b * p.H + h) * p.Tq + row) * HD;
+    float* d = p.dbg_o + (((int64_t)b * p.H + h) * p.Tq + row) * HD + d0;
 #pragma unroll
-    for (int j = 0; j < HD; ++j) d[j] = o[j];
+    for (int j = 0; j < ND; ++j) d[j] = o[j];
   }
   float gate = 1.f;
   if (p.gate_logits) {
@@ -209,19 +211,20 @@ __device__ __forceinline__ void store_row(float (&o)[HD], const AttnParams& p, f
     const Qdq qd_c = load_qdq(p.qdq_ctx, p.int_max);
     if (p.ctx_qdq_before_gate) {                       // OPT: tap on PV, then gate (quantized_opt.py:210)
 #pragma unroll
-      for (int j = 0; j < HD; ++j) o[j] = qd_c(o[j] * mul) * gate;
+      for (int j = 0; j < ND; ++j) o[j] = qd_c(o[j] * mul) * gate;
     } else {                                           // BERT: gate, then tap (quantized_bert.py:434)
 #pragma unroll
-      for (int j = 0; j < HD; ++j) o[j] = qd_c(o[j] * mul * gate);
+      for (int j = 0; j < ND; ++j) o[j] = qd_c(o[j] * mul * gate);
     }
   } else {
     mul *= gate;
 #pragma unroll
-    for (int j = 0; j < HD; ++j) o[j] *= mul;
+    for (int j = 0; j < ND; ++j) o[j] *= mul;
   }
-  uint8_t* optr = reinterpret_cast<uint8_t*>(p.out) + 2 * ((int64_t)b * p.os0 + (int64_t)h * p.os1 + (int64_t)row * p.os2);
+  uint8_t* optr = reinterpret_cast<uint8_t*>(p.out) +
+                  2 * ((int64_t)b * p.os0 + (int64_t)h * p.os1 + (int64_t)row * p.os2 + d0);
 #pragma unroll
-  for (int c = 0; c < HD / 8; ++c) {
+  for (int c = 0; c < ND / 8; ++c) {
     uint4 v;
     v.x = pack2<kBF16>(o[c * 8 + 0], o[c * 8 + 1]);
     v.y = pack2<kBF16>(o[c * 8 + 2], o[c * 8 + 3]);
