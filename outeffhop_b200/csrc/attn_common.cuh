@@ -155,22 +155,40 @@ __device__ __forceinline__ float row_max(const float (&s)[N]) {
   return max4(m0, m1, m2, m3);
 }
 
-// s[j] <- exp2(s[j]*mul - m); returns the row sum (4 independent accumulators)
+// s[j] <- exp2(s[j]*mul - m); returns the row sum.  The scale/subtract FMAs and the sum run as packed fp32x2
+// instructions (FFMA2 / FADD2: half the issue slots, same per-lane IEEE results); 4 independent partial sums.
 template <int N>
 __device__ __forceinline__ float exp2_and_sum(float (&s)[N], float mul, float m) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const uint64_t mul2 = ptx::pack2f(mul, mul), nm2 = ptx::pack2f(-m, -m);
+  uint64_t acc0 = ptx::pack2f(0.f, 0.f), acc1 = acc0;
 #pragma unroll
   for (int j = 0; j < N; j += 4) {
-    s[j] = ptx::ex2(fmaf(s[j], mul, -m));
-    s[j + 1] = ptx::ex2(fmaf(s[j + 1], mul, -m));
-    s[j + 2] = ptx::ex2(fmaf(s[j + 2], mul, -m));
-    s[j + 3] = ptx::ex2(fmaf(s[j + 3], mul, -m));
-    a0 += s[j];
-    a1 += s[j + 1];
-    a2 += s[j + 2];
-    a3 += s[j + 3];
+    float a, b, c, d;
+    ptx::unpack2f(ptx::ffma2(ptx::pack2f(s[j], s[j + 1]), mul2, nm2), a, b);
+    ptx::unpack2f(ptx::ffma2(ptx::pack2f(s[j + 2], s[j + 3]), mul2, nm2), c, d);
+    s[j] = ptx::ex2(a);
+    s[j + 1] = ptx::ex2(b);
+    s[j + 2] = ptx::ex2(c);
+    s[j + 3] = ptx::ex2(d);
+    acc0 = ptx::fadd2(acc0, ptx::pack2f(s[j], s[j + 1]));
+    acc1 = ptx::fadd2(acc1, ptx::pack2f(s[j + 2], s[j + 3]));
   }
-  return (a0 + a1) + (a2 + a3);
+  float x, y;
+  ptx::unpack2f(ptx::fadd2(acc0, acc1), x, y);
+  return x + y;
+}
+
+// s[j] <- exp2(s[j]*mul - m) without the sum (PV pass of the two-pass modes)
+template <int N>
+__device__ __forceinline__ void exp2_only(float (&s)[N], float mul, float m) {
+  const uint64_t mul2 = ptx::pack2f(mul, mul), nm2 = ptx::pack2f(-m, -m);
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+    float a, b;
+    ptx::unpack2f(ptx::ffma2(ptx::pack2f(s[j], s[j + 1]), mul2, nm2), a, b);
+    s[j] = ptx::ex2(a);
+    s[j + 1] = ptx::ex2(b);
+  }
 }
 
 // normalised modes: p = e * inv_den, then clip((eta-gamma)*p + gamma, 0, 1) and / or the probs fake-quant tap

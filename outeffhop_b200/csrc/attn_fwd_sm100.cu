@@ -405,15 +405,20 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
   const int ki = (a->dtype == OEH_BF16 ? 2 : 0) + (generic ? 1 : 0);
   if (use_ws) {
-    static const KernelFn kernels[4] = {attn_ws::attn_fwd_ws_kernel<false, false>, attn_ws::attn_fwd_ws_kernel<false, true>,
-                                        attn_ws::attn_fwd_ws_kernel<true, false>, attn_ws::attn_fwd_ws_kernel<true, true>};
-    static bool attr_done[4] = {false, false, false, false};
-    if (!attr_done[ki]) {
-      OEH_CUDA_OK(cudaFuncSetAttribute(kernels[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, attn_ws::kSmemBytes));
-      attr_done[ki] = true;
+    const bool norm = a->kind >= OEH_SOFTMAX_CLIPPED || a->qdq_probs != nullptr;   // two-pass variants
+    const int kw = ki + (norm ? 4 : 0);
+    static const KernelFn kernels[8] = {
+        attn_ws::attn_fwd_ws_kernel<false, false, false>, attn_ws::attn_fwd_ws_kernel<false, true, false>,
+        attn_ws::attn_fwd_ws_kernel<true, false, false>,  attn_ws::attn_fwd_ws_kernel<true, true, false>,
+        attn_ws::attn_fwd_ws_kernel<false, false, true>,  attn_ws::attn_fwd_ws_kernel<false, true, true>,
+        attn_ws::attn_fwd_ws_kernel<true, false, true>,   attn_ws::attn_fwd_ws_kernel<true, true, true>};
+    static bool attr_done[8] = {false, false, false, false, false, false, false, false};
+    if (!attr_done[kw]) {
+      OEH_CUDA_OK(cudaFuncSetAttribute(kernels[kw], cudaFuncAttributeMaxDynamicSharedMemorySize, attn_ws::kSmemBytes));
+      attr_done[kw] = true;
     }
     dim3 grid((unsigned)((a->Tq + attn_ws::kQRows - 1) / attn_ws::kQRows), (unsigned)a->H, (unsigned)a->B);
-    kernels[ki]<<<grid, attn_ws::kThreads, attn_ws::kSmemBytes, st>>>(tmq, tmk, tmv, p);
+    kernels[kw]<<<grid, attn_ws::kThreads, attn_ws::kSmemBytes, st>>>(tmq, tmk, tmv, p);
     return check_launch("attn_fwd_ws_kernel");
   }
   static const KernelFn kernels[4] = {attn_fwd_kernel<false, false>, attn_fwd_kernel<false, true>,

@@ -71,7 +71,7 @@ constexpr int kSmemBytes = 2 * kTileBytes + 2 * kStages * kSubBytes + 1024;   //
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColO0 = 256;                                   // S_t[b] at (2t+b)*64, O_{t,h} at 256 + (2t+h)*64
 constexpr float kLazyRescale = 8.f;                                // log2 units
-constexpr int kSoftmaxRegs = 104, kAuxRegs = 40;                   // 16*32*104 + 4*32*40 <= 640 * 96
+constexpr int kSoftmaxRegs = 112, kAuxRegs = 24;                   // 16*32*112 + 4*32*24 <= 640 * 96
 
 struct Barriers {
   uint64_t q_full;
@@ -90,7 +90,9 @@ __device__ __forceinline__ void reg_dealloc() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
 }
 
-template <bool kBF16, bool kGeneric>
+// kNorm: P must be normalised before PV (clipped variants / probs fake-quant) -> two-pass; compiled separately so the
+// one-pass hot loop carries none of the two-pass branches.
+template <bool kBF16, bool kGeneric, bool kNorm>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                    const __grid_constant__ CUtensorMap tmv, const __grid_constant__ AttnParams p) {
@@ -146,7 +148,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   }
   const bool softmax1 = (p.kind == OEH_SOFTMAX_1 || p.kind == OEH_SOFTMAX_CLIPPED1);
   const bool clipped = p.kind >= OEH_SOFTMAX_CLIPPED;
-  const bool normalized = clipped || (kGeneric && p.qdq_probs != nullptr);
+  constexpr bool normalized = kNorm;                              // host: clipped || qdq_probs
   const int nA = normalized ? n_kv : 0;                          // stats-pass steps (QK^T only)
   const int n_iter = nA + n_kv;
 
@@ -292,6 +294,12 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       m_run = m;
     };
 
+#ifdef OEH_STAGGER   // experiment: start Q tile 1 out of phase with Q tile 0
+    if (t == 1) {
+      const long long c0 = clock64();
+      while (clock64() - c0 < OEH_STAGGER) { }
+    }
+#endif
     for (int i = 0; i < n_iter; ++i) {
       const int sb = i & 1;
       const uint32_t tS = tS0 + sb * 64u;
@@ -344,8 +352,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
           const float den = softmax1 ? l_run + ptx::ex2(-m_safe) : l_run;
           inv_den = __frcp_rn(den);
         }
-#pragma unroll
-        for (int j = 0; j < BNH; ++j) s[j] = ptx::ex2(fmaf(s[j], mul, -m_safe));
+        exp2_only<BNH>(s, mul, m_safe);
         normalize_probs<BNH, kGeneric>(s, p, inv_den, clipped, has_qp, qd_p);
       } else {
         // online softmax with lazy rescale
