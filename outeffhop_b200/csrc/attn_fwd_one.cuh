@@ -1,0 +1,219 @@
+// Fused attention forward for sm_100a when all keys fit ONE K/V tile (Tk <= 128): the BERT eval shape
+// (B=32, H=12, T=128: 384 (batch, head) items of 1.6 GFLOP / 25 MB in total -- HBM- and latency-bound, not tensor-bound).
+//
+// What matters here is how many independent items an SM has in flight, so this variant is built to be small:
+//   * 128 threads (thread == query row == TMEM lane), 3 smem tiles (Q, K, V: 48 KB), 128 TMEM columns
+//     -> FOUR CTAs per SM (the multi-tile kernel: two), i.e. the whole C-BERT grid (384 CTAs) is resident at once
+//     on 148 x 4 slots and one CTA's TMA / MMA latency hides behind its neighbours' softmax.
+//   * S is never held in registers as a whole row.  The row is walked in 32-column chunks straight out of TMEM:
+//       pass 1  max  (generic mode: the transformed scores are written back in place, so masks / taps are read once)
+//       pass 2  e = exp2(s*mul - m), row sum; online kinds pack e to 16 bit and store it as P right away,
+//               normalised kinds (clipped / probs tap) park e (fp32) in place
+//       pass 3  (normalised kinds only) p = clip(stretch*e/den + gamma, 0, 1) [-> tap] -> P
+//     P chunk c lands in columns [16c, 16c+16), which the same thread has already consumed (lane-private, in order).
+//   * O [128 x 64] fp32 reuses columns 64..127: by the time the PV MMA is issued every thread has turned its S row
+//     into P (columns 0..63), so S's upper half is dead.
+// Same arithmetic as the other two kernels (attn_common.cuh); the two-pass "stats then PV" of the clipped modes
+// collapses into one QK^T because the whole row is on chip.
+#pragma once
+
+#include "attn_common.cuh"
+
+namespace oeh {
+namespace attn_one {
+
+using namespace attn;
+
+constexpr int BM = 128;                          // query rows per CTA == threads per CTA
+constexpr int CH = 32;                           // columns per softmax chunk
+constexpr int kSmemBytes = 3 * kTileBytes + 1024;
+constexpr uint32_t kTmemCols = 128;
+constexpr uint32_t kColO = 64;
+
+template <int N>
+__device__ __forceinline__ void hide_invisible(float (&s)[N], int vis) {
+  if (vis < N - 1) {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (j > vis) s[j] = -INFINITY;
+  }
+}
+
+template <bool kBF16, bool kGeneric>
+__global__ void __launch_bounds__(BM, 4)
+attn_fwd_one_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
+                    const __grid_constant__ CUtensorMap tmv, const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[3];      // q+k, v, mma
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
+  const int row = q0 + tid;
+
+  const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem0, sK = smem0 + kTileBytes, sV = smem0 + 2 * kTileBytes;
+  const uint32_t bar_qk = ptx::smem_u32(&bars[0]), bar_v = ptx::smem_u32(&bars[1]), bar_mma = ptx::smem_u32(&bars[2]);
+
+  constexpr uint32_t kIdescQK = ptx::make_idesc_f16(kBF16, BM, BN, false, false);
+  constexpr uint32_t kIdescPV = ptx::make_idesc_f16(kBF16, BM, HD, false, true);
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::mbar_init(bar_qk, 1);
+    ptx::mbar_init(bar_v, 1);
+    ptx::mbar_init(bar_mma, 1);
+    ptx::fence_mbar_init();
+    // loads first: their latency covers the TMEM allocation and the barrier below
+    ptx::mbar_expect_tx(bar_qk, 2 * kTileBytes);
+    tma_tile(sQ, &tmq, bar_qk, p.cq, q0, h, b);
+    tma_tile(sK, &tmk, bar_qk, p.ck, 0, h, b);
+    ptx::mbar_expect_tx(bar_v, kTileBytes);
+    tma_tile(sV, &tmv, bar_v, p.cv, 0, h, b);
+  }
+  __syncwarp();
+  if (warp == 0) ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(&tmem_base_slot));
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::mbar_wait(bar_qk, 0);
+    ptx::tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < HD / 16; ++k)
+      ptx::mma_ss(tmem, ptx::make_smem_desc_sw128(sQ + k * 32, 16, 1024), ptx::make_smem_desc_sw128(sK + k * 32, 16, 1024),
+                  kIdescQK, k > 0);
+    ptx::mma_commit(bar_mma);
+  }
+  __syncwarp();
+
+  // ---- per-row state (overlaps the loads / QK^T) -------------------------------------------------------------------
+  const bool softmax1 = (p.kind == OEH_SOFTMAX_1 || p.kind == OEH_SOFTMAX_CLIPPED1);
+  const bool clipped = p.kind >= OEH_SOFTMAX_CLIPPED;
+  const bool has_qs = kGeneric && p.qdq_scores != nullptr;
+  const bool has_qp = kGeneric && p.qdq_probs != nullptr;
+  const bool has_mask = kGeneric && p.mask != nullptr;
+  const bool normalized = clipped || has_qp;
+  const bool xf = kGeneric && (has_qs || has_mask || p.clamp_min);   // transform_scores rewrites the scores
+  Qdq qd_s{1.f, 1.f, 0.f, p.int_max}, qd_p{1.f, 1.f, 0.f, p.int_max};
+  if (has_qs) qd_s = load_qdq(p.qdq_scores, p.int_max);
+  if (has_qp) qd_p = load_qdq(p.qdq_probs, p.int_max);
+  const int64_t mask_row = p.mask ? ((int64_t)b * p.ms0 + (int64_t)h * p.ms1 + (int64_t)(row < p.Tq ? row : 0) * p.ms2) : 0;
+  const int causal_lim = p.causal ? row + (p.Tk - p.Tq) : 0x7fffffff;
+  const int n_ch = (p.Tk + CH - 1) / CH;          // chunks that hold real keys (1..4)
+
+  ptx::mbar_wait(bar_mma, 0);
+  ptx::tc_fence_after();
+
+  // ---- pass 1: row maximum --------------------------------------------------------------------------------------
+  float mul = p.scale * kLog2e, m_run = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < n_ch; ++c) {
+    float s[CH];
+    ptx::tmem_ld32(t_lane + c * CH, reinterpret_cast<uint32_t*>(s));
+    ptx::tmem_wait_ld();
+    if (kGeneric && p.dbg_s && row < p.Tq) {
+      float* d = p.dbg_s + (((int64_t)b * p.H + h) * p.Tq + row) * BN + c * CH;
+#pragma unroll
+      for (int j = 0; j < CH; ++j) d[j] = s[j];
+    }
+    const int k0 = c * CH, valid = min(p.Tk - k0, CH), vis = min(valid - 1, causal_lim - k0);
+    mul = transform_scores<CH, kGeneric>(s, p, qd_s, has_qs, has_mask, mask_row, k0, valid, vis);
+    m_run = fmaxf(m_run, row_max<CH>(s) * mul);
+    if (xf) ptx::tmem_st32(t_lane + c * CH, reinterpret_cast<const uint32_t*>(s));
+  }
+  if (xf) ptx::tmem_wait_st();
+  const float m_safe = m_run == -INFINITY ? 0.f : m_run;
+
+  // ---- pass 2: exponentials and the row sum ------------------------------------------------------------------------
+  float l_run = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t pk[CH / 2];
+    if (c < n_ch) {
+      float s[CH];
+      ptx::tmem_ld32(t_lane + c * CH, reinterpret_cast<uint32_t*>(s));
+      ptx::tmem_wait_ld();
+      if (!xf) {
+        const int k0 = c * CH, valid = min(p.Tk - k0, CH);
+        hide_invisible<CH>(s, min(valid - 1, causal_lim - k0));
+      }
+      l_run += exp2_and_sum<CH>(s, mul, m_safe);
+      if (normalized) {
+        ptx::tmem_st32(t_lane + c * CH, reinterpret_cast<const uint32_t*>(s));
+        continue;
+      }
+#pragma unroll
+      for (int j = 0; j < CH / 2; ++j) pk[j] = pack2<kBF16>(s[2 * j], s[2 * j + 1]);
+    } else {
+      if (normalized) continue;
+#pragma unroll
+      for (int j = 0; j < CH / 2; ++j) pk[j] = 0u;   // keys beyond Tk: P = 0 (the PV MMA always spans 128 keys)
+    }
+    ptx::tmem_st16(t_lane + c * (CH / 2), pk);
+  }
+
+  // ---- pass 3 (normalised kinds): clip / tap, then P ------------------------------------------------------------------
+  float omul = 1.f;
+  {
+    const float den = softmax1 ? l_run + ptx::ex2(-m_safe) : l_run;
+    const float inv_den = __frcp_rn(den);
+    if (normalized) {
+      ptx::tmem_wait_st();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[CH / 2];
+        if (c < n_ch) {
+          float s[CH];
+          ptx::tmem_ld32(t_lane + c * CH, reinterpret_cast<uint32_t*>(s));
+          ptx::tmem_wait_ld();
+          normalize_probs<CH, kGeneric>(s, p, inv_den, clipped, has_qp, qd_p);
+          // (columns past Tk inside this chunk may hold clip(gamma) != 0: their V rows are TMA zero fill)
+#pragma unroll
+          for (int j = 0; j < CH / 2; ++j) pk[j] = pack2<kBF16>(s[2 * j], s[2 * j + 1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH / 2; ++j) pk[j] = 0u;
+        }
+        ptx::tmem_st16(t_lane + c * (CH / 2), pk);
+      }
+    } else {
+      omul = inv_den;
+    }
+  }
+  ptx::tmem_wait_st();
+  ptx::tc_fence_before();
+  __syncthreads();
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::tc_fence_after();
+    ptx::mbar_wait(bar_v, 0);
+    ptx::tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < BN / 16; ++k)
+      ptx::mma_ts(tmem + kColO, tmem + k * 8, ptx::make_smem_desc_sw128(sV + k * 2048, 1024, 1024), kIdescPV, k > 0);
+    ptx::mma_commit(bar_mma);
+  }
+  __syncwarp();
+
+  // ---- epilogue -----------------------------------------------------------------------------------------------------
+  ptx::mbar_wait(bar_mma, 1);
+  ptx::tc_fence_after();
+  float o[HD];
+  {
+    uint32_t* orr = reinterpret_cast<uint32_t*>(o);
+    ptx::tmem_ld32(t_lane + kColO, orr);
+    ptx::tmem_ld32(t_lane + kColO + 32, orr + 32);
+    ptx::tmem_wait_ld();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem);
+  if (row >= p.Tq) return;
+  store_row<kBF16, kGeneric>(o, p, omul, b, h, row);
+}
+
+}  // namespace attn_one
+}  // namespace oeh

@@ -21,6 +21,7 @@
 #include <cstring>
 
 #include "attn_common.cuh"
+#include "attn_fwd_one.cuh"
 #include "attn_fwd_ws.cuh"
 
 namespace oeh {
@@ -363,11 +364,13 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
   // Kernel choice: sequences longer than one Q tile use the warp-specialised two-tile kernel (64-key sub-tiles);
   // up to 128 query rows there is nothing to ping-pong with, and the single-tile kernel (2 CTAs / SM) has the
   // lower latency.  OEH_ATTN_KERNEL=tile|ws overrides (tests exercise both on the same shapes).
-  bool use_ws = a->Tq > BM;
+  // When all keys fit one K/V tile (Tk <= 128, the BERT eval shape) the small one-tile kernel (4 CTAs / SM) runs.
+  bool use_ws = a->Tq > BM, use_one = a->Tk <= BN;
   if (const char* f = getenv("OEH_ATTN_KERNEL")) {
-    if (!strcmp(f, "tile")) use_ws = false;
-    if (!strcmp(f, "ws")) use_ws = true;
+    if (!strcmp(f, "tile")) use_ws = use_one = false;
+    if (!strcmp(f, "ws")) { use_ws = true; use_one = false; }
   }
+  if (use_one) use_ws = false;
   const int kv_box = use_ws ? attn_ws::BNW : BN;
 
   CUtensorMap tmq, tmk, tmv;
@@ -420,6 +423,18 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
     dim3 grid((unsigned)((a->Tq + attn_ws::kQRows - 1) / attn_ws::kQRows), (unsigned)a->H, (unsigned)a->B);
     kernels[kw]<<<grid, attn_ws::kThreads, attn_ws::kSmemBytes, st>>>(tmq, tmk, tmv, p);
     return check_launch("attn_fwd_ws_kernel");
+  }
+  if (use_one) {
+    static const KernelFn kernels[4] = {attn_one::attn_fwd_one_kernel<false, false>, attn_one::attn_fwd_one_kernel<false, true>,
+                                        attn_one::attn_fwd_one_kernel<true, false>, attn_one::attn_fwd_one_kernel<true, true>};
+    static bool attr_done[4] = {false, false, false, false};
+    if (!attr_done[ki]) {
+      OEH_CUDA_OK(cudaFuncSetAttribute(kernels[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, attn_one::kSmemBytes));
+      attr_done[ki] = true;
+    }
+    dim3 grid((unsigned)((a->Tq + BM - 1) / BM), (unsigned)a->H, (unsigned)a->B);
+    kernels[ki]<<<grid, attn_one::BM, attn_one::kSmemBytes, st>>>(tmq, tmk, tmv, p);
+    return check_launch("attn_fwd_one_kernel");
   }
   static const KernelFn kernels[4] = {attn_fwd_kernel<false, false>, attn_fwd_kernel<false, true>,
                                       attn_fwd_kernel<true, false>, attn_fwd_kernel<true, true>};

@@ -67,11 +67,12 @@ def attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: f
                   gate_logits: Optional[torch.Tensor] = None, gate_scale: float = 1.0,
                   qdq_scores: Optional[torch.Tensor] = None, qdq_probs: Optional[torch.Tensor] = None,
                   qdq_ctx: Optional[torch.Tensor] = None, n_bits: int = 8, ctx_qdq_before_gate: bool = False,
-                  out_layout: str = "bthd", _debug=None) -> torch.Tensor:
+                  out_layout: str = "bthd", out: Optional[torch.Tensor] = None, _debug=None) -> torch.Tensor:
     """Fused attention core (oeh_attn_fwd).  q,k,v: (B,H,T,d) strided views, fp16/bf16.
     Returns (B,Tq,H*d) for out_layout="bthd" (the reference's permute+view folded into the store,
     bert_attention.py:335-337 / opt_attention.py:318-322) or (B,H,Tq,d) for "bhtd".
-    qdq_* are device tensors [scale, zero_point] (e.g. ``state[4:6]`` of a quantizer state)."""
+    qdq_* are device tensors [scale, zero_point] (e.g. ``state[4:6]`` of a quantizer state).
+    ``out``: optional preallocated contiguous result of exactly that shape and dtype."""
     _require_cuda(q, k, v, mask, gate_logits)
     B, H, Tq, d = q.shape
     Tk = k.shape[2]
@@ -79,13 +80,17 @@ def attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: f
         raise ValueError(f"q/k/v shape mismatch: {tuple(q.shape)} {tuple(k.shape)} {tuple(v.shape)}")
     if not (q.dtype == k.dtype == v.dtype):
         raise ValueError("q, k, v must share a dtype")
-    if out_layout == "bthd":
-        base = torch.empty((B, Tq, H, d), dtype=q.dtype, device=q.device)
-        out_view = base.permute(0, 2, 1, 3)
-    elif out_layout == "bhtd":
-        base = out_view = torch.empty((B, H, Tq, d), dtype=q.dtype, device=q.device)
-    else:
+    if out_layout not in ("bthd", "bhtd"):
         raise ValueError(f"unknown out_layout {out_layout!r}")
+    if out is not None:
+        want = (B, Tq, H * d) if out_layout == "bthd" else (B, H, Tq, d)
+        if tuple(out.shape) != want or out.dtype != q.dtype or out.device != q.device or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous {want} tensor of q's dtype on q's device")
+    if out_layout == "bthd":
+        base = out.view(B, Tq, H, d) if out is not None else torch.empty((B, Tq, H, d), dtype=q.dtype, device=q.device)
+        out_view = base.permute(0, 2, 1, 3)
+    else:
+        base = out_view = out if out is not None else torch.empty((B, H, Tq, d), dtype=q.dtype, device=q.device)
     a = L.OehAttnArgs()
     a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out_view.data_ptr()
     a.q_strides, a.k_strides, a.v_strides = _bht_strides(q), _bht_strides(k), _bht_strides(v)

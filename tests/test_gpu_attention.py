@@ -44,7 +44,8 @@ KINDS = [(0, 0.0, 1.0), (1, 0.0, 1.0), (2, -0.025, 1.0), (3, -0.025, 1.1), (2, 0
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("kind,gamma,eta", KINDS)
-@pytest.mark.parametrize("shape", [(2, 3, 128, 128), (1, 2, 64, 64), (2, 2, 50, 77), (1, 2, 256, 384), (1, 1, 130, 1)])
+@pytest.mark.parametrize("shape", [(2, 3, 128, 128), (1, 2, 64, 64), (2, 2, 50, 77), (1, 2, 256, 384), (1, 1, 130, 1),
+                                   (1, 2, 100, 300), (1, 2, 300, 100), (1, 1, 5, 33)])
 def test_attention_vs_oracle(dtype, kind, gamma, eta, shape):
     ops = _ops()
     B, H, Tq, Tk = shape
@@ -77,6 +78,23 @@ def test_attention_causal(kind, gamma, eta, T):
     out = ops.attention_fwd(q, k, v, scale=1.0 / 8, kind=kind, gamma=gamma, eta=eta, causal=True, out_layout="bhtd")
     ref = _oracle(q, k, v, scale=1.0 / 8, kind=kind, gamma=gamma, eta=eta, causal=True)
     np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=TOL, rtol=0)
+
+
+@pytest.mark.parametrize("kernel", ["tile", "ws"])
+@pytest.mark.parametrize("kind,gamma,eta", KINDS[:4])
+def test_attention_kernel_override_same_result(kernel, kind, gamma, eta, monkeypatch):
+    """The three kernels (one-tile / multi-tile / warp-specialised) are interchangeable on a shape all of them accept."""
+    ops = _ops()
+    q, k, v = _mk(2, 2, 128, 128, torch.float16, seed=11 + kind, layout="bthd")
+    logits = torch.randn(2, 2, 128).cuda()
+    kw = dict(scale=0.125, kind=kind, gamma=gamma, eta=eta, gate_logits=logits, causal=(kind % 2 == 1))
+    base = ops.attention_fwd(q, k, v, **kw).float()
+    monkeypatch.setenv("OEH_ATTN_KERNEL", kernel)
+    other = ops.attention_fwd(q, k, v, **kw).float()
+    assert (base - other).abs().max().item() <= 1e-3
+    ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=(kind % 2 == 1), gate=O.sigmoid(logits.cpu().numpy()))
+    ref = ref.transpose(0, 2, 1, 3).reshape(2, 128, 128)
+    np.testing.assert_allclose(other.cpu().numpy(), ref, atol=TOL, rtol=0)
 
 
 @pytest.mark.parametrize("kind,gamma,eta", KINDS[:4])
