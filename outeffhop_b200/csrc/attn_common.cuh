@@ -155,6 +155,48 @@ __device__ __forceinline__ float row_max(const float (&s)[N]) {
   return max4(m0, m1, m2, m3);
 }
 
+// exp2 of two log2-domain values on the FMA / ALU pipes instead of the MUFU (XU) pipe: at d = 64 the attention loop is
+// bound by MUFU.EX2 (16 results/clk/SM against 512 tensor-pipe clocks per 128x128 tile), while the FMA pipe is
+// mostly idle, so a fixed share of every row's exponentials is evaluated as
+//     2^t = 2^n * p(f),  n = round(t),  f = t - n in [-0.5, 0.5],  p = minimax cubic (max rel. error 7.5e-5,
+// below the 2^-12 rounding of the fp16 / bf16 P operand it feeds), 2^n applied by adding n to the exponent bits.
+// Cost: 11 issue slots per PAIR (packed fp32x2 arithmetic) instead of 2 MUFU slots of 8 XU clocks each.
+__device__ __forceinline__ void exp2_poly2(uint64_t t2, float& e0, float& e1) {
+  float a, b;
+  ptx::unpack2f(t2, a, b);
+  a = fmaxf(a, -126.f);                                // keeps 2^n a normal number; also maps -inf (masked) to ~0
+  b = fmaxf(b, -126.f);
+  t2 = ptx::pack2f(a, b);
+  const uint64_t r2 = ptx::fadd2(t2, ptx::pack2f(12582912.f, 12582912.f));        // 1.5 * 2^23: n in the low mantissa bits
+  const uint64_t n2 = ptx::fadd2(r2, ptx::pack2f(-12582912.f, -12582912.f));
+  const uint64_t f2 = ptx::ffma2(n2, ptx::pack2f(-1.f, -1.f), t2);
+  uint64_t p2 = ptx::ffma2(f2, ptx::pack2f(0.0551716685f, 0.0551716685f), ptx::pack2f(0.242611125f, 0.242611125f));
+  p2 = ptx::ffma2(p2, f2, ptx::pack2f(0.693260968f, 0.693260968f));
+  p2 = ptx::ffma2(p2, f2, ptx::pack2f(0.999928057f, 0.999928057f));
+  float ra, rb, pa, pb;
+  ptx::unpack2f(r2, ra, rb);
+  ptx::unpack2f(p2, pa, pb);
+  e0 = __int_as_float(__float_as_int(pa) + (__float_as_int(ra) << 23));
+  e1 = __int_as_float(__float_as_int(pb) + (__float_as_int(rb) << 23));
+}
+
+#ifndef OEH_POLY_PAIRS
+#define OEH_POLY_PAIRS 0     // pairs out of every 16 (= 32 columns) that take the polynomial path
+#endif
+// pair pi of a row chunk goes to the FMA pipe if this is true (evenly spread over the chunk)
+__host__ __device__ constexpr bool poly_pair(int pi) { return ((pi % 16) * OEH_POLY_PAIRS) % 16 < OEH_POLY_PAIRS; }
+
+__device__ __forceinline__ void exp2_pair(uint64_t t2, int pi, float& e0, float& e1) {
+  if (poly_pair(pi)) {
+    exp2_poly2(t2, e0, e1);
+  } else {
+    float a, b;
+    ptx::unpack2f(t2, a, b);
+    e0 = ptx::ex2(a);
+    e1 = ptx::ex2(b);
+  }
+}
+
 // s[j] <- exp2(s[j]*mul - m); returns the row sum.  The scale/subtract FMAs and the sum run as packed fp32x2
 // instructions (FFMA2 / FADD2: half the issue slots, same per-lane IEEE results); 4 independent partial sums.
 template <int N>
@@ -163,13 +205,8 @@ __device__ __forceinline__ float exp2_and_sum(float (&s)[N], float mul, float m)
   uint64_t acc0 = ptx::pack2f(0.f, 0.f), acc1 = acc0;
 #pragma unroll
   for (int j = 0; j < N; j += 4) {
-    float a, b, c, d;
-    ptx::unpack2f(ptx::ffma2(ptx::pack2f(s[j], s[j + 1]), mul2, nm2), a, b);
-    ptx::unpack2f(ptx::ffma2(ptx::pack2f(s[j + 2], s[j + 3]), mul2, nm2), c, d);
-    s[j] = ptx::ex2(a);
-    s[j + 1] = ptx::ex2(b);
-    s[j + 2] = ptx::ex2(c);
-    s[j + 3] = ptx::ex2(d);
+    exp2_pair(ptx::ffma2(ptx::pack2f(s[j], s[j + 1]), mul2, nm2), j / 2, s[j], s[j + 1]);
+    exp2_pair(ptx::ffma2(ptx::pack2f(s[j + 2], s[j + 3]), mul2, nm2), j / 2 + 1, s[j + 2], s[j + 3]);
     acc0 = ptx::fadd2(acc0, ptx::pack2f(s[j], s[j + 1]));
     acc1 = ptx::fadd2(acc1, ptx::pack2f(s[j + 2], s[j + 3]));
   }
@@ -183,12 +220,8 @@ template <int N>
 __device__ __forceinline__ void exp2_only(float (&s)[N], float mul, float m) {
   const uint64_t mul2 = ptx::pack2f(mul, mul), nm2 = ptx::pack2f(-m, -m);
 #pragma unroll
-  for (int j = 0; j < N; j += 2) {
-    float a, b;
-    ptx::unpack2f(ptx::ffma2(ptx::pack2f(s[j], s[j + 1]), mul2, nm2), a, b);
-    s[j] = ptx::ex2(a);
-    s[j + 1] = ptx::ex2(b);
-  }
+  for (int j = 0; j < N; j += 2)
+    exp2_pair(ptx::ffma2(ptx::pack2f(s[j], s[j + 1]), mul2, nm2), j / 2, s[j], s[j + 1]);
 }
 
 // normalised modes: p = e * inv_den, then clip((eta-gamma)*p + gamma, 0, 1) and / or the probs fake-quant tap

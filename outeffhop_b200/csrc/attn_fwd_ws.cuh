@@ -44,12 +44,16 @@
 
 #include "attn_common.cuh"
 
-#ifdef OEH_TRACE   // per-phase cycle trace of one lane per role in CTA (0,0,0); printed at the end of the kernel
+#ifdef OEH_TRACE   // per-phase cycle trace of one lane per role in CTA (0,0,0) -> g_trace[warp][0..9], read back with oeh_trace_read()
+__device__ long long g_trace[20][12];
 #define OEH_T(k) do { if (trace) { long long c_ = clock64(); tacc[k] += c_ - tprev; tprev = c_; } } while (0)
-#define OEH_T_DECL const bool trace = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid & 31) == 0 && ((warp & 3) == 0 || warp >= 16); \
+#define OEH_T_DECL const bool trace = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid & 31) == 0; \
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64(), tstart = tprev
-#define OEH_T_PRINT(role, n) do { if (trace) printf("%s w%d steps %d total/step %lld | %lld %lld %lld %lld %lld %lld %lld %lld\n", role, warp, n, \
-  (clock64() - tstart) / (n), tacc[0] / (n), tacc[1] / (n), tacc[2] / (n), tacc[3] / (n), tacc[4] / (n), tacc[5] / (n), tacc[6] / (n), tacc[7] / (n)); } while (0)
+#define OEH_T_PRINT(role, n) do { if (trace) { g_trace[warp][0] = (n); g_trace[warp][1] = clock64() - tstart; \
+  for (int k_ = 0; k_ < 8; ++k_) g_trace[warp][2 + k_] = tacc[k_]; } } while (0)
+extern "C" int oeh_trace_read(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 20 * 12);
+}
 #else
 #define OEH_T(k) do { } while (0)
 #define OEH_T_DECL do { } while (0)

@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--dtype", type=str, default="float16")
     ap.add_argument("--out", type=str, default="")
     ap.add_argument("--no-quant", action="store_true")
+    ap.add_argument("--no-causal", action="store_true")
     a = ap.parse_args()
     dt = getattr(torch, a.dtype)
     res = {"attn": [], "quant": []}
@@ -58,7 +59,7 @@ def main():
         k = torch.randn(B, H, T, 64, device="cuda", dtype=dt)
         v = torch.randn(B, H, T, 64, device="cuda", dtype=dt)
         for kind in [int(x) for x in a.kinds.split(",")]:
-            for causal in (False, True):
+            for causal in ((False,) if a.no_causal else (False, True)):
                 fn = lambda: ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=-0.025, eta=1.1, causal=causal)
                 med, best = time_fn(fn)
                 flops = 4.0 * B * H * T * T * 64 if not causal else 2.0 * B * H * T * (T + 1) * 64
