@@ -177,6 +177,61 @@ int oeh_estimate_and_quantize(const void* x, void* y, int64_t n, int32_t dtype, 
                               int32_t n_bits, double eps, void* workspace, size_t workspace_bytes,
                               oeh_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Percentile range estimation: np.percentile(x, (q_lo, q_hi)), default 'linear' method, over
+ * the WHOLE tensor, as RunningMinMaxEstimator / CurrentMinMaxEstimator evaluate it on a host copy
+ * (quantization/range_estimators.py:89-94, :62-69; --percentile at transformers_language/args.py:399).
+ * Exact: the four neighbouring order statistics are found by radix select on the device, the interpolation follows
+ * numpy's _lerp (difference rounded to the tensor dtype, the rest in float64).  out2: DEVICE [p(q_lo), p(q_hi)] as
+ * float64 (the reference's torch.tensor(np.float64)).  fp32 / fp16 only (numpy has no bfloat16).  Any NaN -> NaN.
+ *
+ * oeh_percentile runs everything for one process.  The step-wise entry points exist so that a caller can all-reduce
+ * (SUM, int32) the histogram -- the first 4*2048 uint32 of the workspace -- across ranks between _hist and _scan:
+ * the result is then the percentile of the union of all ranks' tensors (n_total = sum of n in oeh_percentile_plan).
+ *   plan(host) -> begin -> for pass in 0..passes-1: hist, [all-reduce], scan -> finish
+ * ------------------------------------------------------------------------------------------- */
+size_t oeh_percentile_workspace_bytes(void);
+int oeh_percentile_passes(int32_t dtype);   /* 3 for fp32, 2 for fp16, 0 = unsupported dtype */
+int oeh_percentile_plan(int64_t n_total, double q_lo, double q_hi, int64_t ranks_out[4], double gamma_out[2]);
+int oeh_percentile_begin(void* workspace, size_t workspace_bytes, const int64_t ranks[4], oeh_stream_t stream);
+int oeh_percentile_hist(const void* x, int64_t n, int32_t dtype, int32_t pass, void* workspace, oeh_stream_t stream);
+int oeh_percentile_scan(int32_t dtype, int32_t pass, void* workspace, oeh_stream_t stream);
+int oeh_percentile_finish(int32_t dtype, const double gamma[2], double* out2, void* workspace, oeh_stream_t stream);
+int oeh_percentile(const void* x, int64_t n, int32_t dtype, double q_lo, double q_hi, double* out2, void* workspace,
+                   size_t workspace_bytes, oeh_stream_t stream);
+
+/* RunningMinMaxEstimator EMA + set_quant_range for the float64 ranges of the percentile branch
+ * (range_estimators.py:99-104 on float64 0-dim tensors; uniform_quantizers.py:199-224).  state64: DEVICE
+ * [cur_min, cur_max, _delta, _zero_float, initialised] as float64; qstate: the OEH_QS_FLOATS fp32 state the quantize
+ * kernels read (scale / zero_point rounded to fp32, as ATen does when it applies a 0-dim float64 to an fp32 tensor). */
+int oeh_range_update_f64(double* state64, float* qstate, const double* new_minmax, double momentum, int32_t n_bits,
+                         double eps, oeh_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Residual add fused with the activation fake-quant tap:
+ *   y = qdq(a + b)    -- QuantizedBertSelfOutput / QuantizedBertOutput.forward
+ *                        (transformers_language/models/quantized_bert.py:566-567, :602-603),
+ *                        QuantizedOPTDecoderLayer residual sums (quantized_opt.py:342-345, :367-369).
+ * The sum is rounded once to the tensor dtype (as ATen's add), then quantised exactly like oeh_fake_quant_asym:
+ * bit-exact with the reference for fp32.  Fixed ranges only (qparams = DEVICE [scale, zero_point]); range
+ * estimation needs min/max of the sum first and uses the unfused kernels.  y may alias a or b.
+ * ------------------------------------------------------------------------------------------- */
+int oeh_add_fake_quant(const void* a, const void* b, void* y, int64_t n, int32_t dtype, const float* qparams,
+                       int32_t n_bits, oeh_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Outlier metrics of an activation tensor viewed as (rows, cols): per row
+ *   inf_norm[r] = max_j |x[r,j]|                      (x.norm(dim=1, p=inf), validate_mlm_config.py:513-518)
+ *   kurt[r]     = mean((x-mu)^4) / (std^4 + eps)      (kurtosis(), transformers_language/utils.py:9-20;
+ *                                                      std unbiased, eps = 1e-6)
+ * in ONE pass over x (power sums accumulated in float64), replacing per-sample .item() host syncs.
+ * out_inf / out_kurt: DEVICE fp32 (rows).  meter (optional, DEVICE, 3 float64): running AverageMeter state
+ * [sum of inf-norms, sum of kurtoses, samples] += this call's rows, so a whole eval needs one read-back.
+ * ------------------------------------------------------------------------------------------- */
+size_t oeh_outlier_stats_workspace_bytes(int64_t rows, int64_t cols);
+int oeh_outlier_stats(const void* x, int64_t rows, int64_t cols, int32_t dtype, double eps, float* out_inf,
+                      float* out_kurt, double* meter, void* workspace, size_t workspace_bytes, oeh_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,10 @@ def num_threads() -> int:
     return lib().oeh_ref_num_threads()
 
 
+def set_threads(n: int) -> None:
+    lib().oeh_ref_set_threads(C.c_int(int(n)))
+
+
 def softmax_rows(x: np.ndarray, kind: int, gamma: float = 0.0, eta: float = 1.0) -> np.ndarray:
     x = np.ascontiguousarray(x, np.float32)
     y = np.empty_like(x)

@@ -59,6 +59,7 @@ def time_bert_eval_cpu(attn_softmax: str, batch: int, seq: int, steps: int, warm
     import os
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
+    CO.set_threads(threads)            # OpenMP side too: torchrun exports OMP_NUM_THREADS=1
     model = build_bert_base_cpu(attn_softmax, seed)
     g = torch.Generator().manual_seed(seed)
     ids = torch.randint(0, 30522, (batch, seq), generator=g)

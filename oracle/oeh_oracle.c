@@ -30,6 +30,14 @@ int oeh_ref_num_threads(void) {
 #endif
 }
 
+void oeh_ref_set_threads(int n) {   /* torchrun exports OMP_NUM_THREADS=1: the bench sets the count explicitly */
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* One row of softmax.py / vutils/softmax_1.py, in place.
  * vanilla  : e/sum(e)                               (softmax.py:23, F.softmax)
  * softmax1 : e/(sum(e) + exp(-m))                   (vutils/softmax_1.py:11-21)

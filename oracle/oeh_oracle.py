@@ -363,3 +363,83 @@ def opt_attention_forward(hidden, wq, bq, wk, bk, wv, bv, wo, bo, num_heads: int
     b, h, t, _ = ctx.shape
     out = ctx.transpose(0, 2, 1, 3).reshape(b, t, h * d)               # :318-322
     return _linear(out, wo, bo)                                         # :324
+
+
+# ---------------------------------------------------------------------------------------------
+# percentile ranges, residual-sum tap, outlier metrics
+# ---------------------------------------------------------------------------------------------
+
+def percentile_linear(x: np.ndarray, q_lo: float, q_hi: float) -> Tuple[np.float64, np.float64]:
+    """np.percentile(x, (q_lo, q_hi)) restated (numpy `_quantile`, method 'linear', called at
+    quantization/range_estimators.py:91 with (100-p, p) and at :65-67 with (p, 100-p)): full sort instead of
+    numpy's partition, then numpy's `_lerp` with the difference rounded to the array dtype.  Pinned against
+    np.percentile itself in tests/test_oracle_golden.py (numpy is the reference's own implementation here)."""
+    flat = np.sort(np.asarray(x).reshape(-1), kind="stable")      # NaN sorts last, like numpy's partition
+    n = flat.size
+    out = []
+    for q in (q_lo, q_hi):
+        virt = (n - 1) * (np.float64(q) / 100.0)
+        prev = int(np.floor(virt))
+        nxt = prev + 1
+        prev_for_gamma = float(prev)
+        if virt >= n - 1:                                          # _get_indexes: index -1
+            prev = nxt = n - 1
+            prev_for_gamma = -1.0
+        if virt < 0:
+            prev = nxt = 0
+        a, b = flat[prev], flat[nxt]
+        t = np.float64(virt - prev_for_gamma)
+        with np.errstate(invalid="ignore", over="ignore"):
+            d = np.float64(flat.dtype.type(b - a))                 # subtract(b, a) in the array dtype
+            r = np.float64(b) - d * (1 - t) if t >= 0.5 else np.float64(a) + d * t
+        if np.isnan(flat[-1]):
+            r = np.float64("nan")
+        out.append(np.float64(r))
+    return out[0], out[1]
+
+
+class RunningMinMaxPercentile:
+    """RunningMinMaxEstimator, percentile branch (range_estimators.py:89-94, 99-104): float64 ranges."""
+
+    def __init__(self, percentile: float, momentum: float = 0.9):
+        self.percentile, self.momentum = percentile, momentum
+        self.current_xmin = self.current_xmax = None
+
+    def update(self, x: np.ndarray):
+        lo, hi = percentile_linear(x, 100 - self.percentile, self.percentile)
+        if self.current_xmin is None:
+            self.current_xmin, self.current_xmax = lo, hi
+        else:
+            self.current_xmin = (1 - self.momentum) * lo + self.momentum * self.current_xmin
+            self.current_xmax = (1 - self.momentum) * hi + self.momentum * self.current_xmax
+        return self.current_xmin, self.current_xmax
+
+
+def asym_set_quant_range_f64(x_min, x_max, n_bits: int = 8, eps: float = 1e-8):
+    """set_quant_range on float64 0-dim tensors (uniform_quantizers.py:199-200, 218-219) -> (_delta, _zero_float,
+    scale, zero_point) as float64; the quantize step then uses float32(scale), float32(zero_point) (ATen converts a
+    0-dim operand to the dimensioned tensor's dtype)."""
+    x_min = np.minimum(np.float64(x_min), 0.0)
+    x_max = np.maximum(np.float64(x_max), np.float64(eps))
+    int_max = 2.0 ** n_bits - 1
+    delta = (x_max - x_min) / int_max
+    zero_float = -x_min / delta
+    scale = np.maximum(delta, eps)
+    zp = np.clip(np.round(zero_float), 0.0, int_max)
+    return delta, zero_float, scale, zp
+
+
+def add_fake_quant(a: np.ndarray, b: np.ndarray, delta, zero_float, n_bits: int = 8, eps: float = 1e-8) -> np.ndarray:
+    """res_act_quantizer(hidden_states + input_tensor) (quantized_bert.py:566-567, 602-603; quantized_opt.py:342-345)."""
+    return asym_quantize(a + b, delta, zero_float, n_bits, eps)
+
+
+def outlier_stats(x: np.ndarray, eps: float = 1e-6):
+    """Per-sample inf-norm (validate_mlm_config.py:513-518) and kurtosis (transformers_language/utils.py:9-20) of x
+    viewed as (B, -1), evaluated in float64 (the reference works in the tensor dtype; compared with a tolerance)."""
+    x2 = np.asarray(x, dtype=np.float64).reshape(x.shape[0], -1)
+    inf = np.abs(x2).max(axis=1)
+    mu = x2.mean(axis=1, keepdims=True)
+    s = x2.std(axis=1, ddof=1)                                     # torch.std: unbiased
+    mu4 = ((x2 - mu) ** 4.0).mean(axis=1)
+    return inf, mu4 / (s ** 4.0 + eps)

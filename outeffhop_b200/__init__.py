@@ -5,7 +5,10 @@ Public surface (same names as the reference):
     SOFTMAX_MAPPING, AttentionGateType, logit,
     BertSelfAttentionWithExtras, OPTAttentionWithExtras,
     AsymmetricUniformQuantizer, RunningMinMaxEstimator, QuantizationManager, QuantizedActivation,
-    QuantizedBertSelfAttentionWithExtras, QuantizedOPTAttentionWithExtras
+    QuantizedBertSelfAttentionWithExtras, QuantizedOPTAttentionWithExtras,
+  SURVEY section 8f rows: percentile range estimation (RunningMinMaxEstimator(percentile=...)), QuantLayerNorm /
+    QuantizedBertSelfOutput / QuantizedBertOutput, kurtosis / OutlierMeter, ViTSelfAttentionWithExtras,
+    Association / Hopfield / HopfieldPooling
 All compute goes through liboeh.so (include/oeh.h); there is no CPU fallback.
 """
 __version__ = "0.1.0"
@@ -13,7 +16,7 @@ __version__ = "0.1.0"
 import importlib
 
 _SUBMODULES = ("_lib", "ops", "softmax", "quantization", "bert_attention", "opt_attention", "quantized_attention",
-               "build", "eval_harness")
+               "build", "eval_harness", "vit_attention", "hopfield", "quantized_layers", "outlier_metrics")
 _EXPORTS = {
     "SOFTMAX_MAPPING": "softmax", "SoftmaxFn": "softmax", "softmax_1": "softmax", "clipped_softmax": "softmax",
     "clipped_softmax1": "softmax", "parse_attn_softmax": "softmax",
@@ -26,6 +29,11 @@ _EXPORTS = {
     "Qstates": "quantization", "QuantizerNotInitializedError": "quantization", "set_range_sync": "quantization",
     "QuantizedBertSelfAttentionWithExtras": "quantized_attention",
     "QuantizedOPTAttentionWithExtras": "quantized_attention", "QuantizedModel": "quantized_attention",
+    "ViTSelfAttentionWithExtras": "vit_attention",
+    "Association": "hopfield", "Hopfield": "hopfield", "HopfieldPooling": "hopfield",
+    "QuantLayerNorm": "quantized_layers", "QuantizedBertSelfOutput": "quantized_layers",
+    "QuantizedBertOutput": "quantized_layers",
+    "kurtosis": "outlier_metrics", "OutlierMeter": "outlier_metrics", "attach_bert_outlier_hooks": "outlier_metrics",
 }
 
 

@@ -67,6 +67,22 @@ SYMBOLS = {
     "oeh_set_quant_range_host": (C.c_int, [C.c_float, C.c_float, C.c_int32, C.c_double, C.POINTER(C.c_float)]),
     "oeh_estimate_and_quantize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_double,
                                             C.c_int32, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "oeh_percentile_workspace_bytes": (C.c_size_t, []),
+    "oeh_percentile_passes": (C.c_int, [C.c_int32]),
+    "oeh_percentile_plan": (C.c_int, [C.c_int64, C.c_double, C.c_double, _I64P, C.POINTER(C.c_double)]),
+    "oeh_percentile_begin": (C.c_int, [C.c_void_p, C.c_size_t, _I64P, C.c_void_p]),
+    "oeh_percentile_hist": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "oeh_percentile_scan": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "oeh_percentile_finish": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "oeh_percentile": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+                                 C.c_size_t, C.c_void_p]),
+    "oeh_range_update_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_double,
+                                       C.c_void_p]),
+    "oeh_add_fake_quant": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
+                                     C.c_void_p]),
+    "oeh_outlier_stats_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "oeh_outlier_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 # test-only entry point (not part of the public header)
 _PRIVATE = {

@@ -92,6 +92,57 @@ __global__ void __launch_bounds__(kThreads) fake_quant_scalar_kernel(const T* __
     y[t] = DT<T>::from_f(qdq_one<T>(DT<T>::to_f(x[t]), scale, zp, int_max, codes));
 }
 
+
+// ---- residual add + fake-quant (quantized_bert.py:566-567, 602-603; quantized_opt.py:342-345, 367-369) ---------
+// sum = round_T(a + b) exactly as ATen's add kernel (one rounding to the tensor dtype), then the qdq chain above.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) add_fake_quant_kernel(const T* __restrict__ a, const T* __restrict__ b,
+                                                                  T* __restrict__ y, int64_t n,
+                                                                  const float* __restrict__ qparams, float int_max,
+                                                                  int aligned) {
+  using V = Vec16<T>;
+  constexpr int N = V::N;
+  const float scale = DT<T>::rnd(__ldg(qparams));
+  const float zp = DT<T>::rnd(__ldg(qparams + 1));
+  auto one = [&](T av, T bv) {
+    const float s = DT<T>::rnd(__fadd_rn(DT<T>::to_f(av), DT<T>::to_f(bv)));
+    return DT<T>::from_f(qdq_one<T>(s, scale, zp, int_max, false));
+  };
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  int64_t done = 0;
+  if (aligned) {
+    const int64_t nvec = n / N;
+    const V* av = reinterpret_cast<const V*>(a);
+    const V* bv = reinterpret_cast<const V*>(b);
+    V* yv = reinterpret_cast<V*>(y);
+    int64_t i = tid;
+    for (; i + stride < nvec; i += 2 * stride) {          // 2 x (two 16-byte loads) in flight per thread
+      V ia[2], ib[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        ia[u] = ld_stream(av + i + u * stride);
+        ib[u] = ld_stream(bv + i + u * stride);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        V out;
+#pragma unroll
+        for (int e = 0; e < N; ++e) out.v[e] = one(ia[u].v[e], ib[u].v[e]);
+        st_stream(yv + i + u * stride, out);
+      }
+    }
+    for (; i < nvec; i += stride) {
+      V ia = av[i], ib = bv[i], out;
+#pragma unroll
+      for (int e = 0; e < N; ++e) out.v[e] = one(ia.v[e], ib.v[e]);
+      yv[i] = out;
+    }
+    done = nvec * N;
+  }
+  for (int64_t t = done + tid; t < n; t += stride) y[t] = one(a[t], b[t]);
+}
+
 // ---- min/max ---------------------------------------------------------------------------------
 struct MinMax {
   float lo, hi;
@@ -235,6 +286,16 @@ int launch_minmax(const void* x, int64_t n, float* out2, float* partial, cudaStr
   return check_launch("minmax_stage2_kernel");
 }
 
+template <typename T>
+int launch_add_fake_quant(const void* a, const void* b, void* y, int64_t n, const float* qparams, int n_bits,
+                          cudaStream_t st) {
+  const float int_max = (float)((1 << n_bits) - 1);
+  const int aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  const int grid = grid_for(aligned ? (n / Vec16<T>::N + 1) / 2 + 1 : n);
+  add_fake_quant_kernel<T><<<grid, kThreads, 0, st>>>((const T*)a, (const T*)b, (T*)y, n, qparams, int_max, aligned);
+  return check_launch("add_fake_quant_kernel");
+}
+
 }  // namespace
 }  // namespace oeh
 
@@ -253,6 +314,21 @@ extern "C" int oeh_fake_quant_asym(const void* x, void* y, int64_t n, int32_t dt
     case OEH_BF16: return launch_fake_quant<__nv_bfloat16>(x, y, n, qparams, n_bits, emit_codes, st);
   }
   return set_error(OEH_ERR_BAD_ARG, "oeh_fake_quant_asym: unknown dtype %d", dtype);
+}
+
+extern "C" int oeh_add_fake_quant(const void* a, const void* b, void* y, int64_t n, int32_t dtype, const float* qparams,
+                                  int32_t n_bits, oeh_stream_t stream) {
+  OEH_CHECK_ARG(n >= 0, "oeh_add_fake_quant: n=%lld < 0", (long long)n);
+  OEH_CHECK_ARG(n_bits >= 1 && n_bits <= 16, "oeh_add_fake_quant: n_bits=%d outside [1,16]", n_bits);
+  if (n == 0) return OEH_OK;
+  OEH_CHECK_ARG(a && b && y && qparams, "oeh_add_fake_quant: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case OEH_F32: return launch_add_fake_quant<float>(a, b, y, n, qparams, n_bits, st);
+    case OEH_F16: return launch_add_fake_quant<__half>(a, b, y, n, qparams, n_bits, st);
+    case OEH_BF16: return launch_add_fake_quant<__nv_bfloat16>(a, b, y, n, qparams, n_bits, st);
+  }
+  return set_error(OEH_ERR_BAD_ARG, "oeh_add_fake_quant: unknown dtype %d", dtype);
 }
 
 extern "C" size_t oeh_minmax_workspace_bytes(int64_t n) {

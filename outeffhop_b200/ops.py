@@ -233,3 +233,95 @@ def estimate_and_quantize(x: torch.Tensor, state: torch.Tensor, momentum: float 
                                           float(momentum), int(n_bits), float(eps), ws.data_ptr(), ws.numel(),
                                           _stream()))
     return y
+
+
+# ---- percentile ranges, fused residual tap, outlier metrics ----------------------------
+
+PCT_HIST_WORDS = 4 * 2048       # leading uint32 words of the percentile workspace = the histograms (all-reducible)
+
+
+def percentile(x: torch.Tensor, q_lo: float, q_hi: float, group=None, sync: bool = False) -> torch.Tensor:
+    """np.percentile(x, (q_lo, q_hi)) over the whole tensor, exact, as a 2-element CUDA float64 tensor
+    (oeh_percentile; range_estimators.py:89-94).  With ``sync`` and an initialised process group the histograms are
+    SUM-all-reduced between the select passes, so every rank gets the percentile of the union of all ranks' tensors
+    (equal-sized shards), bit-identical to one process holding the concatenated batch.  No host sync."""
+    _require_cuda(x)
+    if x.dtype not in (torch.float32, torch.float16):
+        raise TypeError(f"Got unsupported ScalarType {str(x.dtype).replace('torch.', '').capitalize()}")   # Tensor.numpy()
+    xc = x.contiguous()
+    if xc.numel() == 0:
+        raise IndexError("index -1 is out of bounds for axis 0 with size 0")                               # np.percentile([])
+    lib = L.lib()
+    out = torch.empty(2, dtype=torch.float64, device=x.device)
+    need = lib.oeh_percentile_workspace_bytes()
+    ws = _workspace(x.device, need)
+    code, n = _dtype_code(xc), xc.numel()
+    world = 1
+    if sync:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            world = dist.get_world_size(group)
+    if world == 1:
+        L.check(lib.oeh_percentile(xc.data_ptr(), n, code, float(q_lo), float(q_hi), out.data_ptr(), ws.data_ptr(),
+                                   ws.numel(), _stream()))
+        return out
+    import torch.distributed as dist
+    ranks, gamma = (C.c_int64 * 4)(), (C.c_double * 2)()
+    L.check(lib.oeh_percentile_plan(n * world, float(q_lo), float(q_hi), ranks, gamma))
+    L.check(lib.oeh_percentile_begin(ws.data_ptr(), ws.numel(), ranks, _stream()))
+    hist = ws[:PCT_HIST_WORDS * 4].view(torch.int32)
+    for p in range(lib.oeh_percentile_passes(code)):
+        L.check(lib.oeh_percentile_hist(xc.data_ptr(), n, code, p, ws.data_ptr(), _stream()))
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+        L.check(lib.oeh_percentile_scan(code, p, ws.data_ptr(), _stream()))
+    L.check(lib.oeh_percentile_finish(code, gamma, out.data_ptr(), ws.data_ptr(), _stream()))
+    return out
+
+
+def new_qstate64(device) -> torch.Tensor:
+    """float64 side of a percentile-estimated range: [cur_min, cur_max, _delta, _zero_float, initialised]."""
+    return torch.zeros(5, dtype=torch.float64, device=device)
+
+
+def range_update_f64(state64: torch.Tensor, state: torch.Tensor, new_minmax: torch.Tensor, momentum: float = 0.9,
+                     n_bits: int = 8, eps: float = 1e-8) -> None:
+    """float64 EMA + set_quant_range, mirrored into the fp32 kernel state (oeh_range_update_f64)."""
+    _require_cuda(state64, state, new_minmax)
+    if state64.dtype != torch.float64 or new_minmax.dtype != torch.float64 or state.dtype != torch.float32:
+        raise ValueError("range_update_f64: state64/new_minmax must be float64, state float32")
+    L.check(L.lib().oeh_range_update_f64(state64.data_ptr(), state.data_ptr(), new_minmax.data_ptr(), float(momentum),
+                                         int(n_bits), float(eps), _stream()))
+
+
+def add_fake_quant(a: torch.Tensor, b: torch.Tensor, qparams: torch.Tensor, n_bits: int = 8,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qdq(a + b) in one pass (oeh_add_fake_quant): the residual-sum activation tap with fixed ranges."""
+    _require_cuda(a, b, qparams)
+    if a.shape != b.shape or a.dtype != b.dtype:
+        raise ValueError("add_fake_quant: a and b must have the same shape and dtype")
+    ac, bc = a.contiguous(), b.contiguous()
+    y = out if out is not None else torch.empty_like(ac)
+    L.check(L.lib().oeh_add_fake_quant(ac.data_ptr(), bc.data_ptr(), y.data_ptr(), ac.numel(), _dtype_code(ac),
+                                       qparams.data_ptr(), int(n_bits), _stream()))
+    return y
+
+
+def outlier_stats(x: torch.Tensor, eps: float = 1e-6, meter: Optional[torch.Tensor] = None):
+    """Per-sample (inf_norm, kurtosis) of x viewed as (x.size(0), -1) (oeh_outlier_stats;
+    validate_mlm_config.py:513-528, transformers_language/utils.py:9-20).  ``meter``: optional CUDA float64[3]
+    running [sum inf_norm, sum kurtosis, samples], updated in place on the device."""
+    _require_cuda(x, meter)
+    xc = x.contiguous()
+    rows = xc.size(0)
+    cols = xc.numel() // max(rows, 1)
+    inf = torch.empty(rows, dtype=torch.float32, device=x.device)
+    kurt = torch.empty(rows, dtype=torch.float32, device=x.device)
+    lib = L.lib()
+    need = lib.oeh_outlier_stats_workspace_bytes(rows, cols)
+    ws = _workspace(x.device, need)
+    if meter is not None and (meter.dtype != torch.float64 or meter.numel() < 3):
+        raise ValueError("meter must be a CUDA float64 tensor of 3 elements")
+    L.check(lib.oeh_outlier_stats(xc.data_ptr(), rows, cols, _dtype_code(xc), float(eps), inf.data_ptr(), kurt.data_ptr(),
+                                  meter.data_ptr() if meter is not None else None, ws.data_ptr(), ws.numel(),
+                                  _stream()))
+    return inf, kurt

@@ -100,6 +100,9 @@ class _StateHolder(nn.Module):
         self._qstate: Optional[torch.Tensor] = None
         self._owns_state = True
         self._host_init = False        # host mirror of state[QS_INITIALIZED]: no device read in forward
+        # percentile branch only: float64 [cur_min, cur_max, _delta, _zero_float, initialised] (the reference keeps
+        # np.percentile's float64 through the EMA and set_quant_range); shared estimator <-> quantizer like _qstate
+        self._qstate64: Optional[torch.Tensor] = None
 
     def _ensure_state(self, device) -> torch.Tensor:
         if self._qstate is None:
@@ -112,11 +115,20 @@ class _StateHolder(nn.Module):
         self._qstate = state
         self._owns_state = False
 
+    def _ensure_state64(self, device) -> torch.Tensor:
+        if self._qstate64 is None:
+            self._qstate64 = ops.new_qstate64(device)
+        elif self._qstate64.device != torch.device(device):
+            self._qstate64 = self._qstate64.to(device)
+        return self._qstate64
+
     def _apply(self, fn, *a, **k):
         super()._apply(fn, *a, **k)
         if self._owns_state and self._qstate is not None:
             moved = fn(self._qstate)
             self._qstate = moved if moved.dtype == torch.float32 else self._qstate.to(moved.device)
+        if self._qstate64 is not None and self._qstate is not None:
+            self._qstate64 = self._qstate64.to(self._qstate.device)
         return self
 
 
@@ -162,26 +174,36 @@ class AsymmetricUniformQuantizer(QuantizerBase):
         self.scale_domain = scale_domain
         self.grad_scaling = grad_scaling
         self.eps = eps
+        self._range_is_f64 = False
 
     # -- reference buffers as views of the device state --------------------------------------------
     @property
+    def _f64(self) -> bool:
+        """The current range came from float64 tensors (percentile estimation): buffers are float64 like the reference's."""
+        return self._qstate64 is not None and self._range_is_f64
+
+    @property
     def _delta(self):
-        return self._qstate[L.QS_DELTA] if self._host_init else None
+        if not self._host_init:
+            return None
+        return self._qstate64[2] if self._f64 else self._qstate[L.QS_DELTA]
 
     @property
     def _zero_float(self):
-        return self._qstate[L.QS_ZERO_FLOAT] if self._host_init else None
+        if not self._host_init:
+            return None
+        return self._qstate64[3] if self._f64 else self._qstate[L.QS_ZERO_FLOAT]
 
     @property
     def delta(self):
         if self._host_init:
-            return self._qstate[L.QS_DELTA]
+            return self._delta
         raise QuantizerNotInitializedError()
 
     @property
     def zero_float(self):
         if self._host_init:
-            return self._qstate[L.QS_ZERO_FLOAT]
+            return self._zero_float
         raise QuantizerNotInitializedError()
 
     @property
@@ -234,7 +256,21 @@ class AsymmetricUniformQuantizer(QuantizerBase):
         """uniform_quantizers.py:204-224.  Host scalars go through oeh_set_quant_range_host, device tensors
         through oeh_range_update semantics without the EMA (same fp32 op order either way)."""
         self.x_min_fp32, self.x_max_fp32 = x_min, x_max
-        if torch.is_tensor(x_min) and x_min.is_cuda:
+        self._range_is_f64 = False
+        if torch.is_tensor(x_min) and x_min.is_cuda and x_min.dtype == torch.float64:
+            # float64 tensors (percentile estimators): the reference's arithmetic stays in float64 (:218-219)
+            if x_min.dim() > 0 and x_min.numel() > 1:
+                raise ValueError("x_min and x_max must be a float or 1-D Tensor for per-tensor quantization "
+                                 "(per_channel=False)")
+            st = self._ensure_state(x_min.device)
+            st64 = self._ensure_state64(x_min.device)
+            mm = torch.stack((x_min.reshape(()), x_max.reshape(())))
+            keep32, keep64 = st[:2].clone(), st64[:2].clone()
+            st64[4] = 0.0                                    # take the range as is (no EMA)
+            ops.range_update_f64(st64, st, mm, 0.0, self.n_bits, self.eps)
+            st[:2], st64[:2] = keep32, keep64
+            self._range_is_f64 = True
+        elif torch.is_tensor(x_min) and x_min.is_cuda:
             st = self._ensure_state(x_min.device)
             if x_min.dim() > 0 and x_min.numel() > 1:
                 raise ValueError("x_min and x_max must be a float or 1-D Tensor for per-tensor quantization "
@@ -387,23 +423,29 @@ class RangeEstimatorBase(_StateHolder):
 
     @property
     def current_xmin(self):
-        return self._qstate[L.QS_CUR_MIN] if self._host_init else None
+        if not self._host_init:
+            return None
+        return self._qstate64[0] if getattr(self, "percentile", None) else self._qstate[L.QS_CUR_MIN]
 
     @property
     def current_xmax(self):
-        return self._qstate[L.QS_CUR_MAX] if self._host_init else None
+        if not self._host_init:
+            return None
+        return self._qstate64[1] if getattr(self, "percentile", None) else self._qstate[L.QS_CUR_MAX]
 
     def reset(self):
         self._host_init = False
         if self._qstate is not None:
             self._qstate[:2].zero_()
             self._qstate[L.QS_INITIALIZED] = 0.0
+        if self._qstate64 is not None:
+            self._qstate64.zero_()
 
     def _save_to_state_dict(self, destination, prefix, keep_vars):
         super()._save_to_state_dict(destination, prefix, keep_vars)
         if self._host_init:
-            destination[prefix + "current_xmin"] = self._qstate[L.QS_CUR_MIN].clone()
-            destination[prefix + "current_xmax"] = self._qstate[L.QS_CUR_MAX].clone()
+            destination[prefix + "current_xmin"] = self.current_xmin.clone()
+            destination[prefix + "current_xmax"] = self.current_xmax.clone()
         # the reference registers the quantizer as a submodule of its estimator (range_estimators.py:18), so its
         # checkpoints carry the quantizer buffers a second time under "<estimator>.quantizer.*": emit them too
         q = self.quantizer
@@ -432,16 +474,22 @@ class RangeEstimatorBase(_StateHolder):
 
 
 class CurrentMinMaxEstimator(RangeEstimatorBase):
-    """range_estimators.py:54-74 (no-percentile, per-tensor branch)."""
+    """range_estimators.py:54-74, per-tensor.  With ``percentile`` the range is np.percentile(x, (p, 100-p)) --
+    the reference passes the pair in THIS order (:65-67), i.e. x_min is the upper percentile; kept as is."""
 
     def __init__(self, *args, percentile=None, **kwargs):
-        if percentile:
-            raise NotImplementedError("percentile range estimation is a 'next' row (SURVEY section 8f rank 1)")
-        self.percentile = percentile
         super().__init__(*args, **kwargs)
+        self.percentile = percentile
 
     def forward(self, x):
         st = self._ensure_state(x.device)
+        if self.percentile:
+            st64 = self._ensure_state64(x.device)
+            st64[:2] = ops.percentile(x, self.percentile, 100 - self.percentile, group=_RANGE_SYNC_GROUP,
+                                      sync=_RANGE_SYNC_ENABLED)
+            st[:2] = st64[:2].float()
+            self._host_init = True
+            return st64[0], st64[1]
         mm = _sync_minmax(ops.minmax(x))
         st[:2] = mm
         self._host_init = True
@@ -452,15 +500,25 @@ class RunningMinMaxEstimator(RangeEstimatorBase):
     """range_estimators.py:77-106: EMA of the per-batch global min/max, first batch taken as is."""
 
     def __init__(self, *args, momentum=0.9, percentile=None, **kwargs):
-        if percentile:
-            raise NotImplementedError("percentile range estimation is a 'next' row (SURVEY section 8f rank 1)")
+        super().__init__(*args, **kwargs)
         self.momentum = momentum
         self.percentile = percentile
-        super().__init__(*args, **kwargs)
 
     def _ema_into_state(self, x, n_bits: int, eps: float):
-        """min/max -> [all-reduce] -> EMA -> set_quant_range, all on the device (state shared with the quantizer)."""
+        """min/max -> [all-reduce] -> EMA -> set_quant_range, all on the device (state shared with the quantizer).
+        Percentile branch (range_estimators.py:89-94): exact np.percentile(x, (100-p, p)) by radix select (histograms
+        all-reduced when range sync is on), then the EMA and set_quant_range in float64 like the reference."""
         st = self._ensure_state(x.device)
+        if self.percentile:
+            st64 = self._ensure_state64(x.device)
+            mm64 = ops.percentile(x, 100 - self.percentile, self.percentile, group=_RANGE_SYNC_GROUP,
+                                  sync=_RANGE_SYNC_ENABLED)
+            ops.range_update_f64(st64, st, mm64, self.momentum, n_bits, eps)
+            self._host_init = True
+            q = self.quantizer
+            if q is not None and isinstance(q, _StateHolder) and q._qstate is st:
+                q._qstate64, q._range_is_f64 = st64, True
+            return st
         mm = _sync_minmax(ops.minmax(x))
         ops.range_update(st, mm, self.momentum, n_bits, eps)
         self._host_init = True
@@ -469,6 +527,8 @@ class RunningMinMaxEstimator(RangeEstimatorBase):
     def forward(self, x):
         q = self.quantizer
         st = self._ema_into_state(x, q.n_bits if q is not None else 8, q.eps if q is not None else 1e-8)
+        if self.percentile:
+            return self._qstate64[0], self._qstate64[1]
         return st[L.QS_CUR_MIN], st[L.QS_CUR_MAX]
 
 

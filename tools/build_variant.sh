@@ -1,12 +1,18 @@
 #!/bin/bash
-# Build an experimental variant of liboeh.so with extra -D flags for the attention kernels:
-#   tools/build_variant.sh NAME -DOEH_EXP=1      -> outeffhop_b200/lib/liboeh_NAME.so   (use with OEH_LIB_PATH)
+# Build an experimental copy of the library with extra -D switches (kernel experiments only; the product is lib/liboeh.so):
+#   tools/build_variant.sh NAME -DOEH_POLY_PAIRS=4 ...   -> outeffhop_b200/lib/liboeh_NAME.so   (see tools/run_variants.sh)
 set -e
-cd "$(dirname "$0")/.."
 NAME=$1; shift
-C=outeffhop_b200/csrc
-nvcc -c $C/attn_fwd_sm100.cu -o $C/_obj/attn_fwd_sm100_$NAME.o -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
-  --expt-relaxed-constexpr -Xcompiler -fPIC,-O2 -I include "$@"
-nvcc -shared -o outeffhop_b200/lib/liboeh_$NAME.so $C/_obj/api.o $C/_obj/quant.o $C/_obj/softmax_rows.o $C/_obj/gate.o \
-  $C/_obj/attn_fwd_sm100_$NAME.o -gencode arch=compute_100a,code=sm_100a
-echo outeffhop_b200/lib/liboeh_$NAME.so
+ROOT=$(cd "$(dirname "$0")/.." && pwd)
+OBJ=/tmp/oeh_variant_$NAME
+mkdir -p $OBJ $ROOT/outeffhop_b200/lib
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC,-O2 -I $ROOT/include"
+pids=()
+for s in api quant softmax_rows gate attn_fwd_sm100 percentile outlier_stats; do
+  [ -f $ROOT/outeffhop_b200/csrc/$s.cu ] || continue
+  nvcc -c $ROOT/outeffhop_b200/csrc/$s.cu -o $OBJ/$s.o $FLAGS "$@" &
+  pids+=($!)
+done
+for p in "${pids[@]}"; do wait $p; done
+nvcc -shared -o $ROOT/outeffhop_b200/lib/liboeh_$NAME.so $OBJ/*.o -gencode arch=compute_100a,code=sm_100a
+echo built $ROOT/outeffhop_b200/lib/liboeh_$NAME.so
