@@ -111,8 +111,8 @@ def test_module_construction_and_state_dict_keys_without_gpu():
             m(torch.randn(1, 4, 128))
     with pytest.raises(NotImplementedError):
         o.AsymmetricUniformQuantizer(n_bits=8, per_channel=True)
-    with pytest.raises(NotImplementedError):
-        o.RunningMinMaxEstimator(percentile=99.999)
+    est = o.RunningMinMaxEstimator(percentile=99.999)                              # range_estimators.py:89-94, now on device
+    assert est.percentile == 99.999
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
