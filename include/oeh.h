@@ -232,6 +232,21 @@ size_t oeh_outlier_stats_workspace_bytes(int64_t rows, int64_t cols);
 int oeh_outlier_stats(const void* x, int64_t rows, int64_t cols, int32_t dtype, double eps, float* out_inf,
                       float* out_kurt, double* meter, void* workspace, size_t workspace_bytes, oeh_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Mean cross-entropy of one evaluation batch from the model's logits: the per-batch
+ * `outputs.loss` the eval loops aggregate (validate_mlm_config.py:489-496, validate_clm.py:555-561), i.e. HF's
+ * CrossEntropyLoss()(prediction_scores.view(-1, V), labels.view(-1)) evaluated in fp32:
+ *   loss = mean over rows with label != ignore_index of ( logsumexp_j x[i,j] - x[i,label_i] ).
+ * logits: (rows, vocab) of `dtype`, row stride `row_stride` elements (>= vocab: the vocabulary dimension may be
+ * padded so rows stay 16-byte aligned); labels: DEVICE int64 (rows).  out_loss: DEVICE fp32 scalar (NaN when no row
+ * is labelled, like ATen); out_count (optional): DEVICE fp32 number of labelled rows.  The per-row losses are left
+ * in the workspace (rows fp32; 0 for ignored rows).  One pass over the labelled rows, no fp32 copy of the logits.
+ * ------------------------------------------------------------------------------------------- */
+size_t oeh_ce_loss_workspace_bytes(int64_t rows);
+int oeh_ce_loss(const void* logits, int64_t rows, int64_t vocab, int64_t row_stride, int32_t dtype,
+                const int64_t* labels, int64_t ignore_index, float* out_loss, float* out_count, void* workspace,
+                size_t workspace_bytes, oeh_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -443,3 +443,22 @@ def outlier_stats(x: np.ndarray, eps: float = 1e-6):
     s = x2.std(axis=1, ddof=1)                                     # torch.std: unbiased
     mu4 = ((x2 - mu) ** 4.0).mean(axis=1)
     return inf, mu4 / (s ** 4.0 + eps)
+
+
+def ce_loss_mean(logits: np.ndarray, labels: np.ndarray, ignore_index: int = -100):
+    """Per-batch eval loss: HF's CrossEntropyLoss()(prediction_scores.view(-1, V), labels.view(-1))
+    behind `outputs.loss` at validate_mlm_config.py:489-496 / validate_clm.py:555-561 = mean over the rows whose label
+    is not ignore_index of logsumexp(x_i) - x_i[label_i].  Evaluated in float64 on the given (rows, V) logits; returns
+    (mean, per-row losses with 0 for ignored rows).  No labelled row -> NaN mean (ATen's 0/0)."""
+    x = np.asarray(logits, dtype=np.float64)
+    lab = np.asarray(labels, dtype=np.int64).reshape(-1)
+    keep = lab != ignore_index
+    m = x.max(axis=1, keepdims=True)
+    m_safe = np.where(np.isfinite(m), m, 0.0)
+    lse = np.log(np.exp(x - m_safe).sum(axis=1)) + m_safe[:, 0]
+    rows = np.zeros(x.shape[0], dtype=np.float64)
+    idx = np.nonzero(keep)[0]
+    rows[idx] = lse[idx] - x[idx, lab[idx]]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mean = rows[idx].sum() / np.float64(idx.size) if idx.size else np.float64(np.nan)
+    return mean, rows

@@ -242,6 +242,25 @@ __device__ __forceinline__ void normalize_probs(float (&s)[N], const AttnParams&
   }
 }
 
+// Normalised modes: log2-domain bound below which an unnormalised e = 2^t is GUARANTEED to end as P == 0 exactly:
+//   clipped:  clip(stretch*p + gamma, 0, 1) == 0            <=>  p <= -gamma/stretch            (gamma < 0 < stretch)
+//   probs tap: qdq(x) == 0  <=>  rint(x/scale) == 0          <=   x <  scale/2                   (zero_point is in range)
+// with p = e/den.  1 % safety margin (ex2.approx and the reciprocal are good to ~2^-22).  -inf = nothing can be skipped.
+__device__ __forceinline__ float zero_prob_threshold(const AttnParams& p, bool clipped, bool has_qp, const Qdq& qd_p,
+                                                     float den) {
+  const float x0 = has_qp ? 0.49f * qd_p.scale : 0.f;          // post-clip values below x0 quantise to 0
+  float pmin;
+  if (clipped) {
+    if (!(p.stretch > 0.f)) return -INFINITY;
+    pmin = (x0 - p.gamma) / p.stretch;
+  } else {
+    pmin = x0;
+  }
+  pmin *= 0.99f;
+  if (!(pmin > 0.f) || !(den > 0.f) || !(den < INFINITY)) return -INFINITY;
+  return log2f(pmin * den);
+}
+
 // Epilogue of one query row (ND = 64: the whole row; ND = 32: the half starting at head-dim column d0):
 // o[] holds the PV accumulator; mul = 1/denominator (1 in the normalised modes).
 // ctx -> [qdq before gate] -> * sigmoid(gate logit)*gate_scale -> [qdq after gate] -> ND/8 x 16-byte stores.

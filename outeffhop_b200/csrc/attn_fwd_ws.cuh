@@ -281,7 +281,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         p.mask ? ((int64_t)b * p.ms0 + (int64_t)h * p.ms1 + (int64_t)(row < p.Tq ? row : 0) * p.ms2) : 0;
     const int causal_lim = p.causal ? row + (p.Tk - p.Tq) : 0x7fffffff;
 
-    float m_run = -INFINITY, l_run = 0.f, inv_den = 1.f;
+    float m_run = -INFINITY, l_run = 0.f, inv_den = 1.f, skip_thr = -INFINITY;
     OEH_T_DECL;
 
     // merge (m_h, l_h) of the two halves of a row: afterwards both hold the row's m and l in the common frame
@@ -355,9 +355,21 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         if (i == nA) {
           const float den = softmax1 ? l_run + ptx::ex2(-m_safe) : l_run;
           inv_den = __frcp_rn(den);
+          skip_thr = zero_prob_threshold(p, clipped, has_qp, qd_p, den);
         }
-        exp2_only<BNH>(s, mul, m_safe);
-        normalize_probs<BNH, kGeneric>(s, p, inv_den, clipped, has_qp, qd_p);
+#ifndef OEH_NO_SPARSE_SKIP
+        // Clipped softmax with gamma < 0 (and / or the probs tap) maps every probability below a fixed bound to an
+        // exact 0: at most 1/bound keys of a row survive, whatever the sequence length.  If none of this warp's
+        // 32 rows x 32 keys can survive, P is 0 without a single exponential (the stats pass already paid for them).
+        if (!__any_sync(0xffffffffu, tile_max - m_safe > skip_thr)) {
+#pragma unroll
+          for (int j = 0; j < BNH; ++j) s[j] = 0.f;
+        } else
+#endif
+        {
+          exp2_only<BNH>(s, mul, m_safe);
+          normalize_probs<BNH, kGeneric>(s, p, inv_den, clipped, has_qp, qd_p);
+        }
       } else {
         // online softmax with lazy rescale
         const bool move = tile_max > m_run + kLazyRescale || m_run == -INFINITY;

@@ -72,9 +72,55 @@ def synthetic_clm_batch(batch: int, seq: int, vocab: int = 50272, seed: int = 0,
 # un-padded (validate_mlm_config.py:344-357), so the BERT mask is all zeros and the OPT mask is the plain causal one:
 # these forwards call the same HF submodules in the same order with that knowledge baked in.
 
+def _padded_decoder(linear: torch.nn.Linear, multiple: int = 64):
+    """(weight, bias, vocab) of an output projection with the vocabulary dimension zero-padded to a multiple of 64 rows.
+    BERT's 30522-wide fp16 decoder gives logits rows that are only 4-byte aligned, which drops cuBLAS onto an
+    `align2` sm80 kernel (736 us of a 3.1 ms step, profiles/r01_launches_bert_step.summary.txt); 30528 keeps the fast
+    path.  The pad columns are never read by the loss kernel (``vocab`` < row stride).  Cached on the module; eval only."""
+    V = linear.out_features
+    Vp = (V + multiple - 1) // multiple * multiple
+    if Vp == V:
+        return linear.weight, linear.bias, V
+    key = (linear.weight.data_ptr(), linear.weight._version, None if linear.bias is None else linear.bias.data_ptr())
+    cached = getattr(linear, "_oeh_padded", None)
+    if cached is None or cached[0] != key:
+        with torch.no_grad():
+            w = linear.weight.new_zeros((Vp, linear.in_features))
+            w[:V].copy_(linear.weight)
+            b = None
+            if linear.bias is not None:
+                b = linear.bias.new_zeros((Vp,))
+                b[:V].copy_(linear.bias)
+        cached = (key, w, b)
+        linear._oeh_padded = cached
+    return cached[1], cached[2], V
+
+
+def bert_mlm_logits(model, input_ids: torch.Tensor):
+    """embeddings -> 12 x BertLayer (attention_mask=None) -> MLM head.  Returns ((B*T, V_padded) logits, V)."""
+    bert = model.bert
+    h = bert.embeddings(input_ids=input_ids)
+    for layer in bert.encoder.layer:
+        out = layer(h, attention_mask=None)
+        h = out[0] if isinstance(out, tuple) else out
+    pred = model.cls.predictions
+    w, b, V = _padded_decoder(pred.decoder)
+    logits = torch.nn.functional.linear(pred.transform(h), w, b)
+    return logits.view(-1, logits.shape[-1]), V
+
+
 def bert_mlm_loss(model, input_ids: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
-    """BertForMaskedLM.forward for un-padded batches: embeddings -> 12 x BertLayer (attention_mask=None) -> MLM head ->
-    mean CE over the labelled tokens, evaluated in fp32 (a fp16 mean would round the loss to 3 decimal digits)."""
+    """BertForMaskedLM.forward for un-padded batches: mean CE over the labelled tokens, evaluated in fp32 by
+    ``oeh_ce_loss`` directly on the fp16 logits (a fp16 mean would round the loss to 3 decimal digits; ATen needs a
+    1 GB/step fp32 copy + log-softmax for the same number)."""
+    from . import ops
+    logits, V = bert_mlm_logits(model, input_ids)
+    return ops.ce_loss(logits, labels.reshape(-1), vocab=V)
+
+
+def bert_mlm_loss_aten(model, input_ids: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """The same loss through ATen only (unpadded decoder GEMM, fp32 copy, F.cross_entropy): the check for
+    ``bert_mlm_loss`` in tests, and the pre-fusion baseline of bench.py --aten-loss."""
     bert = model.bert
     h = bert.embeddings(input_ids=input_ids)
     for layer in bert.encoder.layer:
@@ -85,7 +131,7 @@ def bert_mlm_loss(model, input_ids: torch.Tensor, labels: torch.Tensor) -> torch
 
 
 def opt_clm_loss(model, input_ids: torch.Tensor, labels: torch.Tensor, causal_mask: torch.Tensor,
-                 position_ids: torch.Tensor) -> torch.Tensor:
+                 position_ids: torch.Tensor, aten_loss: bool = False) -> torch.Tensor:
     """OPTForCausalLM.forward for un-padded blocks: token + learned position embeddings -> 12 x OPTDecoderLayer with the
     (B,1,T,T) causal mask -> final LayerNorm -> lm_head -> shifted mean CE in fp32."""
     dec = model.model.decoder
@@ -101,9 +147,16 @@ def opt_clm_loss(model, input_ids: torch.Tensor, labels: torch.Tensor, causal_ma
         h = dec.final_layer_norm(h)
     if dec.project_out is not None:
         h = dec.project_out(h)
-    logits = model.lm_head(h)
-    V = logits.shape[-1]
-    return torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, V).float(), labels[:, 1:].reshape(-1))
+    w, b, V = _padded_decoder(model.lm_head)
+    logits = torch.nn.functional.linear(h, w, b)
+    if aten_loss:
+        return torch.nn.functional.cross_entropy(logits[:, :-1, :V].reshape(-1, V).float(), labels[:, 1:].reshape(-1))
+    # shifted CE without slicing / copying the logits: row (b, t) is scored against labels[b, t+1], the last row
+    # of every block is ignored (same set of B*(T-1) terms as HF's shift, validate_clm.py:555-561)
+    from . import ops
+    shifted = torch.full_like(labels, -100)
+    shifted[:, :-1] = labels[:, 1:]
+    return ops.ce_loss(logits.view(-1, logits.shape[-1]), shifted.view(-1), vocab=V)
 
 
 def make_causal_mask(batch: int, seq: int, dtype, device) -> torch.Tensor:

@@ -325,3 +325,32 @@ def outlier_stats(x: torch.Tensor, eps: float = 1e-6, meter: Optional[torch.Tens
                                   meter.data_ptr() if meter is not None else None, ws.data_ptr(), ws.numel(),
                                   _stream()))
     return inf, kurt
+
+
+def ce_loss(logits: torch.Tensor, labels: torch.Tensor, vocab: Optional[int] = None, ignore_index: int = -100,
+            return_row_losses: bool = False):
+    """Mean cross-entropy in fp32 straight from (rows, >=vocab) logits (oeh_ce_loss): F.cross_entropy(
+    logits[:, :vocab].float(), labels) without the fp32 copy or a materialised log-softmax.  ``logits`` may be a
+    column-padded 2-D view (last dimension contiguous, any row stride); ``labels`` int64 (rows).  Returns a 0-dim
+    fp32 device tensor (and the per-row fp32 losses when asked)."""
+    _require_cuda(logits, labels)
+    if logits.dim() != 2 or logits.stride(1) != 1:
+        raise ValueError("ce_loss: expected 2-D logits whose last dimension is contiguous")
+    if labels.dtype != torch.int64 or labels.numel() != logits.size(0):
+        raise ValueError("ce_loss: labels must be int64 with one entry per logits row")
+    rows = logits.size(0)
+    vocab = logits.size(1) if vocab is None else int(vocab)
+    if vocab > logits.size(1):
+        raise ValueError("ce_loss: vocab exceeds the logits width")
+    lab = labels.contiguous()
+    lib = L.lib()
+    out = torch.empty((), dtype=torch.float32, device=logits.device)
+    if return_row_losses:
+        ws = torch.empty(rows, dtype=torch.float32, device=logits.device)
+        ws_ptr, ws_bytes = ws.data_ptr(), ws.numel() * 4
+    else:
+        ws = _workspace(logits.device, lib.oeh_ce_loss_workspace_bytes(rows))
+        ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
+    L.check(lib.oeh_ce_loss(logits.data_ptr(), rows, vocab, logits.stride(0), _dtype_code(logits), lab.data_ptr(),
+                            int(ignore_index), out.data_ptr(), None, ws_ptr, ws_bytes, _stream()))
+    return (out, ws) if return_row_losses else out

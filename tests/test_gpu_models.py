@@ -66,7 +66,7 @@ def test_bert_base_eval_perplexity_matches_fp32_reference(key, gated):
             ours.append(step.run().item())
             eager.load(b)
             assert abs(eager.run().item() - ours[-1]) < 2e-3           # graph replay ~ eager launch (cuBLAS may pick other algos)
-            refl.append(EH.bert_mlm_loss(ref, b["input_ids"].cuda(), b["labels"].cuda()).item())
+            refl.append(EH.bert_mlm_loss_aten(ref, b["input_ids"].cuda(), b["labels"].cuda()).item())
     ppl_ours = math.exp(sum(ours) / len(ours))
     ppl_ref = math.exp(sum(refl) / len(refl))
     assert abs(ppl_ours / ppl_ref - 1) < 1e-3, (ppl_ours, ppl_ref)
@@ -115,7 +115,7 @@ def test_opt_125m_eval_perplexity_matches_fp32_reference(key, gated, causal_hint
         for b in batches:
             step.load(b)
             ours.append(step.run().item())
-            refl.append(EH.opt_clm_loss(ref, b["input_ids"].cuda(), b["labels"].cuda(), mask, pos).item())
+            refl.append(EH.opt_clm_loss(ref, b["input_ids"].cuda(), b["labels"].cuda(), mask, pos, aten_loss=True).item())
     ppl_ours, ppl_ref = math.exp(sum(ours) / 2), math.exp(sum(refl) / 2)
     assert abs(ppl_ours / ppl_ref - 1) < 1e-3, (ppl_ours, ppl_ref)
 

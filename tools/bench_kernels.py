@@ -48,6 +48,9 @@ def main():
     ap.add_argument("--out", type=str, default="")
     ap.add_argument("--no-quant", action="store_true")
     ap.add_argument("--no-causal", action="store_true")
+    ap.add_argument("--gamma", type=float, default=-0.025, help="clipped kinds: gamma (>= 0 disables the sparse skip)")
+    ap.add_argument("--eta", type=float, default=1.1)
+    ap.add_argument("--qscale", type=float, default=1.0, help="multiply q by this (peaked attention rows)")
     a = ap.parse_args()
     dt = getattr(torch, a.dtype)
     res = {"attn": [], "quant": []}
@@ -55,15 +58,15 @@ def main():
         B = max(1, a.tokens // T)
         H = 12
         torch.manual_seed(1000 + T)
-        q = torch.randn(B, H, T, 64, device="cuda", dtype=dt)
+        q = (torch.randn(B, H, T, 64, device="cuda", dtype=torch.float32) * a.qscale).to(dt)
         k = torch.randn(B, H, T, 64, device="cuda", dtype=dt)
         v = torch.randn(B, H, T, 64, device="cuda", dtype=dt)
         for kind in [int(x) for x in a.kinds.split(",")]:
             for causal in ((False,) if a.no_causal else (False, True)):
-                fn = lambda: ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=-0.025, eta=1.1, causal=causal)
+                fn = lambda: ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=a.gamma, eta=a.eta, causal=causal)
                 med, best = time_fn(fn)
                 flops = 4.0 * B * H * T * T * 64 if not causal else 2.0 * B * H * T * (T + 1) * 64
-                r = dict(T=T, B=B, kind=kind, causal=causal, ms=med, ms_best=best, tflops=flops / med / 1e9,
+                r = dict(T=T, B=B, kind=kind, causal=causal, gamma=a.gamma, qscale=a.qscale, ms=med, ms_best=best, tflops=flops / med / 1e9,
                          tflops_best=flops / best / 1e9)
                 res["attn"].append(r)
                 print(json.dumps(r), flush=True)
