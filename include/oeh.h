@@ -247,6 +247,23 @@ int oeh_ce_loss(const void* logits, int64_t rows, int64_t vocab, int64_t row_str
                 const int64_t* labels, int64_t ignore_index, float* out_loss, float* out_count, void* workspace,
                 size_t workspace_bytes, oeh_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Residual add + LayerNorm in one pass, optionally with the two fake-quant taps of the INT8 residual blocks
+ * (SURVEY 8f rank 2):   y = [qdq_out] LayerNorm( [qdq_res] (a + b) )
+ *   FP   (qparams_* NULL): BertSelfOutput / BertOutput.forward, the HF modules wrapped at
+ *                          transformers_language/models/quantized_bert.py:540-605.
+ *   INT8 (fixed ranges)  : QuantizedBertSelfOutput / QuantizedBertOutput.forward (quantized_bert.py:566-568, :602-604):
+ *                          res_act_quantizer on the sum, then QuantLayerNorm (quantization/autoquant_utils.py:62-70)
+ *                          with its output tap.
+ * a, b (b may be NULL: plain LayerNorm), y: (rows, cols) contiguous of `dtype`; weight / bias (bias may be NULL): (cols)
+ * of the same dtype.  The sum is rounded once to the tensor dtype (ATen add), statistics / affine map in fp32 (biased
+ * variance, rsqrt(var + eps)), one rounding of y; taps exactly as oeh_fake_quant_asym.  cols must be a multiple of
+ * 16/sizeof(dtype) and at most 256 such vectors (2048 fp16 / 1024 fp32 columns); all pointers 16-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+int oeh_add_layer_norm(const void* a, const void* b, const void* weight, const void* bias, void* y, int64_t rows,
+                       int64_t cols, double eps, int32_t dtype, const float* qparams_res, const float* qparams_out,
+                       int32_t n_bits, oeh_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@
 #include "attn_common.cuh"
 #include "attn_fwd_one.cuh"
 #include "attn_fwd_ws.cuh"
+#include "attn_fwd_ws2.cuh"
 
 namespace oeh {
 namespace {
@@ -366,9 +367,15 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
   // lower latency.  OEH_ATTN_KERNEL=tile|ws overrides (tests exercise both on the same shapes).
   // When all keys fit one K/V tile (Tk <= 128, the BERT eval shape) the small one-tile kernel (4 CTAs / SM) runs.
   bool use_ws = a->Tq > BM, use_one = a->Tk <= BN;
+#ifdef OEH_DEFAULT_WS2
+  bool use_ws2 = true;        // which warp-specialised kernel serves the long sequences (parity streams / column halves)
+#else
+  bool use_ws2 = false;
+#endif
   if (const char* f = getenv("OEH_ATTN_KERNEL")) {
     if (!strcmp(f, "tile")) use_ws = use_one = false;
-    if (!strcmp(f, "ws")) { use_ws = true; use_one = false; }
+    if (!strcmp(f, "ws")) { use_ws = true; use_one = false; use_ws2 = false; }
+    if (!strcmp(f, "ws2")) { use_ws = true; use_one = false; use_ws2 = true; }
   }
   if (use_one) use_ws = false;
   const int kv_box = use_ws ? attn_ws::BNW : BN;
@@ -421,6 +428,20 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
       attr_done[kw] = true;
     }
     dim3 grid((unsigned)((a->Tq + attn_ws::kQRows - 1) / attn_ws::kQRows), (unsigned)a->H, (unsigned)a->B);
+    if (use_ws2) {
+      static const KernelFn kernels2[8] = {
+          attn_ws2::attn_fwd_ws2_kernel<false, false, false>, attn_ws2::attn_fwd_ws2_kernel<false, true, false>,
+          attn_ws2::attn_fwd_ws2_kernel<true, false, false>,  attn_ws2::attn_fwd_ws2_kernel<true, true, false>,
+          attn_ws2::attn_fwd_ws2_kernel<false, false, true>,  attn_ws2::attn_fwd_ws2_kernel<false, true, true>,
+          attn_ws2::attn_fwd_ws2_kernel<true, false, true>,   attn_ws2::attn_fwd_ws2_kernel<true, true, true>};
+      static bool attr_done2[8] = {false, false, false, false, false, false, false, false};
+      if (!attr_done2[kw]) {
+        OEH_CUDA_OK(cudaFuncSetAttribute(kernels2[kw], cudaFuncAttributeMaxDynamicSharedMemorySize, attn_ws2::kSmemBytes));
+        attr_done2[kw] = true;
+      }
+      kernels2[kw]<<<grid, attn_ws2::kThreads, attn_ws2::kSmemBytes, st>>>(tmq, tmk, tmv, p);
+      return check_launch("attn_fwd_ws2_kernel");
+    }
     kernels[kw]<<<grid, attn_ws::kThreads, attn_ws::kSmemBytes, st>>>(tmq, tmk, tmv, p);
     return check_launch("attn_fwd_ws_kernel");
   }

@@ -1,0 +1,409 @@
+// Warp-specialised fused attention forward for sm_100a, "parity streams" (the long-sequence kernel, Tq > 128).
+//
+// One CTA per SM works on TWO 128-row Q tiles of one (batch, head) and walks the keys in 64-wide steps.  Each Q tile
+// has two S buffers in TMEM (step parity) and each (tile, parity) pair is owned by ONE softmax stream of four warps:
+//
+//   warps 0-15  softmax: stream = warp >> 2 = 2*tile + parity; thread == query row == TMEM lane; the stream takes
+//               every other step of its tile (64 keys) and keeps its OWN running max m_b, row sum l_b and accumulator
+//               O_{t,b} += P(i) . V(i)  (i = b mod 2) -- a split of the key range by step parity, merged once in the
+//               epilogue:  ctx = (O_0 2^(m_0-m) + O_1 2^(m_1-m)) / (l_0 2^(m_0-m) + l_1 2^(m_1-m) [+ 2^-m]).
+//   warp  16    MMA issuer of Q tile 0 (one elected lane issues its tcgen05.mma / tcgen05.commit)
+//   warp  17    TMA producer (one elected lane; Q once, K / V steps through kStages-deep rings)
+//   warp  18    MMA issuer of Q tile 1
+//   warp  19    idle (warps 16-19 give their registers to the softmax warps with setmaxnreg)
+//
+//   TMEM (512 columns):  S_t[b] at (2t+b)*64 (its packed P over the first 32 of them)     O_{t,b} at 256 + (2t+b)*64
+//
+// Why parity streams (vs. attn_fwd_ws.cuh, where the two streams of a tile split every step in column halves): at
+// d = 64 the loop is bound by the exp2 (MUFU/XU) pipe, and what keeps the XU below its rate is not issue slots but
+// the fixed cost around every step (barrier wait, tcgen05.ld latency, wait::st, fence, arrive, issuer wake-up).
+// A parity stream pays that once per 64 keys instead of once per 32, its two streams are half a period out of
+// phase by construction (the halves of the other kernel run in lockstep: same barrier, same phase), and because
+// S_t(i) is committed behind PV_t(i-2) in the issuer's in-order MMA stream, owning S_t(i) implies O_{t,b} is
+// quiescent: the O rescale needs no barrier of its own.
+//
+//   mbarriers:  q_full | k_full/k_empty[kStages] | v_full/v_empty[kStages]   (TMA <-> MMA; *_empty take one
+//                                                                              tcgen05.commit from EACH issuer)
+//               s_full[t][b]  (MMA -> softmax: S_t of a step with parity b is complete, and so is PV_t(i-2))
+//               p_full[t][b]  (softmax -> MMA, 4 arrivals = one elected lane per warp of the stream: P is in TMEM /
+//                              S_t has been consumed)
+//               o_final[t]    (MMA -> softmax: the last PV_t has completed -> epilogue)
+//   MMA issue order of issuer t per step i:  [p_full_t(i)] PV_t(i) QK_t(i+2)
+//
+// Lazy rescale, softmax_1's +1 term, the two-pass normalised modes and the sparse skip are as in attn_fwd_ws.cuh.
+#pragma once
+
+#include "attn_fwd_ws.cuh"   // trace macros, reg_alloc / reg_dealloc
+
+namespace oeh {
+namespace attn_ws2 {
+
+using namespace attn;
+
+constexpr int BNW = 64;                                            // keys per step
+constexpr int kSubBytes = BNW * HD * 2;                            // 8 KB
+constexpr int kStages = 8;
+constexpr int kThreads = 640;                                      // 20 warps
+constexpr int kQRows = 256;                                        // query rows per CTA (two tiles)
+constexpr int kSmemBytes = 2 * kTileBytes + 2 * kStages * kSubBytes + 1024;   // Q0 Q1 | K ring | V ring
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColO0 = 256;                                   // S_t[b] at (2t+b)*64, O_{t,b} at 256 + (2t+b)*64
+constexpr float kLazyRescale = 8.f;                                // log2 units
+constexpr int kSoftmaxRegs = 112, kAuxRegs = 24;                   // 16*32*112 + 4*32*24 <= 640 * 96
+
+struct Barriers {
+  uint64_t q_full;
+  uint64_t k_full[kStages], k_empty[kStages];
+  uint64_t v_full[kStages], v_empty[kStages];
+  uint64_t s_full[2][2], p_full[2][2];
+  uint64_t o_final[2];
+};
+
+template <bool kBF16, bool kGeneric, bool kNorm>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_fwd_ws2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
+                    const __grid_constant__ CUtensorMap tmv, const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) Barriers bars;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float xch_m[2][2][128], xch_l[2][2][128];            // (tile, parity, row): statistics merged across streams
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // causal: heaviest Q tiles of a head first, so the last CTAs of the grid are the short ones
+  const int qt = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int q0 = qt * kQRows, h = blockIdx.y, b = blockIdx.z;
+
+  const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem0;                                    // 2 tiles of 128 rows
+  const uint32_t sK = smem0 + 2 * kTileBytes;                   // kStages steps of 64 keys
+  const uint32_t sV = sK + kStages * kSubBytes;
+
+  if (tid == 0) {
+    ptx::mbar_init(ptx::smem_u32(&bars.q_full), 1);
+#pragma unroll
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&bars.k_full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars.k_empty[i]), 2);       // one tcgen05.commit from each MMA issuer
+      ptx::mbar_init(ptx::smem_u32(&bars.v_full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars.v_empty[i]), 2);
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+#pragma unroll
+      for (int sb = 0; sb < 2; ++sb) {
+        ptx::mbar_init(ptx::smem_u32(&bars.s_full[t][sb]), 1);
+        ptx::mbar_init(ptx::smem_u32(&bars.p_full[t][sb]), 4);  // one elected lane of each of the stream's 4 warps
+      }
+      ptx::mbar_init(ptx::smem_u32(&bars.o_final[t]), 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 16) ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(&tmem_base_slot));
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+
+  // ---- step plan (shared by all roles) ---------------------------------------------------------------------------
+  int n_kv = (p.Tk + BNW - 1) / BNW;
+  if (p.causal) {
+    const int last_row = min(q0 + kQRows, p.Tq) - 1;            // last real query row of this CTA
+    const int lim = (last_row + (p.Tk - p.Tq)) / BNW + 1;
+    n_kv = lim < n_kv ? lim : n_kv;
+  }
+  const bool softmax1 = (p.kind == OEH_SOFTMAX_1 || p.kind == OEH_SOFTMAX_CLIPPED1);
+  const bool clipped = p.kind >= OEH_SOFTMAX_CLIPPED;
+  constexpr bool normalized = kNorm;                              // host: clipped || qdq_probs
+  const int nA = normalized ? n_kv : 0;                          // stats-pass steps (QK^T only)
+  const int n_iter = nA + n_kv;
+
+  if (warp >= 16) attn_ws::reg_dealloc<kAuxRegs>();
+  if (warp == 17) {
+    // ================================ TMA producer (whole warp waits, one elected lane issues) ============
+    if (ptx::elect_one()) {
+      ptx::prefetch_tmap(&tmq);
+      ptx::prefetch_tmap(&tmk);
+      ptx::prefetch_tmap(&tmv);
+      const uint32_t bq = ptx::smem_u32(&bars.q_full);
+      ptx::mbar_expect_tx(bq, 2 * kTileBytes);
+      tma_tile(sQ, &tmq, bq, p.cq, q0, h, b);
+      tma_tile(sQ + kTileBytes, &tmq, bq, p.cq, q0 + 128, h, b);
+    }
+    __syncwarp();
+    auto load_k = [&](int i) {                                  // K of step i -> ring slot i % kStages
+      const int s = i % kStages, n = i / kStages;
+      if (n > 0) ptx::mbar_wait(ptx::smem_u32(&bars.k_empty[s]), (uint32_t)(n - 1) & 1u);
+      if (ptx::elect_one()) {
+        const uint32_t bf = ptx::smem_u32(&bars.k_full[s]);
+        ptx::mbar_expect_tx(bf, kSubBytes);
+        tma_tile(sK + s * kSubBytes, &tmk, bf, p.ck, (i < nA ? i : i - nA) * BNW, h, b);
+      }
+      __syncwarp();
+    };
+    load_k(0);
+    if (n_iter > 1) load_k(1);
+    for (int i = 0; i < n_iter; ++i) {                          // K runs two steps ahead of V, like the MMA issuers
+      if (i + 2 < n_iter) load_k(i + 2);
+      if (i >= nA) {
+        const int v = i - nA, s = v % kStages, n = v / kStages;
+        if (n > 0) ptx::mbar_wait(ptx::smem_u32(&bars.v_empty[s]), (uint32_t)(n - 1) & 1u);
+        if (ptx::elect_one()) {
+          const uint32_t bf = ptx::smem_u32(&bars.v_full[s]);
+          ptx::mbar_expect_tx(bf, kSubBytes);
+          tma_tile(sV + s * kSubBytes, &tmv, bf, p.cv, v * BNW, h, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 16 || warp == 18) {
+    // ================================ MMA issuers: warp 16 serves Q tile 0, warp 18 Q tile 1 ===============
+    const int t = (warp - 16) >> 1;
+    constexpr uint32_t kIdescQK = ptx::make_idesc_f16(kBF16, 128, BNW, false, false);
+    constexpr uint32_t kIdescPV = ptx::make_idesc_f16(kBF16, 128, HD, false, true);
+    constexpr uint64_t kTileUnits = kTileBytes >> 4;             // descriptor address units (16 B)
+    constexpr uint64_t kSubUnits = kSubBytes >> 4;
+    const uint64_t dq = ptx::make_smem_desc_sw128(sQ, 16, 1024) + t * kTileUnits;
+    const uint64_t dk = ptx::make_smem_desc_sw128(sK, 16, 1024);
+    const uint64_t dv = ptx::make_smem_desc_sw128(sV, 1024, 1024);
+    const uint32_t tS0 = tmem + (uint32_t)(2 * t) * 64u, tO0 = tmem + kColO0 + (uint32_t)(2 * t) * 64u;
+    auto issue_qk = [&](int sb, int stage) {                     // S_t[sb] = Q_t . K(stage)^T    (128 x 64, K = 64)
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k)
+        ptx::mma_ss(tS0 + sb * 64, dq + k * 2, dk + stage * kSubUnits + k * 2, kIdescQK, k > 0);
+    };
+    auto issue_pv = [&](int sb, int stage, bool first) {         // O_{t,sb} (+)= P_t[sb] . V(stage)  (K = 64 keys)
+#pragma unroll
+      for (int k = 0; k < BNW / 16; ++k)
+        ptx::mma_ts(tO0 + sb * 64, tS0 + sb * 64 + k * 8, dv + stage * kSubUnits + k * 128, kIdescPV,
+                    (first && k == 0) ? 0u : 1u);
+    };
+    ptx::mbar_wait(ptx::smem_u32(&bars.q_full), 0);
+    OEH_T_DECL;
+    for (int i = 0; i < 2 && i < n_iter; ++i) {                  // prologue: S_t(0), S_t(1)
+      ptx::mbar_wait(ptx::smem_u32(&bars.k_full[i % kStages]), 0);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        issue_qk(i, i % kStages);
+        ptx::mma_commit(ptx::smem_u32(&bars.s_full[t][i]));
+        ptx::mma_commit(ptx::smem_u32(&bars.k_empty[i % kStages]));
+      }
+      __syncwarp();
+    }
+    for (int i = 0; i < n_iter; ++i) {
+      const int sb = i & 1;
+      const bool pv = i >= nA;
+      const int v = i - nA, vs = pv ? v % kStages : 0;
+      const bool more = i + 2 < n_iter;
+      const bool last = i + 1 == n_iter;
+      const int ks = (i + 2) % kStages;
+      OEH_T(0);
+      if (pv) ptx::mbar_wait(ptx::smem_u32(&bars.v_full[vs]), (uint32_t)(v / kStages) & 1u);
+      if (more) ptx::mbar_wait(ptx::smem_u32(&bars.k_full[ks]), (uint32_t)((i + 2) / kStages) & 1u);
+      OEH_T(1);
+      ptx::mbar_wait(ptx::smem_u32(&bars.p_full[t][sb]), (uint32_t)(i >> 1) & 1u);
+      ptx::tc_fence_after();
+      OEH_T(2);
+      if (ptx::elect_one()) {
+        if (pv) {
+          issue_pv(sb, vs, v < 2);                               // the first PV step of each parity starts its accumulator
+          if (last) ptx::mma_commit(ptx::smem_u32(&bars.o_final[t]));
+          ptx::mma_commit(ptx::smem_u32(&bars.v_empty[vs]));
+        }
+        if (more) {
+          issue_qk(sb, ks);
+          ptx::mma_commit(ptx::smem_u32(&bars.s_full[t][sb]));
+          ptx::mma_commit(ptx::smem_u32(&bars.k_empty[ks]));
+        }
+      }
+      __syncwarp();
+      OEH_T(3);
+    }
+    OEH_T_PRINT("issuer: loop kv_full p_full issue", n_iter);
+  } else if (warp < 16) {
+    // ================================ softmax streams ======================================================
+    attn_ws::reg_alloc<kSoftmaxRegs>();
+    const int t = warp >> 3, par = (warp >> 2) & 1;               // Q tile, step parity
+    const int r = (warp & 3) * 32 + (tid & 31);                   // row within the tile == TMEM lane
+    const int row = q0 + t * 128 + r;                             // this thread's query row
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t tS = t_lane + (uint32_t)(2 * t + par) * 64u;              // this stream's S / P columns
+    const uint32_t tO = t_lane + kColO0 + (uint32_t)(2 * t + par) * 64u;     // this stream's accumulator
+    const uint32_t bar_s = ptx::smem_u32(&bars.s_full[t][par]), bar_p = ptx::smem_u32(&bars.p_full[t][par]);
+
+    const bool has_qs = kGeneric && p.qdq_scores != nullptr;
+    const bool has_qp = kGeneric && p.qdq_probs != nullptr;
+    const bool has_mask = kGeneric && p.mask != nullptr;
+    Qdq qd_s{1.f, 1.f, 0.f, p.int_max}, qd_p{1.f, 1.f, 0.f, p.int_max};
+    if (has_qs) qd_s = load_qdq(p.qdq_scores, p.int_max);
+    if (has_qp) qd_p = load_qdq(p.qdq_probs, p.int_max);
+    const int64_t mask_row =
+        p.mask ? ((int64_t)b * p.ms0 + (int64_t)h * p.ms1 + (int64_t)(row < p.Tq ? row : 0) * p.ms2) : 0;
+    const int causal_lim = p.causal ? row + (p.Tk - p.Tq) : 0x7fffffff;
+
+    float m_run = -INFINITY, l_run = 0.f, inv_den = 1.f, skip_thr = -INFINITY;
+    bool merged = false, started = false;                         // statistics merged / accumulator holds a PV result
+    OEH_T_DECL;
+
+    // merge (m_b, l_b) of the two streams of a row: afterwards both hold the row's m in the common frame
+    auto merge_streams = [&](float& a_own, float& a_other, float& l_other) {
+      xch_m[t][par][r] = m_run;
+      xch_l[t][par][r] = l_run;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+      const float m_o = xch_m[t][par ^ 1][r];
+      l_other = xch_l[t][par ^ 1][r];
+      const float m = fmaxf(m_run, m_o);
+      const float m_safe = m == -INFINITY ? 0.f : m;
+      a_own = ptx::ex2(m_run - m_safe);                           // -inf -> 0
+      a_other = ptx::ex2(m_o - m_safe);
+      m_run = m;
+    };
+
+    for (int i = par; i < n_iter; i += 2) {
+      const bool pv_iter = i >= nA;
+      const int k0 = (pv_iter ? i - nA : i) * BNW;
+      if (normalized && pv_iter && !merged) {                     // stats pass done: the row statistics become common
+        float a_own, a_other, l_other;
+        merge_streams(a_own, a_other, l_other);
+        l_run = l_run * a_own + l_other * a_other;
+        merged = true;
+      }
+      OEH_T(0);
+      ptx::mbar_wait(bar_s, (uint32_t)(i >> 1) & 1u);
+      ptx::tc_fence_after();
+      OEH_T(1);
+      float s[BNW];
+      ptx::tmem_ld32(tS, reinterpret_cast<uint32_t*>(s));
+      ptx::tmem_ld32(tS + 32, reinterpret_cast<uint32_t*>(s) + 32);
+      ptx::tmem_wait_ld();
+      OEH_T(2);
+      if (!pv_iter) {                                             // stats pass: S is consumed, QK^T(i+2) may start
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (ptx::elect_one()) ptx::mbar_arrive(bar_p);
+      }
+      if (kGeneric && p.dbg_s && i < 2 && row < p.Tq) {           // raw S of keys [0,128)
+        float* d = p.dbg_s + (((int64_t)b * p.H + h) * p.Tq + row) * BN + k0;
+#pragma unroll
+        for (int j = 0; j < BNW; ++j) d[j] = s[j];
+      }
+
+      const int valid = min(p.Tk - k0, BNW);
+      const int vis = min(valid - 1, causal_lim - k0);
+      const float mul = transform_scores<BNW, kGeneric>(s, p, qd_s, has_qs, has_mask, mask_row, k0, valid, vis);
+      const float tile_max = row_max<BNW>(s) * mul;
+      OEH_T(3);
+
+      if (!pv_iter) {
+        // stats pass: exact running (m, l) of this stream
+        const float m_new = fmaxf(m_run, tile_max);
+        const float m_safe = m_new == -INFINITY ? 0.f : m_new;
+        const float alpha = ptx::ex2(m_run - m_safe);
+        l_run = fmaf(l_run, alpha, exp2_and_sum<BNW>(s, mul, m_safe));
+        m_run = m_new;
+        continue;
+      }
+      if (normalized) {
+        // PV pass of the two-pass mode: (m, l) are final and common to both streams
+        const float m_safe = m_run == -INFINITY ? 0.f : m_run;
+        if (!started) {
+          const float den = softmax1 ? l_run + ptx::ex2(-m_safe) : l_run;
+          inv_den = __frcp_rn(den);
+          skip_thr = zero_prob_threshold(p, clipped, has_qp, qd_p, den);
+        }
+#ifndef OEH_NO_SPARSE_SKIP
+        // see attn_fwd_ws.cuh: none of this warp's 32 rows x 64 keys can survive the clip / the probs tap -> P = 0
+        if (!__any_sync(0xffffffffu, tile_max - m_safe > skip_thr)) {
+#pragma unroll
+          for (int j = 0; j < BNW; ++j) s[j] = 0.f;
+        } else
+#endif
+        {
+          exp2_only<BNW>(s, mul, m_safe);
+          normalize_probs<BNW, kGeneric>(s, p, inv_den, clipped, has_qp, qd_p);
+        }
+      } else {
+        // online softmax with lazy rescale
+        const bool move = tile_max > m_run + kLazyRescale || m_run == -INFINITY;
+        const float m_new = move ? tile_max : m_run;              // tile_max may be -inf only if m_run is too
+        const float m_safe = m_new == -INFINITY ? 0.f : m_new;
+        const float alpha = move ? ptx::ex2(m_run - m_safe) : 1.f;
+        l_run = fmaf(l_run, alpha, exp2_and_sum<BNW>(s, mul, m_safe));
+        m_run = m_new;
+        if (started && !__all_sync(0xffffffffu, alpha == 1.f)) {
+          // O_{t,par} *= alpha.  No barrier: S_t(i) was committed behind PV_t(i-2) -- the last MMA that wrote this
+          // accumulator -- in the issuer's in-order stream, and PV_t(i) needs the P this thread has not written yet.
+#pragma unroll
+          for (int c = 0; c < HD / 16; ++c) {
+            uint32_t o[16];
+            ptx::tmem_ld16(tO + c * 16, o);
+            ptx::tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+            ptx::tmem_st16(tO + c * 16, o);
+          }
+        }
+      }
+      started = true;
+      OEH_T(4);
+
+      // P -> TMEM (packed 16-bit pairs) over the first 32 columns of the S buffer this thread has consumed
+      {
+        uint32_t pk[BNW / 2];
+#pragma unroll
+        for (int j = 0; j < BNW / 2; ++j) pk[j] = pack2<kBF16>(s[2 * j], s[2 * j + 1]);
+        ptx::tmem_st32(tS, pk);
+      }
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (ptx::elect_one()) ptx::mbar_arrive(bar_p);
+      OEH_T(5);
+    }
+    OEH_T_PRINT("softmax: top s_full ld max exp pack+arrive", n_iter);
+
+    // ---- epilogue: merge the streams, O / denominator -> gate / taps -> global -----------------------------------
+    float a_own = 1.f, a_other = 1.f, omul = 1.f;                 // scales of the two accumulators; 1/denominator
+    if (!normalized) {
+      float l_other;
+      merge_streams(a_own, a_other, l_other);
+      const float m_safe = m_run == -INFINITY ? 0.f : m_run;
+      float den = l_run * a_own + l_other * a_other;
+      if (softmax1) den += ptx::ex2(-m_safe);
+      omul = __frcp_rn(den);
+    } else if (!merged) {                                         // a stream without PV steps still owes the barrier
+      float l_other;
+      merge_streams(a_own, a_other, l_other);
+      a_own = a_other = 1.f;
+    }
+    // an accumulator exists iff some PV step had its parity (only n_kv == 1 leaves one of them untouched)
+    const bool has0 = n_kv > 1 || (nA & 1) == 0, has1 = n_kv > 1 || (nA & 1) == 1;
+    const float a0 = par ? a_other : a_own, a1 = par ? a_own : a_other;
+    ptx::mbar_wait(ptx::smem_u32(&bars.o_final[t]), 0);
+    ptx::tc_fence_after();
+    // this thread finishes head-dim columns [32par, 32par+32) of its row from both accumulators
+    float o[32];
+    {
+      uint32_t u0[32], u1[32];
+      const uint32_t tOt = t_lane + kColO0 + (uint32_t)(2 * t) * 64u + par * 32u;
+      ptx::tmem_ld32(tOt, u0);
+      ptx::tmem_ld32(tOt + 64, u1);
+      ptx::tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        o[j] = (has0 ? __uint_as_float(u0[j]) * a0 : 0.f) + (has1 ? __uint_as_float(u1[j]) * a1 : 0.f);
+    }
+    if (row < p.Tq) store_row<kBF16, kGeneric, 32>(o, p, omul, b, h, row, par * 32);
+  }
+
+  // ---- teardown ------------------------------------------------------------------------------------------------
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    __syncwarp();
+    ptx::tmem_dealloc<kTmemCols>(tmem);
+  }
+}
+
+}  // namespace attn_ws2
+}  // namespace oeh

@@ -1,0 +1,153 @@
+// Residual add + LayerNorm in one pass, with the optional fake-quant taps of the INT8 path fused in:
+//   FP  :  y = LayerNorm(a + b)                      BertSelfOutput / BertOutput.forward (HF shell of the eval step; the
+//                                                    module the reference wraps at quantized_bert.py:540-605)
+//   INT8:  y = qdq_out(LayerNorm(qdq_res(a + b)))    QuantizedBertSelfOutput / QuantizedBertOutput.forward with fixed
+//                                                    ranges (quantized_bert.py:566-568, :602-604): res_act_quantizer on
+//                                                    the sum, QuantLayerNorm's output tap (autoquant_utils.py:62-70)
+// ATen needs add (3 passes) + LayerNorm (2 passes) [+ 2 x ~11 passes of qdq elementwise ops]; here every element of a, b
+// is read once and y written once: bytes = rows*cols*3*size (2*size without b).  HBM-bound.
+// One warp per row, the row lives in registers (<= 8 x 16 B per lane): exact two-pass mean / variance in fp32.
+// Arithmetic mirrors ATen: sum rounded once to the tensor dtype (add kernel), statistics and the affine map in fp32,
+// y = gamma * (rstd * (x - mean)) + beta rounded once to the tensor dtype (vectorized_layer_norm_kernel); taps as in
+// quant.cu (every op rounded to the tensor dtype).
+#include "oeh_common.cuh"
+
+namespace oeh {
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+template <typename T, int kVecs>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ gamma,
+                      const T* __restrict__ beta, T* __restrict__ y, int64_t rows, int cols, float eps,
+                      const float* __restrict__ q_res, const float* __restrict__ q_out, float int_max) {
+  using V = Vec16<T>;
+  constexpr int N = V::N;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = cols / N;
+  const V* av = reinterpret_cast<const V*>(a + row * cols);
+  const V* bv = b ? reinterpret_cast<const V*>(b + row * cols) : nullptr;
+
+  float rs = 1.f, rz = 0.f, os = 1.f, oz = 0.f;
+  if (q_res) { rs = DT<T>::rnd(__ldg(q_res)); rz = DT<T>::rnd(__ldg(q_res + 1)); }
+  if (q_out) { os = DT<T>::rnd(__ldg(q_out)); oz = DT<T>::rnd(__ldg(q_out + 1)); }
+
+  float x[kVecs][N];
+  V va[kVecs], vb[kVecs];
+#pragma unroll
+  for (int v = 0; v < kVecs; ++v) {                        // all loads of the row in flight before the first use
+    const int i = lane + 32 * v;
+    if (i < nvec) {
+      int4 raw = __ldcs(reinterpret_cast<const int4*>(av + i));
+      va[v] = *reinterpret_cast<V*>(&raw);
+      if (bv) {
+        raw = __ldcs(reinterpret_cast<const int4*>(bv + i));
+        vb[v] = *reinterpret_cast<V*>(&raw);
+      }
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int v = 0; v < kVecs; ++v) {
+    const int i = lane + 32 * v;
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+      float s = 0.f;
+      if (i < nvec) {
+        s = DT<T>::to_f(va[v].v[e]);
+        if (bv) s = DT<T>::rnd(__fadd_rn(s, DT<T>::to_f(vb[v].v[e])));
+        if (q_res) s = qdq_one<T>(s, rs, rz, int_max, false);
+      }
+      x[v][e] = s;
+      sum += s;
+    }
+  }
+  const float mean = warp_sum(sum) / (float)cols;
+  float ssq = 0.f;
+#pragma unroll
+  for (int v = 0; v < kVecs; ++v) {
+    if (lane + 32 * v < nvec) {
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        const float d = x[v][e] - mean;
+        ssq = fmaf(d, d, ssq);
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ssq) / (float)cols + eps);
+
+  const V* gv = reinterpret_cast<const V*>(gamma);
+  const V* bev = reinterpret_cast<const V*>(beta);
+  V* yv = reinterpret_cast<V*>(y + row * cols);
+#pragma unroll
+  for (int v = 0; v < kVecs; ++v) {
+    const int i = lane + 32 * v;
+    if (i < nvec) {
+      const V g = gv[i];
+      V be, out;
+      if (beta) be = bev[i];
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        float r = DT<T>::to_f(g.v[e]) * (rstd * (x[v][e] - mean));
+        if (beta) r += DT<T>::to_f(be.v[e]);
+        r = DT<T>::rnd(r);
+        if (q_out) r = qdq_one<T>(r, os, oz, int_max, false);
+        out.v[e] = DT<T>::from_f(r);
+      }
+      __stcs(reinterpret_cast<int4*>(yv + i), *reinterpret_cast<const int4*>(&out));
+    }
+  }
+}
+
+template <typename T>
+int launch(const void* a, const void* b, const void* gamma, const void* beta, void* y, int64_t rows, int64_t cols, float eps,
+           const float* q_res, const float* q_out, int n_bits, cudaStream_t st) {
+  constexpr int N = Vec16<T>::N;
+  if (cols % N != 0 || cols / N > 32 * 8)
+    return set_error(OEH_ERR_UNSUPPORTED, "oeh_add_layer_norm: cols=%lld must be a multiple of %d and at most %d",
+                     (long long)cols, N, 32 * 8 * N);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(gamma) |
+                       reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(y);
+  if (al & 15) return set_error(OEH_ERR_UNSUPPORTED, "oeh_add_layer_norm: pointers must be 16-byte aligned");
+  const int kv = (int)((cols / N + 31) / 32);
+  const float int_max = (float)((1 << n_bits) - 1);
+  const unsigned grid = (unsigned)((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+#define OEH_LN_CASE(K)                                                                                               \
+  case K:                                                                                                            \
+    add_layer_norm_kernel<T, K><<<grid, kWarpsPerBlock * 32, 0, st>>>((const T*)a, (const T*)b, (const T*)gamma,     \
+                                                                     (const T*)beta, (T*)y, rows, (int)cols, eps,   \
+                                                                     q_res, q_out, int_max);                        \
+    break;
+  switch (kv) {
+    OEH_LN_CASE(1) OEH_LN_CASE(2) OEH_LN_CASE(3) OEH_LN_CASE(4) OEH_LN_CASE(5) OEH_LN_CASE(6) OEH_LN_CASE(7) OEH_LN_CASE(8)
+  }
+#undef OEH_LN_CASE
+  return check_launch("add_layer_norm_kernel");
+}
+
+}  // namespace
+}  // namespace oeh
+
+using namespace oeh;
+
+extern "C" int oeh_add_layer_norm(const void* a, const void* b, const void* weight, const void* bias, void* y, int64_t rows,
+                                  int64_t cols, double eps, int32_t dtype, const float* qparams_res,
+                                  const float* qparams_out, int32_t n_bits, oeh_stream_t stream) {
+  OEH_CHECK_ARG(rows >= 0 && cols > 0, "oeh_add_layer_norm: bad shape (%lld, %lld)", (long long)rows, (long long)cols);
+  if (rows == 0) return OEH_OK;
+  OEH_CHECK_ARG(a && weight && y, "oeh_add_layer_norm: null pointer");
+  OEH_CHECK_ARG(rows <= 0x7fffffffLL * 8, "oeh_add_layer_norm: too many rows");
+  if (qparams_res || qparams_out) OEH_CHECK_ARG(n_bits >= 1 && n_bits <= 16, "oeh_add_layer_norm: n_bits=%d outside [1,16]", n_bits);
+  if (!(qparams_res || qparams_out)) n_bits = 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case OEH_F32: return launch<float>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_res, qparams_out, n_bits, st);
+    case OEH_F16: return launch<__half>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_res, qparams_out, n_bits, st);
+    case OEH_BF16:
+      return launch<__nv_bfloat16>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_res, qparams_out, n_bits, st);
+  }
+  return set_error(OEH_ERR_BAD_ARG, "oeh_add_layer_norm: unknown dtype %d", dtype);
+}

@@ -88,6 +88,22 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// AsymmetricUniformQuantizer.forward / to_integer_forward for ONE element (uniform_quantizers.py:92-148), shared by the
+// standalone quantizer (quant.cu) and the fused taps (quant.cu add+qdq, layernorm.cu).
+template <typename T>
+__device__ __forceinline__ float qdq_one(float x, float scale, float zp, float int_max, bool codes) {
+  // For T=float DT::rnd is the identity and this is exactly the reference's fp32 chain.
+  // For 16-bit T every intermediate is rounded to T, as ATen does per elementwise op.
+  using D = DT<T>;
+  float q = D::rnd(__fdiv_rn(x, scale));             // x_float / scale
+  float r = rintf(q);                                // round_ste_func (half-to-even)
+  float xi = D::rnd(__fadd_rn(r, zp));               // + zero_point
+  xi = xi < 0.f ? 0.f : (xi > int_max ? int_max : xi);   // clamp keeps NaN like torch.clamp
+  if (codes) return xi;
+  float diff = D::rnd(__fsub_rn(xi, zp));            // x_int - zero_point
+  return D::rnd(__fmul_rn(scale, diff));             // scale * (...)
+}
+
 // AsymmetricUniformQuantizer.set_quant_range + scale/zero_point (uniform_quantizers.py:72-82,
 // 199-200, 218-219) with the reference's fp32 op order.  Usable on host and device.
 __host__ __device__ inline void set_quant_range_f32(float x_min, float x_max, int n_bits, float eps, float* delta,

@@ -30,20 +30,6 @@ __device__ __forceinline__ void st_stream(V* p, const V& v) {
 }
 
 template <typename T>
-__device__ __forceinline__ float qdq_one(float x, float scale, float zp, float int_max, bool codes) {
-  // For T=float DT::rnd is the identity and this is exactly the reference's fp32 chain.
-  // For 16-bit T every intermediate is rounded to T, as ATen does per elementwise op.
-  using D = DT<T>;
-  float q = D::rnd(__fdiv_rn(x, scale));             // x_float / scale
-  float r = rintf(q);                                // round_ste_func (half-to-even)
-  float xi = D::rnd(__fadd_rn(r, zp));               // + zero_point
-  xi = xi < 0.f ? 0.f : (xi > int_max ? int_max : xi);   // clamp keeps NaN like torch.clamp
-  if (codes) return xi;
-  float diff = D::rnd(__fsub_rn(xi, zp));            // x_int - zero_point
-  return D::rnd(__fmul_rn(scale, diff));             // scale * (...)
-}
-
-template <typename T>
 __global__ void __launch_bounds__(kThreads) fake_quant_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n,
                                                               const float* __restrict__ qparams, float int_max,
                                                               int codes) {

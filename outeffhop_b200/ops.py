@@ -354,3 +354,28 @@ def ce_loss(logits: torch.Tensor, labels: torch.Tensor, vocab: Optional[int] = N
     L.check(lib.oeh_ce_loss(logits.data_ptr(), rows, vocab, logits.stride(0), _dtype_code(logits), lab.data_ptr(),
                             int(ignore_index), out.data_ptr(), None, ws_ptr, ws_bytes, _stream()))
     return (out, ws) if return_row_losses else out
+
+
+def add_layer_norm(a: torch.Tensor, b: Optional[torch.Tensor], weight: torch.Tensor, bias: Optional[torch.Tensor],
+                   eps: float = 1e-12, qparams_res: Optional[torch.Tensor] = None,
+                   qparams_out: Optional[torch.Tensor] = None, n_bits: int = 8,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[qdq_out] LayerNorm([qdq_res](a + b)) over the last dimension in one pass (oeh_add_layer_norm).  ``b`` None =
+    plain LayerNorm; ``qparams_*`` = device [scale, zero_point] of fixed-range taps."""
+    _require_cuda(a, b, weight, bias, qparams_res, qparams_out)
+    if b is not None and (b.shape != a.shape or b.dtype != a.dtype):
+        raise ValueError("add_layer_norm: a and b must have the same shape and dtype")
+    cols = a.shape[-1]
+    if weight.shape != (cols,) or weight.dtype != a.dtype or (bias is not None and (bias.shape != (cols,) or bias.dtype != a.dtype)):
+        raise ValueError("add_layer_norm: weight / bias must be (cols,) tensors of the input dtype")
+    ac = a.contiguous()
+    bc = b.contiguous() if b is not None else None
+    wc = weight.contiguous()
+    bic = bias.contiguous() if bias is not None else None
+    y = out if out is not None else torch.empty_like(ac)
+    rows = ac.numel() // max(cols, 1)
+    L.check(L.lib().oeh_add_layer_norm(ac.data_ptr(), bc.data_ptr() if bc is not None else None, wc.data_ptr(),
+                                       bic.data_ptr() if bic is not None else None, y.data_ptr(), rows, cols, float(eps),
+                                       _dtype_code(ac), qparams_res.data_ptr() if qparams_res is not None else None,
+                                       qparams_out.data_ptr() if qparams_out is not None else None, int(n_bits), _stream()))
+    return y
