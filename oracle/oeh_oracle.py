@@ -462,3 +462,25 @@ def ce_loss_mean(logits: np.ndarray, labels: np.ndarray, ignore_index: int = -10
     with np.errstate(invalid="ignore", divide="ignore"):
         mean = rows[idx].sum() / np.float64(idx.size) if idx.size else np.float64(np.nan)
     return mean, rows
+
+
+def add_layer_norm(a: np.ndarray, b, weight: np.ndarray, bias, eps: float = 1e-12, q_res=None, q_out=None,
+                   n_bits: int = 8) -> np.ndarray:
+    """BertSelfOutput / BertOutput tail ``LayerNorm(hidden_states + input_tensor)`` (HF modeling_bert; wrapped by the
+    reference at quantized_bert.py:540-605) and, with the taps, QuantizedBertSelfOutput.forward (:566-568): fp32
+    restatement -- sum, optional res tap (delta, zero_float), biased-variance LayerNorm, optional output tap."""
+    x = np.asarray(a, dtype=F32)
+    if b is not None:
+        x = (x + np.asarray(b, dtype=F32)).astype(F32)
+    if q_res is not None:
+        x = asym_quantize(x, q_res[0], q_res[1], n_bits)
+    x64 = x.astype(np.float64)
+    mu = x64.mean(-1, keepdims=True)
+    var = x64.var(-1, keepdims=True)
+    y = ((x64 - mu) / np.sqrt(var + eps)) * np.asarray(weight, dtype=np.float64)
+    if bias is not None:
+        y = y + np.asarray(bias, dtype=np.float64)
+    y = y.astype(F32)
+    if q_out is not None:
+        y = asym_quantize(y, q_out[0], q_out[1], n_bits)
+    return y

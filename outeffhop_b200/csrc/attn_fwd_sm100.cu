@@ -24,6 +24,7 @@
 #include "attn_fwd_one.cuh"
 #include "attn_fwd_ws.cuh"
 #include "attn_fwd_ws2.cuh"
+#include "attn_fwd_ws3.cuh"
 
 namespace oeh {
 namespace {
@@ -367,15 +368,21 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
   // lower latency.  OEH_ATTN_KERNEL=tile|ws overrides (tests exercise both on the same shapes).
   // When all keys fit one K/V tile (Tk <= 128, the BERT eval shape) the small one-tile kernel (4 CTAs / SM) runs.
   bool use_ws = a->Tq > BM, use_one = a->Tk <= BN;
-#ifdef OEH_DEFAULT_WS2
-  bool use_ws2 = true;        // which warp-specialised kernel serves the long sequences (parity streams / column halves)
-#else
-  bool use_ws2 = false;
+  // which warp-specialised kernel serves the long sequences: 1 = column halves (attn_fwd_ws.cuh), 2 = parity streams
+  // with P in TMEM (attn_fwd_ws2.cuh), 3 = parity streams with P through smem (attn_fwd_ws3.cuh)
+#ifndef OEH_WS_ONEPASS
+#define OEH_WS_ONEPASS 2
 #endif
+#ifndef OEH_WS_TWOPASS
+#define OEH_WS_TWOPASS 1
+#endif
+  const bool norm_mode = a->kind >= OEH_SOFTMAX_CLIPPED || a->qdq_probs != nullptr;   // two-pass variants
+  int ws_ver = norm_mode ? OEH_WS_TWOPASS : OEH_WS_ONEPASS;
   if (const char* f = getenv("OEH_ATTN_KERNEL")) {
     if (!strcmp(f, "tile")) use_ws = use_one = false;
-    if (!strcmp(f, "ws")) { use_ws = true; use_one = false; use_ws2 = false; }
-    if (!strcmp(f, "ws2")) { use_ws = true; use_one = false; use_ws2 = true; }
+    if (!strcmp(f, "ws")) { use_ws = true; use_one = false; ws_ver = 1; }
+    if (!strcmp(f, "ws2")) { use_ws = true; use_one = false; ws_ver = 2; }
+    if (!strcmp(f, "ws3")) { use_ws = true; use_one = false; ws_ver = 3; }
   }
   if (use_one) use_ws = false;
   const int kv_box = use_ws ? attn_ws::BNW : BN;
@@ -415,7 +422,7 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
   const int ki = (a->dtype == OEH_BF16 ? 2 : 0) + (generic ? 1 : 0);
   if (use_ws) {
-    const bool norm = a->kind >= OEH_SOFTMAX_CLIPPED || a->qdq_probs != nullptr;   // two-pass variants
+    const bool norm = norm_mode;
     const int kw = ki + (norm ? 4 : 0);
     static const KernelFn kernels[8] = {
         attn_ws::attn_fwd_ws_kernel<false, false, false>, attn_ws::attn_fwd_ws_kernel<false, true, false>,
@@ -428,7 +435,7 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
       attr_done[kw] = true;
     }
     dim3 grid((unsigned)((a->Tq + attn_ws::kQRows - 1) / attn_ws::kQRows), (unsigned)a->H, (unsigned)a->B);
-    if (use_ws2) {
+    if (ws_ver == 2) {
       static const KernelFn kernels2[8] = {
           attn_ws2::attn_fwd_ws2_kernel<false, false, false>, attn_ws2::attn_fwd_ws2_kernel<false, true, false>,
           attn_ws2::attn_fwd_ws2_kernel<true, false, false>,  attn_ws2::attn_fwd_ws2_kernel<true, true, false>,
@@ -441,6 +448,20 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
       }
       kernels2[kw]<<<grid, attn_ws2::kThreads, attn_ws2::kSmemBytes, st>>>(tmq, tmk, tmv, p);
       return check_launch("attn_fwd_ws2_kernel");
+    }
+    if (ws_ver == 3) {
+      static const KernelFn kernels3[8] = {
+          attn_ws3::attn_fwd_ws3_kernel<false, false, false>, attn_ws3::attn_fwd_ws3_kernel<false, true, false>,
+          attn_ws3::attn_fwd_ws3_kernel<true, false, false>,  attn_ws3::attn_fwd_ws3_kernel<true, true, false>,
+          attn_ws3::attn_fwd_ws3_kernel<false, false, true>,  attn_ws3::attn_fwd_ws3_kernel<false, true, true>,
+          attn_ws3::attn_fwd_ws3_kernel<true, false, true>,   attn_ws3::attn_fwd_ws3_kernel<true, true, true>};
+      static bool attr_done3[8] = {false, false, false, false, false, false, false, false};
+      if (!attr_done3[kw]) {
+        OEH_CUDA_OK(cudaFuncSetAttribute(kernels3[kw], cudaFuncAttributeMaxDynamicSharedMemorySize, attn_ws3::kSmemBytes));
+        attr_done3[kw] = true;
+      }
+      kernels3[kw]<<<grid, attn_ws3::kThreads, attn_ws3::kSmemBytes, st>>>(tmq, tmk, tmv, p);
+      return check_launch("attn_fwd_ws3_kernel");
     }
     kernels[kw]<<<grid, attn_ws::kThreads, attn_ws::kSmemBytes, st>>>(tmq, tmk, tmv, p);
     return check_launch("attn_fwd_ws_kernel");

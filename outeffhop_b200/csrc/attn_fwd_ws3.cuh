@@ -1,51 +1,42 @@
-// Warp-specialised fused attention forward for sm_100a, "parity streams" (the long-sequence kernel, Tq > 128).
+// Warp-specialised fused attention forward for sm_100a, parity streams with P staged through SHARED memory
+// (the long-sequence kernel, Tq > 128).
 //
-// One CTA per SM works on TWO 128-row Q tiles of one (batch, head) and walks the keys in 64-wide steps.  Each Q tile
-// has two S buffers in TMEM (step parity) and each (tile, parity) pair is owned by ONE softmax stream of four warps:
+// Same decomposition as attn_fwd_ws2.cuh -- one CTA per SM, two 128-row Q tiles, 64-key steps, one softmax stream of
+// four warps per (tile, step parity) with its own (m, l, O) merged in the epilogue -- but P no longer aliases the S
+// buffer in TMEM.  In ws2 the stream's next scores S_t(i+2) can only be issued behind PV_t(i), i.e. after the stream has
+// finished its exponentials and stored P(i): the MMA round trip (issuer wake-up, PV + QK^T execution behind the other
+// tile's MMAs, commit) is fully exposed, ~30 % of every stream iteration (s_full wait in profiles/r01_trace_ws2_sm1_f.txt).
+// Here the stream releases its S buffer as soon as the scores are in registers (s_free), the issuer refills it at once,
+// and P goes to a 16 KB K-major / 128-byte-swizzled smem tile that PV reads as an SS-mode A operand (48 instead of 32
+// clocks per M128 N64 K16 MMA, profiles/r01_micro_mma.txt -- the tensor pipe has the slack, the XU pipe does not).
 //
-//   warps 0-15  softmax: stream = warp >> 2 = 2*tile + parity; thread == query row == TMEM lane; the stream takes
-//               every other step of its tile (64 keys) and keeps its OWN running max m_b, row sum l_b and accumulator
-//               O_{t,b} += P(i) . V(i)  (i = b mod 2) -- a split of the key range by step parity, merged once in the
-//               epilogue:  ctx = (O_0 2^(m_0-m) + O_1 2^(m_1-m)) / (l_0 2^(m_0-m) + l_1 2^(m_1-m) [+ 2^-m]).
-//   warp  16    MMA issuer of Q tile 0 (one elected lane issues its tcgen05.mma / tcgen05.commit)
-//   warp  17    TMA producer (one elected lane; Q once, K / V steps through kStages-deep rings)
-//   warp  18    MMA issuer of Q tile 1
-//   warp  19    idle (warps 16-19 give their registers to the softmax warps with setmaxnreg)
-//
-//   TMEM (512 columns):  S_t[b] at (2t+b)*64 (its packed P over the first 32 of them)     O_{t,b} at 256 + (2t+b)*64
-//
-// Why parity streams (vs. attn_fwd_ws.cuh, where the two streams of a tile split every step in column halves): at
-// d = 64 the loop is bound by the exp2 (MUFU/XU) pipe, and what keeps the XU below its rate is not issue slots but
-// the fixed cost around every step (barrier wait, tcgen05.ld latency, wait::st, fence, arrive, issuer wake-up).
-// A parity stream pays that once per 64 keys instead of once per 32, its two streams are half a period out of
-// phase by construction (the halves of the other kernel run in lockstep: same barrier, same phase), and because
-// S_t(i) is committed behind PV_t(i-2) in the issuer's in-order MMA stream, owning S_t(i) implies O_{t,b} is
-// quiescent: the O rescale needs no barrier of its own.
-//
-//   mbarriers:  q_full | k_full/k_empty[kStages] | v_full/v_empty[kStages]   (TMA <-> MMA; *_empty take one
-//                                                                              tcgen05.commit from EACH issuer)
-//               s_full[t][b]  (MMA -> softmax: S_t of a step with parity b is complete, and so is PV_t(i-2))
-//               p_full[t][b]  (softmax -> MMA, 4 arrivals = one elected lane per warp of the stream: P is in TMEM /
-//                              S_t has been consumed)
-//               o_final[t]    (MMA -> softmax: the last PV_t has completed -> epilogue)
-//   MMA issue order of issuer t per step i:  [p_full_t(i)] PV_t(i) QK_t(i+2)
-//
-// Lazy rescale, softmax_1's +1 term, the two-pass normalised modes and the sparse skip are as in attn_fwd_ws.cuh.
+//   warps 0-15  softmax streams (stream = warp >> 2 = 2*tile + parity), thread == query row == TMEM lane
+//   warp  16/18 MMA issuers of Q tile 0 / 1      warp 17  TMA producer      warp 19  idle
+//   TMEM (512 columns):  S_t[b] at (2t+b)*64      O_{t,b} at 256 + (2t+b)*64
+//   smem: Q0 Q1 | K ring | V ring (kStages x 8 KB each) | P_{t,b} (4 x 16 KB)
+//   mbarriers:  q_full | k_full/k_empty | v_full/v_empty (TMA <-> MMA)
+//               s_full[t][b]   MMA -> stream: S_t of a step with parity b is complete
+//               s_free[t][b]   stream -> MMA (4 arrivals): the scores are in registers, the buffer may be refilled
+//               p_full[t][b]   stream -> MMA (4 arrivals): P is in smem (fence.proxy.async) and O is rescaled
+//               pv_done[t][b]  MMA -> stream: PV of that parity has completed (P buffer free, O quiescent)
+//               o_final[t]     MMA -> streams: last PV_t completed -> epilogue
+//   MMA issue order of issuer t per step i:  [s_free_t(i)] QK_t(i+2)   [p_full_t(i)] PV_t(i)
 #pragma once
 
 #include "attn_fwd_ws.cuh"   // trace macros, reg_alloc / reg_dealloc
 
 namespace oeh {
-namespace attn_ws2 {
+namespace attn_ws3 {
 
 using namespace attn;
 
 constexpr int BNW = 64;                                            // keys per step
 constexpr int kSubBytes = BNW * HD * 2;                            // 8 KB
-constexpr int kStages = 8;
+constexpr int kStages = 6;
+constexpr int kPBytes = 128 * BNW * 2;                                // one P tile [128 rows][64 keys] x 16 bit
 constexpr int kThreads = 640;                                      // 20 warps
 constexpr int kQRows = 256;                                        // query rows per CTA (two tiles)
-constexpr int kSmemBytes = 2 * kTileBytes + 2 * kStages * kSubBytes + 1024;   // Q0 Q1 | K ring | V ring
+constexpr int kSmemBytes = 2 * kTileBytes + 2 * kStages * kSubBytes + 4 * kPBytes + 1024;   // Q0 Q1 | K ring | V ring | P
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColO0 = 256;                                   // S_t[b] at (2t+b)*64, O_{t,b} at 256 + (2t+b)*64
 constexpr float kLazyRescale = 8.f;                                // log2 units
@@ -55,13 +46,13 @@ struct Barriers {
   uint64_t q_full;
   uint64_t k_full[kStages], k_empty[kStages];
   uint64_t v_full[kStages], v_empty[kStages];
-  uint64_t s_full[2][2], p_full[2][2];
+  uint64_t s_full[2][2], s_free[2][2], p_full[2][2], pv_done[2][2];
   uint64_t o_final[2];
 };
 
 template <bool kBF16, bool kGeneric, bool kNorm>
 __global__ void __launch_bounds__(kThreads, 1)
-attn_fwd_ws2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
+attn_fwd_ws3_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                     const __grid_constant__ CUtensorMap tmv, const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) Barriers bars;
@@ -77,6 +68,7 @@ attn_fwd_ws2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   const uint32_t sQ = smem0;                                    // 2 tiles of 128 rows
   const uint32_t sK = smem0 + 2 * kTileBytes;                   // kStages steps of 64 keys
   const uint32_t sV = sK + kStages * kSubBytes;
+  const uint32_t sP = sV + kStages * kSubBytes;                 // P_{t,b} at sP + (2t+b) * kPBytes
 
   if (tid == 0) {
     ptx::mbar_init(ptx::smem_u32(&bars.q_full), 1);
@@ -92,7 +84,9 @@ attn_fwd_ws2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
 #pragma unroll
       for (int sb = 0; sb < 2; ++sb) {
         ptx::mbar_init(ptx::smem_u32(&bars.s_full[t][sb]), 1);
-        ptx::mbar_init(ptx::smem_u32(&bars.p_full[t][sb]), 4);  // one elected lane of each of the stream's 4 warps
+        ptx::mbar_init(ptx::smem_u32(&bars.s_free[t][sb]), 4);  // one elected lane of each of the stream's 4 warps
+        ptx::mbar_init(ptx::smem_u32(&bars.p_full[t][sb]), 4);
+        ptx::mbar_init(ptx::smem_u32(&bars.pv_done[t][sb]), 1);
       }
       ptx::mbar_init(ptx::smem_u32(&bars.o_final[t]), 1);
     }
@@ -172,10 +166,11 @@ attn_fwd_ws2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       for (int k = 0; k < HD / 16; ++k)
         ptx::mma_ss(tS0 + sb * 64, dq + k * 2, dk + stage * kSubUnits + k * 2, kIdescQK, k > 0);
     };
-    auto issue_pv = [&](int sb, int stage, bool first) {         // O_{t,sb} (+)= P_t[sb] . V(stage)  (K = 64 keys)
+    const uint64_t dp = ptx::make_smem_desc_sw128(sP, 16, 1024) + (uint64_t)(2 * t) * (kPBytes >> 4);
+    auto issue_pv = [&](int sb, int stage, bool first) {         // O_{t,sb} (+)= P_{t,sb} . V(stage)  (K = 64 keys, SS)
 #pragma unroll
       for (int k = 0; k < BNW / 16; ++k)
-        ptx::mma_ts(tO0 + sb * 64, tS0 + sb * 64 + k * 8, dv + stage * kSubUnits + k * 128, kIdescPV,
+        ptx::mma_ss(tO0 + sb * 64, dp + (uint64_t)sb * (kPBytes >> 4) + k * 2, dv + stage * kSubUnits + k * 128, kIdescPV,
                     (first && k == 0) ? 0u : 1u);
     };
     ptx::mbar_wait(ptx::smem_u32(&bars.q_full), 0);
@@ -198,25 +193,31 @@ attn_fwd_ws2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       const bool last = i + 1 == n_iter;
       const int ks = (i + 2) % kStages;
       OEH_T(0);
-      if (pv) ptx::mbar_wait(ptx::smem_u32(&bars.v_full[vs]), (uint32_t)(v / kStages) & 1u);
-      if (more) ptx::mbar_wait(ptx::smem_u32(&bars.k_full[ks]), (uint32_t)((i + 2) / kStages) & 1u);
-      OEH_T(1);
-      ptx::mbar_wait(ptx::smem_u32(&bars.p_full[t][sb]), (uint32_t)(i >> 1) & 1u);
-      ptx::tc_fence_after();
-      OEH_T(2);
-      if (ptx::elect_one()) {
-        if (pv) {
-          issue_pv(sb, vs, v < 2);                               // the first PV step of each parity starts its accumulator
-          if (last) ptx::mma_commit(ptx::smem_u32(&bars.o_final[t]));
-          ptx::mma_commit(ptx::smem_u32(&bars.v_empty[vs]));
-        }
-        if (more) {
+      if (more) {                                                // refill S_t[sb] as soon as the stream has read it
+        ptx::mbar_wait(ptx::smem_u32(&bars.k_full[ks]), (uint32_t)((i + 2) / kStages) & 1u);
+        ptx::mbar_wait(ptx::smem_u32(&bars.s_free[t][sb]), (uint32_t)(i >> 1) & 1u);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
           issue_qk(sb, ks);
           ptx::mma_commit(ptx::smem_u32(&bars.s_full[t][sb]));
           ptx::mma_commit(ptx::smem_u32(&bars.k_empty[ks]));
         }
+        __syncwarp();
       }
-      __syncwarp();
+      OEH_T(1);
+      if (pv) {
+        ptx::mbar_wait(ptx::smem_u32(&bars.v_full[vs]), (uint32_t)(v / kStages) & 1u);
+        ptx::mbar_wait(ptx::smem_u32(&bars.p_full[t][sb]), (uint32_t)(v >> 1) & 1u);
+        ptx::tc_fence_after();
+        OEH_T(2);
+        if (ptx::elect_one()) {
+          issue_pv(sb, vs, v < 2);                               // the first PV step of each parity starts its accumulator
+          ptx::mma_commit(ptx::smem_u32(&bars.pv_done[t][sb]));
+          if (last) ptx::mma_commit(ptx::smem_u32(&bars.o_final[t]));
+          ptx::mma_commit(ptx::smem_u32(&bars.v_empty[vs]));
+        }
+        __syncwarp();
+      }
       OEH_T(3);
     }
     OEH_T_PRINT("issuer: loop kv_full p_full issue", n_iter);
@@ -230,6 +231,10 @@ attn_fwd_ws2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     const uint32_t tS = t_lane + (uint32_t)(2 * t + par) * 64u;              // this stream's S / P columns
     const uint32_t tO = t_lane + kColO0 + (uint32_t)(2 * t + par) * 64u;     // this stream's accumulator
     const uint32_t bar_s = ptx::smem_u32(&bars.s_full[t][par]), bar_p = ptx::smem_u32(&bars.p_full[t][par]);
+    const uint32_t bar_f = ptx::smem_u32(&bars.s_free[t][par]), bar_d = ptx::smem_u32(&bars.pv_done[t][par]);
+    const uint32_t p_row = sP + (uint32_t)(2 * t + par) * kPBytes + (uint32_t)r * 128u;   // this row of P_{t,par}
+    const uint32_t p_xor = (uint32_t)(r & 7);                     // 128-byte swizzle: 16-byte chunk c lives at c ^ (row & 7)
+    int n_pv = 0;                                                 // PV steps this stream has handed over
 
     const bool has_qs = kGeneric && p.qdq_scores != nullptr;
     const bool has_qp = kGeneric && p.qdq_probs != nullptr;
@@ -277,11 +282,9 @@ attn_fwd_ws2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       ptx::tmem_ld32(tS + 32, reinterpret_cast<uint32_t*>(s) + 32);
       ptx::tmem_wait_ld();
       OEH_T(2);
-      if (!pv_iter) {                                             // stats pass: S is consumed, QK^T(i+2) may start
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (ptx::elect_one()) ptx::mbar_arrive(bar_p);
-      }
+      ptx::tc_fence_before();                                     // the scores are in registers: QK^T(i+2) may refill S
+      __syncwarp();
+      if (ptx::elect_one()) ptx::mbar_arrive(bar_f);
       if (kGeneric && p.dbg_s && i < 2 && row < p.Tq) {           // raw S of keys [0,128)
         float* d = p.dbg_s + (((int64_t)b * p.H + h) * p.Tq + row) * BN + k0;
 #pragma unroll
@@ -315,14 +318,13 @@ attn_fwd_ws2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         // see attn_fwd_ws.cuh: none of this warp's 32 rows x 64 keys can survive the clip / the probs tap -> P = 0.
         // (Own store path: merging the two branches through s[] makes ptxas spill the packed row.)
         if (!__any_sync(0xffffffffu, tile_max - m_safe > skip_thr)) {
-          uint32_t z[BNW / 2];
+          if (n_pv > 0) ptx::mbar_wait(bar_d, (uint32_t)(n_pv - 1) & 1u);
 #pragma unroll
-          for (int j = 0; j < BNW / 2; ++j) z[j] = 0u;
-          ptx::tmem_st32(tS, z);
-          ptx::tmem_wait_st();
-          ptx::tc_fence_before();
+          for (int c = 0; c < BNW / 8; ++c) ptx::st_shared_v4(p_row + (((uint32_t)c ^ p_xor) << 4), 0u, 0u, 0u, 0u);
+          ptx::fence_proxy_async_smem();
           __syncwarp();
           if (ptx::elect_one()) ptx::mbar_arrive(bar_p);
+          ++n_pv;
           started = true;
           continue;
         }
@@ -338,8 +340,9 @@ attn_fwd_ws2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         l_run = fmaf(l_run, alpha, exp2_and_sum<BNW>(s, mul, m_safe));
         m_run = m_new;
         if (started && !__all_sync(0xffffffffu, alpha == 1.f)) {
-          // O_{t,par} *= alpha.  No barrier: S_t(i) was committed behind PV_t(i-2) -- the last MMA that wrote this
-          // accumulator -- in the issuer's in-order stream, and PV_t(i) needs the P this thread has not written yet.
+          // O_{t,par} *= alpha: PV of this stream's previous step must have completed
+          ptx::mbar_wait(bar_d, (uint32_t)(n_pv - 1) & 1u);
+          ptx::tc_fence_after();
 #pragma unroll
           for (int c = 0; c < HD / 16; ++c) {
             uint32_t o[16];
@@ -349,22 +352,26 @@ attn_fwd_ws2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
             for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
             ptx::tmem_st16(tO + c * 16, o);
           }
+          ptx::tmem_wait_st();
+          ptx::tc_fence_before();
         }
       }
       started = true;
       OEH_T(4);
 
-      // P -> TMEM (packed 16-bit pairs) over the first 32 columns of the S buffer this thread has consumed
-      {
-        uint32_t pk[BNW / 2];
+      // P -> smem tile P_{t,par} (K-major rows of 64 keys = 128 B, 128-byte swizzle), free once this stream's previous PV
+      // has completed
+      if (n_pv > 0) ptx::mbar_wait(bar_d, (uint32_t)(n_pv - 1) & 1u);
 #pragma unroll
-        for (int j = 0; j < BNW / 2; ++j) pk[j] = pack2<kBF16>(s[2 * j], s[2 * j + 1]);
-        ptx::tmem_st32(tS, pk);
+      for (int c = 0; c < BNW / 8; ++c) {
+        const uint32_t w0 = pack2<kBF16>(s[8 * c + 0], s[8 * c + 1]), w1 = pack2<kBF16>(s[8 * c + 2], s[8 * c + 3]);
+        const uint32_t w2 = pack2<kBF16>(s[8 * c + 4], s[8 * c + 5]), w3 = pack2<kBF16>(s[8 * c + 6], s[8 * c + 7]);
+        ptx::st_shared_v4(p_row + (((uint32_t)c ^ p_xor) << 4), w0, w1, w2, w3);
       }
-      ptx::tmem_wait_st();
-      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();                              // generic-proxy stores -> visible to tcgen05.mma (async proxy)
       __syncwarp();
       if (ptx::elect_one()) ptx::mbar_arrive(bar_p);
+      ++n_pv;
       OEH_T(5);
     }
     OEH_T_PRINT("softmax: top s_full ld max exp pack+arrive", n_iter);
@@ -412,5 +419,5 @@ attn_fwd_ws2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   }
 }
 
-}  // namespace attn_ws2
+}  // namespace attn_ws3
 }  // namespace oeh

@@ -67,6 +67,12 @@ __device__ __forceinline__ void nbar_arrive(int id, int nthreads, float& dep) {
   asm volatile("bar.arrive %1, %2;" : "+f"(dep) : "r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- shared-memory stores that feed the async proxy (tcgen05.mma operands written by threads) ----------------
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---- TMA --------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -100,3 +100,30 @@ def swap_opt_attention(model, attn_softmax: str = "vanilla", alpha: Optional[flo
         p = next(old.parameters())
         layer.self_attn = new.to(device=p.device, dtype=p.dtype).train(old.training)
     return model
+
+
+class BertResidualLayerNormFused(torch.nn.Module):
+    """BertSelfOutput / BertOutput (the HF modules the reference wraps at quantized_bert.py:540-605) with the residual
+    add and the LayerNorm in one kernel: ``LayerNorm(dropout(dense(hidden_states)) + input_tensor)``.  Same submodule
+    names (dense, LayerNorm, dropout), so state_dicts and the quantized wrappers keep working."""
+
+    def __init__(self, org):
+        super().__init__()
+        self.dense, self.LayerNorm, self.dropout = org.dense, org.LayerNorm, org.dropout
+
+    def forward(self, hidden_states, input_tensor):
+        hidden_states = self.dropout(self.dense(hidden_states))
+        ln = self.LayerNorm
+        if self.training or (torch.is_grad_enabled() and hidden_states.requires_grad):
+            return ln(hidden_states + input_tensor)                # training graph: autograd needs the ATen ops
+        from . import ops
+        return ops.add_layer_norm(hidden_states, input_tensor, ln.weight, ln.bias, ln.eps)
+
+
+def fuse_bert_residual_blocks(model):
+    """Swap every ``layer.attention.output`` / ``layer.output`` of a BERT encoder for the fused module (eval only)."""
+    bert = getattr(model, "bert", model)
+    for layer in bert.encoder.layer:
+        layer.attention.output = BertResidualLayerNormFused(layer.attention.output).train(layer.training)
+        layer.output = BertResidualLayerNormFused(layer.output).train(layer.training)
+    return model

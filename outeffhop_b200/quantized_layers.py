@@ -8,7 +8,9 @@
 With fixed ranges the residual add and its tap are ONE kernel (``oeh_add_fake_quant``: 3 tensor passes instead of the
 reference's ~14: add = 3, qdq = 6 elementwise ops with temporaries); while the tap is still estimating its range the
 sum is materialised and goes through minmax -> EMA -> qdq (the range of the SAME tensor is needed before it is
-quantised, quantization_manager.py:94-102).  LayerNorm itself stays the library kernel (F.layer_norm), as the GEMMs do.
+quantised, quantization_manager.py:94-102).  Once BOTH taps of a residual block are frozen the whole tail
+add -> res tap -> LayerNorm -> output tap is one kernel (``oeh_add_layer_norm``); a stand-alone QuantLayerNorm still
+calls F.layer_norm.
 """
 from __future__ import annotations
 
@@ -17,7 +19,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from . import ops
-from .quantization import (CurrentMinMaxEstimator, QuantizationManager, QuantizedActivation, QuantizedModule, QuantLinear)
+from .quantization import (AsymmetricUniformQuantizer, CurrentMinMaxEstimator, QuantizationManager, QuantizedActivation, QuantizedModule, QuantLinear)
 from .quantized_attention import QuantizedModel, _linear_params
 
 
@@ -85,9 +87,33 @@ class _QuantizedBertResidualBlock(QuantizedModel):
         self.res_act_quantizer = QuantizedActivation(**qp)
         self.LayerNorm = QuantLayerNorm.from_layer_norm(org_model.LayerNorm, **qp)
 
+    def _fusable(self, hidden_states, input_tensor) -> bool:
+        """Both taps quantise with frozen asymmetric ranges of the same width (or are off): add -> tap -> LayerNorm -> tap
+        is ONE kernel (oeh_add_layer_norm)."""
+        tap, ln = self.res_act_quantizer, self.LayerNorm
+        if self.training or not hidden_states.is_cuda or hidden_states.shape != input_tensor.shape \
+                or hidden_states.dtype != input_tensor.dtype or ln.weight.dtype != hidden_states.dtype or ln.bias is None:
+            return False
+        if tap.active and not tap.fixed:
+            return False
+        out = ln.activation_quantizer
+        if ln._qa_host and (out.estimating or not isinstance(out.quantizer, AsymmetricUniformQuantizer)):
+            return False
+        if tap.active and ln._qa_host and tap.activation_quantizer.n_bits != out.n_bits:
+            return False
+        return True
+
     def forward(self, hidden_states, input_tensor):
         hidden_states = self.dense(hidden_states)
         hidden_states = self.dropout(hidden_states)
+        if self._fusable(hidden_states, input_tensor):
+            tap, ln = self.res_act_quantizer, self.LayerNorm
+            weight, bias = ln.get_params()
+            n_bits = tap.activation_quantizer.n_bits if tap.active else ln.activation_quantizer.n_bits
+            return ops.add_layer_norm(hidden_states, input_tensor, weight, bias, ln.eps,
+                                      qparams_res=tap.kernel_qparams() if tap.active else None,
+                                      qparams_out=ln.activation_quantizer.quantizer.qparams if ln._qa_host else None,
+                                      n_bits=n_bits)
         hidden_states = _residual_tap(self.res_act_quantizer, hidden_states, input_tensor)   # add + tap
         return self.LayerNorm(hidden_states)
 

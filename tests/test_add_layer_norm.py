@@ -1,0 +1,102 @@
+"""Fused residual add + LayerNorm (+ fake-quant taps) -- SURVEY 8f rank 2 -- against the oracle and ATen.
+Tolerance: the kernel rounds the sum to the tensor dtype like ATen and normalises in fp32; results agree with
+F.layer_norm(a + b) to 1 ulp of the tensor dtype (fp32: 2e-6 relative to the row scale)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oeh_oracle as O  # checker only
+
+_T = {"float32": torch.float32, "float16": torch.float16, "bfloat16": torch.bfloat16}
+_TOL = {"float32": 3e-6, "float16": 2e-3, "bfloat16": 1.6e-2}
+
+
+def test_oracle_add_layer_norm_equals_aten_fp32():
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn(37, 768, generator=g) * 2, torch.randn(37, 768, generator=g)
+    w, bias = torch.rand(768, generator=g) + 0.5, torch.randn(768, generator=g) * 0.1
+    want = torch.nn.functional.layer_norm(a + b, (768,), w, bias, 1e-12).numpy()
+    got = O.add_layer_norm(a.numpy(), b.numpy(), w.numpy(), bias.numpy(), 1e-12)
+    np.testing.assert_allclose(got, want, rtol=0, atol=3e-6)
+
+
+def test_symbol_declared():
+    import os
+    from outeffhop_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "oeh.h")).read()
+    assert "oeh_add_layer_norm(" in hdr and "oeh_add_layer_norm" in _lib.SYMBOLS
+    getattr(_lib.lib(), "oeh_add_layer_norm")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float32", "float16", "bfloat16"])
+@pytest.mark.parametrize("rows,cols", [(1, 8), (5, 64), (4096, 768), (33, 1024), (7, 2048), (64, 3072 // 4)])
+@pytest.mark.parametrize("residual", [True, False])
+def test_add_layer_norm_vs_aten_and_oracle(dtype, rows, cols, residual):
+    from outeffhop_b200 import ops
+    if dtype == "float32" and cols > 1024:
+        pytest.skip("fp32 rows hold at most 1024 columns in registers")
+    t = _T[dtype]
+    g = torch.Generator(device="cuda").manual_seed(rows * 7 + cols)
+    a = (torch.randn(rows, cols, device="cuda", generator=g) * 3).to(t)
+    b = torch.randn(rows, cols, device="cuda", generator=g).to(t) if residual else None
+    w = (torch.rand(cols, device="cuda", generator=g) + 0.5).to(t)
+    bias = (torch.randn(cols, device="cuda", generator=g) * 0.2).to(t)
+    got = ops.add_layer_norm(a, b, w, bias, 1e-12)
+    x = a + b if residual else a
+    want = torch.nn.functional.layer_norm(x, (cols,), w, bias, 1e-12)
+    assert got.dtype == t and got.shape == a.shape
+    assert (got.float() - want.float()).abs().max().item() <= _TOL[dtype] * max(1.0, want.float().abs().max().item())
+    f = lambda z: z.float().cpu().numpy()
+    orc = O.add_layer_norm(f(x), None, f(w), f(bias), 1e-12)
+    assert np.abs(f(got) - orc).max() <= _TOL[dtype] * max(1.0, np.abs(orc).max())
+
+
+@pytest.mark.gpu
+def test_add_layer_norm_with_taps_fp32_matches_unfused_chain():
+    """INT8 residual block, fixed ranges: one kernel == add_fake_quant -> F.layer_norm -> fake_quant (bit-exact taps;
+    LayerNorm itself to 1 fp32 ulp, so at most a few output codes may differ by one bin)."""
+    from outeffhop_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a, b = torch.randn(512, 768, device="cuda", generator=g) * 2, torch.randn(512, 768, device="cuda", generator=g)
+    w, bias = torch.rand(768, device="cuda", generator=g) + 0.5, torch.randn(768, device="cuda", generator=g) * 0.1
+    q_res = torch.tensor([0.05, 131.0], device="cuda")
+    q_out = torch.tensor([0.03, 120.0], device="cuda")
+    got = ops.add_layer_norm(a, b, w, bias, 1e-12, qparams_res=q_res, qparams_out=q_out)
+    s = ops.add_fake_quant(a, b, q_res)
+    ln = torch.nn.functional.layer_norm(s, (768,), w, bias, 1e-12)
+    want = ops.fake_quant_asym(ln, q_out)
+    diff = (got - want).abs()
+    assert diff.max().item() <= 0.03 * 1.001 and (diff > 0).float().mean().item() < 1e-3
+    orc = O.add_layer_norm(a.cpu().numpy(), b.cpu().numpy(), w.cpu().numpy(), bias.cpu().numpy(), 1e-12,
+                           q_res=(np.float32(0.05), np.float32(131.0)), q_out=(np.float32(0.03), np.float32(120.0)))
+    d2 = np.abs(got.cpu().numpy() - orc)
+    assert d2.max() <= 0.03 * 1.001 and (d2 > 0).mean() < 1e-3
+
+
+@pytest.mark.gpu
+def test_add_layer_norm_rejects_bad_shapes():
+    from outeffhop_b200 import ops
+    a = torch.randn(4, 12, device="cuda", dtype=torch.float16)      # 12 is not a multiple of 8
+    w = torch.ones(12, device="cuda", dtype=torch.float16)
+    with pytest.raises(NotImplementedError):
+        ops.add_layer_norm(a, None, w, w)
+    with pytest.raises(ValueError):
+        ops.add_layer_norm(a, a[:2], w, w)
+    with pytest.raises(RuntimeError):
+        ops.add_layer_norm(a.cpu(), None, w.cpu(), w.cpu())
+
+
+@pytest.mark.gpu
+def test_fused_bert_residual_modules_match_hf():
+    from outeffhop_b200 import eval_harness as EH
+    model = EH.build_bert_base(seed=1, num_hidden_layers=2, fuse_residual=False)
+    b = EH.synthetic_mlm_batch(4, 128, seed=9)
+    ids, lab = b["input_ids"].cuda(), b["labels"].cuda()
+    with torch.no_grad():
+        want = EH.bert_mlm_loss_aten(model, ids, lab).item()
+        EH.fuse_bert_residual_blocks(model)
+        got = EH.bert_mlm_loss(model, ids, lab).item()
+    assert abs(got - want) < 2e-3 * abs(want)
+    sd = model.state_dict()
+    assert "bert.encoder.layer.0.attention.output.LayerNorm.weight" in sd and "bert.encoder.layer.1.output.dense.bias" in sd

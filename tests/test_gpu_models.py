@@ -52,8 +52,9 @@ class RefBertSelfAttention(torch.nn.Module):
 def test_bert_base_eval_perplexity_matches_fp32_reference(key, gated):
     from outeffhop_b200 import eval_harness as EH
     kw = dict(attn_gate_type="conditional_per_token", attn_gate_init=0.25) if gated else {}
-    model = EH.build_bert_base(seed=3000, dtype=torch.float16, attn_softmax=key, **kw)
-    ref = copy.deepcopy(model).float()
+    model = EH.build_bert_base(seed=3000, dtype=torch.float16, attn_softmax=key, fuse_residual=False, **kw)
+    ref = copy.deepcopy(model).float()                                  # reference keeps HF's ATen add + LayerNorm
+    EH.fuse_bert_residual_blocks(model)
     for lo, lr in zip(model.bert.encoder.layer, ref.bert.encoder.layer):
         lr.attention.self = RefBertSelfAttention(lo.attention.self).cuda()
     batches = [EH.synthetic_mlm_batch(32, 128, seed=3000 + i) for i in range(3)]
