@@ -215,6 +215,30 @@ class BertSelfAttentionWithExtras(GateMixin, nn.Module):
     def _gate_scale(self) -> float:
         return self.gate_scaling_factor
 
+    def _fused_qkv(self, hidden_states: torch.Tensor):
+        """Plain self-attention in eval: ONE (B*T, D) x (D, 3D) library GEMM for query/key/value instead of three (a
+        768-wide output is < 1 wave of GEMM tiles on 148 SMs; 2304 wide fills them).  The concatenated weight is a cache
+        keyed on the three Linear parameters (``query/key/value`` stay the modules of record: state_dict, hooks,
+        quantized wrappers); q, k, v come back as (B,H,T,d) strided views of the (B,T,3,H,d) result, which the fused
+        kernel's tensor maps take as they are.  Returns None whenever the three modules must run themselves."""
+        mods = (self.query, self.key, self.value)
+        if self.training or any(type(m) is not nn.Linear or m._forward_hooks or m._forward_pre_hooks for m in mods) \
+                or any((m.bias is None) != (mods[0].bias is None) for m in mods):
+            return None
+        key = tuple((m.weight.data_ptr(), m.weight._version, 0 if m.bias is None else m.bias.data_ptr(),
+                     0 if m.bias is None else m.bias._version) for m in mods)
+        cache = self.__dict__.get("_qkv_cache")
+        if cache is None or cache[0] != key:
+            with torch.no_grad():
+                w = torch.cat([m.weight for m in mods], dim=0)
+                b = None if mods[0].bias is None else torch.cat([m.bias for m in mods], dim=0)
+            cache = (key, w, b)
+            self.__dict__["_qkv_cache"] = cache
+        y = nn.functional.linear(hidden_states, cache[1], cache[2])
+        B, T = y.shape[0], y.shape[1]
+        y = y.view(B, T, 3, self.num_attention_heads, self.attention_head_size)
+        return tuple(y[:, :, j].permute(0, 2, 1, 3) for j in range(3))
+
     def transpose_for_scores(self, x: torch.Tensor) -> torch.Tensor:
         new_x_shape = x.size()[:-1] + (self.num_attention_heads, self.attention_head_size)
         return x.view(new_x_shape).permute(0, 2, 1, 3)
@@ -309,8 +333,14 @@ class BertSelfAttentionWithExtras(GateMixin, nn.Module):
         _check_no_grad(hidden_states, self.query.weight)
 
         is_cross_attention = encoder_hidden_states is not None
-        q = self.transpose_for_scores(self.query(hidden_states))                               # :183, :220
-        if is_cross_attention and past_key_value is not None:                                  # :190-194
+        fused_qkv = self._fused_qkv(hidden_states) if not is_cross_attention and past_key_value is None else None
+        if fused_qkv is not None:
+            q, k, v = fused_qkv
+        else:
+            q = self.transpose_for_scores(self.query(hidden_states))                           # :183, :220
+        if fused_qkv is not None:
+            pass
+        elif is_cross_attention and past_key_value is not None:                                # :190-194
             k, v = past_key_value[0], past_key_value[1]
             attention_mask = encoder_attention_mask
         elif is_cross_attention:                                                               # :195-198

@@ -186,8 +186,11 @@ __device__ __forceinline__ void exp2_poly2(uint64_t t2, float& e0, float& e1) {
 // pair pi of a row chunk goes to the FMA pipe if this is true (evenly spread over the chunk)
 __host__ __device__ constexpr bool poly_pair(int pi) { return ((pi % 16) * OEH_POLY_PAIRS) % 16 < OEH_POLY_PAIRS; }
 
+// kPoly = false: every exponential on the MUFU pipe.  The generic kernels (fake-quant taps / masks) use that: with the
+// probs tap a 7.5e-5 relative error moves P across quantisation bin edges more often than the ex2.approx one does.
+template <bool kPoly>
 __device__ __forceinline__ void exp2_pair(uint64_t t2, int pi, float& e0, float& e1) {
-  if (poly_pair(pi)) {
+  if (kPoly && poly_pair(pi)) {
     exp2_poly2(t2, e0, e1);
   } else {
     float a, b;
@@ -199,14 +202,14 @@ __device__ __forceinline__ void exp2_pair(uint64_t t2, int pi, float& e0, float&
 
 // s[j] <- exp2(s[j]*mul - m); returns the row sum.  The scale/subtract FMAs and the sum run as packed fp32x2
 // instructions (FFMA2 / FADD2: half the issue slots, same per-lane IEEE results); 4 independent partial sums.
-template <int N>
+template <int N, bool kPoly = true>
 __device__ __forceinline__ float exp2_and_sum(float (&s)[N], float mul, float m) {
   const uint64_t mul2 = ptx::pack2f(mul, mul), nm2 = ptx::pack2f(-m, -m);
   uint64_t acc0 = ptx::pack2f(0.f, 0.f), acc1 = acc0;
 #pragma unroll
   for (int j = 0; j < N; j += 4) {
-    exp2_pair(ptx::ffma2(ptx::pack2f(s[j], s[j + 1]), mul2, nm2), j / 2, s[j], s[j + 1]);
-    exp2_pair(ptx::ffma2(ptx::pack2f(s[j + 2], s[j + 3]), mul2, nm2), j / 2 + 1, s[j + 2], s[j + 3]);
+    exp2_pair<kPoly>(ptx::ffma2(ptx::pack2f(s[j], s[j + 1]), mul2, nm2), j / 2, s[j], s[j + 1]);
+    exp2_pair<kPoly>(ptx::ffma2(ptx::pack2f(s[j + 2], s[j + 3]), mul2, nm2), j / 2 + 1, s[j + 2], s[j + 3]);
     acc0 = ptx::fadd2(acc0, ptx::pack2f(s[j], s[j + 1]));
     acc1 = ptx::fadd2(acc1, ptx::pack2f(s[j + 2], s[j + 3]));
   }
@@ -216,12 +219,12 @@ __device__ __forceinline__ float exp2_and_sum(float (&s)[N], float mul, float m)
 }
 
 // s[j] <- exp2(s[j]*mul - m) without the sum (PV pass of the two-pass modes)
-template <int N>
+template <int N, bool kPoly = true>
 __device__ __forceinline__ void exp2_only(float (&s)[N], float mul, float m) {
   const uint64_t mul2 = ptx::pack2f(mul, mul), nm2 = ptx::pack2f(-m, -m);
 #pragma unroll
   for (int j = 0; j < N; j += 2)
-    exp2_pair(ptx::ffma2(ptx::pack2f(s[j], s[j + 1]), mul2, nm2), j / 2, s[j], s[j + 1]);
+    exp2_pair<kPoly>(ptx::ffma2(ptx::pack2f(s[j], s[j + 1]), mul2, nm2), j / 2, s[j], s[j + 1]);
 }
 
 // normalised modes: p = e * inv_den, then clip((eta-gamma)*p + gamma, 0, 1) and / or the probs fake-quant tap

@@ -47,7 +47,9 @@ attn_fwd_one_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   __shared__ __align__(8) uint64_t bars[3];      // q+k, v, mma
   __shared__ uint32_t tmem_base_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from it
+  // (role, TMEM lane base, barrier / descriptor addresses) on the uniform datapath instead of R2UR-ing it at every use
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
   const int row = q0 + tid;
 
@@ -140,7 +142,7 @@ attn_fwd_one_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         const int k0 = c * CH, valid = min(p.Tk - k0, CH);
         hide_invisible<CH>(s, min(valid - 1, causal_lim - k0));
       }
-      l_run += exp2_and_sum<CH>(s, mul, m_safe);
+      l_run += exp2_and_sum<CH, !kGeneric>(s, mul, m_safe);
       if (normalized) {
         ptx::tmem_st32(t_lane + c * CH, reinterpret_cast<const uint32_t*>(s));
         continue;

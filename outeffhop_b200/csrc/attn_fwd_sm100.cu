@@ -23,8 +23,6 @@
 #include "attn_common.cuh"
 #include "attn_fwd_one.cuh"
 #include "attn_fwd_ws.cuh"
-#include "attn_fwd_ws2.cuh"
-#include "attn_fwd_ws3.cuh"
 
 namespace oeh {
 namespace {
@@ -368,21 +366,10 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
   // lower latency.  OEH_ATTN_KERNEL=tile|ws overrides (tests exercise both on the same shapes).
   // When all keys fit one K/V tile (Tk <= 128, the BERT eval shape) the small one-tile kernel (4 CTAs / SM) runs.
   bool use_ws = a->Tq > BM, use_one = a->Tk <= BN;
-  // which warp-specialised kernel serves the long sequences: 1 = column halves (attn_fwd_ws.cuh), 2 = parity streams
-  // with P in TMEM (attn_fwd_ws2.cuh), 3 = parity streams with P through smem (attn_fwd_ws3.cuh)
-#ifndef OEH_WS_ONEPASS
-#define OEH_WS_ONEPASS 2
-#endif
-#ifndef OEH_WS_TWOPASS
-#define OEH_WS_TWOPASS 1
-#endif
   const bool norm_mode = a->kind >= OEH_SOFTMAX_CLIPPED || a->qdq_probs != nullptr;   // two-pass variants
-  int ws_ver = norm_mode ? OEH_WS_TWOPASS : OEH_WS_ONEPASS;
   if (const char* f = getenv("OEH_ATTN_KERNEL")) {
     if (!strcmp(f, "tile")) use_ws = use_one = false;
-    if (!strcmp(f, "ws")) { use_ws = true; use_one = false; ws_ver = 1; }
-    if (!strcmp(f, "ws2")) { use_ws = true; use_one = false; ws_ver = 2; }
-    if (!strcmp(f, "ws3")) { use_ws = true; use_one = false; ws_ver = 3; }
+    if (!strcmp(f, "ws")) { use_ws = true; use_one = false; }
   }
   if (use_one) use_ws = false;
   const int kv_box = use_ws ? attn_ws::BNW : BN;
@@ -435,34 +422,6 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
       attr_done[kw] = true;
     }
     dim3 grid((unsigned)((a->Tq + attn_ws::kQRows - 1) / attn_ws::kQRows), (unsigned)a->H, (unsigned)a->B);
-    if (ws_ver == 2) {
-      static const KernelFn kernels2[8] = {
-          attn_ws2::attn_fwd_ws2_kernel<false, false, false>, attn_ws2::attn_fwd_ws2_kernel<false, true, false>,
-          attn_ws2::attn_fwd_ws2_kernel<true, false, false>,  attn_ws2::attn_fwd_ws2_kernel<true, true, false>,
-          attn_ws2::attn_fwd_ws2_kernel<false, false, true>,  attn_ws2::attn_fwd_ws2_kernel<false, true, true>,
-          attn_ws2::attn_fwd_ws2_kernel<true, false, true>,   attn_ws2::attn_fwd_ws2_kernel<true, true, true>};
-      static bool attr_done2[8] = {false, false, false, false, false, false, false, false};
-      if (!attr_done2[kw]) {
-        OEH_CUDA_OK(cudaFuncSetAttribute(kernels2[kw], cudaFuncAttributeMaxDynamicSharedMemorySize, attn_ws2::kSmemBytes));
-        attr_done2[kw] = true;
-      }
-      kernels2[kw]<<<grid, attn_ws2::kThreads, attn_ws2::kSmemBytes, st>>>(tmq, tmk, tmv, p);
-      return check_launch("attn_fwd_ws2_kernel");
-    }
-    if (ws_ver == 3) {
-      static const KernelFn kernels3[8] = {
-          attn_ws3::attn_fwd_ws3_kernel<false, false, false>, attn_ws3::attn_fwd_ws3_kernel<false, true, false>,
-          attn_ws3::attn_fwd_ws3_kernel<true, false, false>,  attn_ws3::attn_fwd_ws3_kernel<true, true, false>,
-          attn_ws3::attn_fwd_ws3_kernel<false, false, true>,  attn_ws3::attn_fwd_ws3_kernel<false, true, true>,
-          attn_ws3::attn_fwd_ws3_kernel<true, false, true>,   attn_ws3::attn_fwd_ws3_kernel<true, true, true>};
-      static bool attr_done3[8] = {false, false, false, false, false, false, false, false};
-      if (!attr_done3[kw]) {
-        OEH_CUDA_OK(cudaFuncSetAttribute(kernels3[kw], cudaFuncAttributeMaxDynamicSharedMemorySize, attn_ws3::kSmemBytes));
-        attr_done3[kw] = true;
-      }
-      kernels3[kw]<<<grid, attn_ws3::kThreads, attn_ws3::kSmemBytes, st>>>(tmq, tmk, tmv, p);
-      return check_launch("attn_fwd_ws3_kernel");
-    }
     kernels[kw]<<<grid, attn_ws::kThreads, attn_ws::kSmemBytes, st>>>(tmq, tmk, tmv, p);
     return check_launch("attn_fwd_ws_kernel");
   }

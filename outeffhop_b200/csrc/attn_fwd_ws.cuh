@@ -1,45 +1,45 @@
-// Warp-specialised fused attention forward for sm_100a (the long-sequence kernel, Tq > 128).
+// Warp-specialised fused attention forward for sm_100a, "parity streams" (the long-sequence kernel, Tq > 128).
 //
-// One CTA per SM works on TWO 128-row Q tiles of one (batch, head) and walks the keys in 64-wide sub-tiles.  Each
-// S sub-tile [128 x 64] is consumed by TWO independent softmax streams, one per 32-column half, so that FOUR softmax
-// warps share every SM sub-partition:
+// One CTA per SM works on TWO 128-row Q tiles of one (batch, head) and walks the keys in 64-wide steps.  Each Q tile
+// has two S buffers in TMEM (step parity) and each (tile, parity) pair is owned by ONE softmax stream of four warps:
 //
-//   warps 0-15  softmax: stream s = warp >> 2 = 2*tile + half;  thread == query row == TMEM lane, 32 keys per step
+//   warps 0-15  softmax: stream = warp >> 2 = 2*tile + parity; thread == query row == TMEM lane; the stream takes
+//               every other step of its tile (64 keys) and keeps its OWN running max m_b, row sum l_b and accumulator
+//               O_{t,b} += P(i) . V(i)  (i = b mod 2) -- a split of the key range by step parity, merged once in the
+//               epilogue:  ctx = (O_0 2^(m_0-m) + O_1 2^(m_1-m)) / (l_0 2^(m_0-m) + l_1 2^(m_1-m) [+ 2^-m]).
 //   warp  16    MMA issuer of Q tile 0 (one elected lane issues its tcgen05.mma / tcgen05.commit)
-//   warp  17    TMA producer (one elected lane; Q once, K / V sub-tiles through kStages-deep rings)
+//   warp  17    TMA producer (one elected lane; Q once, K / V steps through kStages-deep rings)
 //   warp  18    MMA issuer of Q tile 1
 //   warp  19    idle (warps 16-19 give their registers to the softmax warps with setmaxnreg)
 //
-//   TMEM (512 columns):  S_t[b] at (2t+b)*64 (b = step parity; half h owns columns 32h..32h+31, its packed P the first
-//                        16 of them)          O_{t,h} at 256 + (2t+h)*64
+//   TMEM (512 columns):  S_t[b] at (2t+b)*64 (its packed P over the first 32 of them)     O_{t,b} at 256 + (2t+b)*64
 //
-// Why four streams: at d = 64 this kernel is bound by the exp2 (MUFU/XU) pipe -- 16 results/clk/SM, against 512
-// tensor cycles per 128x128 tile -- and ONE warp can drive its sub-partition's XU to at most 78 % (microbenchmark
-// tools/micro/mufu_bench.cu), only while it is in its exp phase.  With two softmax warps per sub-partition (the
-// FlashAttention-4 layout, versions 1-3 of this kernel) the measured XU utilisation stayed at 50 % (exactly 8
-// exp/clk/SM) however S was buffered: the two warps run in lockstep through exp / non-exp phases (cycle trace in
-// profiles/README.md).  Splitting each row in two column halves doubles the warps without extra TMEM: every half
-// keeps its OWN running maximum m_h, row sum l_h and accumulator O_{t,h} += P_{t,h} . V[32h..32h+31] (a split-K of
-// the PV product: same MMA work, K = 32 per half), so the halves never synchronise inside the key loop; they are
-// merged once in the epilogue:  ctx = (O_0 2^(m_0-m) + O_1 2^(m_1-m)) / (l_0 2^(m_0-m) + l_1 2^(m_1-m) [+ 2^-m]).
+// Why parity streams (an earlier version split every step of a tile in two column halves, one stream each): at
+// d = 64 the loop is bound by the exp2 (MUFU/XU) pipe, and what keeps the XU below its rate is not issue slots but
+// the fixed cost around every step (barrier wait, tcgen05.ld latency, wait::st, fence, arrive, issuer wake-up).
+// A parity stream pays that once per 64 keys instead of once per 32, its two streams are half a period out of
+// phase by construction (column halves run in lockstep: same barrier, same phase; 784 vs 898 TFLOP/s at T = 8192,
+// profiles/r01_ws2_variants_f.txt), and because
+// S_t(i) is committed behind PV_t(i-2) in the issuer's in-order MMA stream, owning S_t(i) implies O_{t,b} is
+// quiescent: the O rescale needs no barrier of its own.
 //
 //   mbarriers:  q_full | k_full/k_empty[kStages] | v_full/v_empty[kStages]   (TMA <-> MMA; *_empty take one
 //                                                                              tcgen05.commit from EACH issuer)
-//               s_full[t][b]  (MMA -> softmax: S_t of a step with parity b is complete)
-//               p_full[t][b]  (softmax -> MMA, 8 arrivals = one elected lane per warp of tile t: P_{t,0}, P_{t,1} are
-//                              in TMEM / S_t has been consumed)
-//               o_done[t][b]  (MMA -> softmax: PV_t(v), v % 2 == b, has completed; waited only before an O rescale;
-//                              one barrier per parity keeps the waiter at most one phase behind)
+//               s_full[t][b]  (MMA -> softmax: S_t of a step with parity b is complete, and so is PV_t(i-2))
+//               p_full[t][b]  (softmax -> MMA, 4 arrivals = one elected lane per warp of the stream: P is in TMEM /
+//                              S_t has been consumed)
 //               o_final[t]    (MMA -> softmax: the last PV_t has completed -> epilogue)
-//   MMA issue order of issuer t per step i:  [p_full_t(i)] PV_{t,0}(i) PV_{t,1}(i) QK_t(i+2)
-//   (tcgen05.mma executes in issue order, so QK_t(i+2) may overwrite the columns PV_t(i) just read P from).
+//   MMA issue order of issuer t per step i:  [p_full_t(i)] PV_t(i) QK_t(i+2)
 //
-// The running maximum is only moved when a sub-tile's maximum exceeds it by more than 2^8 ("lazy rescale"): P stays
+// The running maximum is only moved when a step's maximum exceeds it by more than 2^8 ("lazy rescale"): P stays
 // <= 256 (exact in fp16/bf16 range, fp32 row sums), the result is identical after the final normalisation, and the O
-// round trip through TMEM almost never happens after the first sub-tiles.  softmax_1 adds exp2(-m) to the final
+// round trip through TMEM almost never happens after the first steps.  softmax_1 adds exp2(-m) to the final
 // denominator in the same frame (vutils/softmax_1.py:18-20).  Clipped / probs-quantised modes run a stats pass
-// (QK^T only, exact running (m_h, l_h)), merge the halves' statistics through shared memory, and then a PV pass
-// that recomputes QK^T (two-pass; see attn_fwd_sm100.cu).
+// (QK^T only, exact running (m_b, l_b)), merge the streams' statistics through shared memory, and then a PV pass
+// that recomputes QK^T (two-pass; see attn_fwd_sm100.cu).  In that PV pass a warp whose 32 rows x 64 keys all fall
+// below the clip / quantisation threshold writes P = 0 without evaluating a single exponential ("sparse skip").
+// Tried and dropped: staging P through shared memory so that S can be refilled before P is ready (SS-mode PV costs
+// 48 instead of 32 clocks per MMA and the extra smem traffic made it 22 % slower, profiles/r01_ws3_variants_g.txt).
 #pragma once
 
 #include "attn_common.cuh"
@@ -60,30 +60,22 @@ extern "C" int oeh_trace_read(long long* host_out) {
 #define OEH_T_PRINT(role, n) do { } while (0)
 #endif
 
+
 namespace oeh {
 namespace attn_ws {
 
 using namespace attn;
 
-constexpr int BNW = 64;                                            // keys per sub-tile (one MMA step)
-constexpr int BNH = 32;                                            // keys per softmax stream and step
+constexpr int BNW = 64;                                            // keys per step
 constexpr int kSubBytes = BNW * HD * 2;                            // 8 KB
 constexpr int kStages = 8;
 constexpr int kThreads = 640;                                      // 20 warps
 constexpr int kQRows = 256;                                        // query rows per CTA (two tiles)
 constexpr int kSmemBytes = 2 * kTileBytes + 2 * kStages * kSubBytes + 1024;   // Q0 Q1 | K ring | V ring
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColO0 = 256;                                   // S_t[b] at (2t+b)*64, O_{t,h} at 256 + (2t+h)*64
+constexpr uint32_t kColO0 = 256;                                   // S_t[b] at (2t+b)*64, O_{t,b} at 256 + (2t+b)*64
 constexpr float kLazyRescale = 8.f;                                // log2 units
 constexpr int kSoftmaxRegs = 112, kAuxRegs = 24;                   // 16*32*112 + 4*32*24 <= 640 * 96
-
-struct Barriers {
-  uint64_t q_full;
-  uint64_t k_full[kStages], k_empty[kStages];
-  uint64_t v_full[kStages], v_empty[kStages];
-  uint64_t s_full[2][2], p_full[2][2], o_done[2][2];
-  uint64_t o_final[2];
-};
 
 template <int kRegs>
 __device__ __forceinline__ void reg_alloc() {
@@ -94,26 +86,34 @@ __device__ __forceinline__ void reg_dealloc() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
 }
 
-// kNorm: P must be normalised before PV (clipped variants / probs fake-quant) -> two-pass; compiled separately so the
-// one-pass hot loop carries none of the two-pass branches.
+struct Barriers {
+  uint64_t q_full;
+  uint64_t k_full[kStages], k_empty[kStages];
+  uint64_t v_full[kStages], v_empty[kStages];
+  uint64_t s_full[2][2], p_full[2][2];
+  uint64_t o_final[2];
+};
+
 template <bool kBF16, bool kGeneric, bool kNorm>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
-                   const __grid_constant__ CUtensorMap tmv, const __grid_constant__ AttnParams p) {
+                    const __grid_constant__ CUtensorMap tmv, const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) Barriers bars;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float xch_m[2][2][128], xch_l[2][2][128];            // (tile, half, row): statistics merged across halves
+  __shared__ float xch_m[2][2][128], xch_l[2][2][128];            // (tile, parity, row): statistics merged across streams
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from it
+  // (role, TMEM lane base, barrier / descriptor addresses) on the uniform datapath instead of R2UR-ing it at every use
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   // causal: heaviest Q tiles of a head first, so the last CTAs of the grid are the short ones
   const int qt = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
   const int q0 = qt * kQRows, h = blockIdx.y, b = blockIdx.z;
 
   const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem0;                                    // 2 tiles of 128 rows
-  const uint32_t sK = smem0 + 2 * kTileBytes;                   // kStages sub-tiles of 64 keys
-  const uint32_t sV = sK + kStages * kSubBytes;                 // kStages sub-tiles
+  const uint32_t sK = smem0 + 2 * kTileBytes;                   // kStages steps of 64 keys
+  const uint32_t sV = sK + kStages * kSubBytes;
 
   if (tid == 0) {
     ptx::mbar_init(ptx::smem_u32(&bars.q_full), 1);
@@ -129,8 +129,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
 #pragma unroll
       for (int sb = 0; sb < 2; ++sb) {
         ptx::mbar_init(ptx::smem_u32(&bars.s_full[t][sb]), 1);
-        ptx::mbar_init(ptx::smem_u32(&bars.p_full[t][sb]), 8);  // one elected lane of each of the tile's 8 softmax warps
-        ptx::mbar_init(ptx::smem_u32(&bars.o_done[t][sb]), 1);
+        ptx::mbar_init(ptx::smem_u32(&bars.p_full[t][sb]), 4);  // one elected lane of each of the stream's 4 warps
       }
       ptx::mbar_init(ptx::smem_u32(&bars.o_final[t]), 1);
     }
@@ -169,7 +168,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       tma_tile(sQ + kTileBytes, &tmq, bq, p.cq, q0 + 128, h, b);
     }
     __syncwarp();
-    auto load_k = [&](int i) {                                  // K sub-tile of step i -> ring slot i % kStages
+    auto load_k = [&](int i) {                                  // K of step i -> ring slot i % kStages
       const int s = i % kStages, n = i / kStages;
       if (n > 0) ptx::mbar_wait(ptx::smem_u32(&bars.k_empty[s]), (uint32_t)(n - 1) & 1u);
       if (ptx::elect_one()) {
@@ -196,7 +195,6 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     }
   } else if (warp == 16 || warp == 18) {
     // ================================ MMA issuers: warp 16 serves Q tile 0, warp 18 Q tile 1 ===============
-    // (whole warp waits, one elected lane issues)
     const int t = (warp - 16) >> 1;
     constexpr uint32_t kIdescQK = ptx::make_idesc_f16(kBF16, 128, BNW, false, false);
     constexpr uint32_t kIdescPV = ptx::make_idesc_f16(kBF16, 128, HD, false, true);
@@ -211,13 +209,11 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       for (int k = 0; k < HD / 16; ++k)
         ptx::mma_ss(tS0 + sb * 64, dq + k * 2, dk + stage * kSubUnits + k * 2, kIdescQK, k > 0);
     };
-    auto issue_pv = [&](int sb, int stage, bool first) {         // O_{t,hf} (+)= P_{t,hf}[sb] . V(stage)[32hf..]  (K = 32)
+    auto issue_pv = [&](int sb, int stage, bool first) {         // O_{t,sb} (+)= P_t[sb] . V(stage)  (K = 64 keys)
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf)
-#pragma unroll
-        for (int k = 0; k < BNH / 16; ++k)
-          ptx::mma_ts(tO0 + hf * 64, tS0 + sb * 64 + hf * 32 + k * 8, dv + stage * kSubUnits + (hf * 2 + k) * 128, kIdescPV,
-                      (first && k == 0) ? 0u : 1u);
+      for (int k = 0; k < BNW / 16; ++k)
+        ptx::mma_ts(tO0 + sb * 64, tS0 + sb * 64 + k * 8, dv + stage * kSubUnits + k * 128, kIdescPV,
+                    (first && k == 0) ? 0u : 1u);
     };
     ptx::mbar_wait(ptx::smem_u32(&bars.q_full), 0);
     OEH_T_DECL;
@@ -247,8 +243,8 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       OEH_T(2);
       if (ptx::elect_one()) {
         if (pv) {
-          issue_pv(sb, vs, v == 0);
-          ptx::mma_commit(ptx::smem_u32(last ? &bars.o_final[t] : &bars.o_done[t][v & 1]));
+          issue_pv(sb, vs, v < 2);                               // the first PV step of each parity starts its accumulator
+          if (last) ptx::mma_commit(ptx::smem_u32(&bars.o_final[t]));
           ptx::mma_commit(ptx::smem_u32(&bars.v_empty[vs]));
         }
         if (more) {
@@ -264,12 +260,13 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   } else if (warp < 16) {
     // ================================ softmax streams ======================================================
     reg_alloc<kSoftmaxRegs>();
-    const int t = warp >> 3, hf = (warp >> 2) & 1;                // Q tile, column half
+    const int t = warp >> 3, par = (warp >> 2) & 1;               // Q tile, step parity
     const int r = (warp & 3) * 32 + (tid & 31);                   // row within the tile == TMEM lane
     const int row = q0 + t * 128 + r;                             // this thread's query row
     const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t tS0 = t_lane + (uint32_t)(2 * t) * 64u + hf * 32u;       // + sb*64: this stream's S / P columns
-    const uint32_t tO = t_lane + kColO0 + (uint32_t)(2 * t + hf) * 64u;    // this stream's accumulator
+    const uint32_t tS = t_lane + (uint32_t)(2 * t + par) * 64u;              // this stream's S / P columns
+    const uint32_t tO = t_lane + kColO0 + (uint32_t)(2 * t + par) * 64u;     // this stream's accumulator
+    const uint32_t bar_s = ptx::smem_u32(&bars.s_full[t][par]), bar_p = ptx::smem_u32(&bars.p_full[t][par]);
 
     const bool has_qs = kGeneric && p.qdq_scores != nullptr;
     const bool has_qp = kGeneric && p.qdq_probs != nullptr;
@@ -282,15 +279,16 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     const int causal_lim = p.causal ? row + (p.Tk - p.Tq) : 0x7fffffff;
 
     float m_run = -INFINITY, l_run = 0.f, inv_den = 1.f, skip_thr = -INFINITY;
+    bool merged = false, started = false;                         // statistics merged / accumulator holds a PV result
     OEH_T_DECL;
 
-    // merge (m_h, l_h) of the two halves of a row: afterwards both hold the row's m and l in the common frame
-    auto merge_halves = [&](float& a_own, float& a_other, float& l_other) {
-      xch_m[t][hf][r] = m_run;
-      xch_l[t][hf][r] = l_run;
+    // merge (m_b, l_b) of the two streams of a row: afterwards both hold the row's m in the common frame
+    auto merge_streams = [&](float& a_own, float& a_other, float& l_other) {
+      xch_m[t][par][r] = m_run;
+      xch_l[t][par][r] = l_run;
       asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
-      const float m_o = xch_m[t][hf ^ 1][r];
-      l_other = xch_l[t][hf ^ 1][r];
+      const float m_o = xch_m[t][par ^ 1][r];
+      l_other = xch_l[t][par ^ 1][r];
       const float m = fmaxf(m_run, m_o);
       const float m_safe = m == -INFINITY ? 0.f : m;
       a_own = ptx::ex2(m_run - m_safe);                           // -inf -> 0
@@ -298,29 +296,22 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       m_run = m;
     };
 
-#ifdef OEH_STAGGER   // experiment: start Q tile 1 out of phase with Q tile 0
-    if (t == 1) {
-      const long long c0 = clock64();
-      while (clock64() - c0 < OEH_STAGGER) { }
-    }
-#endif
-    for (int i = 0; i < n_iter; ++i) {
-      const int sb = i & 1;
-      const uint32_t tS = tS0 + sb * 64u;
-      const uint32_t bar_p = ptx::smem_u32(&bars.p_full[t][sb]);
+    for (int i = par; i < n_iter; i += 2) {
       const bool pv_iter = i >= nA;
-      const int k0 = (pv_iter ? i - nA : i) * BNW + hf * BNH;
-      if (normalized && i == nA) {                                // stats pass done: the row statistics become common
+      const int k0 = (pv_iter ? i - nA : i) * BNW;
+      if (normalized && pv_iter && !merged) {                     // stats pass done: the row statistics become common
         float a_own, a_other, l_other;
-        merge_halves(a_own, a_other, l_other);
+        merge_streams(a_own, a_other, l_other);
         l_run = l_run * a_own + l_other * a_other;
+        merged = true;
       }
       OEH_T(0);
-      ptx::mbar_wait(ptx::smem_u32(&bars.s_full[t][sb]), (uint32_t)(i >> 1) & 1u);
+      ptx::mbar_wait(bar_s, (uint32_t)(i >> 1) & 1u);
       ptx::tc_fence_after();
       OEH_T(1);
-      float s[BNH];
+      float s[BNW];
       ptx::tmem_ld32(tS, reinterpret_cast<uint32_t*>(s));
+      ptx::tmem_ld32(tS + 32, reinterpret_cast<uint32_t*>(s) + 32);
       ptx::tmem_wait_ld();
       OEH_T(2);
       if (!pv_iter) {                                             // stats pass: S is consumed, QK^T(i+2) may start
@@ -328,80 +319,86 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         __syncwarp();
         if (ptx::elect_one()) ptx::mbar_arrive(bar_p);
       }
-      if (kGeneric && p.dbg_s && i < 2 && k0 == i * BNW + hf * BNH && row < p.Tq) {   // raw S of keys [0,128)
+      if (kGeneric && p.dbg_s && i < 2 && row < p.Tq) {           // raw S of keys [0,128)
         float* d = p.dbg_s + (((int64_t)b * p.H + h) * p.Tq + row) * BN + k0;
 #pragma unroll
-        for (int j = 0; j < BNH; ++j) d[j] = s[j];
+        for (int j = 0; j < BNW; ++j) d[j] = s[j];
       }
 
-      const int valid = min(p.Tk - k0, BNH);
+      const int valid = min(p.Tk - k0, BNW);
       const int vis = min(valid - 1, causal_lim - k0);
-      const float mul = transform_scores<BNH, kGeneric>(s, p, qd_s, has_qs, has_mask, mask_row, k0, valid, vis);
-      const float tile_max = row_max<BNH>(s) * mul;
+      const float mul = transform_scores<BNW, kGeneric>(s, p, qd_s, has_qs, has_mask, mask_row, k0, valid, vis);
+      const float tile_max = row_max<BNW>(s) * mul;
       OEH_T(3);
 
       if (!pv_iter) {
-        // stats pass: exact running (m, l) of this half
+        // stats pass: exact running (m, l) of this stream
         const float m_new = fmaxf(m_run, tile_max);
         const float m_safe = m_new == -INFINITY ? 0.f : m_new;
         const float alpha = ptx::ex2(m_run - m_safe);
-        l_run = fmaf(l_run, alpha, exp2_and_sum<BNH>(s, mul, m_safe));
+        l_run = fmaf(l_run, alpha, exp2_and_sum<BNW, !kGeneric>(s, mul, m_safe));
         m_run = m_new;
         continue;
       }
       if (normalized) {
-        // PV pass of the two-pass mode: (m, l) are final and common to both halves
+        // PV pass of the two-pass mode: (m, l) are final and common to both streams
         const float m_safe = m_run == -INFINITY ? 0.f : m_run;
-        if (i == nA) {
+        if (!started) {
           const float den = softmax1 ? l_run + ptx::ex2(-m_safe) : l_run;
           inv_den = __frcp_rn(den);
           skip_thr = zero_prob_threshold(p, clipped, has_qp, qd_p, den);
         }
 #ifndef OEH_NO_SPARSE_SKIP
-        // Clipped softmax with gamma < 0 (and / or the probs tap) maps every probability below a fixed bound to an
-        // exact 0: at most 1/bound keys of a row survive, whatever the sequence length.  If none of this warp's
-        // 32 rows x 32 keys can survive, P is 0 without a single exponential (the stats pass already paid for them).
+        // Clipped softmax with gamma < 0 (and / or the probs tap) maps every probability below a fixed bound to an exact
+        // 0: at most 1/bound keys of a row survive, whatever the sequence length.  If none of this warp's 32 rows x
+        // 64 keys can survive, P is 0 without a single exponential (the stats pass already paid for them).
+        // (Own store path: merging the two branches through s[] makes ptxas spill the packed row.)
         if (!__any_sync(0xffffffffu, tile_max - m_safe > skip_thr)) {
+          uint32_t z[BNW / 2];
 #pragma unroll
-          for (int j = 0; j < BNH; ++j) s[j] = 0.f;
-        } else
-#endif
-        {
-          exp2_only<BNH>(s, mul, m_safe);
-          normalize_probs<BNH, kGeneric>(s, p, inv_den, clipped, has_qp, qd_p);
+          for (int j = 0; j < BNW / 2; ++j) z[j] = 0u;
+          ptx::tmem_st32(tS, z);
+          ptx::tmem_wait_st();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (ptx::elect_one()) ptx::mbar_arrive(bar_p);
+          started = true;
+          continue;
         }
+#endif
+        exp2_only<BNW, !kGeneric>(s, mul, m_safe);
+        normalize_probs<BNW, kGeneric>(s, p, inv_den, clipped, has_qp, qd_p);
       } else {
         // online softmax with lazy rescale
         const bool move = tile_max > m_run + kLazyRescale || m_run == -INFINITY;
         const float m_new = move ? tile_max : m_run;              // tile_max may be -inf only if m_run is too
         const float m_safe = m_new == -INFINITY ? 0.f : m_new;
         const float alpha = move ? ptx::ex2(m_run - m_safe) : 1.f;
-        l_run = fmaf(l_run, alpha, exp2_and_sum<BNH>(s, mul, m_safe));
+        l_run = fmaf(l_run, alpha, exp2_and_sum<BNW, !kGeneric>(s, mul, m_safe));
         m_run = m_new;
-        if (i > nA && !__all_sync(0xffffffffu, alpha == 1.f)) {
-          // O_{t,hf} *= alpha; needs PV_t(v-1) complete.  Its o_done barrier is at most one phase behind: PV_t(v-2)
-          // is complete (S_t(i) was committed behind it) and PV_t(v) needs the P this thread has not written yet.
-          const int v1 = i - nA - 1;
-          ptx::mbar_wait(ptx::smem_u32(&bars.o_done[t][v1 & 1]), (uint32_t)(v1 >> 1) & 1u);
-          ptx::tc_fence_after();
-          uint32_t o[HD];
-          ptx::tmem_ld32(tO, o);
-          ptx::tmem_ld32(tO + 32, o + 32);
-          ptx::tmem_wait_ld();
+        if (started && !__all_sync(0xffffffffu, alpha == 1.f)) {
+          // O_{t,par} *= alpha.  No barrier: S_t(i) was committed behind PV_t(i-2) -- the last MMA that wrote this
+          // accumulator -- in the issuer's in-order stream, and PV_t(i) needs the P this thread has not written yet.
 #pragma unroll
-          for (int j = 0; j < HD; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-          ptx::tmem_st32(tO, o);
-          ptx::tmem_st32(tO + 32, o + 32);
+          for (int c = 0; c < HD / 16; ++c) {
+            uint32_t o[16];
+            ptx::tmem_ld16(tO + c * 16, o);
+            ptx::tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+            ptx::tmem_st16(tO + c * 16, o);
+          }
         }
       }
+      started = true;
       OEH_T(4);
 
-      // P_{t,hf} -> TMEM (packed 16-bit pairs) over the first 16 columns of the S half this thread has consumed
+      // P -> TMEM (packed 16-bit pairs) over the first 32 columns of the S buffer this thread has consumed
       {
-        uint32_t pk[BNH / 2];
+        uint32_t pk[BNW / 2];
 #pragma unroll
-        for (int j = 0; j < BNH / 2; ++j) pk[j] = pack2<kBF16>(s[2 * j], s[2 * j + 1]);
-        ptx::tmem_st16(tS, pk);
+        for (int j = 0; j < BNW / 2; ++j) pk[j] = pack2<kBF16>(s[2 * j], s[2 * j + 1]);
+        ptx::tmem_st32(tS, pk);
       }
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
@@ -411,32 +408,38 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     }
     OEH_T_PRINT("softmax: top s_full ld max exp pack+arrive", n_iter);
 
-    // ---- epilogue: merge the halves, O / denominator -> gate / taps -> global ----------------------------------
-    float a0 = 1.f, a1 = 1.f, omul = 1.f;                         // scales of O_{t,0}, O_{t,1}; 1/denominator
+    // ---- epilogue: merge the streams, O / denominator -> gate / taps -> global -----------------------------------
+    float a_own = 1.f, a_other = 1.f, omul = 1.f;                 // scales of the two accumulators; 1/denominator
     if (!normalized) {
-      float a_own, a_other, l_other;
-      merge_halves(a_own, a_other, l_other);
+      float l_other;
+      merge_streams(a_own, a_other, l_other);
       const float m_safe = m_run == -INFINITY ? 0.f : m_run;
       float den = l_run * a_own + l_other * a_other;
       if (softmax1) den += ptx::ex2(-m_safe);
       omul = __frcp_rn(den);
-      a0 = hf ? a_other : a_own;
-      a1 = hf ? a_own : a_other;
+    } else if (!merged) {                                         // a stream without PV steps still owes the barrier
+      float l_other;
+      merge_streams(a_own, a_other, l_other);
+      a_own = a_other = 1.f;
     }
+    // an accumulator exists iff some PV step had its parity (only n_kv == 1 leaves one of them untouched)
+    const bool has0 = n_kv > 1 || (nA & 1) == 0, has1 = n_kv > 1 || (nA & 1) == 1;
+    const float a0 = par ? a_other : a_own, a1 = par ? a_own : a_other;
     ptx::mbar_wait(ptx::smem_u32(&bars.o_final[t]), 0);
     ptx::tc_fence_after();
-    // this thread finishes head-dim columns [32hf, 32hf+32) of its row from both accumulators
-    float o[BNH];
+    // this thread finishes head-dim columns [32par, 32par+32) of its row from both accumulators
+    float o[32];
     {
-      uint32_t u0[BNH], u1[BNH];
-      const uint32_t tOt = t_lane + kColO0 + (uint32_t)(2 * t) * 64u + hf * 32u;
+      uint32_t u0[32], u1[32];
+      const uint32_t tOt = t_lane + kColO0 + (uint32_t)(2 * t) * 64u + par * 32u;
       ptx::tmem_ld32(tOt, u0);
       ptx::tmem_ld32(tOt + 64, u1);
       ptx::tmem_wait_ld();
 #pragma unroll
-      for (int j = 0; j < BNH; ++j) o[j] = fmaf(__uint_as_float(u0[j]), a0, __uint_as_float(u1[j]) * a1);
+      for (int j = 0; j < 32; ++j)
+        o[j] = (has0 ? __uint_as_float(u0[j]) * a0 : 0.f) + (has1 ? __uint_as_float(u1[j]) * a1 : 0.f);
     }
-    if (row < p.Tq) store_row<kBF16, kGeneric, BNH>(o, p, omul, b, h, row, hf * BNH);
+    if (row < p.Tq) store_row<kBF16, kGeneric, 32>(o, p, omul, b, h, row, par * 32);
   }
 
   // ---- teardown ------------------------------------------------------------------------------------------------

@@ -96,6 +96,8 @@ class _QuantizedBertResidualBlock(QuantizedModel):
             return False
         if tap.active and not tap.fixed:
             return False
+        if ln._forward_hooks or ln._forward_pre_hooks or tap._forward_hooks or tap._forward_pre_hooks:
+            return False                                            # somebody observes the intermediate tensors
         out = ln.activation_quantizer
         if ln._qa_host and (out.estimating or not isinstance(out.quantizer, AsymmetricUniformQuantizer)):
             return False
