@@ -37,7 +37,7 @@ ATTN_SOFTMAX = "clippedsoftmax1(-.025:1)"
 BATCH, SEQ, HEADS, HEAD_DIM, LAYERS = 32, 128, 12, 64, 12
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel (ncu --set full capture under
 # profiles/); None until a capture of the current kernel is committed
-NCU_TRAFFIC_BYTES_PER_LAUNCH = None
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 18895872   # profiles/r01_ncu_one_clip1_T128.txt: 18.90 MB read + 0 written (ctx still in L2)
 WORKLOAD = "BERT-base fp16 eval, --attn_softmax clippedsoftmax1(-.025:1), seq 128, batch 32 per GPU (BASELINE config 2)"
 
 

@@ -181,7 +181,7 @@ __device__ __forceinline__ void exp2_poly2(uint64_t t2, float& e0, float& e1) {
 }
 
 #ifndef OEH_POLY_PAIRS
-#define OEH_POLY_PAIRS 2     // pairs out of every 16 (= 32 columns) that take the polynomial path
+#define OEH_POLY_PAIRS 3     // pairs out of every 16 (= 32 columns) that take the polynomial path
 #endif
 // pair pi of a row chunk goes to the FMA pipe if this is true (evenly spread over the chunk)
 __host__ __device__ constexpr bool poly_pair(int pi) { return ((pi % 16) * OEH_POLY_PAIRS) % 16 < OEH_POLY_PAIRS; }
