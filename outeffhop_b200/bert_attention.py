@@ -162,6 +162,30 @@ def _check_no_grad(*tensors):
             "(training / backward is outside the hot-path scope, SURVEY section 2 #15)")
 
 
+def fused_qkv_projection(owner: nn.Module, mods, hidden_states: torch.Tensor, num_heads: int, head_dim: int):
+    """Plain self-attention in eval: ONE (B*T, D) x (D, 3D) library GEMM for the three projections instead of three (a
+    768-wide output is < 1 wave of GEMM tiles on 148 SMs; 2304 wide fills them).  The concatenated weight is a cache
+    keyed on the three Linear parameters (the q/k/v Linear modules stay the modules of record: state_dict, hooks,
+    quantized wrappers); q, k, v come back as (B,H,T,d) strided views of the (B,T,3,H,d) result, which the fused
+    kernel's tensor maps take as they are.  Returns None whenever the three modules must run themselves."""
+    if owner.training or any(type(m) is not nn.Linear or m._forward_hooks or m._forward_pre_hooks for m in mods) \
+            or any((m.bias is None) != (mods[0].bias is None) for m in mods):
+        return None
+    key = tuple((m.weight.data_ptr(), m.weight._version, 0 if m.bias is None else m.bias.data_ptr(),
+                 0 if m.bias is None else m.bias._version) for m in mods)
+    cache = owner.__dict__.get("_qkv_cache")
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            w = torch.cat([m.weight for m in mods], dim=0)
+            b = None if mods[0].bias is None else torch.cat([m.bias for m in mods], dim=0)
+        cache = (key, w, b)
+        owner.__dict__["_qkv_cache"] = cache
+    y = nn.functional.linear(hidden_states, cache[1], cache[2])
+    B, T = y.shape[0], y.shape[1]
+    y = y.view(B, T, 3, num_heads, head_dim)
+    return tuple(y[:, :, j].permute(0, 2, 1, 3) for j in range(3))
+
+
 class BertSelfAttentionWithExtras(GateMixin, nn.Module):
     def __init__(self, config, position_embedding_type=None, softmax_fn=torch.nn.functional.softmax, alpha=None,
                  ssm_eps=None, tau=None, max_seq_length=None, skip_attn=False,
@@ -216,28 +240,8 @@ class BertSelfAttentionWithExtras(GateMixin, nn.Module):
         return self.gate_scaling_factor
 
     def _fused_qkv(self, hidden_states: torch.Tensor):
-        """Plain self-attention in eval: ONE (B*T, D) x (D, 3D) library GEMM for query/key/value instead of three (a
-        768-wide output is < 1 wave of GEMM tiles on 148 SMs; 2304 wide fills them).  The concatenated weight is a cache
-        keyed on the three Linear parameters (``query/key/value`` stay the modules of record: state_dict, hooks,
-        quantized wrappers); q, k, v come back as (B,H,T,d) strided views of the (B,T,3,H,d) result, which the fused
-        kernel's tensor maps take as they are.  Returns None whenever the three modules must run themselves."""
-        mods = (self.query, self.key, self.value)
-        if self.training or any(type(m) is not nn.Linear or m._forward_hooks or m._forward_pre_hooks for m in mods) \
-                or any((m.bias is None) != (mods[0].bias is None) for m in mods):
-            return None
-        key = tuple((m.weight.data_ptr(), m.weight._version, 0 if m.bias is None else m.bias.data_ptr(),
-                     0 if m.bias is None else m.bias._version) for m in mods)
-        cache = self.__dict__.get("_qkv_cache")
-        if cache is None or cache[0] != key:
-            with torch.no_grad():
-                w = torch.cat([m.weight for m in mods], dim=0)
-                b = None if mods[0].bias is None else torch.cat([m.bias for m in mods], dim=0)
-            cache = (key, w, b)
-            self.__dict__["_qkv_cache"] = cache
-        y = nn.functional.linear(hidden_states, cache[1], cache[2])
-        B, T = y.shape[0], y.shape[1]
-        y = y.view(B, T, 3, self.num_attention_heads, self.attention_head_size)
-        return tuple(y[:, :, j].permute(0, 2, 1, 3) for j in range(3))
+        return fused_qkv_projection(self, (self.query, self.key, self.value), hidden_states, self.num_attention_heads,
+                                    self.attention_head_size)
 
     def transpose_for_scores(self, x: torch.Tensor) -> torch.Tensor:
         new_x_shape = x.size()[:-1] + (self.num_attention_heads, self.attention_head_size)

@@ -61,6 +61,9 @@ attn_fwd_one_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   constexpr uint32_t kIdescPV = ptx::make_idesc_f16(kBF16, BM, HD, false, true);
 
   if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmq);                    // descriptor fetches overlap the barrier initialisation
+    ptx::prefetch_tmap(&tmk);
+    ptx::prefetch_tmap(&tmv);
     ptx::mbar_init(bar_qk, 1);
     ptx::mbar_init(bar_v, 1);
     ptx::mbar_init(bar_mma, 1);

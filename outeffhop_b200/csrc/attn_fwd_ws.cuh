@@ -39,7 +39,11 @@
 // that recomputes QK^T (two-pass; see attn_fwd_sm100.cu).  In that PV pass a warp whose 32 rows x 64 keys all fall
 // below the clip / quantisation threshold writes P = 0 without evaluating a single exponential ("sparse skip").
 // Tried and dropped: staging P through shared memory so that S can be refilled before P is ready (SS-mode PV costs
-// 48 instead of 32 clocks per MMA and the extra smem traffic made it 22 % slower, profiles/r01_ws3_variants_g.txt).
+// 48 instead of 32 clocks per MMA and the extra smem traffic made it 22 % slower, profiles/r01_ws3_variants_g.txt);
+// one S buffer per tile released right after the tcgen05.ld, with P in its own TMEM region (S 128 + P 128 + O 256
+// columns): the s_full wait halves but the step is no shorter, 951 vs 959 TFLOP/s (profiles/r01_ws4_variants_i.txt) --
+// without any MUFU work both plans stop at ~1000-1030 TFLOP/s, i.e. the FMA / ALU / XU pipes of the four softmax warps
+// per sub-partition overlap imperfectly, and more warps would need TMEM and registers this kernel does not have.
 #pragma once
 
 #include "attn_common.cuh"

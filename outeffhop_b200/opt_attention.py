@@ -24,7 +24,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .bert_attention import FUSED_HEAD_DIM, AttentionGateType, GateMixin, _check_no_grad
+from .bert_attention import FUSED_HEAD_DIM, AttentionGateType, GateMixin, _check_no_grad, fused_qkv_projection
 from .softmax import KIND_CLIPPED, KIND_CLIPPED1, SoftmaxFn, as_softmax_fn
 
 
@@ -166,8 +166,17 @@ class OPTAttentionWithExtras(GateMixin, nn.Module):
         is_cross_attention = key_value_states is not None
         bsz, tgt_len, _ = hidden_states.size()
 
-        q = self._heads(self.q_proj(hidden_states), bsz)
-        if is_cross_attention and past_key_value is not None:                                 # :169-172
+        fused_qkv = None
+        if not is_cross_attention and past_key_value is None:
+            fused_qkv = fused_qkv_projection(self, (self.q_proj, self.k_proj, self.v_proj), hidden_states,
+                                             self.num_heads, self.head_dim)
+        if fused_qkv is not None:
+            q, k, v = fused_qkv
+        else:
+            q = self._heads(self.q_proj(hidden_states), bsz)
+        if fused_qkv is not None:
+            pass
+        elif is_cross_attention and past_key_value is not None:                               # :169-172
             k, v = past_key_value[0], past_key_value[1]
         elif is_cross_attention:                                                              # :173-176
             k = self._heads(self.k_proj(key_value_states), bsz)
