@@ -52,54 +52,81 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    """SM clock and clock-event (throttle) reasons of one GPU sampled every 5 ms DURING the timed region through NVML
+    (a 50-step timed region lasts ~70 ms -- shorter than one `nvidia-smi -lms` period or its start-up time);
+    falls back to one `nvidia-smi --query-gpu` call per second if pynvml is unavailable."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4),
+               ("hw_power_brake_slowdown", 0x80))
 
-    def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
-        self.rows = []
-        self.proc = None
+    def __init__(self, gpu_index: int, uuid: str = ""):
+        self.gpu, self.uuid = gpu_index, uuid
+        self.rows = []                       # (time, sm_mhz, reason bit mask)
+        self.max_mhz = None
+        self.stop_flag = threading.Event()
         self.thread = None
+        self.backend = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        if self.uuid:
+            try:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(self.uuid if self.uuid.startswith("GPU-") else "GPU-" + self.uuid)
+            except Exception:
+                pass
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = self.gpu
+        if vis and all(x.strip().isdigit() for x in vis.split(",")):
+            idx = int(vis.split(",")[self.gpu])
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
+            nv, h = self._nvml_handle()
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.rows.append((time.time(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self.backend = "nvml"
         except Exception:
-            self.proc = None
-            return
-        self.thread = threading.Thread(target=self._read, daemon=True)
+            def loop():
+                q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+                while not self.stop_flag.is_set():
+                    try:
+                        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                        self.max_mhz = float(out[1])
+                        self.rows.append((time.time(), float(out[0]), int(out[2].strip(), 16)))
+                    except Exception:
+                        pass
+                    time.sleep(1.0)
+            self.backend = "nvidia-smi"
+        self.thread = threading.Thread(target=loop, daemon=True)
         self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
-
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
 
     def summary(self, t0: float, t1: float):
-        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.25 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        rows = inside or [r for r in self.rows if t0 - 0.5 <= r[0] <= t1 + 0.5] or self.rows
         if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
-        reasons = set()
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        mask = 0
         for r in rows:
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                if r[col].lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(rows)}
+            mask |= r[2]
+        return {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": self.max_mhz,
+                "reasons": [name for name, bit in self.REASONS if mask & bit], "samples": len(rows),
+                "samples_inside_timed_region": len(inside), "source": self.backend}
 
 
 def run_reference(args):
@@ -213,7 +240,11 @@ def run_ours(args):
     dev_pool = [{k: v.cuda() for k, v in hb.items()} for hb in host_pool]
     step = make_bert_eval_step(model, host_pool[0], use_graph=not args.no_graph)
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
-    sampler = ClockSampler(local_rank)
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        gpu_uuid = ""
+    sampler = ClockSampler(local_rank, gpu_uuid)
     if rank == 0:
         sampler.start()
 

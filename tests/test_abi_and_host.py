@@ -121,3 +121,46 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU"):
         _lib.lib()
+
+
+# ---- host logic of the eval-step fusions (CPU tensors: these helpers are pure tensor plumbing) ------------------------
+def test_fused_qkv_projection_views_cache_and_opt_outs():
+    import torch
+    from torch import nn
+    from outeffhop_b200.bert_attention import fused_qkv_projection
+    torch.manual_seed(0)
+    H, d = 4, 8
+    owner = nn.Module().eval()
+    mods = tuple(nn.Linear(H * d, H * d) for _ in range(3))
+    x = torch.randn(2, 5, H * d)
+    with torch.no_grad():
+        q, k, v = fused_qkv_projection(owner, mods, x, H, d)
+        for got, m in zip((q, k, v), mods):
+            want = m(x).view(2, 5, H, d).permute(0, 2, 1, 3)
+            assert got.shape == want.shape and got.stride(3) == 1
+            assert torch.allclose(got, want, atol=1e-6)
+        cache = owner.__dict__["_qkv_cache"]
+        fused_qkv_projection(owner, mods, x, H, d)
+        assert owner.__dict__["_qkv_cache"] is cache                      # parameters untouched: cache reused
+        mods[1].weight.mul_(2.0)                                          # in-place update bumps ._version
+        q2, k2, v2 = fused_qkv_projection(owner, mods, x, H, d)
+        assert owner.__dict__["_qkv_cache"] is not cache
+        assert torch.allclose(k2, mods[1](x).view(2, 5, H, d).permute(0, 2, 1, 3), atol=1e-6)
+    assert "_qkv_cache" not in dict(owner.named_buffers()) and not list(owner.parameters())
+    mods[0].register_forward_hook(lambda *a: None)                        # somebody observes `query`: no fusion
+    assert fused_qkv_projection(owner, mods, x, H, d) is None
+    assert fused_qkv_projection(nn.Module().train(), tuple(nn.Linear(4, 4) for _ in range(3)), torch.randn(1, 1, 4), 1, 4) is None
+
+
+def test_padded_decoder_is_zero_padded_and_cached():
+    import torch
+    from torch import nn
+    from outeffhop_b200.eval_harness import _padded_decoder
+    lin = nn.Linear(16, 30522 % 1000 + 3)                                 # 525 outputs -> padded to 576
+    w, b, V = _padded_decoder(lin)
+    assert V == 525 and w.shape == (576, 16) and b.shape == (576,)
+    assert torch.equal(w[:V], lin.weight) and torch.equal(b[:V], lin.bias)
+    assert float(w[V:].abs().sum()) == 0.0 and float(b[V:].abs().sum()) == 0.0
+    assert _padded_decoder(lin)[0] is w
+    aligned = nn.Linear(16, 128)
+    assert _padded_decoder(aligned)[0] is aligned.weight                  # already a multiple of 64: no copy

@@ -88,6 +88,30 @@ def main():
                 r = dict(op="minmax", dtype=dtn, n=n, ms=med, gbs=gb / med * 1e3, gbs_best=gb / best * 1e3)
                 res["quant"].append(r)
                 print(json.dumps(r), flush=True)
+    if not a.no_quant:
+        # fused residual add + LayerNorm (C-BERT rows x 768 and a large case), fused mean cross-entropy (C-BERT logits)
+        for rows, cols in ((4096, 768), (262144, 768)):
+            xa = torch.randn(rows, cols, device="cuda", dtype=torch.float16)
+            xb = torch.randn_like(xa)
+            w, bb = torch.ones(cols, device="cuda", dtype=torch.float16), torch.zeros(cols, device="cuda", dtype=torch.float16)
+            y = torch.empty_like(xa)
+            med, best = time_fn(lambda: ops.add_layer_norm(xa, xb, w, bb, 1e-12, out=y), flush=rows < 100000)
+            gb = rows * cols * 2 * 3 / 1e9
+            r = dict(op="add_layer_norm", dtype="float16", rows=rows, cols=cols, ms=med, gbs=gb / med * 1e3, gbs_best=gb / best * 1e3)
+            res["quant"].append(r)
+            print(json.dumps(r), flush=True)
+        for rows, vocab, pad, frac in ((4096, 30522, 6, 0.15), (4096, 30522, 6, 1.0), (2048, 50272, 0, 1.0)):
+            logits = torch.randn(rows, vocab + pad, device="cuda", dtype=torch.float16)
+            labels = torch.randint(0, vocab, (rows,), device="cuda")
+            labels[torch.rand(rows, device="cuda") >= frac] = -100
+            labels[0] = 1
+            med, best = time_fn(lambda: ops.ce_loss(logits, labels, vocab=vocab))
+            n_lab = int((labels != -100).sum())
+            gb = n_lab * vocab * 2 / 1e9                   # algorithmic bytes: the labelled rows, read once
+            r = dict(op="ce_loss", dtype="float16", rows=rows, vocab=vocab, labelled=n_lab, ms=med, gbs=gb / med * 1e3,
+                     gbs_best=gb / best * 1e3)
+            res["quant"].append(r)
+            print(json.dumps(r), flush=True)
     if a.out:
         with open(a.out, "w") as f:
             json.dump(res, f, indent=1)
