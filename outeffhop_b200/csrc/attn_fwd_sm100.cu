@@ -409,20 +409,37 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
   const int ki = (a->dtype == OEH_BF16 ? 2 : 0) + (generic ? 1 : 0);
   if (use_ws) {
-    const bool norm = norm_mode;
-    const int kw = ki + (norm ? 4 : 0);
-    static const KernelFn kernels[8] = {
-        attn_ws::attn_fwd_ws_kernel<false, false, false>, attn_ws::attn_fwd_ws_kernel<false, true, false>,
-        attn_ws::attn_fwd_ws_kernel<true, false, false>,  attn_ws::attn_fwd_ws_kernel<true, true, false>,
-        attn_ws::attn_fwd_ws_kernel<false, false, true>,  attn_ws::attn_fwd_ws_kernel<false, true, true>,
-        attn_ws::attn_fwd_ws_kernel<true, false, true>,   attn_ws::attn_fwd_ws_kernel<true, true, true>};
-    static bool attr_done[8] = {false, false, false, false, false, false, false, false};
-    if (!attr_done[kw]) {
-      OEH_CUDA_OK(cudaFuncSetAttribute(kernels[kw], cudaFuncAttributeMaxDynamicSharedMemorySize, attn_ws::kSmemBytes));
-      attr_done[kw] = true;
+    const int kw = ki + (norm_mode ? 4 : 0);
+    // Q tiles per CTA: 2 = one 640-thread CTA per SM, 1 = two independent 384-thread CTAs per SM (attn_fwd_ws.cuh, Cfg).
+    // Two small CTAs hide each other's prologue / epilogue (~5.9 us per CTA) but load K / V once per tile and run their
+    // steady state ~10 % slower; measured crossover (profiles/r01_ws_tiles_per_cta_l.txt): the two-pass modes are
+    // faster with one tile at every length, the one-pass modes up to ~24 key steps per query tile on average.
+    const double steps = (double)((a->Tk + attn_ws::BNW - 1) / attn_ws::BNW) * (a->causal ? 0.5 : 1.0);
+    int tiles = (norm_mode || steps <= 24.0) ? 1 : 2;
+#ifdef OEH_WS_TILES
+    tiles = OEH_WS_TILES;
+#endif
+    if (const char* f = getenv("OEH_WS_TILES")) tiles = atoi(f) == 1 ? 1 : 2;
+    static const KernelFn kernels[2][8] = {
+        {attn_ws::attn_fwd_ws_kernel<false, false, false, 1>, attn_ws::attn_fwd_ws_kernel<false, true, false, 1>,
+         attn_ws::attn_fwd_ws_kernel<true, false, false, 1>,  attn_ws::attn_fwd_ws_kernel<true, true, false, 1>,
+         attn_ws::attn_fwd_ws_kernel<false, false, true, 1>,  attn_ws::attn_fwd_ws_kernel<false, true, true, 1>,
+         attn_ws::attn_fwd_ws_kernel<true, false, true, 1>,   attn_ws::attn_fwd_ws_kernel<true, true, true, 1>},
+        {attn_ws::attn_fwd_ws_kernel<false, false, false, 2>, attn_ws::attn_fwd_ws_kernel<false, true, false, 2>,
+         attn_ws::attn_fwd_ws_kernel<true, false, false, 2>,  attn_ws::attn_fwd_ws_kernel<true, true, false, 2>,
+         attn_ws::attn_fwd_ws_kernel<false, false, true, 2>,  attn_ws::attn_fwd_ws_kernel<false, true, true, 2>,
+         attn_ws::attn_fwd_ws_kernel<true, false, true, 2>,   attn_ws::attn_fwd_ws_kernel<true, true, true, 2>}};
+    static bool attr_done[2][8] = {};
+    const int smem = tiles == 1 ? attn_ws::Cfg<1>::kSmemBytes : attn_ws::Cfg<2>::kSmemBytes;
+    const int threads = tiles == 1 ? attn_ws::Cfg<1>::kThreads : attn_ws::Cfg<2>::kThreads;
+    const int qrows = 128 * tiles;
+    KernelFn fn = kernels[tiles - 1][kw];
+    if (!attr_done[tiles - 1][kw]) {
+      OEH_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_done[tiles - 1][kw] = true;
     }
-    dim3 grid((unsigned)((a->Tq + attn_ws::kQRows - 1) / attn_ws::kQRows), (unsigned)a->H, (unsigned)a->B);
-    kernels[kw]<<<grid, attn_ws::kThreads, attn_ws::kSmemBytes, st>>>(tmq, tmk, tmv, p);
+    dim3 grid((unsigned)((a->Tq + qrows - 1) / qrows), (unsigned)a->H, (unsigned)a->B);
+    fn<<<grid, threads, smem, st>>>(tmq, tmk, tmv, p);
     return check_launch("attn_fwd_ws_kernel");
   }
   if (use_one) {

@@ -72,14 +72,27 @@ using namespace attn;
 
 constexpr int BNW = 64;                                            // keys per step
 constexpr int kSubBytes = BNW * HD * 2;                            // 8 KB
-constexpr int kStages = 8;
-constexpr int kThreads = 640;                                      // 20 warps
-constexpr int kQRows = 256;                                        // query rows per CTA (two tiles)
-constexpr int kSmemBytes = 2 * kTileBytes + 2 * kStages * kSubBytes + 1024;   // Q0 Q1 | K ring | V ring
-constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColO0 = 256;                                   // S_t[b] at (2t+b)*64, O_{t,b} at 256 + (2t+b)*64
+// kTiles = Q tiles (of 128 rows) per CTA.  2: one CTA per SM (640 threads, 512 TMEM columns), K / V steps shared by the two
+// tiles.  1: TWO independent CTAs per SM (320 threads, 256 TMEM columns each): the same warps / TMEM per SM, K / V loaded
+// once per tile (twice the L2 -> smem traffic), but a CTA's prologue (TMEM allocation, first Q / K loads, pipeline
+// fill) and epilogue -- ~5.9 us per CTA, a quarter of the run time at T = 2048 -- overlap its neighbour's steady state.
+template <int kTiles>
+struct Cfg {
+  static constexpr int kSoftmaxWarps = 8 * kTiles;
+  static constexpr int kWarpMma0 = kSoftmaxWarps, kWarpTma = kSoftmaxWarps + 1, kWarpMma1 = kSoftmaxWarps + 2;
+  // four auxiliary warps in both shapes (MMA issuer(s), TMA producer, idle): setmaxnreg moves registers between warps of
+  // the SAME sub-partition, so each of the four schedulers needs one warp that gives its registers away
+  static constexpr int kThreads = (kSoftmaxWarps + 4) * 32;          // 640 | 384
+  // launch allocation 96 | 80 registers per thread; 16*112 + 4*24 <= 20*96, 8*104 + 4*24 <= 12*80
+  static constexpr int kSoftmaxRegs = kTiles == 2 ? 112 : 104, kAuxRegs = 24;
+  static constexpr int kCtasPerSm = kTiles == 2 ? 1 : 2;
+  static constexpr int kQRows = 128 * kTiles;                        // query rows per CTA
+  static constexpr int kStages = kTiles == 2 ? 8 : 5;
+  static constexpr int kSmemBytes = kTiles * kTileBytes + 2 * kStages * kSubBytes + 1024;   // Q tiles | K ring | V ring
+  static constexpr uint32_t kTmemCols = 256 * kTiles;
+  static constexpr uint32_t kColO0 = 128 * kTiles;                   // S_t[b] at (2t+b)*64, O_{t,b} at kColO0 + (2t+b)*64
+};
 constexpr float kLazyRescale = 8.f;                                // log2 units
-constexpr int kSoftmaxRegs = 112, kAuxRegs = 24;                   // 16*32*112 + 4*32*24 <= 640 * 96
 
 template <int kRegs>
 __device__ __forceinline__ void reg_alloc() {
@@ -90,6 +103,7 @@ __device__ __forceinline__ void reg_dealloc() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
 }
 
+template <int kStages>
 struct Barriers {
   uint64_t q_full;
   uint64_t k_full[kStages], k_empty[kStages];
@@ -98,14 +112,17 @@ struct Barriers {
   uint64_t o_final[2];
 };
 
-template <bool kBF16, bool kGeneric, bool kNorm>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool kBF16, bool kGeneric, bool kNorm, int kTiles>
+__global__ void __launch_bounds__(Cfg<kTiles>::kThreads, Cfg<kTiles>::kCtasPerSm)
 attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                     const __grid_constant__ CUtensorMap tmv, const __grid_constant__ AttnParams p) {
+  using C = Cfg<kTiles>;
+  constexpr int kStages = C::kStages, kQRows = C::kQRows;
+  constexpr uint32_t kTmemCols = C::kTmemCols, kColO0 = C::kColO0;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) Barriers bars;
+  __shared__ __align__(8) Barriers<kStages> bars;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float xch_m[2][2][128], xch_l[2][2][128];            // (tile, parity, row): statistics merged across streams
+  __shared__ float xch_m[kTiles][2][128], xch_l[kTiles][2][128];  // (tile, parity, row): statistics merged across streams
 
   // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from it
   // (role, TMEM lane base, barrier / descriptor addresses) on the uniform datapath instead of R2UR-ing it at every use
@@ -115,8 +132,8 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   const int q0 = qt * kQRows, h = blockIdx.y, b = blockIdx.z;
 
   const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem0;                                    // 2 tiles of 128 rows
-  const uint32_t sK = smem0 + 2 * kTileBytes;                   // kStages steps of 64 keys
+  const uint32_t sQ = smem0;                                    // kTiles tiles of 128 rows
+  const uint32_t sK = smem0 + kTiles * kTileBytes;              // kStages steps of 64 keys
   const uint32_t sV = sK + kStages * kSubBytes;
 
   if (tid == 0) {
@@ -124,12 +141,12 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
 #pragma unroll
     for (int i = 0; i < kStages; ++i) {
       ptx::mbar_init(ptx::smem_u32(&bars.k_full[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars.k_empty[i]), 2);       // one tcgen05.commit from each MMA issuer
+      ptx::mbar_init(ptx::smem_u32(&bars.k_empty[i]), kTiles);  // one tcgen05.commit from each MMA issuer
       ptx::mbar_init(ptx::smem_u32(&bars.v_full[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars.v_empty[i]), 2);
+      ptx::mbar_init(ptx::smem_u32(&bars.v_empty[i]), kTiles);
     }
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < kTiles; ++t) {
 #pragma unroll
       for (int sb = 0; sb < 2; ++sb) {
         ptx::mbar_init(ptx::smem_u32(&bars.s_full[t][sb]), 1);
@@ -140,7 +157,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     ptx::fence_mbar_init();
   }
   __syncwarp();
-  if (warp == 16) ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(&tmem_base_slot));
+  if (warp == C::kWarpMma0) ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(&tmem_base_slot));
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -159,17 +176,17 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   const int nA = normalized ? n_kv : 0;                          // stats-pass steps (QK^T only)
   const int n_iter = nA + n_kv;
 
-  if (warp >= 16) reg_dealloc<kAuxRegs>();
-  if (warp == 17) {
+  if (warp >= C::kSoftmaxWarps) reg_dealloc<C::kAuxRegs>();
+  if (warp == C::kWarpTma) {
     // ================================ TMA producer (whole warp waits, one elected lane issues) ============
     if (ptx::elect_one()) {
       ptx::prefetch_tmap(&tmq);
       ptx::prefetch_tmap(&tmk);
       ptx::prefetch_tmap(&tmv);
       const uint32_t bq = ptx::smem_u32(&bars.q_full);
-      ptx::mbar_expect_tx(bq, 2 * kTileBytes);
+      ptx::mbar_expect_tx(bq, kTiles * kTileBytes);
       tma_tile(sQ, &tmq, bq, p.cq, q0, h, b);
-      tma_tile(sQ + kTileBytes, &tmq, bq, p.cq, q0 + 128, h, b);
+      if (kTiles == 2) tma_tile(sQ + kTileBytes, &tmq, bq, p.cq, q0 + 128, h, b);
     }
     __syncwarp();
     auto load_k = [&](int i) {                                  // K of step i -> ring slot i % kStages
@@ -197,9 +214,9 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         __syncwarp();
       }
     }
-  } else if (warp == 16 || warp == 18) {
-    // ================================ MMA issuers: warp 16 serves Q tile 0, warp 18 Q tile 1 ===============
-    const int t = (warp - 16) >> 1;
+  } else if (warp == C::kWarpMma0 || (kTiles == 2 && warp == C::kWarpMma1)) {
+    // ================================ MMA issuers: one warp per Q tile =====================================
+    const int t = (warp - C::kWarpMma0) >> 1;
     constexpr uint32_t kIdescQK = ptx::make_idesc_f16(kBF16, 128, BNW, false, false);
     constexpr uint32_t kIdescPV = ptx::make_idesc_f16(kBF16, 128, HD, false, true);
     constexpr uint64_t kTileUnits = kTileBytes >> 4;             // descriptor address units (16 B)
@@ -261,9 +278,9 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       OEH_T(3);
     }
     OEH_T_PRINT("issuer: loop kv_full p_full issue", n_iter);
-  } else if (warp < 16) {
+  } else if (warp < C::kSoftmaxWarps) {
     // ================================ softmax streams ======================================================
-    reg_alloc<kSoftmaxRegs>();
+    reg_alloc<C::kSoftmaxRegs>();
     const int t = warp >> 3, par = (warp >> 2) & 1;               // Q tile, step parity
     const int r = (warp & 3) * 32 + (tid & 31);                   // row within the tile == TMEM lane
     const int row = q0 + t * 128 + r;                             // this thread's query row
@@ -449,7 +466,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   // ---- teardown ------------------------------------------------------------------------------------------------
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 16) {
+  if (warp == C::kWarpMma0) {
     __syncwarp();
     ptx::tmem_dealloc<kTmemCols>(tmem);
   }

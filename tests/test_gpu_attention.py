@@ -80,7 +80,7 @@ def test_attention_causal(kind, gamma, eta, T):
     np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=TOL, rtol=0)
 
 
-@pytest.mark.parametrize("kernel", ["tile", "ws"])
+@pytest.mark.parametrize("kernel", ["tile", "ws", "ws:1", "ws:2"])
 @pytest.mark.parametrize("kind,gamma,eta", KINDS[:4])
 def test_attention_kernel_override_same_result(kernel, kind, gamma, eta, monkeypatch):
     """The three kernels (one-tile / multi-tile / warp-specialised) are interchangeable on a shape all of them accept."""
@@ -89,7 +89,9 @@ def test_attention_kernel_override_same_result(kernel, kind, gamma, eta, monkeyp
     logits = torch.randn(2, 2, 128).cuda()
     kw = dict(scale=0.125, kind=kind, gamma=gamma, eta=eta, gate_logits=logits, causal=(kind % 2 == 1))
     base = ops.attention_fwd(q, k, v, **kw).float()
-    monkeypatch.setenv("OEH_ATTN_KERNEL", kernel)
+    monkeypatch.setenv("OEH_ATTN_KERNEL", kernel.split(":")[0])
+    if ":" in kernel:
+        monkeypatch.setenv("OEH_WS_TILES", kernel.split(":")[1])      # Q tiles per CTA of the warp-specialised kernel
     other = ops.attention_fwd(q, k, v, **kw).float()
     assert (base - other).abs().max().item() <= 1e-3
     ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=(kind % 2 == 1), gate=O.sigmoid(logits.cpu().numpy()))
@@ -212,3 +214,17 @@ def test_attention_fused_int8_taps_vs_oracle(kind, gamma, eta, before_gate, T):
     step = float(qs["c"][0])
     assert diff.max() <= 1.05 * step + 1e-3, (diff.max(), step)           # never more than one context code
     assert (diff > 2e-3).mean() < 0.02, (diff > 2e-3).mean()              # and rarely even that
+
+
+@pytest.mark.parametrize("tiles", ["1", "2"])
+@pytest.mark.parametrize("kind,gamma,eta", KINDS[:4])
+@pytest.mark.parametrize("T,causal", [(700, False), (700, True), (1024, True)])
+def test_attention_ws_tiles_per_cta(tiles, kind, gamma, eta, T, causal, monkeypatch):
+    """Both CTA shapes of the warp-specialised kernel (two Q tiles per CTA / two one-tile CTAs per SM) on ragged and
+    causal long sequences."""
+    ops = _ops()
+    monkeypatch.setenv("OEH_WS_TILES", tiles)
+    q, k, v = _mk(1, 3, T, T, torch.float16, seed=T + kind)
+    out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal, out_layout="bhtd")
+    ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal)
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=TOL, rtol=0)
