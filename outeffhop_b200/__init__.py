@@ -6,6 +6,7 @@ Public surface (same names as the reference):
     BertSelfAttentionWithExtras, OPTAttentionWithExtras,
     AsymmetricUniformQuantizer, RunningMinMaxEstimator, QuantizationManager, QuantizedActivation,
     QuantizedBertSelfAttentionWithExtras, QuantizedOPTAttentionWithExtras,
+    QuantizedBertForMaskedLM, quantize_bert_for_masked_lm, pass_data_for_range_estimation, get_quant_config, val_qparams,
   SURVEY section 8f rows: percentile range estimation (RunningMinMaxEstimator(percentile=...)), QuantLayerNorm /
     QuantizedBertSelfOutput / QuantizedBertOutput, kurtosis / OutlierMeter, ViTSelfAttentionWithExtras,
     Association / Hopfield / HopfieldPooling
@@ -16,7 +17,8 @@ __version__ = "0.1.0"
 import importlib
 
 _SUBMODULES = ("_lib", "ops", "softmax", "quantization", "bert_attention", "opt_attention", "quantized_attention",
-               "build", "eval_harness", "vit_attention", "hopfield", "quantized_layers", "outlier_metrics")
+               "build", "eval_harness", "vit_attention", "hopfield", "quantized_layers", "outlier_metrics", "quantized_models",
+               "hf_compat")
 _EXPORTS = {
     "SOFTMAX_MAPPING": "softmax", "SoftmaxFn": "softmax", "softmax_1": "softmax", "clipped_softmax": "softmax",
     "clipped_softmax1": "softmax", "parse_attn_softmax": "softmax",
@@ -33,6 +35,11 @@ _EXPORTS = {
     "Association": "hopfield", "Hopfield": "hopfield", "HopfieldPooling": "hopfield",
     "QuantLayerNorm": "quantized_layers", "QuantizedBertSelfOutput": "quantized_layers",
     "QuantizedBertOutput": "quantized_layers",
+    "QuantizedBertForMaskedLM": "quantized_models", "QuantizedBertModel": "quantized_models",
+    "QuantizedBertLayer": "quantized_models", "QuantizedBertEmbeddings": "quantized_models",
+    "QuantEmbedding": "quantized_models", "quantize_bert_for_masked_lm": "quantized_models",
+    "pass_data_for_range_estimation": "quantized_models", "get_quant_config": "quantized_models",
+    "val_qparams": "quantized_models", "DotDict": "quantized_models",
     "kurtosis": "outlier_metrics", "OutlierMeter": "outlier_metrics", "attach_bert_outlier_hooks": "outlier_metrics",
 }
 

@@ -247,3 +247,18 @@ def aggregate_perplexity(loss_sum: torch.Tensor, n_batches: int) -> float:
 def shard_indices(n_batches: int, rank: int, world: int):
     """Round-robin batch sharding: rank r takes batches r, r+N, ...."""
     return list(range(rank, n_batches, world))
+
+
+# ---- INT8 (--quantize) evaluation ---------------------------------------------------------------------------------
+
+def make_bert_int8_eval_step(qmodel, example_batch, estimation_batches, use_graph: bool = True) -> EvalStep:
+    """validate_mlm_config.py:466-476 then the eval loop: estimate the activation ranges on ``estimation_batches``
+    (``pass_data_for_range_estimation``, every tap minmax -> EMA -> qdq on the device), freeze them, and capture the
+    fixed-range step -- fused attention with its three taps, one-kernel residual blocks, fused loss -- in a CUDA graph.
+    ``qmodel``: ``quantized_models.quantize_bert_for_masked_lm(...)``."""
+    from .quantized_models import pass_data_for_range_estimation
+    qmodel.estimate_ranges()
+    pass_data_for_range_estimation(estimation_batches, qmodel, act_quant=True, max_num_batches=len(estimation_batches))
+    qmodel.fix_ranges()
+    return make_eval_step(lambda input_ids, labels: qmodel(input_ids=input_ids, labels=labels).loss, example_batch,
+                          device=next(qmodel.parameters()).device, use_graph=use_graph)

@@ -383,7 +383,9 @@ class SymmetricUniformQuantizer(nn.Module):
         self._signed = x_min.min() < 0                                     # :296
         self._signed_host = None
         x_absmax = torch.max(x_min.abs(), x_max)
-        self._delta = (x_absmax / self.int_max).detach()                   # :298-299
+        # :298-299.  Tensor / tensor: ATen-CUDA turns `tensor / python_scalar` into a multiply by the reciprocal (1 ulp off
+        # the IEEE quotient the reference gets on the CPU and the oracle is pinned to)
+        self._delta = torch.div(x_absmax, torch.full_like(x_absmax, self.int_max)).detach()
 
     def to_integer_forward(self, x_float):
         x_int = torch.round(x_float / self.scale) + self.zero_point
