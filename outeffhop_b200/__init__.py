@@ -38,6 +38,8 @@ _EXPORTS = {
     "QuantizedBertForMaskedLM": "quantized_models", "QuantizedBertModel": "quantized_models",
     "QuantizedBertLayer": "quantized_models", "QuantizedBertEmbeddings": "quantized_models",
     "QuantEmbedding": "quantized_models", "quantize_bert_for_masked_lm": "quantized_models",
+    "QuantizedOPTForCausalLM": "quantized_models", "QuantizedOPTDecoder": "quantized_models",
+    "QuantizedOPTDecoderLayer": "quantized_models", "quantize_opt_for_causal_lm": "quantized_models",
     "pass_data_for_range_estimation": "quantized_models", "get_quant_config": "quantized_models",
     "val_qparams": "quantized_models", "DotDict": "quantized_models",
     "kurtosis": "outlier_metrics", "OutlierMeter": "outlier_metrics", "attach_bert_outlier_hooks": "outlier_metrics",

@@ -262,3 +262,19 @@ def make_bert_int8_eval_step(qmodel, example_batch, estimation_batches, use_grap
     qmodel.fix_ranges()
     return make_eval_step(lambda input_ids, labels: qmodel(input_ids=input_ids, labels=labels).loss, example_batch,
                           device=next(qmodel.parameters()).device, use_graph=use_graph)
+
+
+def make_opt_int8_eval_step(qmodel, example_batch, estimation_batches, use_graph: bool = True) -> EvalStep:
+    """validate_clm.py:487-500 then the eval loop, as ``make_bert_int8_eval_step`` (``qmodel``:
+    ``quantized_models.quantize_opt_for_causal_lm(...)``; the reference estimates OPT ranges on the TRAIN loader)."""
+    from .quantized_models import pass_data_for_range_estimation
+    p = next(qmodel.parameters())
+    B, T = example_batch["input_ids"].shape
+    mask = make_causal_mask(B, T, p.dtype, p.device)
+    pos = torch.arange(T, device=p.device).unsqueeze(0).expand(B, T).contiguous()
+    qmodel.estimate_ranges()
+    pass_data_for_range_estimation(estimation_batches, qmodel, act_quant=True, max_num_batches=len(estimation_batches))
+    qmodel.fix_ranges()
+    return make_eval_step(lambda input_ids, labels: qmodel(input_ids=input_ids, attention_mask=mask, position_ids=pos,
+                                                           labels=labels).loss,
+                          example_batch, device=p.device, use_graph=use_graph)

@@ -24,6 +24,8 @@ from enum import Flag, auto
 from functools import partial
 from typing import Optional
 
+import copy
+
 import torch
 from torch import nn
 from torch.nn import functional as F
@@ -832,9 +834,11 @@ class QuantLinear(QuantizedModule, nn.Linear):
 
     def __init__(self, *args, activation=None, **kwargs):
         super().__init__(*args, **kwargs)
-        if activation is not None:
-            raise NotImplementedError("fused activation functions are not used on the attention path")
-        self.activation_function = None
+        if activation is not None and not isinstance(activation, (nn.ReLU, nn.ReLU6, nn.Hardtanh, nn.Sigmoid, nn.Tanh,
+                                                                  nn.GELU, nn.PReLU)):
+            raise NotImplementedError(f"activation {activation} is not in the hijacker's activations_set (hijacker.py:14-24)")
+        # an activation that quantize_sequential fused into the layer runs BEFORE the tap (hijacker.py:115-117)
+        self.activation_function = copy.deepcopy(activation) if activation is not None else None
         self.activation_quantizer = QuantizationManager(qmethod=self.act_method, init=self.act_range_method,
                                                         qparams=self.act_qparams, init_params=self.act_range_options)
         if self.weight_range_method is CurrentMinMaxEstimator:
@@ -846,8 +850,8 @@ class QuantLinear(QuantizedModule, nn.Linear):
                                                     init_params=weight_init_params)
 
     @classmethod
-    def from_linear(cls, lin: nn.Linear, **quant_params):
-        q = cls(lin.in_features, lin.out_features, bias=lin.bias is not None, **quant_params)
+    def from_linear(cls, lin: nn.Linear, activation=None, **quant_params):
+        q = cls(lin.in_features, lin.out_features, bias=lin.bias is not None, activation=activation, **quant_params)
         q.weight = lin.weight
         q.bias = lin.bias
         return q.to(lin.weight.device)
@@ -865,6 +869,8 @@ class QuantLinear(QuantizedModule, nn.Linear):
     def forward(self, x, offsets=None):
         weight, bias = self.get_params()
         res = F.linear(x.contiguous(), weight.contiguous(), bias=bias)
+        if self.activation_function is not None:
+            res = self.activation_function(res)
         if self._qa_host:
             res = self.activation_quantizer(res)
         return res

@@ -283,3 +283,184 @@ def quantize_bert_for_masked_lm(model, config: Optional[DotDict] = None, **overr
     qmodel = QuantizedBertForMaskedLM(model, **qparams).to(p.device).eval()
     qmodel.set_quant_state(weight_quant=bool(config.quant.weight_quant), act_quant=bool(config.quant.act_quant))
     return qmodel
+
+
+# =====================================================================================================================
+# OPT (validate_clm.py --quantize; transformers_language/models/quantized_opt.py)
+# =====================================================================================================================
+from .opt_attention import OPTAttentionWithExtras                      # noqa: E402
+from .quantized_attention import QuantizedOPTAttentionWithExtras       # noqa: E402
+from .quantized_layers import _residual_tap                            # noqa: E402
+
+
+class QuantizedOPTLearnedPositionalEmbedding(QuantizedModel):
+    """quantized_opt.py:27-51: the learned position table (offset 2) as a weight-quantized lookup."""
+
+    def __init__(self, org_model, **quant_params):
+        super().__init__()
+        self.offset = org_model.offset
+        self.quant_embedding = QuantEmbedding.from_embedding(org_model, **quant_params)
+
+    def forward(self, attention_mask: Optional[torch.Tensor] = None, past_key_values_length: int = 0,
+                position_ids: Optional[torch.Tensor] = None):
+        if position_ids is None:                                                                # :41-49
+            attention_mask = attention_mask.long()
+            position_ids = (torch.cumsum(attention_mask, dim=1).type_as(attention_mask) * attention_mask).long() - 1
+            position_ids = position_ids[:, past_key_values_length:]
+        return self.quant_embedding(position_ids + self.offset)
+
+
+class QuantizedOPTDecoderLayer(QuantizedModel):
+    """quantized_opt.py:277-384: [LN] -> attention -> residual add + tap -> [LN] -> fc1+ReLU (tap after the ReLU) -> fc2
+    -> residual add + tap.  With fixed ranges each ``residual + x`` and its tap are one kernel (oeh_add_fake_quant)."""
+
+    def __init__(self, org_model, **quant_params):
+        super().__init__()
+        qp = _linear_params(quant_params)
+        self.embed_dim = org_model.embed_dim
+        self.do_layer_norm_before = org_model.do_layer_norm_before
+        self.dropout = org_model.dropout
+        if not isinstance(org_model.activation_fn, nn.ReLU):
+            raise NotImplementedError("quantized_opt.py:286 asserts a ReLU feed-forward activation")
+        if not isinstance(org_model.self_attn, OPTAttentionWithExtras):
+            raise NotImplementedError("quantize the model after swap_opt_attention() (quantized_opt.py:289 wraps "
+                                      f"OPTAttentionWithExtras), got {type(org_model.self_attn).__name__}")
+        self.self_attn = QuantizedOPTAttentionWithExtras(org_model.self_attn, **quant_params)
+        self.self_attn_layer_norm = QuantLayerNorm.from_layer_norm(org_model.self_attn_layer_norm, **qp)
+        self.fc1_act = QuantLinear.from_linear(org_model.fc1, activation=org_model.activation_fn, **qp)   # :292-294
+        self.fc2 = QuantLinear.from_linear(org_model.fc2, **qp)
+        self.final_layer_norm = QuantLayerNorm.from_layer_norm(org_model.final_layer_norm, **qp)
+        self.self_attn_res_act_quantizer = QuantizedActivation(**qp)
+        self.ffn_res_act_quantizer = QuantizedActivation(**qp)
+
+    def forward(self, hidden_states, attention_mask=None, layer_head_mask=None, output_attentions=False, use_cache=False,
+                past_key_value=None, **unused):
+        residual = hidden_states
+        if self.do_layer_norm_before:
+            hidden_states = self.self_attn_layer_norm(hidden_states)
+        hidden_states, self_attn_weights, present_key_value = OPTAttentionWithExtras.forward(
+            self.self_attn, hidden_states=hidden_states, past_key_value=past_key_value, attention_mask=attention_mask,
+            layer_head_mask=layer_head_mask, output_attentions=output_attentions)
+        hidden_states = F.dropout(hidden_states, p=self.dropout, training=self.training)
+        hidden_states = _residual_tap(self.self_attn_res_act_quantizer, residual, hidden_states)        # :342-345
+        if not self.do_layer_norm_before:
+            hidden_states = self.self_attn_layer_norm(hidden_states)
+        shape = hidden_states.shape
+        hidden_states = hidden_states.reshape(-1, hidden_states.size(-1))
+        residual = hidden_states
+        if self.do_layer_norm_before:
+            hidden_states = self.final_layer_norm(hidden_states)
+        hidden_states = self.fc1_act(hidden_states)                                                      # :360
+        hidden_states = self.fc2(hidden_states)
+        hidden_states = F.dropout(hidden_states, p=self.dropout, training=self.training)
+        hidden_states = _residual_tap(self.ffn_res_act_quantizer, residual, hidden_states).view(shape)   # :367-370
+        if not self.do_layer_norm_before:
+            hidden_states = self.final_layer_norm(hidden_states)
+        outputs = (hidden_states,)
+        if output_attentions:
+            outputs += (self_attn_weights,)
+        if use_cache:
+            outputs += (present_key_value,)
+        return outputs
+
+
+class QuantizedOPTDecoder(QuantizedModel):
+    """quantized_opt.py:387-662 for the eval path (no KV cache, no head masks)."""
+
+    def __init__(self, org_model, **quant_params):
+        super().__init__()
+        qp = _linear_params(quant_params)
+        self.config = org_model.config
+        self.dropout = org_model.dropout
+        self.embed_tokens = QuantEmbedding.from_embedding(org_model.embed_tokens, **qp)
+        self.embed_positions = QuantizedOPTLearnedPositionalEmbedding(org_model.embed_positions, **qp)
+        self.project_out = None if org_model.project_out is None else QuantLinear.from_linear(org_model.project_out, **qp)
+        self.project_in = None if org_model.project_in is None else QuantLinear.from_linear(org_model.project_in, **qp)
+        self.final_layer_norm = (None if org_model.final_layer_norm is None
+                                 else QuantLayerNorm.from_layer_norm(org_model.final_layer_norm, **qp))
+        self.layers = nn.ModuleList([QuantizedOPTDecoderLayer(l, **quant_params) for l in org_model.layers])
+        self.embed_sum_act_quantizer = QuantizedActivation(**qp)
+
+    def forward(self, input_ids, attention_mask: Optional[torch.Tensor] = None, position_ids: Optional[torch.Tensor] = None):
+        """``attention_mask``: the (B,1,T,T) additive causal mask of HF-4.31's ``_prepare_decoder_attention_mask``
+        (``eval_harness.make_causal_mask``) -- the eval data is un-padded -- or None for a single token."""
+        inputs_embeds = self.embed_tokens(input_ids)
+        if position_ids is None:
+            ones = torch.ones(inputs_embeds.shape[:2], dtype=torch.bool, device=inputs_embeds.device)
+            pos_embeds = self.embed_positions(ones, 0)
+        else:
+            pos_embeds = self.embed_positions(position_ids=position_ids)
+        if self.project_in is not None:
+            inputs_embeds = self.project_in(inputs_embeds)
+        hidden_states = self.embed_sum_act_quantizer(inputs_embeds + pos_embeds)                 # :556-559
+        for layer in self.layers:
+            hidden_states = layer(hidden_states, attention_mask=attention_mask)[0]
+        if self.final_layer_norm is not None:
+            hidden_states = self.final_layer_norm(hidden_states)
+        if self.project_out is not None:
+            hidden_states = self.project_out(hidden_states)
+        return hidden_states
+
+
+class _QuantizedOPTModel(QuantizedModel):
+    def __init__(self, org_model, **quant_params):
+        super().__init__()
+        self.decoder = QuantizedOPTDecoder(org_model.decoder, **quant_params)
+
+
+class QuantizedOPTForCausalLM(QuantizedModel):
+    """quantized_opt.py:719-889 with the ``quant_setup`` choices the eval scripts use: ``fp32_head`` (FP lm_head, the
+    README's OPT recipe), ``fp32_head+int16_final_LN`` / ``fp32_head+int16_all_LN`` (16-bit LayerNorm quantizers) and
+    ``all`` (lm_head quantized too).  Loss: shifted mean CE (HF OPTForCausalLM), evaluated by ``oeh_ce_loss``."""
+
+    def __init__(self, org_model, quant_setup="fp32_head", **quant_params):
+        super().__init__()
+        self.config = org_model.config
+        self.model = _QuantizedOPTModel(org_model.model, **quant_params)
+        if quant_setup in ("fp32_head", "fp32_head+int16_final_LN", "fp32_head+int16_all_LN"):
+            self.lm_head = org_model.lm_head
+            lns = []
+            if quant_setup == "fp32_head+int16_final_LN":
+                lns = [self.model.decoder.final_layer_norm]
+            elif quant_setup == "fp32_head+int16_all_LN":
+                lns = [m for m in self.model.modules() if isinstance(m, QuantLayerNorm)]
+            for ln in lns:
+                ln.weight_quantizer.quantizer.n_bits = 16
+                ln.activation_quantizer.quantizer.n_bits = 16
+        elif quant_setup == "all":
+            self.lm_head = QuantLinear.from_linear(org_model.lm_head, **_linear_params(quant_params))
+        else:
+            raise ValueError(f"Quantization setup '{quant_setup}' not supported.")
+
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, labels=None, **unused):
+        from transformers.modeling_outputs import CausalLMOutputWithPast
+        from . import ops
+        from .eval_harness import _padded_decoder, make_causal_mask
+        if attention_mask is None and input_ids.shape[1] > 1:
+            p = next(self.parameters())
+            attention_mask = make_causal_mask(input_ids.shape[0], input_ids.shape[1], p.dtype, input_ids.device)
+        h = self.model.decoder(input_ids, attention_mask, position_ids)
+        if isinstance(self.lm_head, QuantLinear):
+            logits, V = self.lm_head(h), self.lm_head.out_features
+        else:
+            w, b, V = _padded_decoder(self.lm_head)
+            logits = F.linear(h, w, b)
+        loss = None
+        if labels is not None:
+            shifted = torch.full_like(labels, -100)
+            shifted[:, :-1] = labels[:, 1:]
+            loss = ops.ce_loss(logits.view(-1, logits.shape[-1]), shifted.view(-1), vocab=V)
+        return CausalLMOutputWithPast(loss=loss, logits=logits[..., :V])
+
+
+def quantize_opt_for_causal_lm(model, config: Optional[DotDict] = None, quant_setup: str = "fp32_head",
+                               **overrides) -> QuantizedOPTForCausalLM:
+    """validate_clm.py:465-487: ``QuantizedOPTForCausalLM(model, **val_qparams(config))`` + ``set_quant_state``."""
+    config = config or get_quant_config()
+    qparams = val_qparams(config)
+    qparams.update(overrides)
+    qparams.pop("quant_setup", None)
+    p = next(model.parameters())
+    qmodel = QuantizedOPTForCausalLM(model, quant_setup=quant_setup, **qparams).to(p.device).eval()
+    qmodel.set_quant_state(weight_quant=bool(config.quant.weight_quant), act_quant=bool(config.quant.act_quant))
+    return qmodel

@@ -134,3 +134,86 @@ def test_int8_eval_step_graph_equals_eager_and_uses_fused_kernels():
     got = float(step.run())
     assert abs(got - eager) <= 1e-3 * abs(eager), (got, eager)
     assert np.isfinite(got)
+
+
+# ------------------------------------------------------------------------------------------------ OPT (config 4)
+GOLD_OPT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "quantized_opt_model.npz")
+
+
+def _build_opt(g, name):
+    from transformers import OPTConfig, OPTForCausalLM
+    from outeffhop_b200 import hf_compat
+    cfg = OPTConfig(vocab_size=101, hidden_size=128, num_hidden_layers=2, ffn_dim=256, num_attention_heads=2,
+                    word_embed_proj_dim=128, max_position_embeddings=64, do_layer_norm_before=True, dropout=0.0,
+                    attention_dropout=0.0)
+    cfg._attn_implementation = "eager"
+    model = OPTForCausalLM(cfg).eval()
+    gated = bool(int(g[f"{name}::gated"]))
+    kw = dict(attn_gate_type="conditional_per_token", attn_gate_init=0.25) if gated else {}
+    hf_compat.swap_opt_attention(model, attn_softmax=str(g[f"{name}::attn_softmax"]), max_seq_length=32, **kw)
+    sd = {k.split("::w::")[1]: torch.from_numpy(g[k]) for k in g.files if k.startswith(f"{name}::w::")}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    return model.cuda().eval()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["sm1", "gate"])
+def test_quantized_opt_model_vs_live_reference(name):
+    """QuantizedOPTDecoder + FP32 lm_head (quant_setup fp32_head) against the live reference: same tolerances as BERT."""
+    from outeffhop_b200 import quantized_models as QM
+    from outeffhop_b200.quantization import QuantizationManager
+    g = np.load(GOLD_OPT)
+    model = _build_opt(g, name)
+    ids = torch.from_numpy(g[f"{name}::input_ids"])
+    batches = [{"input_ids": ids[i], "labels": ids[i].clone()} for i in range(4)]
+    qmodel = QM.quantize_opt_for_causal_lm(model, quant_setup="fp32_head")
+    QM.pass_data_for_range_estimation(batches[:3], qmodel, act_quant=True, max_num_batches=3)
+    qmodel.fix_ranges()
+    ours = {}
+    for n, m in qmodel.named_modules():
+        if isinstance(m, QuantizationManager) and m.quantizer.is_initialized:
+            d = m.quantizer._delta
+            if d is not None and d.numel() == 1:
+                zf = getattr(m.quantizer, "_zero_float", None)
+                ours[n[len("model.decoder."):]] = (float(d), float(zf) if zf is not None else float("nan"))
+    names = [str(n) for n in g[f"{name}::qnames"]]
+    assert set(names) == set(ours), (sorted(set(names) - set(ours)), sorted(set(ours) - set(names)))
+    loose = 0
+    for n, d_ref, z_ref in zip(names, g[f"{name}::qdelta"], g[f"{name}::qzero_float"]):
+        d, z = ours[n]
+        if n.endswith("weight_quantizer"):
+            assert np.float32(d) == np.float32(d_ref), (n, d, d_ref)
+        else:
+            assert abs(d - d_ref) <= 6e-3 * abs(d_ref), (n, d, d_ref)
+            assert abs(z - z_ref) <= 1.0, (n, z, z_ref)
+            loose += abs(d - d_ref) > 1e-3 * abs(d_ref)
+    assert loose <= 3, loose
+    with torch.no_grad():
+        out = qmodel(input_ids=ids[3].cuda(), labels=ids[3].cuda())
+    loss_ref = float(g[f"{name}::loss_fixed"])
+    assert abs(float(out.loss) - loss_ref) <= 2e-3 * abs(loss_ref), (float(out.loss), loss_ref)
+    diff = out.logits.float().cpu().numpy() - g[f"{name}::logits_fixed"]
+    assert np.abs(diff).mean() < 0.02 * np.abs(g[f"{name}::logits_fixed"]).mean()
+
+
+@pytest.mark.gpu
+def test_opt_int8_eval_step_graph_and_quant_setups():
+    """BASELINE config 4 shape at 2 layers: OPT fp16, softmax1, fp32_head; captured fixed-range step == eager; the
+    int16-LayerNorm setups switch the LayerNorm quantizers to 16 bit; unknown setups raise like the reference."""
+    from outeffhop_b200 import eval_harness as EH, quantized_models as QM
+    from outeffhop_b200.quantized_layers import QuantLayerNorm
+    model = EH.build_opt_125m(seed=6789, num_hidden_layers=2, attn_softmax="softmax1")
+    qmodel = QM.quantize_opt_for_causal_lm(model, quant_setup="fp32_head")
+    batches = [EH.synthetic_clm_batch(2, 512, seed=6789 + i) for i in range(4)]
+    step = EH.make_opt_int8_eval_step(qmodel, batches[0], batches[:3], use_graph=True)
+    with torch.no_grad():
+        eager = float(qmodel(input_ids=batches[3]["input_ids"].cuda(), labels=batches[3]["labels"].cuda()).loss)
+    step.load(batches[3])
+    got = float(step.run())
+    assert np.isfinite(got) and abs(got - eager) <= 1e-3 * abs(eager), (got, eager)
+    m2 = EH.build_opt_125m(seed=1, num_hidden_layers=1)
+    q2 = QM.quantize_opt_for_causal_lm(m2, quant_setup="fp32_head+int16_all_LN")
+    assert all(ln.activation_quantizer.quantizer.n_bits == 16 for ln in q2.modules() if isinstance(ln, QuantLayerNorm))
+    with pytest.raises(ValueError):
+        QM.quantize_opt_for_causal_lm(EH.build_opt_125m(seed=1, num_hidden_layers=1), quant_setup="nope")
