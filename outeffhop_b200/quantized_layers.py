@@ -57,6 +57,16 @@ class QuantLayerNorm(QuantizedModule, nn.LayerNorm):
 
     def forward(self, x, offsets=None):
         weight, bias = self.get_params()
+        out = self.activation_quantizer
+        fixed = (not self._qa_host) or (not out.estimating and isinstance(out.quantizer, AsymmetricUniformQuantizer))
+        if (fixed and not self.training and x.is_cuda and len(self.normalized_shape) == 1 and bias is not None
+                and weight.dtype == x.dtype and not self._forward_hooks):
+            try:                                    # LayerNorm + frozen output tap in one pass (oeh_add_layer_norm)
+                return ops.add_layer_norm(x, None, weight, bias, self.eps,
+                                          qparams_out=out.quantizer.qparams if self._qa_host else None,
+                                          n_bits=out.n_bits if self._qa_host else 8)
+            except NotImplementedError:             # row too wide / unaligned for the register-resident kernel
+                pass
         res = F.layer_norm(input=x.contiguous(), normalized_shape=self.normalized_shape, weight=weight.contiguous(),
                            bias=bias.contiguous(), eps=self.eps)
         if self._qa_host:
