@@ -249,20 +249,34 @@ int oeh_ce_loss(const void* logits, int64_t rows, int64_t vocab, int64_t row_str
 
 /* ---------------------------------------------------------------------------------------------
  * Residual add + LayerNorm in one pass, optionally with the two fake-quant taps of the INT8 residual blocks
- * (SURVEY 8f rank 2):   y = [qdq_out] LayerNorm( [qdq_res] (a + b) )
+ * (SURVEY 8f rank 2):   y = [qdq_out] LayerNorm( [qdq_res] ([qdq_a] a + b) )
  *   FP   (qparams_* NULL): BertSelfOutput / BertOutput.forward, the HF modules wrapped at
  *                          transformers_language/models/quantized_bert.py:540-605.
  *   INT8 (fixed ranges)  : QuantizedBertSelfOutput / QuantizedBertOutput.forward (quantized_bert.py:566-568, :602-604):
- *                          res_act_quantizer on the sum, then QuantLayerNorm (quantization/autoquant_utils.py:62-70)
- *                          with its output tap.
+ *                          [qparams_a: the output tap of the QuantLinear `dense` that produced a,] res_act_quantizer on
+ *                          the sum, then QuantLayerNorm (quantization/autoquant_utils.py:62-70) with its output tap.
  * a, b (b may be NULL: plain LayerNorm), y: (rows, cols) contiguous of `dtype`; weight / bias (bias may be NULL): (cols)
  * of the same dtype.  The sum is rounded once to the tensor dtype (ATen add), statistics / affine map in fp32 (biased
  * variance, rsqrt(var + eps)), one rounding of y; taps exactly as oeh_fake_quant_asym.  cols must be a multiple of
  * 16/sizeof(dtype) and at most 256 such vectors (2048 fp16 / 1024 fp32 columns); all pointers 16-byte aligned.
  * ------------------------------------------------------------------------------------------- */
 int oeh_add_layer_norm(const void* a, const void* b, const void* weight, const void* bias, void* y, int64_t rows,
-                       int64_t cols, double eps, int32_t dtype, const float* qparams_res, const float* qparams_out,
-                       int32_t n_bits, oeh_stream_t stream);
+                       int64_t cols, double eps, int32_t dtype, const float* qparams_a, const float* qparams_res,
+                       const float* qparams_out, int32_t n_bits, oeh_stream_t stream);
+
+/* y = qdq_sum(a + qdq_b(b)): oeh_add_fake_quant with the output tap of the QuantLinear that produced b folded in
+ * (QuantizedOPTDecoderLayer: fc2's tap, the residual add and ffn_res_act_quantizer, quantized_opt.py:362-369).
+ * qparams_b may be NULL (= oeh_add_fake_quant).  Fixed ranges only. */
+int oeh_tap_add_fake_quant(const void* a, const void* b, void* y, int64_t n, int32_t dtype, const float* qparams_b,
+                           const float* qparams_sum, int32_t n_bits, oeh_stream_t stream);
+
+/* Fake-quant of n_seg (<= 4) column segments of seg_cols columns, each with its own DEVICE [scale, zero_point]
+ * (qparams: HOST array of n_seg device pointers); x, y: (rows, n_seg*seg_cols) with row strides in elements.  One
+ * launch taps the output of a fused query|key|value projection whose three QuantLinear modules keep their own ranges
+ * (quantized_bert.py:317-330, quantized_opt.py:113-140).  Same arithmetic as oeh_fake_quant_asym. */
+int oeh_fake_quant_asym_segments(const void* x, void* y, int64_t rows, int32_t seg_cols, int32_t n_seg,
+                                 int64_t x_row_stride, int64_t y_row_stride, int32_t dtype, const float* const* qparams,
+                                 int32_t n_bits, oeh_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,9 +1,10 @@
 // Residual add + LayerNorm in one pass, with the optional fake-quant taps of the INT8 path fused in:
 //   FP  :  y = LayerNorm(a + b)                      BertSelfOutput / BertOutput.forward (HF shell of the eval step; the
 //                                                    module the reference wraps at quantized_bert.py:540-605)
-//   INT8:  y = qdq_out(LayerNorm(qdq_res(a + b)))    QuantizedBertSelfOutput / QuantizedBertOutput.forward with fixed
+//   INT8:  y = qdq_out(LayerNorm(qdq_res(qdq_a(a) + b)))   QuantizedBertSelfOutput / QuantizedBertOutput.forward with fixed
 //                                                    ranges (quantized_bert.py:566-568, :602-604): res_act_quantizer on
-//                                                    the sum, QuantLayerNorm's output tap (autoquant_utils.py:62-70)
+//                                                    the sum, QuantLayerNorm's output tap (autoquant_utils.py:62-70);
+//                                                    qdq_a = the output tap of the QuantLinear `dense` that produced a
 // ATen needs add (3 passes) + LayerNorm (2 passes) [+ 2 x ~11 passes of qdq elementwise ops]; here every element of a, b
 // is read once and y written once: bytes = rows*cols*3*size (2*size without b).  HBM-bound.
 // One warp per row, the row lives in registers (<= 8 x 16 B per lane): exact two-pass mean / variance in fp32.
@@ -21,7 +22,8 @@ template <typename T, int kVecs>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ gamma,
                       const T* __restrict__ beta, T* __restrict__ y, int64_t rows, int cols, float eps,
-                      const float* __restrict__ q_res, const float* __restrict__ q_out, float int_max) {
+                      const float* __restrict__ q_a, const float* __restrict__ q_res, const float* __restrict__ q_out,
+                      float int_max) {
   using V = Vec16<T>;
   constexpr int N = V::N;
   const int lane = threadIdx.x & 31;
@@ -31,7 +33,8 @@ add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T*
   const V* av = reinterpret_cast<const V*>(a + row * cols);
   const V* bv = b ? reinterpret_cast<const V*>(b + row * cols) : nullptr;
 
-  float rs = 1.f, rz = 0.f, os = 1.f, oz = 0.f;
+  float as = 1.f, az = 0.f, rs = 1.f, rz = 0.f, os = 1.f, oz = 0.f;
+  if (q_a) { as = DT<T>::rnd(__ldg(q_a)); az = DT<T>::rnd(__ldg(q_a + 1)); }
   if (q_res) { rs = DT<T>::rnd(__ldg(q_res)); rz = DT<T>::rnd(__ldg(q_res + 1)); }
   if (q_out) { os = DT<T>::rnd(__ldg(q_out)); oz = DT<T>::rnd(__ldg(q_out + 1)); }
 
@@ -58,6 +61,7 @@ add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T*
       float s = 0.f;
       if (i < nvec) {
         s = DT<T>::to_f(va[v].v[e]);
+        if (q_a) s = qdq_one<T>(s, as, az, int_max, false);
         if (bv) s = DT<T>::rnd(__fadd_rn(s, DT<T>::to_f(vb[v].v[e])));
         if (q_res) s = qdq_one<T>(s, rs, rz, int_max, false);
       }
@@ -104,7 +108,7 @@ add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T*
 
 template <typename T>
 int launch(const void* a, const void* b, const void* gamma, const void* beta, void* y, int64_t rows, int64_t cols, float eps,
-           const float* q_res, const float* q_out, int n_bits, cudaStream_t st) {
+           const float* q_a, const float* q_res, const float* q_out, int n_bits, cudaStream_t st) {
   constexpr int N = Vec16<T>::N;
   if (cols % N != 0 || cols / N > 32 * 8)
     return set_error(OEH_ERR_UNSUPPORTED, "oeh_add_layer_norm: cols=%lld must be a multiple of %d and at most %d",
@@ -119,7 +123,7 @@ int launch(const void* a, const void* b, const void* gamma, const void* beta, vo
   case K:                                                                                                            \
     add_layer_norm_kernel<T, K><<<grid, kWarpsPerBlock * 32, 0, st>>>((const T*)a, (const T*)b, (const T*)gamma,     \
                                                                      (const T*)beta, (T*)y, rows, (int)cols, eps,   \
-                                                                     q_res, q_out, int_max);                        \
+                                                                     q_a, q_res, q_out, int_max);                   \
     break;
   switch (kv) {
     OEH_LN_CASE(1) OEH_LN_CASE(2) OEH_LN_CASE(3) OEH_LN_CASE(4) OEH_LN_CASE(5) OEH_LN_CASE(6) OEH_LN_CASE(7) OEH_LN_CASE(8)
@@ -134,20 +138,21 @@ int launch(const void* a, const void* b, const void* gamma, const void* beta, vo
 using namespace oeh;
 
 extern "C" int oeh_add_layer_norm(const void* a, const void* b, const void* weight, const void* bias, void* y, int64_t rows,
-                                  int64_t cols, double eps, int32_t dtype, const float* qparams_res,
-                                  const float* qparams_out, int32_t n_bits, oeh_stream_t stream) {
+                                  int64_t cols, double eps, int32_t dtype, const float* qparams_a,
+                                  const float* qparams_res, const float* qparams_out, int32_t n_bits,
+                                  oeh_stream_t stream) {
   OEH_CHECK_ARG(rows >= 0 && cols > 0, "oeh_add_layer_norm: bad shape (%lld, %lld)", (long long)rows, (long long)cols);
   if (rows == 0) return OEH_OK;
   OEH_CHECK_ARG(a && weight && y, "oeh_add_layer_norm: null pointer");
   OEH_CHECK_ARG(rows <= 0x7fffffffLL * 8, "oeh_add_layer_norm: too many rows");
-  if (qparams_res || qparams_out) OEH_CHECK_ARG(n_bits >= 1 && n_bits <= 16, "oeh_add_layer_norm: n_bits=%d outside [1,16]", n_bits);
-  if (!(qparams_res || qparams_out)) n_bits = 8;
+  if (qparams_a || qparams_res || qparams_out) OEH_CHECK_ARG(n_bits >= 1 && n_bits <= 16, "oeh_add_layer_norm: n_bits=%d outside [1,16]", n_bits);
+  if (!(qparams_a || qparams_res || qparams_out)) n_bits = 8;
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case OEH_F32: return launch<float>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_res, qparams_out, n_bits, st);
-    case OEH_F16: return launch<__half>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_res, qparams_out, n_bits, st);
+    case OEH_F32: return launch<float>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_a, qparams_res, qparams_out, n_bits, st);
+    case OEH_F16: return launch<__half>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_a, qparams_res, qparams_out, n_bits, st);
     case OEH_BF16:
-      return launch<__nv_bfloat16>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_res, qparams_out, n_bits, st);
+      return launch<__nv_bfloat16>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_a, qparams_res, qparams_out, n_bits, st);
   }
   return set_error(OEH_ERR_BAD_ARG, "oeh_add_layer_norm: unknown dtype %d", dtype);
 }

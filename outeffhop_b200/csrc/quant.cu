@@ -85,13 +85,18 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) add_fake_quant_kernel(const T* __restrict__ a, const T* __restrict__ b,
                                                                   T* __restrict__ y, int64_t n,
                                                                   const float* __restrict__ qparams, float int_max,
-                                                                  int aligned) {
+                                                                  int aligned, const float* __restrict__ qparams_b) {
   using V = Vec16<T>;
   constexpr int N = V::N;
   const float scale = DT<T>::rnd(__ldg(qparams));
   const float zp = DT<T>::rnd(__ldg(qparams + 1));
+  // optional tap on b before the add (the output tap of the QuantLinear that produced b: quantized_opt.py:362-369)
+  const float bscale = qparams_b ? DT<T>::rnd(__ldg(qparams_b)) : 1.f;
+  const float bzp = qparams_b ? DT<T>::rnd(__ldg(qparams_b + 1)) : 0.f;
   auto one = [&](T av, T bv) {
-    const float s = DT<T>::rnd(__fadd_rn(DT<T>::to_f(av), DT<T>::to_f(bv)));
+    float bf = DT<T>::to_f(bv);
+    if (qparams_b) bf = qdq_one<T>(bf, bscale, bzp, int_max, false);
+    const float s = DT<T>::rnd(__fadd_rn(DT<T>::to_f(av), bf));
     return DT<T>::from_f(qdq_one<T>(s, scale, zp, int_max, false));
   };
   const int64_t stride = (int64_t)gridDim.x * kThreads;
@@ -274,12 +279,59 @@ int launch_minmax(const void* x, int64_t n, float* out2, float* partial, cudaStr
 
 template <typename T>
 int launch_add_fake_quant(const void* a, const void* b, void* y, int64_t n, const float* qparams, int n_bits,
-                          cudaStream_t st) {
+                          cudaStream_t st, const float* qparams_b = nullptr) {
   const float int_max = (float)((1 << n_bits) - 1);
   const int aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
   const int grid = grid_for(aligned ? (n / Vec16<T>::N + 1) / 2 + 1 : n);
-  add_fake_quant_kernel<T><<<grid, kThreads, 0, st>>>((const T*)a, (const T*)b, (T*)y, n, qparams, int_max, aligned);
+  add_fake_quant_kernel<T><<<grid, kThreads, 0, st>>>((const T*)a, (const T*)b, (T*)y, n, qparams, int_max, aligned, qparams_b);
   return check_launch("add_fake_quant_kernel");
+}
+
+// ---- fake-quant of column segments with their own ranges ---------------------------------------------------------------
+// x, y: (rows, n_seg * seg_cols) with explicit row strides; segment s (columns [s*seg_cols, (s+1)*seg_cols)) uses
+// qp[s].  One launch taps the output of a fused query | key | value projection (quantized_bert.py:317-330: three
+// QuantLinear modules, three ranges).
+struct SegQ {
+  const float* qp[4];
+};
+template <typename T>
+__global__ void __launch_bounds__(kThreads) fake_quant_segments_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                                       int64_t rows, int seg_cols, int n_seg,
+                                                                       int64_t ldx, int64_t ldy, SegQ q, float int_max) {
+  using V = Vec16<T>;
+  constexpr int N = V::N;
+  const int vec_per_seg = seg_cols / N, vec_per_row = vec_per_seg * n_seg;
+  const int64_t total = rows * vec_per_row;
+  float scale[4], zp[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    scale[s] = s < n_seg ? DT<T>::rnd(__ldg(q.qp[s])) : 1.f;
+    zp[s] = s < n_seg ? DT<T>::rnd(__ldg(q.qp[s] + 1)) : 0.f;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+    const int64_t r = i / vec_per_row;
+    const int c = (int)(i - r * vec_per_row);
+    const int s = c / vec_per_seg;
+    const float sc = s == 0 ? scale[0] : (s == 1 ? scale[1] : (s == 2 ? scale[2] : scale[3]));
+    const float z = s == 0 ? zp[0] : (s == 1 ? zp[1] : (s == 2 ? zp[2] : zp[3]));
+    const V in = *reinterpret_cast<const V*>(x + r * ldx + (int64_t)c * N);
+    V out;
+#pragma unroll
+    for (int e = 0; e < N; ++e) out.v[e] = DT<T>::from_f(qdq_one<T>(DT<T>::to_f(in.v[e]), sc, z, int_max, false));
+    *reinterpret_cast<V*>(y + r * ldy + (int64_t)c * N) = out;
+  }
+}
+
+template <typename T>
+int launch_segments(const void* x, void* y, int64_t rows, int seg_cols, int n_seg, int64_t ldx, int64_t ldy, const SegQ& q,
+                    int n_bits, cudaStream_t st) {
+  constexpr int N = Vec16<T>::N;
+  if (seg_cols % N || ldx % N || ldy % N || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15))
+    return set_error(OEH_ERR_UNSUPPORTED, "oeh_fake_quant_asym_segments: segments, strides and pointers must be 16-byte aligned");
+  const float int_max = (float)((1 << n_bits) - 1);
+  const int grid = grid_for(rows * (seg_cols / N) * n_seg);
+  fake_quant_segments_kernel<T><<<grid, kThreads, 0, st>>>((const T*)x, (T*)y, rows, seg_cols, n_seg, ldx, ldy, q, int_max);
+  return check_launch("fake_quant_segments_kernel");
 }
 
 }  // namespace
@@ -315,6 +367,45 @@ extern "C" int oeh_add_fake_quant(const void* a, const void* b, void* y, int64_t
     case OEH_BF16: return launch_add_fake_quant<__nv_bfloat16>(a, b, y, n, qparams, n_bits, st);
   }
   return set_error(OEH_ERR_BAD_ARG, "oeh_add_fake_quant: unknown dtype %d", dtype);
+}
+
+extern "C" int oeh_tap_add_fake_quant(const void* a, const void* b, void* y, int64_t n, int32_t dtype, const float* qparams_b,
+                                      const float* qparams_sum, int32_t n_bits, oeh_stream_t stream) {
+  OEH_CHECK_ARG(n >= 0, "oeh_tap_add_fake_quant: n=%lld < 0", (long long)n);
+  OEH_CHECK_ARG(n_bits >= 1 && n_bits <= 16, "oeh_tap_add_fake_quant: n_bits=%d outside [1,16]", n_bits);
+  if (n == 0) return OEH_OK;
+  OEH_CHECK_ARG(a && b && y && qparams_sum, "oeh_tap_add_fake_quant: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case OEH_F32: return launch_add_fake_quant<float>(a, b, y, n, qparams_sum, n_bits, st, qparams_b);
+    case OEH_F16: return launch_add_fake_quant<__half>(a, b, y, n, qparams_sum, n_bits, st, qparams_b);
+    case OEH_BF16: return launch_add_fake_quant<__nv_bfloat16>(a, b, y, n, qparams_sum, n_bits, st, qparams_b);
+  }
+  return set_error(OEH_ERR_BAD_ARG, "oeh_tap_add_fake_quant: unknown dtype %d", dtype);
+}
+
+extern "C" int oeh_fake_quant_asym_segments(const void* x, void* y, int64_t rows, int32_t seg_cols, int32_t n_seg,
+                                            int64_t x_row_stride, int64_t y_row_stride, int32_t dtype,
+                                            const float* const* qparams, int32_t n_bits, oeh_stream_t stream) {
+  OEH_CHECK_ARG(rows >= 0 && seg_cols > 0 && n_seg >= 1 && n_seg <= 4, "oeh_fake_quant_asym_segments: bad shape");
+  OEH_CHECK_ARG(n_bits >= 1 && n_bits <= 16, "oeh_fake_quant_asym_segments: n_bits=%d outside [1,16]", n_bits);
+  if (rows == 0) return OEH_OK;
+  OEH_CHECK_ARG(x && y && qparams, "oeh_fake_quant_asym_segments: null pointer");
+  OEH_CHECK_ARG(x_row_stride >= (int64_t)seg_cols * n_seg && y_row_stride >= (int64_t)seg_cols * n_seg,
+                "oeh_fake_quant_asym_segments: row stride smaller than the row");
+  SegQ q;
+  for (int s = 0; s < 4; ++s) {
+    q.qp[s] = s < n_seg ? qparams[s] : nullptr;
+    if (s < n_seg) OEH_CHECK_ARG(q.qp[s], "oeh_fake_quant_asym_segments: null qparams[%d]", s);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case OEH_F32: return launch_segments<float>(x, y, rows, seg_cols, n_seg, x_row_stride, y_row_stride, q, n_bits, st);
+    case OEH_F16: return launch_segments<__half>(x, y, rows, seg_cols, n_seg, x_row_stride, y_row_stride, q, n_bits, st);
+    case OEH_BF16:
+      return launch_segments<__nv_bfloat16>(x, y, rows, seg_cols, n_seg, x_row_stride, y_row_stride, q, n_bits, st);
+  }
+  return set_error(OEH_ERR_BAD_ARG, "oeh_fake_quant_asym_segments: unknown dtype %d", dtype);
 }
 
 extern "C" size_t oeh_minmax_workspace_bytes(int64_t n) {

@@ -294,13 +294,18 @@ def range_update_f64(state64: torch.Tensor, state: torch.Tensor, new_minmax: tor
 
 
 def add_fake_quant(a: torch.Tensor, b: torch.Tensor, qparams: torch.Tensor, n_bits: int = 8,
-                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """qdq(a + b) in one pass (oeh_add_fake_quant): the residual-sum activation tap with fixed ranges."""
-    _require_cuda(a, b, qparams)
+                   out: Optional[torch.Tensor] = None, qparams_b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qdq(a + [qdq_b] b) in one pass (oeh_add_fake_quant / oeh_tap_add_fake_quant): the residual-sum activation tap with
+    fixed ranges, optionally with the output tap of the layer that produced ``b`` folded in."""
+    _require_cuda(a, b, qparams, qparams_b)
     if a.shape != b.shape or a.dtype != b.dtype:
         raise ValueError("add_fake_quant: a and b must have the same shape and dtype")
     ac, bc = a.contiguous(), b.contiguous()
     y = out if out is not None else torch.empty_like(ac)
+    if qparams_b is not None:
+        L.check(L.lib().oeh_tap_add_fake_quant(ac.data_ptr(), bc.data_ptr(), y.data_ptr(), ac.numel(), _dtype_code(ac),
+                                               qparams_b.data_ptr(), qparams.data_ptr(), int(n_bits), _stream()))
+        return y
     L.check(L.lib().oeh_add_fake_quant(ac.data_ptr(), bc.data_ptr(), y.data_ptr(), ac.numel(), _dtype_code(ac),
                                        qparams.data_ptr(), int(n_bits), _stream()))
     return y
@@ -359,10 +364,10 @@ def ce_loss(logits: torch.Tensor, labels: torch.Tensor, vocab: Optional[int] = N
 def add_layer_norm(a: torch.Tensor, b: Optional[torch.Tensor], weight: torch.Tensor, bias: Optional[torch.Tensor],
                    eps: float = 1e-12, qparams_res: Optional[torch.Tensor] = None,
                    qparams_out: Optional[torch.Tensor] = None, n_bits: int = 8,
-                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """[qdq_out] LayerNorm([qdq_res](a + b)) over the last dimension in one pass (oeh_add_layer_norm).  ``b`` None =
-    plain LayerNorm; ``qparams_*`` = device [scale, zero_point] of fixed-range taps."""
-    _require_cuda(a, b, weight, bias, qparams_res, qparams_out)
+                   out: Optional[torch.Tensor] = None, qparams_a: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[qdq_out] LayerNorm([qdq_res]([qdq_a] a + b)) over the last dimension in one pass (oeh_add_layer_norm).  ``b``
+    None = plain LayerNorm; ``qparams_*`` = device [scale, zero_point] of fixed-range taps."""
+    _require_cuda(a, b, weight, bias, qparams_a, qparams_res, qparams_out)
     if b is not None and (b.shape != a.shape or b.dtype != a.dtype):
         raise ValueError("add_layer_norm: a and b must have the same shape and dtype")
     cols = a.shape[-1]
@@ -376,6 +381,24 @@ def add_layer_norm(a: torch.Tensor, b: Optional[torch.Tensor], weight: torch.Ten
     rows = ac.numel() // max(cols, 1)
     L.check(L.lib().oeh_add_layer_norm(ac.data_ptr(), bc.data_ptr() if bc is not None else None, wc.data_ptr(),
                                        bic.data_ptr() if bic is not None else None, y.data_ptr(), rows, cols, float(eps),
-                                       _dtype_code(ac), qparams_res.data_ptr() if qparams_res is not None else None,
+                                       _dtype_code(ac), qparams_a.data_ptr() if qparams_a is not None else None,
+                                       qparams_res.data_ptr() if qparams_res is not None else None,
                                        qparams_out.data_ptr() if qparams_out is not None else None, int(n_bits), _stream()))
+    return y
+
+
+def fake_quant_asym_segments(x: torch.Tensor, qparams, n_bits: int = 8, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fake-quant of ``len(qparams)`` equal column segments of a (..., n_seg*seg_cols) tensor, each with its own device
+    [scale, zero_point] (oeh_fake_quant_asym_segments): one launch for the output of a fused q|k|v projection."""
+    _require_cuda(x, *qparams)
+    n_seg = len(qparams)
+    cols = x.shape[-1]
+    if not 1 <= n_seg <= 4 or cols % n_seg:
+        raise ValueError("fake_quant_asym_segments: 1..4 equal segments expected")
+    xc = x.contiguous()
+    y = out if out is not None else torch.empty_like(xc)
+    rows = xc.numel() // max(cols, 1)
+    ptrs = (C.c_void_p * n_seg)(*[q.data_ptr() for q in qparams])
+    L.check(L.lib().oeh_fake_quant_asym_segments(xc.data_ptr(), y.data_ptr(), rows, cols // n_seg, n_seg, cols, cols,
+                                                 _dtype_code(xc), ptrs, int(n_bits), _stream()))
     return y

@@ -114,6 +114,12 @@ class OPTAttentionWithExtras(GateMixin, nn.Module):
         return self._core_unfused(q, k, v, attention_mask, gate_logits, layer_head_mask, output_attentions, bsz,
                                   tgt_len, taps)
 
+    def _fused_qkv(self, hidden_states):
+        """One GEMM for q_proj | k_proj | v_proj in eval (bert_attention.fused_qkv_projection); overridden by the
+        quantized wrapper."""
+        return fused_qkv_projection(self, (self.q_proj, self.k_proj, self.v_proj), hidden_states, self.num_heads,
+                                    self.head_dim)
+
     def _core_unfused(self, q, k, v, attention_mask, gate_logits, layer_head_mask, output_attentions, bsz, tgt_len, taps):
         ts, tp, tc = taps if taps is not None else (None, None, None)
         fn = as_softmax_fn(self.softmax_fn)
@@ -166,10 +172,7 @@ class OPTAttentionWithExtras(GateMixin, nn.Module):
         is_cross_attention = key_value_states is not None
         bsz, tgt_len, _ = hidden_states.size()
 
-        fused_qkv = None
-        if not is_cross_attention and past_key_value is None:
-            fused_qkv = fused_qkv_projection(self, (self.q_proj, self.k_proj, self.v_proj), hidden_states,
-                                             self.num_heads, self.head_dim)
+        fused_qkv = self._fused_qkv(hidden_states) if not is_cross_attention and past_key_value is None else None
         if fused_qkv is not None:
             q, k, v = fused_qkv
         else:

@@ -866,11 +866,29 @@ class QuantLinear(QuantizedModule, nn.Linear):
             self.cached_params = (weight.detach().clone(), bias.detach().clone() if bias is not None else None)
         return weight, bias
 
-    def forward(self, x, offsets=None):
+    def linear_only(self, x):
+        """The layer WITHOUT its output tap (cached fake-quantized weight, optional fused activation): for callers that
+        fold the tap into the next kernel (``tap_fusable`` / ``tap_qparams``)."""
         weight, bias = self.get_params()
         res = F.linear(x.contiguous(), weight.contiguous(), bias=bias)
         if self.activation_function is not None:
             res = self.activation_function(res)
+        return res
+
+    @property
+    def tap_fusable(self) -> bool:
+        """The output tap is off, or quantises with a frozen asymmetric range (can be folded into a consumer kernel)."""
+        if not self._qa_host:
+            return True
+        mgr = self.activation_quantizer
+        return isinstance(mgr, QuantizationManager) and not mgr.estimating and \
+            isinstance(mgr.quantizer, AsymmetricUniformQuantizer) and not self._forward_hooks
+
+    def tap_qparams(self):
+        return self.activation_quantizer.quantizer.qparams if self._qa_host else None
+
+    def forward(self, x, offsets=None):
+        res = self.linear_only(x)
         if self._qa_host:
             res = self.activation_quantizer(res)
         return res

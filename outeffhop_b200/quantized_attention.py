@@ -15,8 +15,10 @@ whole chain -- three taps included -- is one fused tcgen05 kernel launch.
 """
 from __future__ import annotations
 
+import torch
 from torch import nn
 
+from . import ops
 from .bert_attention import BertSelfAttentionWithExtras
 from .opt_attention import OPTAttentionWithExtras
 from .quantization import (QuantizedActivation, QuantizedModule, QuantLinear, _set_layer_estimate_ranges,
@@ -81,6 +83,34 @@ def quantize_linear(lin: nn.Linear, **quant_params) -> QuantLinear:
     return QuantLinear.from_linear(lin, **_linear_params(quant_params))
 
 
+def quantized_fused_qkv(owner: nn.Module, mods, hidden_states: torch.Tensor, num_heads: int, head_dim: int):
+    """Fixed ranges: the three QuantLinear projections as ONE GEMM over the concatenated (cached) fake-quantized weights and
+    ONE segmented tap (each projection keeps its own range: ``oeh_fake_quant_asym_segments``) instead of 3 + 3 launches.
+    Returns (q, k, v) as (B,H,T,d) strided views, or None while any tap is still estimating / taps disagree."""
+    if owner.training or not all(isinstance(m, QuantLinear) and m.tap_fusable and m.activation_function is None
+                                 and not m._forward_pre_hooks for m in mods):
+        return None
+    active = [m._qa_host for m in mods]
+    if any(active) != all(active) or len({m.activation_quantizer.n_bits for m in mods}) != 1 \
+            or any((m.bias is None) != (mods[0].bias is None) for m in mods):
+        return None
+    params = [m.get_params() for m in mods]                   # cached fake-quantized weights (hijacker.py:84-101)
+    key = tuple((id(w), None if b is None else id(b)) for w, b in params)
+    cache = owner.__dict__.get("_qkv_cache")
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            w = torch.cat([w for w, _ in params], dim=0)
+            b = None if params[0][1] is None else torch.cat([b for _, b in params], dim=0)
+        cache = (key, w, b, params)                           # `params` keeps the keyed tensors alive
+        owner.__dict__["_qkv_cache"] = cache
+    y = nn.functional.linear(hidden_states, cache[1], cache[2])
+    if all(active):
+        y = ops.fake_quant_asym_segments(y, [m.tap_qparams() for m in mods], mods[0].activation_quantizer.n_bits)
+    B, T = y.shape[0], y.shape[1]
+    y = y.view(B, T, 3, num_heads, head_dim)
+    return tuple(y[:, :, j].permute(0, 2, 1, 3) for j in range(3))
+
+
 class QuantizedBertSelfAttentionWithExtras(QuantizedModel, BertSelfAttentionWithExtras):
     def __init__(self, org_model, **quant_params):
         nn.Module.__init__(self)
@@ -124,6 +154,10 @@ class QuantizedBertSelfAttentionWithExtras(QuantizedModel, BertSelfAttentionWith
 
     def _taps(self):
         return (self.attn_scores_act_quantizer, self.attn_probs_act_quantizer, self.context_act_quantizer)
+
+    def _fused_qkv(self, hidden_states):
+        return quantized_fused_qkv(self, (self.query, self.key, self.value), hidden_states, self.num_attention_heads,
+                                   self.attention_head_size)
 
     def _gate_scale(self) -> float:
         return 1.0                                # ``context_layer *= gate`` (quantized_bert.py:422)
@@ -169,3 +203,6 @@ class QuantizedOPTAttentionWithExtras(QuantizedModel, OPTAttentionWithExtras):
 
     def _taps(self):
         return (self.attn_scores_act_quantizer, self.attn_probs_act_quantizer, self.context_act_quantizer)
+
+    def _fused_qkv(self, hidden_states):
+        return quantized_fused_qkv(self, (self.q_proj, self.k_proj, self.v_proj), hidden_states, self.num_heads, self.head_dim)

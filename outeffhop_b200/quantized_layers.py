@@ -74,12 +74,16 @@ class QuantLayerNorm(QuantizedModule, nn.LayerNorm):
         return res
 
 
-def _residual_tap(tap: QuantizedActivation, hidden_states: torch.Tensor, input_tensor: torch.Tensor) -> torch.Tensor:
-    """``tap(hidden_states + input_tensor)``: fused when the tap quantises with a frozen range."""
+def _residual_tap(tap: QuantizedActivation, hidden_states: torch.Tensor, input_tensor: torch.Tensor,
+                  qparams_b: "torch.Tensor | None" = None) -> torch.Tensor:
+    """``tap(hidden_states + input_tensor)``: fused when the tap quantises with a frozen range.  ``qparams_b``: frozen
+    output tap of the layer that produced ``input_tensor``, folded into the same kernel."""
     if tap.fixed and hidden_states.is_cuda and hidden_states.shape == input_tensor.shape \
             and hidden_states.dtype == input_tensor.dtype:
-        return ops.add_fake_quant(hidden_states, input_tensor, tap.kernel_qparams(),
-                                  tap.activation_quantizer.n_bits).view(hidden_states.shape)
+        return ops.add_fake_quant(hidden_states, input_tensor, tap.kernel_qparams(), tap.activation_quantizer.n_bits,
+                                  qparams_b=qparams_b).view(hidden_states.shape)
+    if qparams_b is not None:
+        raise RuntimeError("a folded producer tap needs a frozen residual tap")
     return tap(hidden_states + input_tensor)
 
 
@@ -116,18 +120,27 @@ class _QuantizedBertResidualBlock(QuantizedModel):
         return True
 
     def forward(self, hidden_states, input_tensor):
-        hidden_states = self.dense(hidden_states)
-        hidden_states = self.dropout(hidden_states)
-        if self._fusable(hidden_states, input_tensor):
+        dense = self.dense
+        fold_dense_tap = (not self.training) and dense.tap_fusable       # eval: dropout is the identity
+        x = dense.linear_only(hidden_states) if fold_dense_tap else dense(hidden_states)
+        x = self.dropout(x)
+        if self._fusable(x, input_tensor):
             tap, ln = self.res_act_quantizer, self.LayerNorm
-            weight, bias = ln.get_params()
-            n_bits = tap.activation_quantizer.n_bits if tap.active else ln.activation_quantizer.n_bits
-            return ops.add_layer_norm(hidden_states, input_tensor, weight, bias, ln.eps,
-                                      qparams_res=tap.kernel_qparams() if tap.active else None,
-                                      qparams_out=ln.activation_quantizer.quantizer.qparams if ln._qa_host else None,
-                                      n_bits=n_bits)
-        hidden_states = _residual_tap(self.res_act_quantizer, hidden_states, input_tensor)   # add + tap
-        return self.LayerNorm(hidden_states)
+            taps = [m.n_bits for m, on in ((dense.activation_quantizer, fold_dense_tap and dense._qa_host),
+                                           (tap.activation_quantizer, tap.active),
+                                           (ln.activation_quantizer, ln._qa_host)) if on]
+            if len(set(taps)) <= 1:                        # one kernel takes one bit width
+                weight, bias = ln.get_params()
+                # dense tap -> residual add -> res tap -> LayerNorm -> output tap: ONE kernel
+                return ops.add_layer_norm(x, input_tensor, weight, bias, ln.eps,
+                                          qparams_a=dense.tap_qparams() if fold_dense_tap else None,
+                                          qparams_res=tap.kernel_qparams() if tap.active else None,
+                                          qparams_out=ln.activation_quantizer.quantizer.qparams if ln._qa_host else None,
+                                          n_bits=taps[0] if taps else 8)
+        if fold_dense_tap and dense._qa_host:              # not fusable after all: apply the dense tap on its own
+            x = dense.activation_quantizer(x)
+        x = _residual_tap(self.res_act_quantizer, x, input_tensor)   # add + tap
+        return self.LayerNorm(x)
 
 
 class QuantizedBertSelfOutput(_QuantizedBertResidualBlock):

@@ -351,9 +351,16 @@ class QuantizedOPTDecoderLayer(QuantizedModel):
         if self.do_layer_norm_before:
             hidden_states = self.final_layer_norm(hidden_states)
         hidden_states = self.fc1_act(hidden_states)                                                      # :360
-        hidden_states = self.fc2(hidden_states)
-        hidden_states = F.dropout(hidden_states, p=self.dropout, training=self.training)
-        hidden_states = _residual_tap(self.ffn_res_act_quantizer, residual, hidden_states).view(shape)   # :367-370
+        tap, fc2 = self.ffn_res_act_quantizer, self.fc2
+        if (not self.training and tap.fixed and fc2._qa_host and fc2.tap_fusable
+                and fc2.activation_quantizer.n_bits == tap.activation_quantizer.n_bits):
+            # fc2's output tap, the residual add and the residual tap in one kernel (:362-369)
+            hidden_states = _residual_tap(tap, residual, fc2.linear_only(hidden_states),
+                                          qparams_b=fc2.tap_qparams()).view(shape)
+        else:
+            hidden_states = fc2(hidden_states)
+            hidden_states = F.dropout(hidden_states, p=self.dropout, training=self.training)
+            hidden_states = _residual_tap(tap, residual, hidden_states).view(shape)                      # :367-370
         if not self.do_layer_norm_before:
             hidden_states = self.final_layer_norm(hidden_states)
         outputs = (hidden_states,)

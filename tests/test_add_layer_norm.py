@@ -24,8 +24,9 @@ def test_symbol_declared():
     import os
     from outeffhop_b200 import _lib
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "oeh.h")).read()
-    assert "oeh_add_layer_norm(" in hdr and "oeh_add_layer_norm" in _lib.SYMBOLS
-    getattr(_lib.lib(), "oeh_add_layer_norm")
+    for name in ("oeh_add_layer_norm", "oeh_tap_add_fake_quant", "oeh_fake_quant_asym_segments"):
+        assert name + "(" in hdr and name in _lib.SYMBOLS
+        getattr(_lib.lib(), name)
 
 
 @pytest.mark.gpu
@@ -100,3 +101,53 @@ def test_fused_bert_residual_modules_match_hf():
     assert abs(got - want) < 2e-3 * abs(want)
     sd = model.state_dict()
     assert "bert.encoder.layer.0.attention.output.LayerNorm.weight" in sd and "bert.encoder.layer.1.output.dense.bias" in sd
+
+
+# ---- taps folded into consumer kernels (fixed-range INT8 step) --------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float32", "float16"])
+def test_add_layer_norm_with_producer_tap_equals_unfused_chain(dtype):
+    """qparams_a: y == add_layer_norm(fake_quant(a), b, ...) bit for bit (same qdq arithmetic in both kernels)."""
+    from outeffhop_b200 import ops
+    t = _T[dtype]
+    g = torch.Generator(device="cuda").manual_seed(11)
+    a = (torch.randn(300, 768, device="cuda", generator=g) * 2).to(t)
+    b = torch.randn(300, 768, device="cuda", generator=g).to(t)
+    w = (torch.rand(768, device="cuda", generator=g) + 0.5).to(t)
+    bias = (torch.randn(768, device="cuda", generator=g) * 0.1).to(t)
+    qa, qr, qo = (torch.tensor(v, device="cuda") for v in ([0.04, 120.0], [0.05, 131.0], [0.03, 125.0]))
+    fused = ops.add_layer_norm(a, b, w, bias, 1e-12, qparams_a=qa, qparams_res=qr, qparams_out=qo)
+    chain = ops.add_layer_norm(ops.fake_quant_asym(a, qa), b, w, bias, 1e-12, qparams_res=qr, qparams_out=qo)
+    assert torch.equal(fused, chain)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float32", "float16", "bfloat16"])
+@pytest.mark.parametrize("n", [1, 4099, 1 << 20])
+def test_tap_add_fake_quant_equals_unfused_chain(dtype, n):
+    from outeffhop_b200 import ops
+    t = _T[dtype]
+    g = torch.Generator(device="cuda").manual_seed(n)
+    a = (torch.randn(n, device="cuda", generator=g) * 2).to(t)
+    b = (torch.randn(n, device="cuda", generator=g) * 3).to(t)
+    qb, qs = torch.tensor([0.05, 128.0], device="cuda"), torch.tensor([0.07, 119.0], device="cuda")
+    fused = ops.add_fake_quant(a, b, qs, qparams_b=qb)
+    chain = ops.add_fake_quant(a, ops.fake_quant_asym(b, qb), qs)
+    assert torch.equal(fused, chain)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float32", "float16"])
+@pytest.mark.parametrize("n_seg", [1, 3, 4])
+def test_fake_quant_segments_equals_per_segment_fake_quant(dtype, n_seg):
+    from outeffhop_b200 import ops
+    t = _T[dtype]
+    g = torch.Generator(device="cuda").manual_seed(5 + n_seg)
+    x = (torch.randn(2, 37, n_seg * 768, device="cuda", generator=g) * 3).to(t)
+    qps = [torch.tensor([0.02 * (s + 1), 100.0 + 10 * s], device="cuda") for s in range(n_seg)]
+    got = ops.fake_quant_asym_segments(x, qps)
+    for s in range(n_seg):
+        want = ops.fake_quant_asym(x[..., s * 768:(s + 1) * 768].contiguous(), qps[s])
+        assert torch.equal(got[..., s * 768:(s + 1) * 768], want)
+    with pytest.raises(ValueError):
+        ops.fake_quant_asym_segments(x[..., :100], qps[:3] if n_seg >= 3 else qps * 3)
