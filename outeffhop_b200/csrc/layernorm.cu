@@ -52,19 +52,19 @@ add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T*
       }
     }
   }
+  const QdqVec<T> qa(as, az, int_max), qr(rs, rz, int_max), qo(os, oz, int_max);
   float sum = 0.f;
 #pragma unroll
   for (int v = 0; v < kVecs; ++v) {
     const int i = lane + 32 * v;
+    if (i < nvec) {                                        // taps and the sum in the tensor dtype, 16 bytes at a time
+      if (q_a) qa.apply(va[v], false);
+      if (bv) add_vec<T>(va[v], vb[v]);
+      if (q_res) qr.apply(va[v], false);
+    }
 #pragma unroll
     for (int e = 0; e < N; ++e) {
-      float s = 0.f;
-      if (i < nvec) {
-        s = DT<T>::to_f(va[v].v[e]);
-        if (q_a) s = qdq_one<T>(s, as, az, int_max, false);
-        if (bv) s = DT<T>::rnd(__fadd_rn(s, DT<T>::to_f(vb[v].v[e])));
-        if (q_res) s = qdq_one<T>(s, rs, rz, int_max, false);
-      }
+      const float s = i < nvec ? DT<T>::to_f(va[v].v[e]) : 0.f;
       x[v][e] = s;
       sum += s;
     }
@@ -97,10 +97,9 @@ add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T*
       for (int e = 0; e < N; ++e) {
         float r = DT<T>::to_f(g.v[e]) * (rstd * (x[v][e] - mean));
         if (beta) r += DT<T>::to_f(be.v[e]);
-        r = DT<T>::rnd(r);
-        if (q_out) r = qdq_one<T>(r, os, oz, int_max, false);
-        out.v[e] = DT<T>::from_f(r);
+        out.v[e] = DT<T>::from_f(r);                       // one rounding to the tensor dtype
       }
+      if (q_out) qo.apply(out, false);
       __stcs(reinterpret_cast<int4*>(yv + i), *reinterpret_cast<const int4*>(&out));
     }
   }

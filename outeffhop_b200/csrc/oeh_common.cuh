@@ -107,6 +107,94 @@ __device__ __forceinline__ float qdq_one(float x, float scale, float zp, float i
   return D::rnd(__fmul_rn(scale, diff));             // scale * (...)
 }
 
+// ---- the same chain on a 16-byte vector --------------------------------------------------------------------------------
+// 16-bit tensors: two elements per instruction with the hardware's own fp16 / bf16 arithmetic.  Every ATen op of the
+// chain is "compute in fp32, round once to the tensor dtype"; for +, -, x, / on 16-bit operands that equals the correctly
+// rounded 16-bit operation (24 >= 2*11 + 2 mantissa bits: the double rounding is innocuous), which is what HADD2 / HMUL2
+// (.rn) and __h2div deliver -- 7 instead of 22 issue slots per element; the scalar chain was issue-bound at 3.8 of
+// 6.5 TB/s on fp16 tensors.  Used when 2^n_bits - 1 is exactly representable in the dtype (fp16: n <= 11, bf16: n <= 8).
+template <typename T>
+struct P2 {
+  static constexpr bool kPacked = false;
+};
+template <>
+struct P2<__half> {
+  static constexpr bool kPacked = true;
+  using V2 = __half2;
+  static __device__ __forceinline__ V2 bcast(float f) { return __float2half2_rn(f); }
+  static __device__ __forceinline__ bool exact_int(float m) { return m <= 2047.f; }
+};
+template <>
+struct P2<__nv_bfloat16> {
+  static constexpr bool kPacked = true;
+  using V2 = __nv_bfloat162;
+  static __device__ __forceinline__ V2 bcast(float f) { return __float2bfloat162_rn(f); }
+  static __device__ __forceinline__ bool exact_int(float m) { return m <= 255.f; }
+};
+
+template <typename T, bool kPacked = P2<T>::kPacked>
+struct QdqVec;
+
+template <typename T>
+struct QdqVec<T, false> {                         // fp32 tensors: the scalar chain
+  float scale, zp, int_max;
+  __device__ __forceinline__ QdqVec(float scale_, float zp_, float int_max_) : scale(scale_), zp(zp_), int_max(int_max_) {}
+  __device__ __forceinline__ void apply(Vec16<T>& v, bool codes) const {
+#pragma unroll
+    for (int e = 0; e < Vec16<T>::N; ++e) v.v[e] = DT<T>::from_f(qdq_one<T>(DT<T>::to_f(v.v[e]), scale, zp, int_max, codes));
+  }
+};
+
+template <typename T>
+struct QdqVec<T, true> {
+  using V2 = typename P2<T>::V2;
+  float scale, zp, int_max;
+  V2 s2, z2, m2, zero2;
+  bool packed;
+  // scale_ / zp_: already rounded to T (the 0-dim fp32 scalars are cast to the tensor dtype first)
+  __device__ __forceinline__ QdqVec(float scale_, float zp_, float int_max_) : scale(scale_), zp(zp_), int_max(int_max_) {
+    s2 = P2<T>::bcast(scale_);
+    z2 = P2<T>::bcast(zp_);
+    m2 = P2<T>::bcast(int_max_);
+    zero2 = P2<T>::bcast(0.f);
+    packed = P2<T>::exact_int(int_max_);
+  }
+  __device__ __forceinline__ V2 one2(V2 x, bool codes) const {
+    V2 q = __h2div(x, s2);                        // x_float / scale
+    q = h2rint(q);                                // round half to even
+    q = __hadd2_rn(q, z2);                        // + zero_point
+    q = __hmin2_nan(__hmax2_nan(q, zero2), m2);   // clamp (NaN propagates like torch.clamp)
+    if (codes) return q;
+    q = __hsub2_rn(q, z2);                        // x_int - zero_point
+    return __hmul2_rn(s2, q);                     // scale * (...)
+  }
+  __device__ __forceinline__ void apply(Vec16<T>& v, bool codes) const {
+    if (packed) {
+      V2* p = reinterpret_cast<V2*>(v.v);
+#pragma unroll
+      for (int k = 0; k < Vec16<T>::N / 2; ++k) p[k] = one2(p[k], codes);
+    } else {
+#pragma unroll
+      for (int e = 0; e < Vec16<T>::N; ++e) v.v[e] = DT<T>::from_f(qdq_one<T>(DT<T>::to_f(v.v[e]), scale, zp, int_max, codes));
+    }
+  }
+};
+
+// a + b rounded once to the tensor dtype (ATen's add), on a 16-byte vector
+template <typename T>
+__device__ __forceinline__ void add_vec(Vec16<T>& a, const Vec16<T>& b) {
+  if constexpr (P2<T>::kPacked) {
+    using V2 = typename P2<T>::V2;
+    V2* pa = reinterpret_cast<V2*>(a.v);
+    const V2* pb = reinterpret_cast<const V2*>(b.v);
+#pragma unroll
+    for (int k = 0; k < Vec16<T>::N / 2; ++k) pa[k] = __hadd2_rn(pa[k], pb[k]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < Vec16<T>::N; ++e) a.v[e] = DT<T>::from_f(DT<T>::rnd(__fadd_rn(DT<T>::to_f(a.v[e]), DT<T>::to_f(b.v[e]))));
+  }
+}
+
 // AsymmetricUniformQuantizer.set_quant_range + scale/zero_point (uniform_quantizers.py:72-82,
 // 199-200, 218-219) with the reference's fp32 op order.  Usable on host and device.
 __host__ __device__ inline void set_quant_range_f32(float x_min, float x_max, int n_bits, float eps, float* delta,

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(kThreads) fake_quant_kernel(const T* __restric
   // 0-dim fp32 scale / zero_point are converted to the tensor dtype first (ATen-CUDA dynamic cast)
   const float scale = DT<T>::rnd(__ldg(qparams));
   const float zp = DT<T>::rnd(__ldg(qparams + 1));
+  const QdqVec<T> qv(scale, zp, int_max);
   const int64_t nvec = n / N;
   const V* xv = reinterpret_cast<const V*>(x);
   V* yv = reinterpret_cast<V*>(y);
@@ -49,17 +50,14 @@ __global__ void __launch_bounds__(kThreads) fake_quant_kernel(const T* __restric
     for (int u = 0; u < kUnroll; ++u) in[u] = ld_stream(xv + i + u * stride);
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      V out;
-#pragma unroll
-      for (int e = 0; e < N; ++e) out.v[e] = DT<T>::from_f(qdq_one<T>(DT<T>::to_f(in[u].v[e]), scale, zp, int_max, codes));
-      st_stream(yv + i + u * stride, out);
+      qv.apply(in[u], codes);
+      st_stream(yv + i + u * stride, in[u]);
     }
   }
   for (; i < nvec; i += stride) {
-    V in = xv[i], out;
-#pragma unroll
-    for (int e = 0; e < N; ++e) out.v[e] = DT<T>::from_f(qdq_one<T>(DT<T>::to_f(in.v[e]), scale, zp, int_max, codes));
-    yv[i] = out;
+    V in = xv[i];
+    qv.apply(in, codes);
+    yv[i] = in;
   }
   // scalar tail
   for (int64_t t = nvec * N + (int64_t)blockIdx.x * kThreads + threadIdx.x; t < n; t += stride)
@@ -93,6 +91,7 @@ __global__ void __launch_bounds__(kThreads) add_fake_quant_kernel(const T* __res
   // optional tap on b before the add (the output tap of the QuantLinear that produced b: quantized_opt.py:362-369)
   const float bscale = qparams_b ? DT<T>::rnd(__ldg(qparams_b)) : 1.f;
   const float bzp = qparams_b ? DT<T>::rnd(__ldg(qparams_b + 1)) : 0.f;
+  const QdqVec<T> qv(scale, zp, int_max), qb(bscale, bzp, int_max);
   auto one = [&](T av, T bv) {
     float bf = DT<T>::to_f(bv);
     if (qparams_b) bf = qdq_one<T>(bf, bscale, bzp, int_max, false);
@@ -117,10 +116,10 @@ __global__ void __launch_bounds__(kThreads) add_fake_quant_kernel(const T* __res
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        V out;
-#pragma unroll
-        for (int e = 0; e < N; ++e) out.v[e] = one(ia[u].v[e], ib[u].v[e]);
-        st_stream(yv + i + u * stride, out);
+        if (qparams_b) qb.apply(ib[u], false);
+        add_vec<T>(ia[u], ib[u]);
+        qv.apply(ia[u], false);
+        st_stream(yv + i + u * stride, ia[u]);
       }
     }
     for (; i < nvec; i += stride) {
@@ -314,11 +313,9 @@ __global__ void __launch_bounds__(kThreads) fake_quant_segments_kernel(const T* 
     const int s = c / vec_per_seg;
     const float sc = s == 0 ? scale[0] : (s == 1 ? scale[1] : (s == 2 ? scale[2] : scale[3]));
     const float z = s == 0 ? zp[0] : (s == 1 ? zp[1] : (s == 2 ? zp[2] : zp[3]));
-    const V in = *reinterpret_cast<const V*>(x + r * ldx + (int64_t)c * N);
-    V out;
-#pragma unroll
-    for (int e = 0; e < N; ++e) out.v[e] = DT<T>::from_f(qdq_one<T>(DT<T>::to_f(in.v[e]), sc, z, int_max, false));
-    *reinterpret_cast<V*>(y + r * ldy + (int64_t)c * N) = out;
+    V in = *reinterpret_cast<const V*>(x + r * ldx + (int64_t)c * N);
+    QdqVec<T>(sc, z, int_max).apply(in, false);
+    *reinterpret_cast<V*>(y + r * ldy + (int64_t)c * N) = in;
   }
 }
 

@@ -171,3 +171,39 @@ def test_full_size_properties_fp32():
     assert torch.equal(ops.fake_quant_asym(y, state[4:6]), y)                     # idempotent
     codes = ops.fake_quant_asym(x, state[4:6], emit_codes=True)
     assert codes.min().item() >= 0 and codes.max().item() <= 255 and torch.equal(codes, codes.round())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n_bits", [4, 8, 11, 12])
+def test_fake_quant_low_precision_exhaustive_vs_aten_cuda(dtype, n_bits):
+    """EVERY 16-bit pattern (all exponents, denormals, inf, NaN) through the packed half2 / bfloat162 path and the scalar
+    tail, for many ranges, against ATen's per-op-rounded chain on the GPU: bit for bit."""
+    if n_bits > (8 if dtype == torch.bfloat16 else 11):
+        pytest.skip("2^n - 1 is not representable in the tensor dtype: ATen rounds the clamp bound itself; the reference "
+                    "quantises 16-bit activations to 8 bits (16-bit quantizers only on fp32 LayerNorm outputs)")
+    ops = _ops()
+    bits = torch.arange(0, 65536, dtype=torch.int32).to(torch.int16)
+    x = torch.cat([bits, bits[:37]]).cuda().view(dtype)            # 65573 elements: vector body + unaligned scalar tail
+    int_max = float(2 ** n_bits - 1)
+    g = torch.Generator().manual_seed(n_bits)
+    ranges = [(-1.0, 3.0), (0.0, 1.0), (-7.3, 0.2), (-0.01, 0.02), (-300.0, 500.0), (0.0, 1e-3), (-60000.0, 60000.0)]
+    ranges += [(-float(a), float(b)) for a, b in (torch.rand(12, 2, generator=g) * 20.0)]
+    for lo, hi in ranges:
+        d, zf, scale, zp = ops.set_quant_range_host(lo, hi, n_bits)
+        scale_t, zp_t = torch.tensor(scale, device="cuda"), torch.tensor(zp, device="cuda")
+        x_int = torch.clamp(torch.round(x / scale_t) + zp_t, 0.0, int_max)
+        ref = scale_t * (x_int - zp_t)
+        y = ops.fake_quant_asym(x, _qparams(scale, zp), n_bits=n_bits)
+        same = (y.view(torch.int16) == ref.view(torch.int16)) | (torch.isnan(y) & torch.isnan(ref))
+        assert bool(same.all()), (dtype, n_bits, lo, hi, int((~same).sum()), x[~same][:4], y[~same][:4], ref[~same][:4])
+        codes = ops.fake_quant_asym(x, _qparams(scale, zp), n_bits=n_bits, emit_codes=True)
+        same = (codes.view(torch.int16) == x_int.view(torch.int16)) | (torch.isnan(codes) & torch.isnan(x_int))
+        assert bool(same.all()), ("codes", dtype, n_bits, lo, hi, int((~same).sum()))
+        # the fused consumers use the same packed chain: residual add + tap, producer tap + add + tap
+        b = x.flip(0).contiguous()
+        s_ref = x + b
+        s_int = torch.clamp(torch.round(s_ref / scale_t) + zp_t, 0.0, int_max)
+        ref2 = scale_t * (s_int - zp_t)
+        y2 = ops.add_fake_quant(x, b, _qparams(scale, zp), n_bits=n_bits)
+        same = (y2.view(torch.int16) == ref2.view(torch.int16)) | (torch.isnan(y2) & torch.isnan(ref2))
+        assert bool(same.all()), ("add", dtype, n_bits, lo, hi, int((~same).sum()))
