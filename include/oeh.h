@@ -259,10 +259,12 @@ int oeh_ce_loss(const void* logits, int64_t rows, int64_t vocab, int64_t row_str
  * of the same dtype.  The sum is rounded once to the tensor dtype (ATen add), statistics / affine map in fp32 (biased
  * variance, rsqrt(var + eps)), one rounding of y; taps exactly as oeh_fake_quant_asym.  cols must be a multiple of
  * 16/sizeof(dtype) and at most 256 such vectors (2048 fp16 / 1024 fp32 columns); all pointers 16-byte aligned.
+ * sum_out (optional, (rows, cols)): also receives the (tapped) sum -- pre-LayerNorm blocks (OPTDecoderLayer, HF
+ * modeling_opt; quantized_opt.py:338-357) need it as the next residual.
  * ------------------------------------------------------------------------------------------- */
 int oeh_add_layer_norm(const void* a, const void* b, const void* weight, const void* bias, void* y, int64_t rows,
                        int64_t cols, double eps, int32_t dtype, const float* qparams_a, const float* qparams_res,
-                       const float* qparams_out, int32_t n_bits, oeh_stream_t stream);
+                       const float* qparams_out, int32_t n_bits, void* sum_out, oeh_stream_t stream);
 
 /* y = qdq_sum(a + qdq_b(b)): oeh_add_fake_quant with the output tap of the QuantLinear that produced b folded in
  * (QuantizedOPTDecoderLayer: fc2's tap, the residual add and ffn_res_act_quantizer, quantized_opt.py:362-369).

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ gamma,
                       const T* __restrict__ beta, T* __restrict__ y, int64_t rows, int cols, float eps,
                       const float* __restrict__ q_a, const float* __restrict__ q_res, const float* __restrict__ q_out,
-                      float int_max) {
+                      float int_max, T* __restrict__ sum_out) {
   using V = Vec16<T>;
   constexpr int N = V::N;
   const int lane = threadIdx.x & 31;
@@ -61,6 +61,8 @@ add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T*
       if (q_a) qa.apply(va[v], false);
       if (bv) add_vec<T>(va[v], vb[v]);
       if (q_res) qr.apply(va[v], false);
+      if (sum_out)                                         // pre-LN blocks (OPT) keep the sum as the next residual
+        __stcs(reinterpret_cast<int4*>(reinterpret_cast<V*>(sum_out + row * cols) + i), *reinterpret_cast<const int4*>(&va[v]));
     }
 #pragma unroll
     for (int e = 0; e < N; ++e) {
@@ -107,13 +109,13 @@ add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T*
 
 template <typename T>
 int launch(const void* a, const void* b, const void* gamma, const void* beta, void* y, int64_t rows, int64_t cols, float eps,
-           const float* q_a, const float* q_res, const float* q_out, int n_bits, cudaStream_t st) {
+           const float* q_a, const float* q_res, const float* q_out, int n_bits, void* sum_out, cudaStream_t st) {
   constexpr int N = Vec16<T>::N;
   if (cols % N != 0 || cols / N > 32 * 8)
     return set_error(OEH_ERR_UNSUPPORTED, "oeh_add_layer_norm: cols=%lld must be a multiple of %d and at most %d",
                      (long long)cols, N, 32 * 8 * N);
   const uintptr_t al = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(gamma) |
-                       reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(y);
+                       reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(sum_out);
   if (al & 15) return set_error(OEH_ERR_UNSUPPORTED, "oeh_add_layer_norm: pointers must be 16-byte aligned");
   const int kv = (int)((cols / N + 31) / 32);
   const float int_max = (float)((1 << n_bits) - 1);
@@ -122,7 +124,7 @@ int launch(const void* a, const void* b, const void* gamma, const void* beta, vo
   case K:                                                                                                            \
     add_layer_norm_kernel<T, K><<<grid, kWarpsPerBlock * 32, 0, st>>>((const T*)a, (const T*)b, (const T*)gamma,     \
                                                                      (const T*)beta, (T*)y, rows, (int)cols, eps,   \
-                                                                     q_a, q_res, q_out, int_max);                   \
+                                                                     q_a, q_res, q_out, int_max, (T*)sum_out);      \
     break;
   switch (kv) {
     OEH_LN_CASE(1) OEH_LN_CASE(2) OEH_LN_CASE(3) OEH_LN_CASE(4) OEH_LN_CASE(5) OEH_LN_CASE(6) OEH_LN_CASE(7) OEH_LN_CASE(8)
@@ -138,7 +140,7 @@ using namespace oeh;
 
 extern "C" int oeh_add_layer_norm(const void* a, const void* b, const void* weight, const void* bias, void* y, int64_t rows,
                                   int64_t cols, double eps, int32_t dtype, const float* qparams_a,
-                                  const float* qparams_res, const float* qparams_out, int32_t n_bits,
+                                  const float* qparams_res, const float* qparams_out, int32_t n_bits, void* sum_out,
                                   oeh_stream_t stream) {
   OEH_CHECK_ARG(rows >= 0 && cols > 0, "oeh_add_layer_norm: bad shape (%lld, %lld)", (long long)rows, (long long)cols);
   if (rows == 0) return OEH_OK;
@@ -148,10 +150,10 @@ extern "C" int oeh_add_layer_norm(const void* a, const void* b, const void* weig
   if (!(qparams_a || qparams_res || qparams_out)) n_bits = 8;
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case OEH_F32: return launch<float>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_a, qparams_res, qparams_out, n_bits, st);
-    case OEH_F16: return launch<__half>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_a, qparams_res, qparams_out, n_bits, st);
+    case OEH_F32: return launch<float>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_a, qparams_res, qparams_out, n_bits, sum_out, st);
+    case OEH_F16: return launch<__half>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_a, qparams_res, qparams_out, n_bits, sum_out, st);
     case OEH_BF16:
-      return launch<__nv_bfloat16>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_a, qparams_res, qparams_out, n_bits, st);
+      return launch<__nv_bfloat16>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_a, qparams_res, qparams_out, n_bits, sum_out, st);
   }
   return set_error(OEH_ERR_BAD_ARG, "oeh_add_layer_norm: unknown dtype %d", dtype);
 }

@@ -16,7 +16,7 @@ from typing import Callable, Dict, Optional
 
 import torch
 
-from .hf_compat import fuse_bert_residual_blocks, swap_bert_attention, swap_opt_attention
+from .hf_compat import fuse_bert_residual_blocks, fuse_opt_decoder_layers, swap_bert_attention, swap_opt_attention
 
 
 # ---- model / data builders ---------------------------------------------------------------------------------
@@ -36,8 +36,9 @@ def build_bert_base(seed: int = 3000, dtype=torch.float16, device="cuda", attn_s
 
 
 def build_opt_125m(seed: int = 5678, dtype=torch.float16, device="cuda", attn_softmax="vanilla",
-                   num_hidden_layers: int = 12, causal_hint: bool = True, **attn_kw):
-    """OPT-125m shape (Cfg3/Cfg4), random init."""
+                   num_hidden_layers: int = 12, causal_hint: bool = True, fuse_residual: bool = True, **attn_kw):
+    """OPT-125m shape (Cfg3/Cfg4), random init.  ``fuse_residual``: also swap the decoder layers for the fused eval
+    modules (hf_compat.OPTDecoderLayerFused)."""
     from transformers import OPTConfig, OPTForCausalLM
     cfg = OPTConfig(hidden_size=768, num_hidden_layers=num_hidden_layers, ffn_dim=3072, num_attention_heads=12,
                     word_embed_proj_dim=768, max_position_embeddings=2048, do_layer_norm_before=True,
@@ -46,7 +47,8 @@ def build_opt_125m(seed: int = 5678, dtype=torch.float16, device="cuda", attn_so
     torch.manual_seed(seed)
     model = OPTForCausalLM(cfg)
     model = model.to(device=device, dtype=dtype).eval()
-    return swap_opt_attention(model, attn_softmax=attn_softmax, max_seq_length=512, causal_hint=causal_hint, **attn_kw)
+    model = swap_opt_attention(model, attn_softmax=attn_softmax, max_seq_length=512, causal_hint=causal_hint, **attn_kw)
+    return fuse_opt_decoder_layers(model) if fuse_residual else model
 
 
 def synthetic_mlm_batch(batch: int, seq: int, vocab: int = 30522, seed: int = 0, mlm_probability: float = 0.15,

@@ -130,3 +130,50 @@ def fuse_bert_residual_blocks(model):
         layer.attention.output = BertResidualLayerNormFused(layer.attention.output).train(layer.training)
         layer.output = BertResidualLayerNormFused(layer.output).train(layer.training)
     return model
+
+
+class OPTDecoderLayerFused(torch.nn.Module):
+    """HF OPTDecoderLayer (pre-LayerNorm variants: 125m, 1.3b, ...; the module the reference wraps at
+    quantized_opt.py:277-384) for eval with fewer, fused launches: LayerNorm kernels from liboeh, ``residual + attn`` and
+    the following LayerNorm in ONE kernel (sum kept as the next residual), fc1 + bias + ReLU in one cuBLASLt call (the
+    ReLU epilogue is exact).  Same submodule names, so state_dicts and the quantized wrapper keep working."""
+
+    def __init__(self, org):
+        super().__init__()
+        self.embed_dim = org.embed_dim
+        self.do_layer_norm_before = org.do_layer_norm_before
+        self.dropout = org.dropout
+        self.activation_fn = org.activation_fn
+        self.self_attn, self.self_attn_layer_norm = org.self_attn, org.self_attn_layer_norm
+        self.fc1, self.fc2, self.final_layer_norm = org.fc1, org.fc2, org.final_layer_norm
+        self._org_forward = org.forward.__func__
+
+    def _fusable(self, h) -> bool:
+        ln1, ln2 = self.self_attn_layer_norm, self.final_layer_norm
+        return (self.do_layer_norm_before and not self.training and h.is_cuda and isinstance(self.activation_fn, torch.nn.ReLU)
+                and not (torch.is_grad_enabled() and h.requires_grad) and ln1.bias is not None and ln2.bias is not None
+                and not any(m._forward_hooks or m._forward_pre_hooks for m in (ln1, ln2, self.fc1, self.fc2)))
+
+    def forward(self, hidden_states, attention_mask=None, past_key_values=None, use_cache=False, position_ids=None, **kw):
+        if not self._fusable(hidden_states):
+            return self._org_forward(self, hidden_states, attention_mask=attention_mask, past_key_values=past_key_values,
+                                     use_cache=use_cache, position_ids=position_ids, **kw)
+        from . import ops
+        ln1, ln2 = self.self_attn_layer_norm, self.final_layer_norm
+        x = ops.add_layer_norm(hidden_states, None, ln1.weight, ln1.bias, ln1.eps)
+        attn = self.self_attn(hidden_states=x, past_key_values=past_key_values, position_ids=position_ids,
+                              attention_mask=attention_mask, **kw)[0]
+        x2, residual = ops.add_layer_norm(hidden_states, attn, ln2.weight, ln2.bias, ln2.eps, return_sum=True)
+        shape = x2.shape
+        f = torch._addmm_activation(self.fc1.bias, x2.view(-1, shape[-1]), self.fc1.weight.t()) \
+            if self.fc1.bias is not None else torch.relu(self.fc1(x2.view(-1, shape[-1])))
+        f = self.fc2(f)
+        return (residual.view(-1, shape[-1]) + f).view(shape)
+
+
+def fuse_opt_decoder_layers(model):
+    """Swap every decoder layer of an HF OPT model for the fused eval module."""
+    dec = model.model.decoder
+    for i, layer in enumerate(dec.layers):
+        dec.layers[i] = OPTDecoderLayerFused(layer).train(layer.training)
+    return model

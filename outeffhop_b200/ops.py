@@ -364,9 +364,11 @@ def ce_loss(logits: torch.Tensor, labels: torch.Tensor, vocab: Optional[int] = N
 def add_layer_norm(a: torch.Tensor, b: Optional[torch.Tensor], weight: torch.Tensor, bias: Optional[torch.Tensor],
                    eps: float = 1e-12, qparams_res: Optional[torch.Tensor] = None,
                    qparams_out: Optional[torch.Tensor] = None, n_bits: int = 8,
-                   out: Optional[torch.Tensor] = None, qparams_a: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   out: Optional[torch.Tensor] = None, qparams_a: Optional[torch.Tensor] = None,
+                   return_sum: bool = False):
     """[qdq_out] LayerNorm([qdq_res]([qdq_a] a + b)) over the last dimension in one pass (oeh_add_layer_norm).  ``b``
-    None = plain LayerNorm; ``qparams_*`` = device [scale, zero_point] of fixed-range taps."""
+    None = plain LayerNorm; ``qparams_*`` = device [scale, zero_point] of fixed-range taps; ``return_sum``: also return
+    the (tapped) sum, which pre-LayerNorm blocks carry on as the residual."""
     _require_cuda(a, b, weight, bias, qparams_a, qparams_res, qparams_out)
     if b is not None and (b.shape != a.shape or b.dtype != a.dtype):
         raise ValueError("add_layer_norm: a and b must have the same shape and dtype")
@@ -378,13 +380,15 @@ def add_layer_norm(a: torch.Tensor, b: Optional[torch.Tensor], weight: torch.Ten
     wc = weight.contiguous()
     bic = bias.contiguous() if bias is not None else None
     y = out if out is not None else torch.empty_like(ac)
+    total = torch.empty_like(ac) if return_sum else None
     rows = ac.numel() // max(cols, 1)
     L.check(L.lib().oeh_add_layer_norm(ac.data_ptr(), bc.data_ptr() if bc is not None else None, wc.data_ptr(),
                                        bic.data_ptr() if bic is not None else None, y.data_ptr(), rows, cols, float(eps),
                                        _dtype_code(ac), qparams_a.data_ptr() if qparams_a is not None else None,
                                        qparams_res.data_ptr() if qparams_res is not None else None,
-                                       qparams_out.data_ptr() if qparams_out is not None else None, int(n_bits), _stream()))
-    return y
+                                       qparams_out.data_ptr() if qparams_out is not None else None, int(n_bits),
+                                       total.data_ptr() if total is not None else None, _stream()))
+    return (y, total) if return_sum else y
 
 
 def fake_quant_asym_segments(x: torch.Tensor, qparams, n_bits: int = 8, out: Optional[torch.Tensor] = None) -> torch.Tensor:

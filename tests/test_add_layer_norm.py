@@ -151,3 +151,33 @@ def test_fake_quant_segments_equals_per_segment_fake_quant(dtype, n_seg):
         assert torch.equal(got[..., s * 768:(s + 1) * 768], want)
     with pytest.raises(ValueError):
         ops.fake_quant_asym_segments(x[..., :100], qps[:3] if n_seg >= 3 else qps * 3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float32", "float16", "bfloat16"])
+def test_add_layer_norm_returns_the_sum_for_pre_ln_blocks(dtype):
+    from outeffhop_b200 import ops
+    t = _T[dtype]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = (torch.randn(2, 50, 768, device="cuda", generator=g) * 2).to(t)
+    b = torch.randn(2, 50, 768, device="cuda", generator=g).to(t)
+    w, bias = torch.ones(768, device="cuda", dtype=t), torch.zeros(768, device="cuda", dtype=t)
+    y, s = ops.add_layer_norm(a, b, w, bias, 1e-5, return_sum=True)
+    assert torch.equal(s, a + b)                                            # ATen's add, bit for bit
+    assert torch.equal(y, ops.add_layer_norm(a, b, w, bias, 1e-5))
+
+
+@pytest.mark.gpu
+def test_fused_opt_decoder_layer_matches_hf_layer():
+    from outeffhop_b200 import eval_harness as EH
+    model = EH.build_opt_125m(seed=3, num_hidden_layers=2, attn_softmax="softmax1", fuse_residual=False)
+    b = EH.synthetic_clm_batch(2, 512, seed=1)
+    ids, lab = b["input_ids"].cuda(), b["labels"].cuda()
+    mask = EH.make_causal_mask(2, 512, torch.float16, "cuda")
+    pos = torch.arange(512, device="cuda").unsqueeze(0).expand(2, 512).contiguous()
+    with torch.no_grad():
+        want = EH.opt_clm_loss(model, ids, lab, mask, pos, aten_loss=True).item()
+        EH.fuse_opt_decoder_layers(model)
+        got = EH.opt_clm_loss(model, ids, lab, mask, pos).item()
+    assert abs(got - want) < 2e-3 * abs(want), (got, want)
+    assert "model.decoder.layers.1.final_layer_norm.weight" in model.state_dict()

@@ -103,8 +103,10 @@ def test_opt_125m_eval_perplexity_matches_fp32_reference(key, gated, causal_hint
     """BASELINE config 3: OPT-125m causal fp16, conditional_per_token gate (init 0.25), block 512, batch 4."""
     from outeffhop_b200 import eval_harness as EH
     kw = dict(attn_gate_type="conditional_per_token", attn_gate_init=0.25) if gated else {}
-    model = EH.build_opt_125m(seed=5678, dtype=torch.float16, attn_softmax=key, causal_hint=causal_hint, **kw)
-    ref = copy.deepcopy(model).float()
+    model = EH.build_opt_125m(seed=5678, dtype=torch.float16, attn_softmax=key, causal_hint=causal_hint,
+                              fuse_residual=False, **kw)
+    ref = copy.deepcopy(model).float()                                  # reference keeps HF's ATen decoder layers
+    EH.fuse_opt_decoder_layers(model)
     for lo, lr in zip(model.model.decoder.layers, ref.model.decoder.layers):
         lr.self_attn = RefOPTAttention(lo.self_attn).cuda()
     batches = [EH.synthetic_clm_batch(4, 512, seed=5678 + i) for i in range(2)]
