@@ -144,11 +144,25 @@ def opt_clm_loss(model, input_ids: torch.Tensor, labels: torch.Tensor, causal_ma
     if dec.project_in is not None:
         h = dec.project_in(h)
     h = h + pos
-    for layer in dec.layers:
-        out = layer(h, attention_mask=causal_mask, position_ids=position_ids, past_key_values=None, use_cache=False)
-        h = out[0] if isinstance(out, tuple) else out
-    if dec.final_layer_norm is not None:
-        h = dec.final_layer_norm(h)
+    from .hf_compat import OPTDecoderLayerFused
+    layers = list(dec.layers)
+    if (layers and dec.final_layer_norm is not None and dec.final_layer_norm.bias is not None
+            and all(isinstance(l, OPTDecoderLayerFused) and l._fusable(h) for l in layers)):
+        # chained fused layers: every residual add shares a kernel with the LayerNorm that follows it, across layer
+        # boundaries too (the last one is the decoder's final_layer_norm)
+        from . import ops
+        ln = layers[0].self_attn_layer_norm
+        x = ops.add_layer_norm(h, None, ln.weight, ln.bias, ln.eps)
+        for i, layer in enumerate(layers):
+            next_ln = layers[i + 1].self_attn_layer_norm if i + 1 < len(layers) else dec.final_layer_norm
+            x, h = layer.forward_chained(x, h, next_ln, attention_mask=causal_mask, position_ids=position_ids)
+        h = x
+    else:
+        for layer in layers:
+            out = layer(h, attention_mask=causal_mask, position_ids=position_ids, past_key_values=None, use_cache=False)
+            h = out[0] if isinstance(out, tuple) else out
+        if dec.final_layer_norm is not None:
+            h = dec.final_layer_norm(h)
     if dec.project_out is not None:
         h = dec.project_out(h)
     w, b, V = _padded_decoder(model.lm_head)

@@ -171,6 +171,22 @@ class OPTDecoderLayerFused(torch.nn.Module):
         return (residual.view(-1, shape[-1]) + f).view(shape)
 
 
+    def forward_chained(self, x, residual, next_ln, attention_mask=None, position_ids=None):
+        """The same layer for a caller that chains layers: ``x`` = this layer's LayerNorm-ed input (computed by the previous
+        layer's last kernel), ``residual`` = the un-normalised stream.  Returns (LayerNorm_next(residual'), residual') with
+        the final ``residual + ffn`` and the NEXT layer's first LayerNorm (``next_ln``) fused as well."""
+        from . import ops
+        ln2 = self.final_layer_norm
+        attn = self.self_attn(hidden_states=x, past_key_values=None, position_ids=position_ids,
+                              attention_mask=attention_mask)[0]
+        x2, residual = ops.add_layer_norm(residual, attn, ln2.weight, ln2.bias, ln2.eps, return_sum=True)
+        shape = x2.shape
+        f = torch._addmm_activation(self.fc1.bias, x2.view(-1, shape[-1]), self.fc1.weight.t()) \
+            if self.fc1.bias is not None else torch.relu(self.fc1(x2.view(-1, shape[-1])))
+        f = self.fc2(f).view(shape)
+        return ops.add_layer_norm(residual, f, next_ln.weight, next_ln.bias, next_ln.eps, return_sum=True)
+
+
 def fuse_opt_decoder_layers(model):
     """Swap every decoder layer of an HF OPT model for the fused eval module."""
     dec = model.model.decoder
