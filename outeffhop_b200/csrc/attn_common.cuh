@@ -41,6 +41,7 @@ struct AttnParams {
   void* out;
   int64_t os0, os1, os2;
   TmapCoord cq, ck, cv;
+  int n_qt;             // persistent kernel: Q tile groups per (batch, head); work items = n_qt * H * B
   float* dbg_s;         // optional: raw S of K tile 0, (B,H,Tq,BN) fp32
   float* dbg_o;         // optional: raw O accumulator, (B,H,Tq,HD) fp32
 };

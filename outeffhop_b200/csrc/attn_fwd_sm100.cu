@@ -23,6 +23,7 @@
 #include "attn_common.cuh"
 #include "attn_fwd_one.cuh"
 #include "attn_fwd_ws.cuh"
+#include "attn_fwd_wsp.cuh"
 
 namespace oeh {
 namespace {
@@ -415,7 +416,16 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
     // steady state ~10 % slower; measured crossover (profiles/r01_ws_tiles_per_cta_l.txt): the two-pass modes are
     // faster with one tile at every length, the one-pass modes up to ~24 key steps per query tile on average.
     const double steps = (double)((a->Tk + attn_ws::BNW - 1) / attn_ws::BNW) * (a->causal ? 0.5 : 1.0);
-    int tiles = (norm_mode || steps <= 24.0) ? 1 : 2;
+    // Persistent variant (attn_fwd_wsp.cuh): hides the per-CTA prologue / epilogue.  Measured
+    // (profiles/r01_ws_persistent_u.txt): one-pass non-causal +22 % at T = 512, +13 % at 1024, +7 % at 2048, +3 % at 4096,
+    // equal at 8192; causal loses 5-10 % to the static round-robin item order (items differ in length) and the two-pass
+    // modes are faster as two one-tile CTAs per SM, so those keep the non-persistent kernel.
+    int persistent = !norm_mode && !a->causal;
+#ifdef OEH_WS_PERSISTENT
+    persistent = OEH_WS_PERSISTENT;
+#endif
+    if (const char* f = getenv("OEH_WS_PERSISTENT")) persistent = atoi(f) != 0;
+    int tiles = persistent ? 2 : ((norm_mode || steps <= 24.0) ? 1 : 2);
 #ifdef OEH_WS_TILES
     tiles = OEH_WS_TILES;
 #endif
@@ -439,6 +449,31 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
       attr_done[tiles - 1][kw] = true;
     }
     dim3 grid((unsigned)((a->Tq + qrows - 1) / qrows), (unsigned)a->H, (unsigned)a->B);
+    if (persistent) {
+      // persistent variant (attn_fwd_wsp.cuh): one CTA per SM slot walks the work items with stride gridDim.x
+      static const KernelFn pkernels[2][8] = {
+          {attn_wsp::attn_fwd_wsp_kernel<false, false, false, 1>, attn_wsp::attn_fwd_wsp_kernel<false, true, false, 1>,
+           attn_wsp::attn_fwd_wsp_kernel<true, false, false, 1>,  attn_wsp::attn_fwd_wsp_kernel<true, true, false, 1>,
+           attn_wsp::attn_fwd_wsp_kernel<false, false, true, 1>,  attn_wsp::attn_fwd_wsp_kernel<false, true, true, 1>,
+           attn_wsp::attn_fwd_wsp_kernel<true, false, true, 1>,   attn_wsp::attn_fwd_wsp_kernel<true, true, true, 1>},
+          {attn_wsp::attn_fwd_wsp_kernel<false, false, false, 2>, attn_wsp::attn_fwd_wsp_kernel<false, true, false, 2>,
+           attn_wsp::attn_fwd_wsp_kernel<true, false, false, 2>,  attn_wsp::attn_fwd_wsp_kernel<true, true, false, 2>,
+           attn_wsp::attn_fwd_wsp_kernel<false, false, true, 2>,  attn_wsp::attn_fwd_wsp_kernel<false, true, true, 2>,
+           attn_wsp::attn_fwd_wsp_kernel<true, false, true, 2>,   attn_wsp::attn_fwd_wsp_kernel<true, true, true, 2>}};
+      static bool pattr_done[2][8] = {};
+      const int psmem = tiles == 1 ? attn_wsp::Cfg<1>::kSmemBytes : attn_wsp::Cfg<2>::kSmemBytes;
+      KernelFn pfn = pkernels[tiles - 1][kw];
+      if (!pattr_done[tiles - 1][kw]) {
+        OEH_CUDA_OK(cudaFuncSetAttribute(pfn, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem));
+        pattr_done[tiles - 1][kw] = true;
+      }
+      p.n_qt = (int)grid.x;
+      const long long items = (long long)grid.x * grid.y * grid.z;
+      const long long slots = (long long)num_sms() * (tiles == 1 ? 2 : 1);
+      const unsigned pgrid = (unsigned)(items < slots ? items : slots);
+      pfn<<<pgrid, threads, psmem, st>>>(tmq, tmk, tmv, p);
+      return check_launch("attn_fwd_wsp_kernel");
+    }
     fn<<<grid, threads, smem, st>>>(tmq, tmk, tmv, p);
     return check_launch("attn_fwd_ws_kernel");
   }

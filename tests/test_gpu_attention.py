@@ -216,15 +216,31 @@ def test_attention_fused_int8_taps_vs_oracle(kind, gamma, eta, before_gate, T):
     assert (diff > 2e-3).mean() < 0.02, (diff > 2e-3).mean()              # and rarely even that
 
 
+@pytest.mark.parametrize("persistent", ["0", "1"])
 @pytest.mark.parametrize("tiles", ["1", "2"])
 @pytest.mark.parametrize("kind,gamma,eta", KINDS[:4])
 @pytest.mark.parametrize("T,causal", [(700, False), (700, True), (1024, True)])
-def test_attention_ws_tiles_per_cta(tiles, kind, gamma, eta, T, causal, monkeypatch):
-    """Both CTA shapes of the warp-specialised kernel (two Q tiles per CTA / two one-tile CTAs per SM) on ragged and
-    causal long sequences."""
+def test_attention_ws_tiles_per_cta(persistent, tiles, kind, gamma, eta, T, causal, monkeypatch):
+    """Both CTA shapes of the warp-specialised kernel (two Q tiles per CTA / two one-tile CTAs per SM), launched per work
+    item and as persistent CTAs, on ragged and causal long sequences."""
     ops = _ops()
     monkeypatch.setenv("OEH_WS_TILES", tiles)
+    monkeypatch.setenv("OEH_WS_PERSISTENT", persistent)
     q, k, v = _mk(1, 3, T, T, torch.float16, seed=T + kind)
     out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal, out_layout="bhtd")
     ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal)
     np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=TOL, rtol=0)
+
+
+@pytest.mark.parametrize("kind,gamma,eta", KINDS[:4])
+@pytest.mark.parametrize("causal", [False, True])
+def test_attention_persistent_many_items_per_cta(kind, gamma, eta, causal, monkeypatch):
+    """More work items than SM slots: every persistent CTA walks several (Q tile group, head, batch) items, so the ring /
+    parity bookkeeping carries across items (odd and even step counts per item)."""
+    ops = _ops()
+    monkeypatch.setenv("OEH_WS_PERSISTENT", "1")
+    for T in (320, 448):                                   # 5 and 7 key steps of 64: odd -> the stream parities swap per item
+        q, k, v = _mk(7, 12, T, T, torch.float16, seed=T + kind)       # 7*12*2 = 168 items > 148 SMs
+        out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal, out_layout="bhtd")
+        ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal)
+        np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=TOL, rtol=0)
