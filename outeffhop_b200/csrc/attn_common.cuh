@@ -41,7 +41,8 @@ struct AttnParams {
   void* out;
   int64_t os0, os1, os2;
   TmapCoord cq, ck, cv;
-  int n_qt;             // persistent kernel: Q tile groups per (batch, head); work items = n_qt * H * B
+  int n_qt;             // Q tile groups per (batch, head); work items = n_qt * H * B
+  int hb_chunk;         // causal work order: (batch, head) pairs per chunk (see causal_item); 0 = per-head order
   float* dbg_s;         // optional: raw S of K tile 0, (B,H,Tq,BN) fp32
   float* dbg_o;         // optional: raw O accumulator, (B,H,Tq,HD) fp32
 };
@@ -64,6 +65,23 @@ __device__ __forceinline__ Qdq load_qdq(const float* qparams, float int_max) {
   q.inv_scale = __frcp_rn(q.scale);
   q.int_max = int_max;
   return q;
+}
+
+// Causal work order.  Q tile groups of one head differ in length (tile qt attends (qt+1) tile widths of keys), so the
+// order in which the hardware (or a persistent CTA) picks them up decides the tail of the launch: items are numbered
+// HEAVIEST FIRST over a chunk of `hb_chunk` (batch, head) pairs -- all of the chunk's longest tiles, then the next
+// longest, ... -- and chunk after chunk, so that the last CTAs of the grid are the short ones and an SM never gets
+// two long tiles while its neighbour gets two short ones (T = 512, 48 heads, 4 tiles each on 148 SMs x 2 slots:
+// longest SM 5 tile widths instead of 8).  The chunk bounds the K / V working set of the CTAs in flight (the host
+// sizes it to ~32 MB, well inside L2), because tiles of one head share their keys.  Bijective on [0, n_qt*HB).
+__device__ __forceinline__ void causal_item(int item, int n_qt, int HB, int hb_chunk, int& qt, int& hb) {
+  const int G = hb_chunk > 0 ? hb_chunk : 1;
+  const int per_chunk = G * n_qt;
+  const int c = item / per_chunk, rem = item - c * per_chunk;
+  const int g = min(G, HB - c * G);                    // the last chunk may be smaller
+  const int lvl = rem / g;
+  qt = n_qt - 1 - lvl;
+  hb = c * G + (rem - lvl * g);
 }
 
 __device__ __forceinline__ float max4(float a, float b, float c, float d) { return fmaxf(fmaxf(a, b), fmaxf(c, d)); }

@@ -418,14 +418,17 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
     const double steps = (double)((a->Tk + attn_ws::BNW - 1) / attn_ws::BNW) * (a->causal ? 0.5 : 1.0);
     // Persistent variant (attn_fwd_wsp.cuh): hides the per-CTA prologue / epilogue.  Measured
     // (profiles/r01_ws_persistent_u.txt): one-pass non-causal +22 % at T = 512, +13 % at 1024, +7 % at 2048, +3 % at 4096,
-    // equal at 8192; causal loses 5-10 % to the static round-robin item order (items differ in length) and the two-pass
-    // modes are faster as two one-tile CTAs per SM, so those keep the non-persistent kernel.
-    int persistent = !norm_mode && !a->causal;
+    // equal at 8192.  Causal one-pass (profiles/r01_causal_order_w.txt; items sorted heaviest-first and walked in snake
+    // order, see causal_item / item_of): +19 % at T = 512 and +12 % at 1024 as one-tile CTAs, +6 % at 2048 and +1 % at
+    // 4096 as two-tile CTAs; at 8192 the per-item launch is 3 % ahead (the hardware's dynamic CTA scheduling balances the
+    // long items better than any static walk).  The two-pass modes are faster as two one-tile CTAs per SM launched per
+    // item at every length, so those keep the non-persistent kernel.
+    int persistent = !norm_mode && (!a->causal || steps <= 32.0);
 #ifdef OEH_WS_PERSISTENT
     persistent = OEH_WS_PERSISTENT;
 #endif
     if (const char* f = getenv("OEH_WS_PERSISTENT")) persistent = atoi(f) != 0;
-    int tiles = persistent ? 2 : ((norm_mode || steps <= 24.0) ? 1 : 2);
+    int tiles = persistent ? ((a->causal && steps <= 8.0) ? 1 : 2) : ((norm_mode || steps <= 24.0) ? 1 : 2);
 #ifdef OEH_WS_TILES
     tiles = OEH_WS_TILES;
 #endif
@@ -449,6 +452,16 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
       attr_done[tiles - 1][kw] = true;
     }
     dim3 grid((unsigned)((a->Tq + qrows - 1) / qrows), (unsigned)a->H, (unsigned)a->B);
+    p.n_qt = (int)grid.x;
+    if (a->causal) {
+      // causal work order (attn_common.cuh, causal_item): heaviest Q tiles first over chunks of (batch, head) pairs whose
+      // K / V (Tk x 64 x 2 B x 2 per pair) stay within ~32 MB of L2.  OEH_CAUSAL_CHUNK=0 restores the per-head order.
+      long long chunk = (32ll << 20) / ((long long)a->Tk * HD * 2 * 2);
+      const long long hb = (long long)a->H * a->B;
+      chunk = chunk < 1 ? 1 : (chunk > hb ? hb : chunk);
+      if (const char* f = getenv("OEH_CAUSAL_CHUNK")) chunk = atoll(f) > hb ? hb : atoll(f);
+      p.hb_chunk = (int)chunk;
+    }
     if (persistent) {
       // persistent variant (attn_fwd_wsp.cuh): one CTA per SM slot walks the work items with stride gridDim.x
       static const KernelFn pkernels[2][8] = {
@@ -467,7 +480,6 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
         OEH_CUDA_OK(cudaFuncSetAttribute(pfn, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem));
         pattr_done[tiles - 1][kw] = true;
       }
-      p.n_qt = (int)grid.x;
       const long long items = (long long)grid.x * grid.y * grid.z;
       const long long slots = (long long)num_sms() * (tiles == 1 ? 2 : 1);
       const unsigned pgrid = (unsigned)(items < slots ? items : slots);

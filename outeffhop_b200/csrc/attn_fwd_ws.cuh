@@ -127,9 +127,17 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from it
   // (role, TMEM lane base, barrier / descriptor addresses) on the uniform datapath instead of R2UR-ing it at every use
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  // causal: heaviest Q tiles of a head first, so the last CTAs of the grid are the short ones
-  const int qt = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
-  const int q0 = qt * kQRows, h = blockIdx.y, b = blockIdx.z;
+  // causal: heaviest Q tiles first over chunks of heads (attn_common.cuh, causal_item), so the last CTAs of the grid are
+  // the short ones; the grid is walked in launch order (x fastest)
+  int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  if (p.causal) {
+    int hb;
+    causal_item((int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)), (int)gridDim.x,
+                (int)(gridDim.y * gridDim.z), p.hb_chunk, qt, hb);
+    h = hb % (int)gridDim.y;
+    b = hb / (int)gridDim.y;
+  }
+  const int q0 = qt * kQRows;
 
   const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem0;                                    // kTiles tiles of 128 rows

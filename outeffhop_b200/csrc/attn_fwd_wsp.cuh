@@ -117,9 +117,9 @@ attn_fwd_wsp_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   };
   auto make_plan = [&](int item) {
     Plan pl;
-    const int x = item % p.n_qt, hb = item / p.n_qt;
-    // causal: heaviest Q tiles of a head first
-    const int qt = p.causal ? p.n_qt - 1 - x : x;
+    // causal: heaviest Q tiles first over chunks of heads (attn_common.cuh, causal_item)
+    int qt = item % p.n_qt, hb = item / p.n_qt;
+    if (p.causal) causal_item(item, p.n_qt, p.H * p.B, p.hb_chunk, qt, hb);
     pl.q0 = qt * kQRows;
     pl.h = hb % p.H;
     pl.b = hb / p.H;
@@ -135,6 +135,16 @@ attn_fwd_wsp_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     return pl;
   };
 
+  // Item `it` of this CTA.  Non-causal: stride gridDim.x.  Causal: the items are sorted by length (heaviest first), so a
+  // plain stride would hand CTA 0 the longest item of every round; walking odd rounds backwards ("snake") evens the
+  // sums out to within one item.  A CTA without an item in the last, partial round is done (no round follows it).
+  auto item_of = [&](int it) {
+    const int base = it * (int)gridDim.x;
+    if (base >= n_items) return n_items;
+    const int c = (p.causal && (it & 1)) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+    return base + c;
+  };
+
   if (warp >= C::kSoftmaxWarps) reg_dealloc<C::kAuxRegs>();
   if (warp == C::kWarpTma) {
     // ================================ TMA producer (whole warp waits, one elected lane issues) ============
@@ -145,7 +155,7 @@ attn_fwd_wsp_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     }
     __syncwarp();
     int gk = 0, gv = 0;                                         // K loads / V loads issued by earlier items
-    for (int item = blockIdx.x, it = 0; item < n_items; item += gridDim.x, ++it) {
+    for (int it = 0, item; (item = item_of(it)) < n_items; ++it) {
       const Plan pl = make_plan(item);
       const int qb = it & 1;
       if (it >= 2) ptx::mbar_wait(ptx::smem_u32(&bars.q_empty[qb]), (uint32_t)((it >> 1) - 1) & 1u);
@@ -203,7 +213,7 @@ attn_fwd_wsp_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
                     (first && k == 0) ? 0u : 1u);
     };
     int gk = 0, gv = 0;                                          // steps / PV steps of earlier items
-    for (int item = blockIdx.x, it = 0; item < n_items; item += gridDim.x, ++it) {
+    for (int it = 0, item; (item = item_of(it)) < n_items; ++it) {
       const Plan pl = make_plan(item);
       const int qb = it & 1;
       const uint64_t dqi = dq + (uint64_t)qb * (kTiles * kTileUnits);
@@ -272,7 +282,7 @@ attn_fwd_wsp_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     if (has_qs) qd_s = load_qdq(p.qdq_scores, p.int_max);
     if (has_qp) qd_p = load_qdq(p.qdq_probs, p.int_max);
     int gk = 0;                                                   // steps of earlier items
-    for (int item = blockIdx.x, it = 0; item < n_items; item += gridDim.x, ++it) {
+    for (int it = 0, item; (item = item_of(it)) < n_items; ++it) {
     const Plan pl = make_plan(item);
     const int q0 = pl.q0, h = pl.h, b = pl.b, n_kv = pl.n_kv, nA = pl.nA, n_iter = pl.n_iter;
     const int row = q0 + t * 128 + r;                             // this thread's query row

@@ -132,6 +132,36 @@ def fuse_bert_residual_blocks(model):
     return model
 
 
+class GELUFused(torch.nn.Module):
+    """The erf GELU between the two FFN GEMMs (HF ``BertIntermediate.intermediate_act_fn`` = ``ACT2FN["gelu"]``;
+    kept as is by the reference's ``quantize_intermediate``, quantized_bert.py:609-617) through ``oeh_gelu_erf`` for
+    16-bit CUDA tensors in eval; anything else (training graphs, fp32, hooks on this module) takes ATen's kernel."""
+
+    def forward(self, input):
+        if self.training or (torch.is_grad_enabled() and input.requires_grad) or not input.is_cuda \
+                or input.dtype not in (torch.float16, torch.bfloat16) or self._forward_hooks or self._forward_pre_hooks:
+            return torch.nn.functional.gelu(input)
+        from . import ops
+        return ops.gelu(input)
+
+
+def _is_erf_gelu(act) -> bool:
+    if act is torch.nn.functional.gelu:
+        return True
+    if isinstance(act, torch.nn.GELU):
+        return act.approximate == "none"
+    return type(act).__name__ == "GELUActivation" and getattr(act, "act", None) is torch.nn.functional.gelu
+
+
+def fuse_bert_gelu(model):
+    """Swap the erf-GELU activation of every ``layer.intermediate`` for :class:`GELUFused` (other activations stay)."""
+    bert = getattr(model, "bert", model)
+    for layer in bert.encoder.layer:
+        if _is_erf_gelu(layer.intermediate.intermediate_act_fn):
+            layer.intermediate.intermediate_act_fn = GELUFused().train(layer.training)
+    return model
+
+
 class OPTDecoderLayerFused(torch.nn.Module):
     """HF OPTDecoderLayer (pre-LayerNorm variants: 125m, 1.3b, ...; the module the reference wraps at
     quantized_opt.py:277-384) for eval with fewer, fused launches: LayerNorm kernels from liboeh, ``residual + attn`` and

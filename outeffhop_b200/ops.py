@@ -391,6 +391,17 @@ def add_layer_norm(a: torch.Tensor, b: Optional[torch.Tensor], weight: torch.Ten
     return (y, total) if return_sum else y
 
 
+def gelu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """erf GELU ``x * 0.5 * (1 + erf(x / sqrt 2))`` of a fp16 / bf16 tensor (oeh_gelu_erf); ``out`` may be ``x``."""
+    _require_cuda(x)
+    xc = x.contiguous()
+    y = out if out is not None else torch.empty_like(xc)
+    if y.shape != xc.shape or y.dtype != xc.dtype or not y.is_contiguous():
+        raise ValueError("gelu: out must be a contiguous tensor of the input's shape and dtype")
+    L.check(L.lib().oeh_gelu_erf(xc.data_ptr(), y.data_ptr(), xc.numel(), _dtype_code(xc), _stream()))
+    return y
+
+
 def fake_quant_asym_segments(x: torch.Tensor, qparams, n_bits: int = 8, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Fake-quant of ``len(qparams)`` equal column segments of a (..., n_seg*seg_cols) tensor, each with its own device
     [scale, zero_point] (oeh_fake_quant_asym_segments): one launch for the output of a fused q|k|v projection."""

@@ -244,3 +244,19 @@ def test_attention_persistent_many_items_per_cta(kind, gamma, eta, causal, monke
         out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal, out_layout="bhtd")
         ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal)
         np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=TOL, rtol=0)
+
+
+@pytest.mark.parametrize("persistent", ["0", "1"])
+@pytest.mark.parametrize("chunk", ["0", "1", "5", "1000"])
+@pytest.mark.parametrize("kind,gamma,eta", [KINDS[1], KINDS[3]])
+def test_attention_causal_work_order(persistent, chunk, kind, gamma, eta, monkeypatch):
+    """Causal launches number their work items heaviest-first over chunks of (batch, head) pairs (causal_item in
+    csrc/attn_common.cuh).  Any chunk size -- per-head order (0), chunks that do not divide B*H (5 of 14), one chunk for
+    everything -- must visit every (Q tile, head, batch) exactly once: the result does not depend on it."""
+    ops = _ops()
+    monkeypatch.setenv("OEH_WS_PERSISTENT", persistent)
+    monkeypatch.setenv("OEH_CAUSAL_CHUNK", chunk)
+    q, k, v = _mk(2, 7, 600, 600, torch.float16, seed=11 + kind)        # 14 pairs x 5 Q tiles (3 tile groups of 2)
+    out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=True, out_layout="bhtd")
+    ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=True)
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=TOL, rtol=0)
