@@ -5,11 +5,17 @@
 //   * 128 threads (thread == query row == TMEM lane), 3 smem tiles (Q, K, V: 48 KB), 128 TMEM columns
 //     -> FOUR CTAs per SM (the multi-tile kernel: two), i.e. the whole C-BERT grid (384 CTAs) is resident at once
 //     on 148 x 4 slots and one CTA's TMA / MMA latency hides behind its neighbours' softmax.
-//   * S is never held in registers as a whole row.  The row is walked in 32-column chunks straight out of TMEM:
+//   * Softmax over the row, two shapes (template kRegS):
+//     kRegS = false (generic instantiation: taps / masks): S is never held in registers as a whole row.  The row is
+//     walked in 32-column chunks straight out of TMEM:
 //       pass 1  max  (generic mode: the transformed scores are written back in place, so masks / taps are read once)
 //       pass 2  e = exp2(s*mul - m), row sum; online kinds pack e to 16 bit and store it as P right away,
 //               normalised kinds (clipped / probs tap) park e (fp32) in place
 //       pass 3  (normalised kinds only) p = clip(stretch*e/den + gamma, 0, 1) [-> tap] -> P
+//     kRegS = true (plain instantiation): the whole row (128 fp32) is read from TMEM once and stays in registers through
+//     max -> exp / sum -> clip -> P (152 registers, THREE CTAs per SM: 444 slots still hold the 384-CTA grid); 5 % faster
+//     for the clipped kinds, 2 % for softmax1 (profiles/r01_one_tile_regs_y.txt).  The share of polynomial exp2 makes no
+//     difference here (same file): the launch is bound by its serial latency chain, not by the XU pipe.
 //     P chunk c lands in columns [16c, 16c+16), which the same thread has already consumed (lane-private, in order).
 //   * O [128 x 64] fp32 reuses columns 64..127: by the time the PV MMA is issued every thread has turned its S row
 //     into P (columns 0..63), so S's upper half is dead.
@@ -39,8 +45,10 @@ __device__ __forceinline__ void hide_invisible(float (&s)[N], int vis) {
   }
 }
 
-template <bool kBF16, bool kGeneric>
-__global__ void __launch_bounds__(BM, 4)
+// kRegS: the whole S row (128 fp32) lives in registers -- ONE TMEM read instead of the 2-3 chunked passes, at 168
+// registers per thread, i.e. THREE CTAs per SM (444 slots still hold the whole C-BERT grid of 384).
+template <bool kBF16, bool kGeneric, bool kRegS = false>
+__global__ void __launch_bounds__(BM, kRegS ? 3 : 4)
 attn_fwd_one_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                     const __grid_constant__ CUtensorMap tmv, const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -112,6 +120,51 @@ attn_fwd_one_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   ptx::mbar_wait(bar_mma, 0);
   ptx::tc_fence_after();
 
+  float omul = 1.f;
+  if constexpr (kRegS) {
+    // ---- register-resident row: load once, max -> exp / sum -> normalise -> P ---------------------------------------
+    float s[BN];
+#pragma unroll
+    for (int c = 0; c < BN / CH; ++c) ptx::tmem_ld32(t_lane + c * CH, reinterpret_cast<uint32_t*>(s) + c * CH);
+    ptx::tmem_wait_ld();
+    if (kGeneric && p.dbg_s && row < p.Tq) {
+      float* d = p.dbg_s + (((int64_t)b * p.H + h) * p.Tq + row) * BN;
+#pragma unroll
+      for (int j = 0; j < BN; ++j) d[j] = s[j];
+    }
+    float mul = p.scale * kLog2e, m_run = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < BN / CH; ++c) {
+      if (c < n_ch) {
+        float(&sc)[CH] = *reinterpret_cast<float(*)[CH]>(s + c * CH);
+        const int k0 = c * CH, valid = min(p.Tk - k0, CH), vis = min(valid - 1, causal_lim - k0);
+        mul = transform_scores<CH, kGeneric>(sc, p, qd_s, has_qs, has_mask, mask_row, k0, valid, vis);
+        m_run = fmaxf(m_run, row_max<CH>(sc) * mul);
+      }
+    }
+    const float m_safe = m_run == -INFINITY ? 0.f : m_run;
+    float l_run = 0.f;
+#pragma unroll
+    for (int c = 0; c < BN / CH; ++c)
+      if (c < n_ch) l_run += exp2_and_sum<CH, !kGeneric>(*reinterpret_cast<float(*)[CH]>(s + c * CH), mul, m_safe);
+    const float den = softmax1 ? l_run + ptx::ex2(-m_safe) : l_run;
+    const float inv_den = __frcp_rn(den);
+    if (!normalized) omul = inv_den;
+#pragma unroll
+    for (int c = 0; c < BN / CH; ++c) {
+      uint32_t pk[CH / 2];
+      if (c < n_ch) {
+        float(&sc)[CH] = *reinterpret_cast<float(*)[CH]>(s + c * CH);
+        if (normalized) normalize_probs<CH, kGeneric>(sc, p, inv_den, clipped, has_qp, qd_p);
+#pragma unroll
+        for (int j = 0; j < CH / 2; ++j) pk[j] = pack2<kBF16>(sc[2 * j], sc[2 * j + 1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < CH / 2; ++j) pk[j] = 0u;     // keys beyond Tk: P = 0 (the PV MMA always spans 128 keys)
+      }
+      ptx::tmem_st16(t_lane + c * (CH / 2), pk);
+    }
+  } else {
   // ---- pass 1: row maximum --------------------------------------------------------------------------------------
   float mul = p.scale * kLog2e, m_run = -INFINITY;
 #pragma unroll 1
@@ -161,7 +214,6 @@ attn_fwd_one_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   }
 
   // ---- pass 3 (normalised kinds): clip / tap, then P ------------------------------------------------------------------
-  float omul = 1.f;
   {
     const float den = softmax1 ? l_run + ptx::ex2(-m_safe) : l_run;
     const float inv_den = __frcp_rn(den);
@@ -188,6 +240,7 @@ attn_fwd_one_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       omul = inv_den;
     }
   }
+  }   // chunked passes
   ptx::tmem_wait_st();
   ptx::tc_fence_before();
   __syncthreads();

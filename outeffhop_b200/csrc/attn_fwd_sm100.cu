@@ -490,15 +490,24 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
     return check_launch("attn_fwd_ws_kernel");
   }
   if (use_one) {
-    static const KernelFn kernels[4] = {attn_one::attn_fwd_one_kernel<false, false>, attn_one::attn_fwd_one_kernel<false, true>,
-                                        attn_one::attn_fwd_one_kernel<true, false>, attn_one::attn_fwd_one_kernel<true, true>};
-    static bool attr_done[4] = {false, false, false, false};
-    if (!attr_done[ki]) {
-      OEH_CUDA_OK(cudaFuncSetAttribute(kernels[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, attn_one::kSmemBytes));
-      attr_done[ki] = true;
+    // [register-resident S row][bf16 | generic]
+    static const KernelFn kernels[2][4] = {
+        {attn_one::attn_fwd_one_kernel<false, false, false>, attn_one::attn_fwd_one_kernel<false, true, false>,
+         attn_one::attn_fwd_one_kernel<true, false, false>, attn_one::attn_fwd_one_kernel<true, true, false>},
+        {attn_one::attn_fwd_one_kernel<false, false, true>, attn_one::attn_fwd_one_kernel<false, true, true>,
+         attn_one::attn_fwd_one_kernel<true, false, true>, attn_one::attn_fwd_one_kernel<true, true, true>}};
+    static bool attr_done[2][4] = {};
+    // S row in registers (3 CTAs / SM, one TMEM read) vs chunked TMEM passes (4 CTAs / SM): 9.37 vs 9.88 us per launch at
+    // the C-BERT shape for the clipped kinds, 9.29 vs 9.52 us for softmax1 (profiles/r01_one_tile_regs_y.txt).  The generic
+    // instantiation (taps / masks) does not fit 168 registers without spilling and keeps the chunked passes.
+    int regs = generic ? 0 : 1;
+    if (const char* f = getenv("OEH_ONE_REGS")) regs = atoi(f) != 0;
+    if (!attr_done[regs][ki]) {
+      OEH_CUDA_OK(cudaFuncSetAttribute(kernels[regs][ki], cudaFuncAttributeMaxDynamicSharedMemorySize, attn_one::kSmemBytes));
+      attr_done[regs][ki] = true;
     }
     dim3 grid((unsigned)((a->Tq + BM - 1) / BM), (unsigned)a->H, (unsigned)a->B);
-    kernels[ki]<<<grid, attn_one::BM, attn_one::kSmemBytes, st>>>(tmq, tmk, tmv, p);
+    kernels[regs][ki]<<<grid, attn_one::BM, attn_one::kSmemBytes, st>>>(tmq, tmk, tmv, p);
     return check_launch("attn_fwd_one_kernel");
   }
   static const KernelFn kernels[4] = {attn_fwd_kernel<false, false>, attn_fwd_kernel<false, true>,

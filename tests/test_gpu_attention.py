@@ -260,3 +260,19 @@ def test_attention_causal_work_order(persistent, chunk, kind, gamma, eta, monkey
     out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=True, out_layout="bhtd")
     ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=True)
     np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=TOL, rtol=0)
+
+
+@pytest.mark.parametrize("regs", ["0", "1"])
+@pytest.mark.parametrize("kind,gamma,eta", KINDS)
+@pytest.mark.parametrize("shape,causal", [((2, 3, 128, 128), False), ((2, 2, 50, 77), False), ((1, 2, 100, 100), True),
+                                          ((1, 1, 130, 1), False)])
+def test_attention_one_tile_softmax_shapes(regs, kind, gamma, eta, shape, causal, monkeypatch):
+    """One-tile kernel (Tk <= 128): S row held in registers (one TMEM read, 3 CTAs / SM) and the chunked TMEM passes
+    (4 CTAs / SM) against the oracle, on full, ragged, causal and single-key rows."""
+    ops = _ops()
+    monkeypatch.setenv("OEH_ONE_REGS", regs)
+    B, H, Tq, Tk = shape
+    q, k, v = _mk(B, H, Tq, Tk, torch.float16, seed=Tq + Tk + kind)
+    out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal, out_layout="bhtd")
+    ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal)
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=TOL, rtol=0)
