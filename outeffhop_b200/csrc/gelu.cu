@@ -83,7 +83,7 @@ __device__ __forceinline__ void gelu_vec(Vec16<T>& v) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads) gelu_erf_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n,
+__global__ void __launch_bounds__(kThreads, kBlocksPerSm) gelu_erf_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n,
                                                             int aligned) {
   using V = Vec16<T>;
   constexpr int N = V::N;

@@ -16,7 +16,20 @@
 namespace oeh {
 namespace {
 
-constexpr int kWarpsPerBlock = 8;
+#ifndef OEH_LN_WARPS
+#define OEH_LN_WARPS 8
+#endif
+constexpr int kWarpsPerBlock = OEH_LN_WARPS;
+
+// Cache policy of the row traffic.  Streaming (evict-first) suits the big standalone tensors of the kernel sweep; inside a
+// model step the inputs were just written by a GEMM and the output is read by the next one, all within L2.
+#ifdef OEH_LN_PLAIN
+__device__ __forceinline__ int4 ld_row(const int4* p) { return *p; }
+__device__ __forceinline__ void st_row(int4* p, const int4& v) { *p = v; }
+#else
+__device__ __forceinline__ int4 ld_row(const int4* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_row(int4* p, const int4& v) { __stcs(p, v); }
+#endif
 
 template <typename T, int kVecs>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -44,10 +57,10 @@ add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T*
   for (int v = 0; v < kVecs; ++v) {                        // all loads of the row in flight before the first use
     const int i = lane + 32 * v;
     if (i < nvec) {
-      int4 raw = __ldcs(reinterpret_cast<const int4*>(av + i));
+      int4 raw = ld_row(reinterpret_cast<const int4*>(av + i));
       va[v] = *reinterpret_cast<V*>(&raw);
       if (bv) {
-        raw = __ldcs(reinterpret_cast<const int4*>(bv + i));
+        raw = ld_row(reinterpret_cast<const int4*>(bv + i));
         vb[v] = *reinterpret_cast<V*>(&raw);
       }
     }
@@ -62,7 +75,7 @@ add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T*
       if (bv) add_vec<T>(va[v], vb[v]);
       if (q_res) qr.apply(va[v], false);
       if (sum_out)                                         // pre-LN blocks (OPT) keep the sum as the next residual
-        __stcs(reinterpret_cast<int4*>(reinterpret_cast<V*>(sum_out + row * cols) + i), *reinterpret_cast<const int4*>(&va[v]));
+        st_row(reinterpret_cast<int4*>(reinterpret_cast<V*>(sum_out + row * cols) + i), *reinterpret_cast<const int4*>(&va[v]));
     }
 #pragma unroll
     for (int e = 0; e < N; ++e) {
@@ -102,7 +115,7 @@ add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T*
         out.v[e] = DT<T>::from_f(r);                       // one rounding to the tensor dtype
       }
       if (q_out) qo.apply(out, false);
-      __stcs(reinterpret_cast<int4*>(yv + i), *reinterpret_cast<const int4*>(&out));
+      st_row(reinterpret_cast<int4*>(yv + i), *reinterpret_cast<const int4*>(&out));
     }
   }
 }
