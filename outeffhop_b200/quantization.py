@@ -870,9 +870,15 @@ class QuantLinear(QuantizedModule, nn.Linear):
         """The layer WITHOUT its output tap (cached fake-quantized weight, optional fused activation): for callers that
         fold the tap into the next kernel (``tap_fusable`` / ``tap_qparams``)."""
         weight, bias = self.get_params()
+        act = self.activation_function
+        if isinstance(act, nn.ReLU) and bias is not None and x.is_cuda and x.dtype == weight.dtype \
+                and not torch.is_grad_enabled() and not act._forward_hooks and not act._forward_pre_hooks:
+            # eval: bias + ReLU in the GEMM epilogue (one cuBLASLt call; max(., 0) of the same accumulator is exact)
+            x2 = x.contiguous().view(-1, x.shape[-1])
+            return torch._addmm_activation(bias, x2, weight.t()).view(*x.shape[:-1], weight.shape[0])
         res = F.linear(x.contiguous(), weight.contiguous(), bias=bias)
-        if self.activation_function is not None:
-            res = self.activation_function(res)
+        if act is not None:
+            res = act(res)
         return res
 
     @property
