@@ -50,12 +50,22 @@ struct AttnParams {
 // Fixed-range fake-quant tap inside the fused kernel.  x/scale is evaluated as x*(1/scale): the tap's input
 // already differs from the unfused reference in the last bits (tensor-core accumulation order), so codes can
 // flip at bin edges either way; the bit-exact contract belongs to the standalone quantizer (quant.cu).
+//   clamp(rint(v) + zp, 0, M) - zp == rint(clamp(v, -zp, M - zp))   (zp is an integer, rint is monotone)
+// and inside that range (|v| <= 65535) round-half-even is two FADDs with the 1.5 * 2^23 constant -- no FRND on the XU /
+// conversion pipe, which the exponentials of the same loop already load.
 struct Qdq {
   float scale, inv_scale, zp, int_max;
   __device__ __forceinline__ float operator()(float x) const {
+#ifdef OEH_QDQ_FRND                                            // the literal chain (A/B switch, tools/build_variant.sh)
     float xi = rintf(x * inv_scale) + zp;
     xi = fminf(fmaxf(xi, 0.f), int_max);
     return scale * (xi - zp);
+#else
+    const float lo = -zp, hi = int_max - zp;                  // loop invariants
+    float v = fminf(fmaxf(x * inv_scale, lo), hi);
+    v = __fadd_rn(__fadd_rn(v, 12582912.f), -12582912.f);     // rint(v), exact for |v| < 2^22
+    return scale * v;
+#endif
   }
 };
 __device__ __forceinline__ Qdq load_qdq(const float* qparams, float int_max) {
