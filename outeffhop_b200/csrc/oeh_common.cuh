@@ -111,8 +111,18 @@ __device__ __forceinline__ float qdq_one(float x, float scale, float zp, float i
 // 16-bit tensors: two elements per instruction with the hardware's own fp16 / bf16 arithmetic.  Every ATen op of the
 // chain is "compute in fp32, round once to the tensor dtype"; for +, -, x, / on 16-bit operands that equals the correctly
 // rounded 16-bit operation (24 >= 2*11 + 2 mantissa bits: the double rounding is innocuous), which is what HADD2 / HMUL2
-// (.rn) and __h2div deliver -- 7 instead of 22 issue slots per element; the scalar chain was issue-bound at 3.8 of
-// 6.5 TB/s on fp16 tensors.  Used when 2^n_bits - 1 is exactly representable in the dtype (fp16: n <= 11, bf16: n <= 8).
+// (.rn) deliver.  Two steps of the chain have no packed instruction (the compiler expands __h2div into a per-element fp32
+// division with its slow-path call, h2rint into per-element FRND) and are restated exactly:
+//   * x / scale  ->  RN16(fp32(x) * RN32(1 / scale)).  The quotient of two p-bit significands is never a rounding midpoint
+//     of the p-bit grid and stays at least 2^-(2p) away from one, while the fp32 product is within 2^-22 of the quotient
+//     (p = 11: 2^-22 vs an error < 2^-22(1 - 2^-11); p = 8: 2^-16), so both round to the same 16-bit value.  (Results in the
+//     subnormal range may differ in the last bit; they are < 2^-14 and quantise to the same code.)  Used when 1 / scale
+//     is a normal fp32 number; anything else keeps the division.
+//   * fp16, n_bits <= 8:  clamp(rint(q) + zp, 0, M) - zp == rint(clamp(q, -zp, M - zp))  (zp integer), and inside
+//     [-255, 255] round-half-even is (q + 1536) - 1536 in fp16 (unit spacing on [1024, 2048), 1536 even).
+// Both identities were checked on the host over every fp16 input x 3000 scales x 4 zero points, and the kernels are
+// compared with ATen over all 65536 bit patterns on the GPU (tests/test_gpu_quant.py).
+// Used when 2^n_bits - 1 is exactly representable in the dtype (fp16: n <= 11, bf16: n <= 8).
 template <typename T>
 struct P2 {
   static constexpr bool kPacked = false;
@@ -120,18 +130,23 @@ struct P2 {
 template <>
 struct P2<__half> {
   static constexpr bool kPacked = true;
+  static constexpr float kMagic = 1536.f;          // 1.5 * 2^10; 0 = no magic-number rounding for this dtype
   using V2 = __half2;
   static __device__ __forceinline__ V2 bcast(float f) { return __float2half2_rn(f); }
   static __device__ __forceinline__ bool exact_int(float m) { return m <= 2047.f; }
+  static __device__ __forceinline__ float2 to_f2(V2 v) { return __half22float2(v); }
+  static __device__ __forceinline__ V2 from_f2(float a, float b) { return __floats2half2_rn(a, b); }
 };
 template <>
 struct P2<__nv_bfloat16> {
   static constexpr bool kPacked = true;
+  static constexpr float kMagic = 0.f;             // [128, 256) has unit spacing: too narrow for 8-bit codes
   using V2 = __nv_bfloat162;
   static __device__ __forceinline__ V2 bcast(float f) { return __float2bfloat162_rn(f); }
   static __device__ __forceinline__ bool exact_int(float m) { return m <= 255.f; }
+  static __device__ __forceinline__ float2 to_f2(V2 v) { return __bfloat1622float2(v); }
+  static __device__ __forceinline__ V2 from_f2(float a, float b) { return __floats2bfloat162_rn(a, b); }
 };
-
 template <typename T, bool kPacked = P2<T>::kPacked>
 struct QdqVec;
 
@@ -148,22 +163,39 @@ struct QdqVec<T, false> {                         // fp32 tensors: the scalar ch
 template <typename T>
 struct QdqVec<T, true> {
   using V2 = typename P2<T>::V2;
-  float scale, zp, int_max;
-  V2 s2, z2, m2, zero2;
-  bool packed;
+  // kept small on purpose (add_layer_norm holds three of these): rinv = RN32(1 / scale) or 0 (= divide);
+  // a2 = -zp (magic rounding) or int_max; b2 = int_max - zp (magic rounding only)
+  float rinv, int_max;
+  V2 s2, z2, a2, b2;
+  bool packed, magic;
   // scale_ / zp_: already rounded to T (the 0-dim fp32 scalars are cast to the tensor dtype first)
-  __device__ __forceinline__ QdqVec(float scale_, float zp_, float int_max_) : scale(scale_), zp(zp_), int_max(int_max_) {
+  __device__ __forceinline__ QdqVec(float scale_, float zp_, float int_max_) : int_max(int_max_) {
     s2 = P2<T>::bcast(scale_);
     z2 = P2<T>::bcast(zp_);
-    m2 = P2<T>::bcast(int_max_);
-    zero2 = P2<T>::bcast(0.f);
     packed = P2<T>::exact_int(int_max_);
+    rinv = (scale_ >= 1e-30f && scale_ <= 1e30f) ? __frcp_rn(scale_) : 0.f;   // 1 / scale is a normal fp32 number
+    magic = P2<T>::kMagic > 0.f && int_max_ <= 255.f && zp_ >= 0.f && zp_ <= int_max_;
+    a2 = P2<T>::bcast(magic ? -zp_ : int_max_);
+    b2 = P2<T>::bcast(int_max_ - zp_);
   }
   __device__ __forceinline__ V2 one2(V2 x, bool codes) const {
-    V2 q = __h2div(x, s2);                        // x_float / scale
+    V2 q;
+    if (rinv != 0.f) {
+      const float2 xf = P2<T>::to_f2(x);
+      q = P2<T>::from_f2(__fmul_rn(xf.x, rinv), __fmul_rn(xf.y, rinv));   // == x_float / scale (see above)
+    } else {
+      q = __h2div(x, s2);
+    }
+    if (magic) {
+      const V2 k2 = P2<T>::bcast(P2<T>::kMagic);
+      q = __hmin2_nan(__hmax2_nan(q, a2), b2);    // clamp first (NaN propagates like torch.clamp) ...
+      q = __hsub2_rn(__hadd2_rn(q, k2), k2);      // ... then round half to even: == x_int - zero_point
+      if (codes) return __hadd2_rn(q, z2);
+      return __hmul2_rn(s2, q);                   // scale * (...)
+    }
     q = h2rint(q);                                // round half to even
     q = __hadd2_rn(q, z2);                        // + zero_point
-    q = __hmin2_nan(__hmax2_nan(q, zero2), m2);   // clamp (NaN propagates like torch.clamp)
+    q = __hmin2_nan(__hmax2_nan(q, P2<T>::bcast(0.f)), a2);   // clamp (NaN propagates like torch.clamp)
     if (codes) return q;
     q = __hsub2_rn(q, z2);                        // x_int - zero_point
     return __hmul2_rn(s2, q);                     // scale * (...)
@@ -174,12 +206,12 @@ struct QdqVec<T, true> {
 #pragma unroll
       for (int k = 0; k < Vec16<T>::N / 2; ++k) p[k] = one2(p[k], codes);
     } else {
+      const float scale = P2<T>::to_f2(s2).x, zp = P2<T>::to_f2(z2).x;      // exact: both were rounded to T
 #pragma unroll
       for (int e = 0; e < Vec16<T>::N; ++e) v.v[e] = DT<T>::from_f(qdq_one<T>(DT<T>::to_f(v.v[e]), scale, zp, int_max, codes));
     }
   }
 };
-
 // a + b rounded once to the tensor dtype (ATen's add), on a 16-byte vector
 template <typename T>
 __device__ __forceinline__ void add_vec(Vec16<T>& a, const Vec16<T>& b) {
