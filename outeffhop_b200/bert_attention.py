@@ -91,6 +91,20 @@ class GateMixin:
                     module_list.append(fc)
                 self.alpha = nn.ModuleList(module_list)
 
+    @property
+    def effective_gate_scale(self) -> float:
+        """``gate_scaling_factor`` multiplies the CONDITIONAL gates only (bert_attention.py:327, opt_attention.py:309);
+        the unconditional per-head branch is ``context_layer *= gate.view(-1, 1, 1)`` with no factor (:295-297 / :277-279)."""
+        if self.attn_gate_type == AttentionGateType.unconditional_per_head:
+            return 1.0
+        return self.gate_scaling_factor
+
+    def _probes_hooked(self) -> bool:
+        """A forward hook sits on one of the S / P probe Identities (attach_act_hooks hooks every named module): the
+        fused kernel never materialises S / P, so such a call takes the unfused path where the probes see real data."""
+        return any(m._forward_hooks or m._forward_pre_hooks
+                   for m in (self.attn_scores, self.attn_probs_before_dropout, self.attn_probs_after_dropout))
+
     # gate statistics the reference stores eagerly; computed on demand here (read only by training TB code)
     @property
     def last_gate_all_probs(self):
@@ -237,7 +251,7 @@ class BertSelfAttentionWithExtras(GateMixin, nn.Module):
         return None
 
     def _gate_scale(self) -> float:
-        return self.gate_scaling_factor
+        return self.effective_gate_scale
 
     def _fused_qkv(self, hidden_states: torch.Tensor):
         return fused_qkv_projection(self, (self.query, self.key, self.value), hidden_states, self.num_attention_heads,
@@ -259,7 +273,7 @@ class BertSelfAttentionWithExtras(GateMixin, nn.Module):
         fusable_taps = all(t.fixed for t in active)
         fused = (fn is not None and q.dtype in (torch.float16, torch.bfloat16) and d == FUSED_HEAD_DIM
                  and head_mask is None and not output_attentions and not self.materialize_probs
-                 and not training_dropout and fusable_taps
+                 and not self._probes_hooked() and not training_dropout and fusable_taps
                  and self.position_embedding_type not in ("relative_key", "relative_key_query"))
         if fused:
             kw = {}

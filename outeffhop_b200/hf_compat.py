@@ -132,10 +132,16 @@ def fuse_bert_residual_blocks(model):
     return model
 
 
-class GELUFused(torch.nn.Module):
-    """The erf GELU between the two FFN GEMMs (HF ``BertIntermediate.intermediate_act_fn`` = ``ACT2FN["gelu"]``;
-    kept as is by the reference's ``quantize_intermediate``, quantized_bert.py:609-617) through ``oeh_gelu_erf`` for
-    16-bit CUDA tensors in eval; anything else (training graphs, fp32, hooks on this module) takes ATen's kernel."""
+class GELUFused(torch.nn.GELU):
+    """The erf GELU between the two FFN GEMMs through ``oeh_gelu_erf`` for 16-bit CUDA tensors in eval; anything else
+    (training graphs, fp32, hooks on this module) takes ATen's kernel.  An ``nn.GELU`` subclass on purpose: the validate
+    script replaces HF's ``GELUActivation`` with ``nn.GELU()`` before anything else (validate_mlm_config.py:166-168), and
+    ``nn.GELU`` is in the hijacker's ``activations_set`` (hijacker.py:14-24), so ``quantize_intermediate``
+    (quantized_bert.py:609-617) fuses it into the QuantLinear and taps AFTER the activation -- a model prepared with
+    ``fuse_bert_gelu`` quantizes the same way."""
+
+    def __init__(self):
+        super().__init__(approximate="none")
 
     def forward(self, input):
         if self.training or (torch.is_grad_enabled() and input.requires_grad) or not input.is_cuda \

@@ -92,7 +92,7 @@ class OPTAttentionWithExtras(GateMixin, nn.Module):
         active = [t for t in (taps or ()) if t is not None and t.active]
         fused = (fn is not None and q.dtype in (torch.float16, torch.bfloat16) and self.head_dim == FUSED_HEAD_DIM
                  and layer_head_mask is None and not output_attentions and not self.materialize_probs
-                 and not training_dropout and all(t.fixed for t in active))
+                 and not self._probes_hooked() and not training_dropout and all(t.fixed for t in active))
         if attention_mask is not None and attention_mask.size() != (bsz, 1, tgt_len, src_len):
             raise ValueError(
                 f"Attention mask should be of size {(bsz, 1, tgt_len, src_len)}, but is {attention_mask.size()}")
@@ -108,7 +108,7 @@ class OPTAttentionWithExtras(GateMixin, nn.Module):
             out = ops.attention_fwd(q, k, v, scale=self.scaling, kind=fn.kind, gamma=fn.gamma, eta=fn.eta,
                                     causal=use_causal, mask=None if use_causal else attention_mask,
                                     clamp_min=attention_mask is not None and not use_causal,
-                                    gate_logits=gate_logits, gate_scale=self.gate_scaling_factor,
+                                    gate_logits=gate_logits, gate_scale=self.effective_gate_scale,
                                     out_layout="bthd", **kw)
             return out, None
         return self._core_unfused(q, k, v, attention_mask, gate_logits, layer_head_mask, output_attentions, bsz,
@@ -155,7 +155,7 @@ class OPTAttentionWithExtras(GateMixin, nn.Module):
             attn_output = tc(attn_output)                                                     # quantized_opt.py:210
         if gate_logits is not None:                                                           # :276-313
             attn_output = attn_output * (torch.sigmoid(gate_logits).to(attn_output.dtype).unsqueeze(-1)
-                                         * self.gate_scaling_factor)
+                                         * self.effective_gate_scale)
         attn_output = attn_output.transpose(1, 2).reshape(bsz, tgt_len, self.embed_dim)       # :318-322
         return attn_output, attn_weights_reshaped
 

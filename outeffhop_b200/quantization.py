@@ -405,6 +405,24 @@ class SymmetricUniformQuantizer(nn.Module):
     def make_range_trainable(self):
         raise NotImplementedError("learn_ranges is outside the eval hot path")
 
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        # ``_delta`` / ``_signed`` are None buffers until a range is set, so a fresh instance would reject the keys of a
+        # checkpoint saved after one forward.  The reference sizes them with a dummy forward before loading
+        # (base_quantized_model.py:34-82); here they are simply adopted.
+        for name in ("_delta", "_signed"):
+            key = prefix + name
+            if key in state_dict:
+                cur = self._buffers.get(name)
+                if cur is None or cur.shape != state_dict[key].shape:
+                    # sized like the checkpoint's; the base class then copies the value in (0-dim tensors mix with
+                    # CUDA operands on any device)
+                    dev = cur.device if cur is not None else state_dict[key].device
+                    self._buffers[name] = torch.empty_like(state_dict[key], device=dev)
+        self._signed_host = None
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                                      error_msgs)
+
 
 class QMethods(ClassEnumOptions):
     symmetric_uniform = MethodMap(SymmetricUniformQuantizer)

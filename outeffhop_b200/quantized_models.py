@@ -10,9 +10,11 @@ validate_mlm_config.py builds (:445-476) and the range-estimation driver it runs
 The module tree keeps the reference's names (``bert.embeddings.sum_pos_embd_act_quantizer``,
 ``bert.encoder.layer.N.attention.self.query``, ``...intermediate.0``, ``...output.res_act_quantizer``) so quantizer state
 can be compared / loaded name by name.  Two reference behaviours that follow from HF rather than from the paper and are
-kept on purpose: the MLM head stays FP32 (``self.cls = org_model.cls``, :867), and the FFN tap sits on the dense output
-BEFORE the GELU (``quantize_intermediate`` hands ``nn.Sequential(dense, GELUActivation())`` to ``quantize_model``;
-HF's ``GELUActivation`` is not in ``activations_set``, so the activation is neither fused into the QuantLinear nor tapped).
+kept on purpose: the MLM head stays FP32 (``self.cls = org_model.cls``, :867), and the position of the FFN tap depends on
+the activation MODULE: ``quantize_intermediate`` hands ``nn.Sequential(dense, act)`` to ``quantize_model``; HF's
+``GELUActivation`` is not in ``activations_set``, so with a stock HF model the tap sits on the dense output BEFORE the GELU,
+while the validate script's ``nn.GELU()`` replacement (validate_mlm_config.py:166-168; here ``hf_compat.fuse_bert_gelu``) is
+fused into the QuantLinear and tapped AFTER the activation.
 
 During estimation every tap runs minmax -> EMA -> qdq on the device (no host sync); with fixed ranges the attention core,
 the residual blocks (add -> tap -> LayerNorm -> tap) and the loss are single kernels, and the step is CUDA-graph
@@ -206,9 +208,16 @@ class QuantizedBertLayer(QuantizedModel):
             if act is not F.gelu:
                 raise NotImplementedError(f"intermediate activation {act} (quantized_bert.py:609-617)")
             act = nn.GELU()
-        # quantize_intermediate (:609-617): QuantLinear tapped on the dense output, then the activation module as is
-        self.intermediate = nn.Sequential(QuantLinear.from_linear(org_model.intermediate.dense, **_linear_params(quant_params)),
-                                          act)
+        # quantize_intermediate (:609-617) hands Sequential(dense, act) to quantize_sequential: an activation from the
+        # hijacker's activations_set (hijacker.py:14-24; nn.GELU included, also the nn.GELU() substituted for F.gelu) is
+        # FUSED into the QuantLinear and runs BEFORE its tap (autoquant_utils.py:105-176, hijacker.py:115-117); any other
+        # module (HF's GELUActivation is not an nn.GELU) stays a separate Sequential entry behind the tapped dense output.
+        if isinstance(act, (nn.ReLU, nn.ReLU6, nn.Hardtanh, nn.Sigmoid, nn.Tanh, nn.GELU, nn.PReLU)):
+            self.intermediate = nn.Sequential(QuantLinear.from_linear(org_model.intermediate.dense, activation=act,
+                                                                      **_linear_params(quant_params)))
+        else:
+            self.intermediate = nn.Sequential(QuantLinear.from_linear(org_model.intermediate.dense,
+                                                                      **_linear_params(quant_params)), act)
         self.output = QuantizedBertOutput(org_model.output, **quant_params)
 
     def forward(self, hidden_states, attention_mask=None, head_mask=None, **unused):

@@ -66,15 +66,15 @@ class ViTSelfAttentionWithExtras(GateMixin, nn.Module):
         fn = as_softmax_fn(self.softmax_fn)
         training_dropout = self.training and self.attn_drop.p > 0
         if (fn is not None and d == FUSED_HEAD_DIM and x.dtype in (torch.float16, torch.bfloat16)
-                and not training_dropout and not self.materialize_probs):
+                and not training_dropout and not self.materialize_probs and not self._probes_hooked()):
             ctx = ops.attention_fwd(q, k, v, scale=self.scale, kind=fn.kind, gamma=fn.gamma, eta=fn.eta,
-                                    gate_logits=gate_logits, gate_scale=self.gate_scaling_factor, out_layout="bthd")
+                                    gate_logits=gate_logits, gate_scale=self.effective_gate_scale, out_layout="bthd")
         else:                                                                                  # :221-229, S/P materialised
             attn = (q * self.scale) @ k.transpose(-2, -1)
             attn = fn(attn, dim=-1) if fn is not None else self.softmax_fn(attn, dim=-1)
             attn = self.attn_probs_after_dropout(self.attn_drop(self.attn_probs_before_dropout(attn)))
             ctx = attn @ v
             if gate_logits is not None:
-                ctx = ctx * (torch.sigmoid(gate_logits).to(ctx.dtype).unsqueeze(-1) * self.gate_scaling_factor)
+                ctx = ctx * (torch.sigmoid(gate_logits).to(ctx.dtype).unsqueeze(-1) * self.effective_gate_scale)
             ctx = ctx.transpose(1, 2).reshape(B, N, C)                                         # :272
         return self.proj_drop(self.proj(ctx))                                                  # :273-274
