@@ -82,16 +82,21 @@ def set_range_sync(enabled: bool, group=None) -> None:
     _RANGE_SYNC_ENABLED, _RANGE_SYNC_GROUP = bool(enabled), group
 
 
+RANGE_SYNC_COLLECTIVES = 0      # all-reduces issued by _sync_minmax (instrumentation for tests / bench.py)
+
+
 def _sync_minmax(mm: torch.Tensor) -> torch.Tensor:
-    """[min, max] -> all-reduce as MAX over [-min, max] (one collective, exact and order independent)."""
+    """[min, max] (or n stacked pairs, shape (n, 2)) -> ONE all-reduce as MAX over [-min, max] (exact, order independent)."""
+    global RANGE_SYNC_COLLECTIVES
     if not _RANGE_SYNC_ENABLED:
         return mm
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(_RANGE_SYNC_GROUP) == 1:
         return mm
-    buf = torch.stack((-mm[0], mm[1]))
+    buf = torch.stack((-mm[..., 0], mm[..., 1]), dim=-1).contiguous()
     dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=_RANGE_SYNC_GROUP)
-    return torch.stack((-buf[0], buf[1]))
+    RANGE_SYNC_COLLECTIVES += 1
+    return torch.stack((-buf[..., 0], buf[..., 1]), dim=-1).contiguous()
 
 
 class _StateHolder(nn.Module):
@@ -663,6 +668,27 @@ class QuantizationManager(nn.Module):
 
     def extra_repr(self):
         return "state={}".format(self.state.name)
+
+
+def estimate_and_quantize_group(managers, tensors):
+    """``[m(x) for m, x in zip(managers, tensors)]`` for managers in ``estimate_ranges`` state whose inputs do NOT depend
+    on each other's outputs (the q / k / v projection taps of one attention call): the batch (min, max) pairs of the whole
+    group cross the ranks in ONE all-reduce instead of one per tap, then each tap runs its own
+    EMA -> set_quant_range -> quantize exactly as QuantizationManager.forward does (quantization_manager.py:94-102).
+    Returns None when the group is not eligible (the caller then runs the taps one by one)."""
+    for m in managers:
+        if not (isinstance(m, QuantizationManager) and m.estimating and m._shared
+                and isinstance(m.range_estimator, RunningMinMaxEstimator) and not m.range_estimator.percentile):
+            return None
+    mms = _sync_minmax(torch.stack([ops.minmax(x) for x in tensors]))            # (n, 2), one collective
+    outs = []
+    for m, x, mm in zip(managers, tensors, mms):
+        st = m._state_for(x.device)
+        ops.range_update(st, mm, m.range_estimator.momentum, m.quantizer.n_bits, m.quantizer.eps)
+        m.range_estimator._host_init = True
+        m.quantizer._host_init = True
+        outs.append(m.quantizer(x))
+    return outs
 
 
 def _set_layer_fix_ranges(layer):

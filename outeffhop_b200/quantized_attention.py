@@ -22,7 +22,7 @@ from . import ops
 from .bert_attention import BertSelfAttentionWithExtras
 from .opt_attention import OPTAttentionWithExtras
 from .quantization import (QuantizedActivation, QuantizedModule, QuantLinear, _set_layer_estimate_ranges,
-                           _set_layer_estimate_ranges_train, _set_layer_fix_ranges)
+                           _set_layer_estimate_ranges_train, _set_layer_fix_ranges, estimate_and_quantize_group)
 
 
 class QuantizedModel(nn.Module):
@@ -87,6 +87,17 @@ def quantized_fused_qkv(owner: nn.Module, mods, hidden_states: torch.Tensor, num
     """Fixed ranges: the three QuantLinear projections as ONE GEMM over the concatenated (cached) fake-quantized weights and
     ONE segmented tap (each projection keeps its own range: ``oeh_fake_quant_asym_segments``) instead of 3 + 3 launches.
     Returns (q, k, v) as (B,H,T,d) strided views, or None while any tap is still estimating / taps disagree."""
+    if (not owner.training and all(isinstance(m, QuantLinear) and m._qa_host and m.activation_function is None
+                                   and not m._forward_hooks and not m._forward_pre_hooks for m in mods)
+            and all(m.activation_quantizer.estimating for m in mods)):
+        # Range estimation: the three projection taps see independent tensors, so their batch (min, max) pairs cross the
+        # ranks in ONE all-reduce (estimate_and_quantize_group); each tap then updates / quantizes as on its own.
+        ys = [m.linear_only(hidden_states) for m in mods]
+        outs = estimate_and_quantize_group([m.activation_quantizer for m in mods], ys)
+        if outs is None:
+            return None
+        B, T = hidden_states.shape[0], hidden_states.shape[1]
+        return tuple(y.view(B, T, num_heads, head_dim).permute(0, 2, 1, 3) for y in outs)
     if owner.training or not all(isinstance(m, QuantLinear) and m.tap_fusable and m.activation_function is None
                                  and not m._forward_pre_hooks for m in mods):
         return None

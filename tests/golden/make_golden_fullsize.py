@@ -11,6 +11,11 @@ bert: BERT-base (BertConfig() defaults, random init from torch.manual_seed(4000)
 opt:  OPT-125m shape (random init from torch.manual_seed(6789)), 4 x 512 tokens, softmax1, quant_setup fp32_head
       (validate_clm.py:418-499), 4 estimation batches, 2 evaluated.
 
+Each model is run TWICE: as built, and with every Linear bias of the encoder / decoder layers perturbed by N(0, 1e-6)
+(pre-activations have std ~0.55 here, so this is the size of the last-bit differences between two correct fp32 GEMM
+implementations, e.g. MKL on the CPU vs cuBLAS).  The spread between the two REFERENCE runs (``*_pert`` entries) is the
+reference's own sensitivity to such differences -- the noise floor any other implementation is compared against.
+
 Weights are NOT stored: both sides build the HF model from the same seed with the same torch (the fixture carries a
 float64 checksum of the state_dict so a drift in the initialiser shows up as a checksum failure, not as a parity failure).
 Batches come from outeffhop_b200.eval_harness.synthetic_{mlm,clm}_batch (seeded, CPU).  Stored: every activation / weight
@@ -39,6 +44,16 @@ def state_checksum(model) -> np.ndarray:
             s += float(v.double().sum())
             a += float(v.double().abs().sum())
     return np.array([s, a], dtype=np.float64)
+
+
+def perturb_linear_biases(root, seed, sigma=1e-6):
+    """b += N(0, sigma) on every nn.Linear under ``root``: a stand-in for the last-bit differences between two correct
+    fp32 GEMM implementations (biases are not quantized, hijacker.py:84-101)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for m in root.modules():
+            if isinstance(m, torch.nn.Linear) and m.bias is not None:
+                m.bias.add_(torch.randn(m.bias.shape, generator=g) * sigma)
 
 
 def collect_ranges(qmodel, out, strip=""):
@@ -92,43 +107,52 @@ def gen_bert():
     for layer, r in zip(model.bert.encoder.layer, raw):
         layer.attention.self = r
 
-    qparams = val_qparams(get_quant_config())
-    qparams["quant_dict"] = {}
-    qmodel = QuantizedBertForMaskedLM(model, **qparams).eval()
+    def run(tag):
+        qparams = val_qparams(get_quant_config())
+        qparams["quant_dict"] = {}
+        qmodel = QuantizedBertForMaskedLM(model, **qparams).eval()
 
-    def forward(input_ids, labels=None):                                      # quantized_bert.py:725-818, :648-682
-        h = qmodel.bert.embeddings(input_ids=input_ids)
-        for layer in qmodel.bert.encoder.layer:
-            att = layer.attention
-            self_out = att.self(h, None, None)[0]
-            att_out = att.output(self_out, h)
-            h = layer.output(layer.intermediate(att_out), att_out)
-        logits = qmodel.cls(h)
-        loss = None
-        if labels is not None:
-            loss = torch.nn.functional.cross_entropy(logits.view(-1, cfg.vocab_size), labels.view(-1))
-        return loss, logits
+        def forward(input_ids, labels=None):                                  # quantized_bert.py:725-818, :648-682
+            h = qmodel.bert.embeddings(input_ids=input_ids)
+            for layer in qmodel.bert.encoder.layer:
+                att = layer.attention
+                self_out = att.self(h, None, None)[0]
+                att_out = att.output(self_out, h)
+                h = layer.output(layer.intermediate(att_out), att_out)
+            logits = qmodel.cls(h)
+            loss = None
+            if labels is not None:
+                loss = torch.nn.functional.cross_entropy(logits.view(-1, cfg.vocab_size), labels.view(-1))
+            return loss, logits
 
-    class _Wrap(torch.nn.Module):
-        def __init__(self):
-            super().__init__()
-            self.q = qmodel
+        class _Wrap(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.q = qmodel
 
-        def forward(self, input_ids, labels=None):
-            return forward(input_ids, labels)
+            def forward(self, input_ids, labels=None):
+                return forward(input_ids, labels)
 
-    qmodel.set_quant_state(weight_quant=True, act_quant=True)                                   # :466
-    pass_data_for_range_estimation(loader=batches[:N_EST], model=_Wrap().eval(), act_quant=True, max_num_batches=N_EST)
-    qmodel.fix_ranges()                                                                         # :476
-    n = collect_ranges(qmodel, out)
-    losses, slices = [], []
-    with torch.no_grad():
-        for b in batches[N_EST:]:
-            loss, logits = forward(**b)
-            losses.append(float(loss))
-            slices.append(logits[:2, :16, :256].numpy().copy())
-    out["loss_fixed"] = np.array(losses, dtype=np.float64)
-    out["logits_slice"] = np.stack(slices)
+        qmodel.set_quant_state(weight_quant=True, act_quant=True)                               # :466
+        pass_data_for_range_estimation(loader=batches[:N_EST], model=_Wrap().eval(), act_quant=True, max_num_batches=N_EST)
+        qmodel.fix_ranges()                                                                     # :476
+        res = {}
+        n = collect_ranges(qmodel, res)
+        losses, slices = [], []
+        with torch.no_grad():
+            for b in batches[N_EST:]:
+                loss, logits = forward(**b)
+                losses.append(float(loss))
+                slices.append(logits[:2, :16, :256].numpy().copy())
+        res["loss_fixed"] = np.array(losses, dtype=np.float64)
+        res["logits_slice"] = np.stack(slices)
+        for k2, v2 in res.items():
+            out[k2 + tag] = v2
+        return n
+
+    n = run("")
+    perturb_linear_biases(model.bert.encoder, seed + 99)
+    run("_pert")
     print("bert: fp", out["loss_fp"], "int8", out["loss_fixed"], "quantizers", n)
     np.savez_compressed(os.path.join(G.OUT, "fullsize_bert_int8.npz"), **out)
 
@@ -162,48 +186,58 @@ def gen_opt():
         new.load_state_dict(old.state_dict(), strict=False)
         layer.self_attn = new.eval()
     batches = [synthetic_clm_batch(B, T, seed=seed + i, pin=False) for i in range(N_EST + N_EVAL)]
-    qparams = val_qparams(get_quant_config())
-    qparams["quant_dict"] = {}
-    qdec = QuantizedOPTDecoder(model.model.decoder, **qparams).eval()         # quant_setup fp32_head: FP lm_head (:731-732)
     mask = GM.causal_mask_431(B, T, torch.float32)
     ones = torch.ones(B, T, dtype=torch.bool)
 
-    def forward(input_ids, labels=None):                                      # quantized_opt.py:459-662
-        h = qdec.embed_tokens(input_ids) + qdec.embed_positions(ones, 0)
-        h = qdec.embed_sum_act_quantizer(h)
-        for layer in qdec.layers:
-            h = layer(h, attention_mask=mask)[0]
-        h = qdec.final_layer_norm(h)
-        logits = model.lm_head(h)
-        loss = None
-        if labels is not None:
-            loss = torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, cfg.vocab_size), labels[:, 1:].reshape(-1))
-        return loss, logits
+    def run(tag):
+        qparams = val_qparams(get_quant_config())
+        qparams["quant_dict"] = {}
+        qdec = QuantizedOPTDecoder(model.model.decoder, **qparams).eval()     # quant_setup fp32_head: FP lm_head (:731-732)
 
-    class _Wrap(torch.nn.Module):
-        def __init__(self):
-            super().__init__()
-            self.q = qdec
+        def forward(input_ids, labels=None):                                  # quantized_opt.py:459-662
+            h = qdec.embed_tokens(input_ids) + qdec.embed_positions(ones, 0)
+            h = qdec.embed_sum_act_quantizer(h)
+            for layer in qdec.layers:
+                h = layer(h, attention_mask=mask)[0]
+            h = qdec.final_layer_norm(h)
+            logits = model.lm_head(h)
+            loss = None
+            if labels is not None:
+                loss = torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, cfg.vocab_size), labels[:, 1:].reshape(-1))
+            return loss, logits
 
-        def forward(self, input_ids, labels=None):
-            return forward(input_ids, labels)
+        class _Wrap(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.q = qdec
 
-    # FP losses first (activation quantizers off, weights FP)
-    qdec.set_quant_state(weight_quant=False, act_quant=False)
-    with torch.no_grad():
-        out["loss_fp"] = np.array([float(forward(**b)[0]) for b in batches[N_EST:]], dtype=np.float64)
-    qdec.set_quant_state(weight_quant=True, act_quant=True)                                     # validate_clm.py:478-480
-    pass_data_for_range_estimation(loader=batches[:N_EST], model=_Wrap().eval(), act_quant=True, max_num_batches=N_EST)
-    qdec.fix_ranges()                                                                           # :495
-    n = collect_ranges(qdec, out)
-    losses, slices = [], []
-    with torch.no_grad():
-        for b in batches[N_EST:]:
-            loss, logits = forward(**b)
-            losses.append(float(loss))
-            slices.append(logits[:2, :16, :256].numpy().copy())
-    out["loss_fixed"] = np.array(losses, dtype=np.float64)
-    out["logits_slice"] = np.stack(slices)
+            def forward(self, input_ids, labels=None):
+                return forward(input_ids, labels)
+
+        if not tag:                                                           # FP losses (quantizers off, weights FP)
+            qdec.set_quant_state(weight_quant=False, act_quant=False)
+            with torch.no_grad():
+                out["loss_fp"] = np.array([float(forward(**b)[0]) for b in batches[N_EST:]], dtype=np.float64)
+        qdec.set_quant_state(weight_quant=True, act_quant=True)                                 # validate_clm.py:478-480
+        pass_data_for_range_estimation(loader=batches[:N_EST], model=_Wrap().eval(), act_quant=True, max_num_batches=N_EST)
+        qdec.fix_ranges()                                                                       # :495
+        res = {}
+        n = collect_ranges(qdec, res)
+        losses, slices = [], []
+        with torch.no_grad():
+            for b in batches[N_EST:]:
+                loss, logits = forward(**b)
+                losses.append(float(loss))
+                slices.append(logits[:2, :16, :256].numpy().copy())
+        res["loss_fixed"] = np.array(losses, dtype=np.float64)
+        res["logits_slice"] = np.stack(slices)
+        for k2, v2 in res.items():
+            out[k2 + tag] = v2
+        return n
+
+    n = run("")
+    perturb_linear_biases(model.model.decoder.layers, seed + 99)
+    run("_pert")
     print("opt: fp", out["loss_fp"], "int8", out["loss_fixed"], "quantizers", n)
     np.savez_compressed(os.path.join(G.OUT, "fullsize_opt_int8.npz"), **out)
 

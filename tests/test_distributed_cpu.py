@@ -23,13 +23,18 @@ def _worker(rank, world, port, q):
     mm = torch.stack((x.min(), x.max()))
     Q.set_range_sync(True)
     synced = Q._sync_minmax(mm)
+    # 1b. a GROUP of independent taps (q / k / v projections): (n, 2) pairs cross the ranks in ONE all-reduce
+    n0 = Q.RANGE_SYNC_COLLECTIVES
+    grp = torch.stack([torch.stack(((x * s).min(), (x * s).max())) for s in (1.0, 0.5, 3.0)])
+    grp_synced = Q._sync_minmax(grp)
+    grp_calls = Q.RANGE_SYNC_COLLECTIVES - n0
     Q.set_range_sync(False)
     unsynced = Q._sync_minmax(mm)
     # 2. loss aggregation: every batch weighted equally across ranks
     idx = shard_indices(7, rank, world)
     losses = torch.tensor([1.0 + 0.1 * i for i in idx])
     ppl = aggregate_perplexity(losses.sum(), len(idx))
-    q.put((rank, synced.tolist(), unsynced.tolist(), mm.tolist(), idx, ppl))
+    q.put((rank, synced.tolist(), unsynced.tolist(), mm.tolist(), idx, ppl, grp.tolist(), grp_synced.tolist(), grp_calls))
     dist.destroy_process_group()
 
 
@@ -45,7 +50,9 @@ def test_range_sync_and_loss_aggregation_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, s0, u0, m0, i0, p0), (r1, s1, u1, m1, i1, p1) = res
+    (r0, s0, u0, m0, i0, p0, g0, gs0, c0), (r1, s1, u1, m1, i1, p1, g1, gs1, c1) = res
+    assert c0 == c1 == 1                                               # three taps, one collective
+    assert gs0 == gs1 == [[min(a[0], b[0]), max(a[1], b[1])] for a, b in zip(g0, g1)]
     assert s0 == s1 == [min(m0[0], m1[0]), max(m0[1], m1[1])]          # exact, identical on both ranks
     assert u0 == m0 and u1 == m1                                       # disabled: per-process, like the reference
     assert i0 == [0, 2, 4, 6] and i1 == [1, 3, 5]
