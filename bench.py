@@ -187,6 +187,32 @@ def time_attention_kernel(torch, ops, fn, dtype, pool_sets=8, reps=10):
     return sum(ts) / len(ts) * 1e-3     # seconds per launch
 
 
+def _event_time(torch, f, reps=5, warm=3):
+    for _ in range(warm):
+        f()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        f()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e-3 / reps
+
+
+def _skip_fraction(torch, q, k, gamma, eta, b=0, h=0):
+    """Share of (32-row warp block x 64-key step) tiles of one (batch, head) in which clippedsoftmax1 leaves no key alive:
+    exactly the tiles the PV pass of the two-pass kernel skips (attn_fwd_ws.cuh, "sparse skip").  Untimed, torch on the GPU."""
+    s = (q[b, h].float() @ k[b, h].float().t()) * 0.125
+    m = s.max(-1, keepdim=True).values
+    e = torch.exp(s - m)
+    p = e / (e.sum(-1, keepdim=True) + torch.exp(-m))
+    alive = ((eta - gamma) * p + gamma) > 0
+    T = s.shape[0]
+    tiles = alive.view(T // 32, 32, T // 64, 64).any(3).any(1)
+    return 1.0 - tiles.float().mean().item(), alive.float().sum(-1).mean().item()
+
+
 def attention_sweep(torch, ops, peaks):
     """Config-5 style points (12 heads, d=64, B*T = 65536 tokens): attention TFLOP/s vs the tensor roofline."""
     out = {}
@@ -194,22 +220,125 @@ def attention_sweep(torch, ops, peaks):
         B = 65536 // T
         q = torch.randn(B, HEADS, T, HEAD_DIM, device="cuda", dtype=torch.float16)
         k, v = torch.randn_like(q), torch.randn_like(q)
+        # peaky rows: q scaled x1 / x3 / x5 per 32-row block, so that clipped rows keep a handful of surviving keys
+        # (tests/test_gpu_attention_baseline_shapes.py uses the same construction)
+        blk = torch.randint(0, 3, (B, HEADS, T // 32, 1), device="cuda")
+        qp = (q.float() * (1.0 + 2.0 * blk).repeat_interleave(32, dim=2)).half()
         # clippedsoftmax1(-.025:1) zeroes every probability below 0.0222, and on N(0,1) inputs no key of a T >= 2048 row
-        # gets that much: the PV pass skips all exponentials ("sparse skip", data dependent).  The *_dense line is the
-        # same kernel with gamma = 0 (nothing can be skipped): the full two-pass cost.
-        for name, kind, gamma in (("softmax1", 1, 0.0), ("clippedsoftmax1", 3, -0.025), ("clippedsoftmax1_dense", 3, 0.0)):
-            f = lambda: ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=1.1)
-            for _ in range(3):
-                f()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            a.record()
-            for _ in range(5):
-                f()
-            b.record()
-            torch.cuda.synchronize()
-            tf = 4.0 * B * HEADS * T * T * HEAD_DIM * 5 / (a.elapsed_time(b) * 1e-3) / 1e12
+        # gets that much: the PV pass skips all exponentials ("sparse skip", data dependent) -- a DEGENERATE workload whose
+        # output is all zeros, reported only as *_allzero.  Credit the *_peaky line (surviving keys, skip fraction reported)
+        # and the *_dense line (gamma = 0: nothing can be skipped, the full two-pass cost).
+        for name, kind, gamma, qq in (("softmax1", 1, 0.0, q), ("clippedsoftmax1_allzero", 3, -0.025, q),
+                                      ("clippedsoftmax1_peaky", 3, -0.025, qp), ("clippedsoftmax1_dense", 3, 0.0, q),
+                                      ("softmax1_causal", 1, 0.0, q)):
+            causal = name.endswith("causal")
+            t = _event_time(torch, lambda: ops.attention_fwd(qq, k, v, scale=0.125, kind=kind, gamma=gamma, eta=1.1,
+                                                             causal=causal))
+            flops = 2.0 * B * HEADS * T * (T + 1) * HEAD_DIM if causal else 4.0 * B * HEADS * T * T * HEAD_DIM
+            tf = flops / t / 1e12
             out[f"{name}_T{T}"] = {"tflops": round(tf, 1), "frac_of_measured_peak": round(tf / peaks["tensor"], 4)}
+            if name.endswith("peaky"):
+                skip, alive = _skip_fraction(torch, qp, k, gamma, 1.1)
+                out[f"{name}_T{T}"].update(skipped_tile_fraction=round(skip, 4), surviving_keys_per_row=round(alive, 2))
+        del q, k, v, qp
+    return out
+
+
+def quant_kernel_bandwidth(torch, ops, peaks):
+    """Standalone quantizer / range kernels (north_star: "achieved HBM GB/s ... against B200 peak"): algorithmic bytes
+    (fake-quant: read + write, min/max: read) / CUDA-event time, L2 flushed between launches when the tensor
+    fits L2.  N(0,1) activations with 0.01 % outliers x50."""
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for dtn, dt in (("f32", torch.float32), ("f16", torch.float16)):
+        for logn in (24, 28):
+            n = 1 << logn
+            x = torch.randn(n, device="cuda", dtype=dt)
+            x[:: 10000] *= 50
+            y = torch.empty_like(x)
+            mm = torch.empty(2, device="cuda")
+            state = ops.new_qstate("cuda")
+            ops.range_update(state, ops.minmax(x), 0.9, 8, 1e-8)
+            qp = state[4:6]
+            for op, f, nbytes in (("fake_quant", lambda: ops.fake_quant_asym(x, qp, 8, out=y), 2 * n * x.element_size()),
+                                  ("minmax", lambda: ops.minmax(x, out=mm), n * x.element_size())):
+                for _ in range(3):
+                    f()
+                ts = []
+                for _ in range(7):
+                    if logn < 27:
+                        flush.zero_()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    f()
+                    b.record()
+                    torch.cuda.synchronize()
+                    ts.append(a.elapsed_time(b) * 1e-3)
+                t = statistics.median(ts)
+                out[f"{op}_{dtn}_2^{logn}"] = {"gbs": round(nbytes / t / 1e9, 1), "frac_of_hbm_peak": round(nbytes / t / 1e9 / peaks["hbm"], 4),
+                                              "us": round(t * 1e6, 1)}
+            del x, y
+    return out
+
+
+def extra_model_configs(torch, dist, rank, world, steps, warmup, timed):
+    """BASELINE configs 3 and 4 at model level on EVERY rank (weak scaling, batches sharded over ranks like the headline):
+      config3  OPT-125m fp16 causal, vanilla softmax + conditional_per_token gate (init 0.25), block 512, batch 4 per GPU
+      config4  OPT-125m INT8 (--quantize: fp32_head, running_minmax, asymmetric 8-bit activations, symmetric 8-bit weights)
+               with softmax1, block 512, batch 4 per GPU, fp16 activations (the throughput configuration; the fp32 variant is
+               the parity configuration of tests/test_fullsize_int8.py).  Range estimation runs on 4 batches PER RANK with
+               the MIN/MAX all-reduce BEFORE the EMA (NCCL when world > 1), and the resulting quantizer states are gathered
+               and compared bit for bit across ranks inside this run."""
+    from outeffhop_b200 import eval_harness as EH, quantization as Q, quantized_models as QM
+    out = {}
+
+    def run(step, pool, tokens_per_step):
+        def body(n):
+            for i in range(n):
+                for k2, v in pool[i % len(pool)].items():
+                    step.static_inputs[k2].copy_(v, non_blocking=True)
+                step.run()
+        body(warmup)
+        ms, _, _ = timed(lambda: body(steps))
+        return {"value": world * steps * tokens_per_step / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+                "loss": float(step.loss)}
+
+    model = EH.build_opt_125m(seed=5678, attn_softmax="vanilla", attn_gate_type="conditional_per_token", attn_gate_init=0.25)
+    host = [EH.synthetic_clm_batch(4, 512, seed=5678 + 1000 * rank + i) for i in range(8)]
+    pool = [{k2: v.cuda() for k2, v in b.items()} for b in host]
+    step = EH.make_opt_eval_step(model, host[0])
+    out["config3"] = dict(run(step, pool, 4 * 512),
+                          workload="OPT-125m fp16 causal, vanilla + conditional_per_token gate (init 0.25), 4x512 per GPU")
+    del model, step
+
+    model = EH.build_opt_125m(seed=6789, attn_softmax="softmax1")
+    q = QM.quantize_opt_for_causal_lm(model, quant_setup="fp32_head")
+    n_est = 4
+    est = [EH.synthetic_clm_batch(4, 512, seed=6789 + i * world + rank) for i in range(n_est)]   # global batch i: ranks 0..N-1
+    host = [EH.synthetic_clm_batch(4, 512, seed=7789 + 1000 * rank + i) for i in range(8)]
+    pool = [{k2: v.cuda() for k2, v in b.items()} for b in host]
+    Q.set_range_sync(world > 1)
+    c0 = Q.RANGE_SYNC_COLLECTIVES
+    step = EH.make_opt_int8_eval_step(q, host[0], est)
+    Q.set_range_sync(False)
+    states = torch.stack([m.quantizer._qstate.detach().clone() for m in q.modules()
+                          if isinstance(m, Q.QuantizationManager) and isinstance(m.quantizer, Q.AsymmetricUniformQuantizer)
+                          and m.quantizer.is_initialized])
+    identical = None
+    if world > 1:
+        gathered = [torch.empty_like(states) for _ in range(world)]
+        dist.all_gather(gathered, states)
+        identical = all(torch.equal(g, gathered[0]) for g in gathered)
+        if not identical:
+            raise SystemExit("bench.py: activation ranges differ across ranks after the synchronised estimation")
+    out["config4"] = dict(run(step, pool, 4 * 512),
+                          workload="OPT-125m INT8 W8A8 (fp32_head, running_minmax, asymmetric_uniform) softmax1, 4x512 per GPU, "
+                                   "fp16 activations, fixed ranges after 4 estimation batches per rank",
+                          range_sync={"activation_quantizers": int(states.shape[0]), "estimation_batches_per_rank": n_est,
+                                      "all_reduces": Q.RANGE_SYNC_COLLECTIVES - c0, "backend": "nccl" if world > 1 else None,
+                                      "bit_identical_across_ranks": identical})
+    del model, q, step
+    torch.cuda.empty_cache()
     return out
 
 
@@ -300,6 +429,9 @@ def run_ours(args):
     ms_e2e, _, _ = timed(lambda: body_e2e(steps))
     if rank == 0:
         sampler.stop()
+    extra = None
+    if not args.no_extra:
+        extra = extra_model_configs(torch, dist, rank, world, steps, warmup, timed)
 
     tokens = world * steps * BATCH * SEQ
     line = None
@@ -333,8 +465,11 @@ def run_ours(args):
                          "timing": "80 launches back to back in one CUDA graph over 8 input sets (201 MB > L2), CUDA events",
                          "note": "64 flop/B: HBM/latency-bound at T=128; the tensor roofline applies to attn_sweep (T>=2048)"},
         }
+        if extra is not None:
+            line["configs"] = extra
         if not args.no_sweep:
             line["attn_sweep"] = attention_sweep(torch, ops, peaks)
+            line["quant_kernels"] = quant_kernel_bandwidth(torch, ops, peaks)
         if world == 1 and not args.no_cpu:
             from oracle import c_oracle
             from oracle.cpu_model import time_bert_eval_cpu
@@ -359,6 +494,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="run the eval step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-sweep", action="store_true", help="skip the T=2048/8192 attention sweep")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config 3 / config 4 model-level lines")
     ap.add_argument("--profile-one-step", action="store_true",
                     help="bracket one warm eval step with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()

@@ -98,6 +98,7 @@ SYMBOLS = {
 # test-only entry point (not part of the public header)
 _PRIVATE = {
     "oeh_attn_fwd_debug": (C.c_int, [C.POINTER(OehAttnArgs), C.c_void_p, C.c_void_p]),
+    "oeh_set_override": (C.c_int, [C.c_char_p, C.c_longlong]),
 }
 
 _lib = None
@@ -121,6 +122,19 @@ def lib():
             raise RuntimeError(f"liboeh.so version {handle.oeh_version()} does not match the Python shim (100)")
         _lib = handle
     return _lib
+
+
+def set_override(name: str, value) -> None:
+    """Dispatch override of the attention entry point (tests / tuning): ``OEH_ATTN_KERNEL`` ("tile" / "ws"),
+    ``OEH_WS_PERSISTENT``, ``OEH_WS_TILES``, ``OEH_CAUSAL_CHUNK``, ``OEH_ONE_REGS``, ``OEH_MID_KERNEL``; ``None`` clears it.  Process wide,
+    thread-safe; the library reads the environment variables of the same names once, at its first call."""
+    if value is None:
+        v = -1
+    elif name == "OEH_ATTN_KERNEL":
+        v = {"tile": 0, "ws": 1}[value]
+    else:
+        v = int(value)
+    check(lib().oeh_set_override(name.encode(), v))
 
 
 def last_error() -> str:

@@ -17,8 +17,12 @@
 // tile (Tk <= 128, the BERT eval shape) both passes collapse into one.
 // Two CTAs are co-resident per SM (2 x 256 TMEM columns, 2 x 81 KB smem) so one CTA's softmax
 // overlaps the other's MMAs.  Roofline: tensor pipe, 4*B*H*Tq*Tk*d flop per call (causal: unmasked half).
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "attn_common.cuh"
 #include "attn_fwd_one.cuh"
@@ -327,6 +331,47 @@ int make_tmap(CUtensorMap* tm, TmapCoord* coord, const void* base, int dtype, in
   return OEH_OK;
 }
 
+// ---- dispatch overrides (tests / tuning) ---------------------------------------------------------------------------
+// The kernel-choice rules below are measured defaults.  They can be overridden per process through oeh_set_override()
+// (thread-safe; what the tests use) or, for command-line experiments, through environment variables of the same names --
+// read ONCE, at the first call, never on the launch path.  Value < 0 = no override.
+enum TuneKey { kTuneAttnKernel = 0, kTuneWsPersistent, kTuneWsTiles, kTuneCausalChunk, kTuneOneRegs, kTuneMidKernel, kTuneKeys };
+const char* const kTuneNames[kTuneKeys] = {"OEH_ATTN_KERNEL", "OEH_WS_PERSISTENT", "OEH_WS_TILES", "OEH_CAUSAL_CHUNK",
+                                           "OEH_ONE_REGS", "OEH_MID_KERNEL"};
+std::atomic<long long> g_tune[kTuneKeys];
+std::once_flag g_tune_once;
+
+long long parse_tune(int key, const char* v) {
+  if (key == kTuneAttnKernel) return !strcmp(v, "tile") ? 0 : (!strcmp(v, "ws") ? 1 : -1);   // 0 = tile, 1 = ws
+  return atoll(v);
+}
+void tune_init() {
+  std::call_once(g_tune_once, [] {
+    for (int k = 0; k < kTuneKeys; ++k) {
+      const char* v = getenv(kTuneNames[k]);
+      g_tune[k].store(v ? parse_tune(k, v) : -1, std::memory_order_relaxed);
+    }
+  });
+}
+long long tune(int key) {
+  tune_init();
+  return g_tune[key].load(std::memory_order_relaxed);
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel): function attributes belong to the device's
+// context, and two host threads may race to the first launch.
+int ensure_smem(const void* fn, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  int dev = 0;
+  OEH_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({dev, fn})) return OEH_OK;
+  OEH_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.insert({dev, fn});
+  return OEH_OK;
+}
+
 int validate(const OehAttnArgs* a) {
   OEH_CHECK_ARG(a, "oeh_attn_fwd: null args");
   OEH_CHECK_ARG(a->B >= 0 && a->H >= 0 && a->Tq >= 0 && a->Tk >= 0, "oeh_attn_fwd: negative dimension");
@@ -368,9 +413,9 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
   // When all keys fit one K/V tile (Tk <= 128, the BERT eval shape) the small one-tile kernel (4 CTAs / SM) runs.
   bool use_ws = a->Tq > BM, use_one = a->Tk <= BN;
   const bool norm_mode = a->kind >= OEH_SOFTMAX_CLIPPED || a->qdq_probs != nullptr;   // two-pass variants
-  if (const char* f = getenv("OEH_ATTN_KERNEL")) {
-    if (!strcmp(f, "tile")) use_ws = use_one = false;
-    if (!strcmp(f, "ws")) { use_ws = true; use_one = false; }
+  if (const long long f = tune(kTuneAttnKernel); f >= 0) {
+    if (f == 0) use_ws = use_one = false;
+    if (f == 1) { use_ws = true; use_one = false; }
   }
   if (use_one) use_ws = false;
   const int kv_box = use_ws ? attn_ws::BNW : BN;
@@ -427,12 +472,12 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
 #ifdef OEH_WS_PERSISTENT
     persistent = OEH_WS_PERSISTENT;
 #endif
-    if (const char* f = getenv("OEH_WS_PERSISTENT")) persistent = atoi(f) != 0;
+    if (const long long f = tune(kTuneWsPersistent); f >= 0) persistent = f != 0;
     int tiles = persistent ? ((a->causal && steps <= 8.0) ? 1 : 2) : ((norm_mode || steps <= 24.0) ? 1 : 2);
 #ifdef OEH_WS_TILES
     tiles = OEH_WS_TILES;
 #endif
-    if (const char* f = getenv("OEH_WS_TILES")) tiles = atoi(f) == 1 ? 1 : 2;
+    if (const long long f = tune(kTuneWsTiles); f >= 0) tiles = f == 1 ? 1 : 2;
     static const KernelFn kernels[2][8] = {
         {attn_ws::attn_fwd_ws_kernel<false, false, false, 1>, attn_ws::attn_fwd_ws_kernel<false, true, false, 1>,
          attn_ws::attn_fwd_ws_kernel<true, false, false, 1>,  attn_ws::attn_fwd_ws_kernel<true, true, false, 1>,
@@ -442,15 +487,11 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
          attn_ws::attn_fwd_ws_kernel<true, false, false, 2>,  attn_ws::attn_fwd_ws_kernel<true, true, false, 2>,
          attn_ws::attn_fwd_ws_kernel<false, false, true, 2>,  attn_ws::attn_fwd_ws_kernel<false, true, true, 2>,
          attn_ws::attn_fwd_ws_kernel<true, false, true, 2>,   attn_ws::attn_fwd_ws_kernel<true, true, true, 2>}};
-    static bool attr_done[2][8] = {};
     const int smem = tiles == 1 ? attn_ws::Cfg<1>::kSmemBytes : attn_ws::Cfg<2>::kSmemBytes;
     const int threads = tiles == 1 ? attn_ws::Cfg<1>::kThreads : attn_ws::Cfg<2>::kThreads;
     const int qrows = 128 * tiles;
     KernelFn fn = kernels[tiles - 1][kw];
-    if (!attr_done[tiles - 1][kw]) {
-      OEH_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr_done[tiles - 1][kw] = true;
-    }
+    if ((rc = ensure_smem(reinterpret_cast<const void*>(fn), smem))) return rc;
     dim3 grid((unsigned)((a->Tq + qrows - 1) / qrows), (unsigned)a->H, (unsigned)a->B);
     p.n_qt = (int)grid.x;
     if (a->causal) {
@@ -459,7 +500,7 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
       long long chunk = (32ll << 20) / ((long long)a->Tk * HD * 2 * 2);
       const long long hb = (long long)a->H * a->B;
       chunk = chunk < 1 ? 1 : (chunk > hb ? hb : chunk);
-      if (const char* f = getenv("OEH_CAUSAL_CHUNK")) chunk = atoll(f) > hb ? hb : atoll(f);
+      if (const long long f = tune(kTuneCausalChunk); f >= 0) chunk = f > hb ? hb : f;
       p.hb_chunk = (int)chunk;
     }
     if (persistent) {
@@ -473,13 +514,9 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
            attn_wsp::attn_fwd_wsp_kernel<true, false, false, 2>,  attn_wsp::attn_fwd_wsp_kernel<true, true, false, 2>,
            attn_wsp::attn_fwd_wsp_kernel<false, false, true, 2>,  attn_wsp::attn_fwd_wsp_kernel<false, true, true, 2>,
            attn_wsp::attn_fwd_wsp_kernel<true, false, true, 2>,   attn_wsp::attn_fwd_wsp_kernel<true, true, true, 2>}};
-      static bool pattr_done[2][8] = {};
       const int psmem = tiles == 1 ? attn_wsp::Cfg<1>::kSmemBytes : attn_wsp::Cfg<2>::kSmemBytes;
       KernelFn pfn = pkernels[tiles - 1][kw];
-      if (!pattr_done[tiles - 1][kw]) {
-        OEH_CUDA_OK(cudaFuncSetAttribute(pfn, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem));
-        pattr_done[tiles - 1][kw] = true;
-      }
+      if ((rc = ensure_smem(reinterpret_cast<const void*>(pfn), psmem))) return rc;
       const long long items = (long long)grid.x * grid.y * grid.z;
       const long long slots = (long long)num_sms() * (tiles == 1 ? 2 : 1);
       const unsigned pgrid = (unsigned)(items < slots ? items : slots);
@@ -496,30 +533,33 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
          attn_one::attn_fwd_one_kernel<true, false, false>, attn_one::attn_fwd_one_kernel<true, true, false>},
         {attn_one::attn_fwd_one_kernel<false, false, true>, attn_one::attn_fwd_one_kernel<false, true, true>,
          attn_one::attn_fwd_one_kernel<true, false, true>, attn_one::attn_fwd_one_kernel<true, true, true>}};
-    static bool attr_done[2][4] = {};
     // S row in registers (3 CTAs / SM, one TMEM read) vs chunked TMEM passes (4 CTAs / SM): 9.37 vs 9.88 us per launch at
     // the C-BERT shape for the clipped kinds, 9.29 vs 9.52 us for softmax1 (profiles/r01_one_tile_regs_y.txt).  The generic
     // instantiation (taps / masks) does not fit 168 registers without spilling and keeps the chunked passes.
     int regs = generic ? 0 : 1;
-    if (const char* f = getenv("OEH_ONE_REGS")) regs = atoi(f) != 0;
-    if (!attr_done[regs][ki]) {
-      OEH_CUDA_OK(cudaFuncSetAttribute(kernels[regs][ki], cudaFuncAttributeMaxDynamicSharedMemorySize, attn_one::kSmemBytes));
-      attr_done[regs][ki] = true;
-    }
+    if (const long long f = tune(kTuneOneRegs); f >= 0) regs = f != 0;
+    if ((rc = ensure_smem(reinterpret_cast<const void*>(kernels[regs][ki]), attn_one::kSmemBytes))) return rc;
     dim3 grid((unsigned)((a->Tq + BM - 1) / BM), (unsigned)a->H, (unsigned)a->B);
     kernels[regs][ki]<<<grid, attn_one::BM, attn_one::kSmemBytes, st>>>(tmq, tmk, tmv, p);
     return check_launch("attn_fwd_one_kernel");
   }
   static const KernelFn kernels[4] = {attn_fwd_kernel<false, false>, attn_fwd_kernel<false, true>,
                                       attn_fwd_kernel<true, false>, attn_fwd_kernel<true, true>};
-  static bool attr_done[4] = {false, false, false, false};
-  if (!attr_done[ki]) {
-    OEH_CUDA_OK(cudaFuncSetAttribute(kernels[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_done[ki] = true;
-  }
+  if ((rc = ensure_smem(reinterpret_cast<const void*>(kernels[ki]), kSmemBytes))) return rc;
   dim3 grid((unsigned)((a->Tq + BM - 1) / BM), (unsigned)a->H, (unsigned)a->B);
   kernels[ki]<<<grid, BM, kSmemBytes, st>>>(tmq, tmk, tmv, p);
   return check_launch("attn_fwd_kernel");
 }
 
 extern "C" int oeh_attn_fwd(const OehAttnArgs* args) { return oeh_attn_fwd_debug(args, nullptr, nullptr); }
+
+extern "C" int oeh_set_override(const char* name, long long value) {
+  OEH_CHECK_ARG(name, "oeh_set_override: null name");
+  tune_init();
+  for (int k = 0; k < kTuneKeys; ++k)
+    if (!strcmp(name, kTuneNames[k])) {
+      g_tune[k].store(value < 0 ? -1 : value, std::memory_order_relaxed);
+      return OEH_OK;
+    }
+  return set_error(OEH_ERR_BAD_ARG, "oeh_set_override: unknown key '%s'", name);
+}

@@ -36,3 +36,17 @@ def golden():
     def load(name):
         return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
     return load
+
+
+@pytest.fixture
+def override():
+    """Set dispatch overrides of the attention entry point for one test (outeffhop_b200._lib.set_override); cleared after."""
+    from outeffhop_b200 import _lib
+    used = []
+
+    def setter(name, value):
+        _lib.set_override(name, value)
+        used.append(name)
+    yield setter
+    for name in used:
+        _lib.set_override(name, None)

@@ -82,16 +82,16 @@ def test_attention_causal(kind, gamma, eta, T):
 
 @pytest.mark.parametrize("kernel", ["tile", "ws", "ws:1", "ws:2"])
 @pytest.mark.parametrize("kind,gamma,eta", KINDS[:4])
-def test_attention_kernel_override_same_result(kernel, kind, gamma, eta, monkeypatch):
+def test_attention_kernel_override_same_result(kernel, kind, gamma, eta, override):
     """The three kernels (one-tile / multi-tile / warp-specialised) are interchangeable on a shape all of them accept."""
     ops = _ops()
     q, k, v = _mk(2, 2, 128, 128, torch.float16, seed=11 + kind, layout="bthd")
     logits = torch.randn(2, 2, 128).cuda()
     kw = dict(scale=0.125, kind=kind, gamma=gamma, eta=eta, gate_logits=logits, causal=(kind % 2 == 1))
     base = ops.attention_fwd(q, k, v, **kw).float()
-    monkeypatch.setenv("OEH_ATTN_KERNEL", kernel.split(":")[0])
+    override("OEH_ATTN_KERNEL", kernel.split(":")[0])
     if ":" in kernel:
-        monkeypatch.setenv("OEH_WS_TILES", kernel.split(":")[1])      # Q tiles per CTA of the warp-specialised kernel
+        override("OEH_WS_TILES", kernel.split(":")[1])      # Q tiles per CTA of the warp-specialised kernel
     other = ops.attention_fwd(q, k, v, **kw).float()
     assert (base - other).abs().max().item() <= 1e-3
     ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=(kind % 2 == 1), gate=O.sigmoid(logits.cpu().numpy()))
@@ -220,12 +220,12 @@ def test_attention_fused_int8_taps_vs_oracle(kind, gamma, eta, before_gate, T):
 @pytest.mark.parametrize("tiles", ["1", "2"])
 @pytest.mark.parametrize("kind,gamma,eta", KINDS[:4])
 @pytest.mark.parametrize("T,causal", [(700, False), (700, True), (1024, True)])
-def test_attention_ws_tiles_per_cta(persistent, tiles, kind, gamma, eta, T, causal, monkeypatch):
+def test_attention_ws_tiles_per_cta(persistent, tiles, kind, gamma, eta, T, causal, override):
     """Both CTA shapes of the warp-specialised kernel (two Q tiles per CTA / two one-tile CTAs per SM), launched per work
     item and as persistent CTAs, on ragged and causal long sequences."""
     ops = _ops()
-    monkeypatch.setenv("OEH_WS_TILES", tiles)
-    monkeypatch.setenv("OEH_WS_PERSISTENT", persistent)
+    override("OEH_WS_TILES", tiles)
+    override("OEH_WS_PERSISTENT", persistent)
     q, k, v = _mk(1, 3, T, T, torch.float16, seed=T + kind)
     out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal, out_layout="bhtd")
     ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal)
@@ -234,11 +234,11 @@ def test_attention_ws_tiles_per_cta(persistent, tiles, kind, gamma, eta, T, caus
 
 @pytest.mark.parametrize("kind,gamma,eta", KINDS[:4])
 @pytest.mark.parametrize("causal", [False, True])
-def test_attention_persistent_many_items_per_cta(kind, gamma, eta, causal, monkeypatch):
+def test_attention_persistent_many_items_per_cta(kind, gamma, eta, causal, override):
     """More work items than SM slots: every persistent CTA walks several (Q tile group, head, batch) items, so the ring /
     parity bookkeeping carries across items (odd and even step counts per item)."""
     ops = _ops()
-    monkeypatch.setenv("OEH_WS_PERSISTENT", "1")
+    override("OEH_WS_PERSISTENT", "1")
     for T in (320, 448):                                   # 5 and 7 key steps of 64: odd -> the stream parities swap per item
         q, k, v = _mk(7, 12, T, T, torch.float16, seed=T + kind)       # 7*12*2 = 168 items > 148 SMs
         out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal, out_layout="bhtd")
@@ -249,13 +249,13 @@ def test_attention_persistent_many_items_per_cta(kind, gamma, eta, causal, monke
 @pytest.mark.parametrize("persistent", ["0", "1"])
 @pytest.mark.parametrize("chunk", ["0", "1", "5", "1000"])
 @pytest.mark.parametrize("kind,gamma,eta", [KINDS[1], KINDS[3]])
-def test_attention_causal_work_order(persistent, chunk, kind, gamma, eta, monkeypatch):
+def test_attention_causal_work_order(persistent, chunk, kind, gamma, eta, override):
     """Causal launches number their work items heaviest-first over chunks of (batch, head) pairs (causal_item in
     csrc/attn_common.cuh).  Any chunk size -- per-head order (0), chunks that do not divide B*H (5 of 14), one chunk for
     everything -- must visit every (Q tile, head, batch) exactly once: the result does not depend on it."""
     ops = _ops()
-    monkeypatch.setenv("OEH_WS_PERSISTENT", persistent)
-    monkeypatch.setenv("OEH_CAUSAL_CHUNK", chunk)
+    override("OEH_WS_PERSISTENT", persistent)
+    override("OEH_CAUSAL_CHUNK", chunk)
     q, k, v = _mk(2, 7, 600, 600, torch.float16, seed=11 + kind)        # 14 pairs x 5 Q tiles (3 tile groups of 2)
     out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=True, out_layout="bhtd")
     ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=True)
@@ -266,11 +266,11 @@ def test_attention_causal_work_order(persistent, chunk, kind, gamma, eta, monkey
 @pytest.mark.parametrize("kind,gamma,eta", KINDS)
 @pytest.mark.parametrize("shape,causal", [((2, 3, 128, 128), False), ((2, 2, 50, 77), False), ((1, 2, 100, 100), True),
                                           ((1, 1, 130, 1), False)])
-def test_attention_one_tile_softmax_shapes(regs, kind, gamma, eta, shape, causal, monkeypatch):
+def test_attention_one_tile_softmax_shapes(regs, kind, gamma, eta, shape, causal, override):
     """One-tile kernel (Tk <= 128): S row held in registers (one TMEM read, 3 CTAs / SM) and the chunked TMEM passes
     (4 CTAs / SM) against the oracle, on full, ragged, causal and single-key rows."""
     ops = _ops()
-    monkeypatch.setenv("OEH_ONE_REGS", regs)
+    override("OEH_ONE_REGS", regs)
     B, H, Tq, Tk = shape
     q, k, v = _mk(B, H, Tq, Tk, torch.float16, seed=Tq + Tk + kind)
     out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal, out_layout="bhtd")

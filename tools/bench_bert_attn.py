@@ -33,10 +33,8 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     nbytes = 4 * B * H * T * 64 * 2
     for kern in a.kernels.split(","):
-        if kern == "default":
-            os.environ.pop("OEH_ATTN_KERNEL", None)
-        else:
-            os.environ["OEH_ATTN_KERNEL"] = kern
+        from outeffhop_b200 import _lib
+        _lib.set_override("OEH_ATTN_KERNEL", None if kern == "default" else kern)
         for kind in [int(x) for x in a.kinds.split(",")]:
             run = lambda s: ops.attention_fwd(s[0], s[1], s[2], scale=0.125, kind=kind, gamma=-0.025, eta=1.1, out=s[3])
             for s in pool:
