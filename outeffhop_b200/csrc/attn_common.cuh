@@ -68,6 +68,26 @@ struct Qdq {
 #endif
   }
 };
+// rint(clamp(x2 * a2, lo, hi)) on two values: the quotient and both halves of the magic-number rounding run as packed
+// fp32x2 instructions (FMUL2 / FADD2: one FMA-pipe slot per PAIR), the clamp as scalar FMNMX on the ALU pipe.
+__device__ __forceinline__ uint64_t code2(uint64_t x2, uint64_t a2, float lo, float hi) {
+  float a, b;
+  ptx::unpack2f(ptx::fmul2(x2, a2), a, b);
+  a = fminf(fmaxf(a, lo), hi);
+  b = fminf(fmaxf(b, lo), hi);
+  const uint64_t r2 = ptx::fadd2(ptx::pack2f(a, b), ptx::pack2f(12582912.f, 12582912.f));
+  return ptx::fadd2(r2, ptx::pack2f(-12582912.f, -12582912.f));
+}
+
+// The probs tap can hand the PV MMA the integer (code - zero_point) itself -- exact in the 16-bit operand format up to
+// 2^8 (bf16) / 2^11 (fp16) -- and leave the multiplication by the quantizer's scale to the epilogue:
+//     sum_j scale_p (c_j - z) v_j  ==  scale_p * sum_j (c_j - z) v_j.
+// One multiply per element less, and the P operand carries NO rounding error at all.
+template <bool kBF16>
+__device__ __forceinline__ bool probs_as_codes(const AttnParams& p) {
+  return p.qdq_probs != nullptr && p.int_max <= (kBF16 ? 255.f : 2047.f);
+}
+
 __device__ __forceinline__ Qdq load_qdq(const float* qparams, float int_max) {
   Qdq q;
   q.scale = __ldg(qparams);
@@ -130,7 +150,16 @@ template <int N, bool kGeneric>
 __device__ __forceinline__ float transform_scores(float (&s)[N], const AttnParams& p, const Qdq& qd_s, bool has_qs,
                                                   bool has_mask, int64_t mask_row, int k0, int valid, int vis) {
   float mul = p.scale * kLog2e;
-  if (kGeneric && (has_qs || has_mask || p.clamp_min)) {
+  if (kGeneric && has_qs && !has_mask && !p.clamp_min) {
+    // Scores tap with nothing between it and the softmax (causal flag / no mask: the BERT eval data and the causal-hint OPT
+    // path): keep the INTEGER c = code - zero_point, i.e. s_q = scale_q * c, and fold scale_q * log2e into the multiplier
+    // the exponential applies anyway.  3.5 issue slots per element (packed) instead of 9.
+    const float a = p.scale * qd_s.inv_scale, lo = -qd_s.zp, hi = qd_s.int_max - qd_s.zp;
+    const uint64_t a2 = ptx::pack2f(a, a);
+#pragma unroll
+    for (int j = 0; j < N; j += 2) ptx::unpack2f(code2(ptx::pack2f(s[j], s[j + 1]), a2, lo, hi), s[j], s[j + 1]);
+    mul = qd_s.scale * kLog2e;
+  } else if (kGeneric && (has_qs || has_mask || p.clamp_min)) {
     mul = 1.f;
     const float scale = p.scale;
 #pragma unroll
@@ -256,19 +285,27 @@ __device__ __forceinline__ void exp2_only(float (&s)[N], float mul, float m) {
     exp2_pair<kPoly>(ptx::ffma2(ptx::pack2f(s[j], s[j + 1]), mul2, nm2), j / 2, s[j], s[j + 1]);
 }
 
-// normalised modes: p = e * inv_den, then clip((eta-gamma)*p + gamma, 0, 1) and / or the probs fake-quant tap
-template <int N, bool kGeneric>
+// normalised modes: p = e * inv_den, then clip((eta-gamma)*p + gamma, 0, 1) and / or the probs fake-quant tap.
+// With the tap and a code range that is exact in the operand format (probs_as_codes) the result is the integer
+// (code - zero_point); the epilogue multiplies the context by the tap's scale (store_row).
+template <int N, bool kGeneric, bool kBF16>
 __device__ __forceinline__ void normalize_probs(float (&s)[N], const AttnParams& p, float inv_den, bool clipped,
                                                 bool has_qp, const Qdq& qd_p) {
+  const bool codes = kGeneric && has_qp && probs_as_codes<kBF16>(p);
   if (clipped) {
     const float st = p.stretch * inv_den, gm = p.gamma;
 #pragma unroll
     for (int j = 0; j < N; ++j) s[j] = __saturatef(fmaf(s[j], st, gm));
-  } else {
+  } else if (!codes) {
 #pragma unroll
     for (int j = 0; j < N; ++j) s[j] *= inv_den;
   }
-  if (kGeneric && has_qp) {
+  if (codes) {
+    const float a = clipped ? qd_p.inv_scale : inv_den * qd_p.inv_scale, lo = -qd_p.zp, hi = qd_p.int_max - qd_p.zp;
+    const uint64_t a2 = ptx::pack2f(a, a);
+#pragma unroll
+    for (int j = 0; j < N; j += 2) ptx::unpack2f(code2(ptx::pack2f(s[j], s[j + 1]), a2, lo, hi), s[j], s[j + 1]);
+  } else if (kGeneric && has_qp) {
 #pragma unroll
     for (int j = 0; j < N; ++j) s[j] = qd_p(s[j]);
   }
@@ -304,6 +341,7 @@ __device__ __forceinline__ void store_row(float (&o)[ND], const AttnParams& p, f
 #pragma unroll
     for (int j = 0; j < ND; ++j) d[j] = o[j];
   }
+  if (kGeneric && probs_as_codes<kBF16>(p)) mul *= __ldg(p.qdq_probs);   // P was (code - zp): see normalize_probs
   float gate = 1.f;
   if (p.gate_logits) {
     const float z = __ldg(p.gate_logits + ((int64_t)b * p.H + h) * p.Tq + row);

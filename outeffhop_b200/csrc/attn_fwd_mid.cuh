@@ -1,0 +1,250 @@
+// Fused attention forward for sm_100a when all keys of a query tile fit TMEM at once: 128 < Tk <= 512 (the OPT eval
+// shape, block 512: BASELINE configs 3 / 4).  ONE pass for every softmax kind, including the normalised ones (clipped
+// softmax / probs fake-quant tap) that the long-sequence kernel runs as stats pass + recomputed-QK^T PV pass:
+//
+//   the whole score row block S [128 x Tk] (fp32) stays in TMEM (up to 512 columns = all of it), so QK^T is computed
+//   once, every exponential is evaluated once, and the row is normalised in place -- the trick attn_fwd_one.cuh plays at
+//   Tk <= 128, stretched over four K/V tiles.  At B=4, H=12, T=512 causal with the three INT8 taps the two-pass kernel
+//   needs 30.7 us per launch (1.6 GFLOP: prologue / epilogue bound, profiles/r01_launches_int8_opt_step_aa.summary.txt).
+//
+// One CTA = one 128-row Q tile of one (batch, head); Q, all K tiles and all V tiles resident in shared memory (144 KB).
+//   warp 8      producer / issuer: TMA loads (Q + K tile 0 | K tiles 1..3 | V, separate mbarriers), QK^T of tile t as soon
+//               as K(t) lands (one commit per tile), P.V after the softmax warps have written all of P
+//   warps 0-7   softmax, TWO threads per query row: warp w and warp w+4 share TMEM lane quarter w & 3 and split the
+//               row's 64-key chunks by parity (half h = w >> 2 takes chunks 2i + h), so both halves start as soon as tile 0
+//               is complete and a row's serial work is halved.
+//     pass A  chunk by chunk: scale / taps / mask, chunk max, e = exp2(s - m_i) in the running-max frame m_i of that moment,
+//             written back over S as fp32; running (m, l).  One exchange of (m, l) through shared memory between the two
+//             halves of a row -> common max and denominator (softmax_1: + 2^-m, vutils/softmax_1.py:18-20).
+//     pass B  e * 2^(m_i - m) / den -> clip((eta-gamma) p + gamma, 0, 1) -> [probs tap] -> 16-bit P, packed into the TMEM
+//             columns the PV MMA reads its A operand from.  P(2i), P(2i+1) land exactly on the columns of e-chunk i, which
+//             its owner read in iteration i / 2: a 64-thread named barrier per iteration orders the two halves of a row.
+//   O [128 x 64] takes columns 448..511 (dead once the last e-chunk has been read); epilogue as in the other kernels.
+#pragma once
+
+#include "attn_common.cuh"
+
+namespace oeh {
+namespace attn_mid {
+
+using namespace attn;
+
+constexpr int BM = 128;                          // query rows per CTA
+constexpr int CW = 64;                           // keys per softmax chunk
+constexpr int kMaxTiles = 4;                     // K / V tiles of 128 keys resident at once (Tk <= 512)
+constexpr int kSoftmaxWarps = 8, kThreads = (kSoftmaxWarps + 1) * 32;
+constexpr int kSmemBytes = (1 + 2 * kMaxTiles) * kTileBytes + 1024;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColO = 448;
+
+struct Barriers {
+  uint64_t k_full[kMaxTiles];                    // K tile t landed (k_full[0] also covers Q)
+  uint64_t v_full;                               // all V tiles landed
+  uint64_t s_full[kMaxTiles];                    // S tile t complete
+  uint64_t p_full;                               // P complete (one arrival per softmax warp)
+  uint64_t o_full;                               // O complete
+};
+
+template <bool kBF16, bool kGeneric>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
+                    const __grid_constant__ CUtensorMap tmv, const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) Barriers bars;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float xch_m[2][BM], xch_l[2][BM];
+
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  if (p.causal) {                                 // heaviest Q tiles first (attn_common.cuh, causal_item)
+    int hb;
+    causal_item((int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)), (int)gridDim.x,
+                (int)(gridDim.y * gridDim.z), p.hb_chunk, qt, hb);
+    h = hb % (int)gridDim.y;
+    b = hb / (int)gridDim.y;
+  }
+  const int q0 = qt * BM;
+
+  const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem0, sK = smem0 + kTileBytes, sV = sK + kMaxTiles * kTileBytes;
+
+  // K / V tiles this Q tile needs
+  int n_kv = (p.Tk + BN - 1) / BN;
+  if (p.causal) {
+    const int last_row = min(q0 + BM, p.Tq) - 1;
+    const int lim = (last_row + (p.Tk - p.Tq)) / BN + 1;
+    n_kv = lim < n_kv ? lim : n_kv;
+  }
+
+  if (warp == kSoftmaxWarps && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmq);
+    ptx::prefetch_tmap(&tmk);
+    ptx::prefetch_tmap(&tmv);
+#pragma unroll
+    for (int t = 0; t < kMaxTiles; ++t) {
+      ptx::mbar_init(ptx::smem_u32(&bars.k_full[t]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars.s_full[t]), 1);
+    }
+    ptx::mbar_init(ptx::smem_u32(&bars.v_full), 1);
+    ptx::mbar_init(ptx::smem_u32(&bars.p_full), kSoftmaxWarps);
+    ptx::mbar_init(ptx::smem_u32(&bars.o_full), 1);
+    ptx::fence_mbar_init();
+    // loads first: their latency covers the TMEM allocation and the block barrier below
+    const uint32_t b0 = ptx::smem_u32(&bars.k_full[0]);
+    ptx::mbar_expect_tx(b0, 2 * kTileBytes);
+    tma_tile(sQ, &tmq, b0, p.cq, q0, h, b);
+    tma_tile(sK, &tmk, b0, p.ck, 0, h, b);
+    for (int t = 1; t < n_kv; ++t) {
+      const uint32_t bt = ptx::smem_u32(&bars.k_full[t]);
+      ptx::mbar_expect_tx(bt, kTileBytes);
+      tma_tile(sK + t * kTileBytes, &tmk, bt, p.ck, t * BN, h, b);
+    }
+    const uint32_t bv = ptx::smem_u32(&bars.v_full);
+    ptx::mbar_expect_tx(bv, n_kv * kTileBytes);
+    for (int t = 0; t < n_kv; ++t) tma_tile(sV + t * kTileBytes, &tmv, bv, p.cv, t * BN, h, b);
+  }
+  __syncwarp();
+  if (warp == 0) ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(&tmem_base_slot));
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+
+  if (warp == kSoftmaxWarps) {
+    // ================================ producer / MMA issuer ===========================================================
+    constexpr uint32_t kIdescQK = ptx::make_idesc_f16(kBF16, BM, BN, false, false);
+    constexpr uint32_t kIdescPV = ptx::make_idesc_f16(kBF16, BM, HD, false, true);
+    for (int t = 0; t < n_kv; ++t) {                           // S tile t = Q . K(t)^T  -> columns [128 t, 128 t + 128)
+      ptx::mbar_wait(ptx::smem_u32(&bars.k_full[t]), 0);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          ptx::mma_ss(tmem + t * BN, ptx::make_smem_desc_sw128(sQ + k * 32, 16, 1024),
+                      ptx::make_smem_desc_sw128(sK + t * kTileBytes + k * 32, 16, 1024), kIdescQK, k > 0);
+        ptx::mma_commit(ptx::smem_u32(&bars.s_full[t]));
+      }
+      __syncwarp();
+    }
+    ptx::mbar_wait(ptx::smem_u32(&bars.p_full), 0);            // every softmax warp has written its share of P
+    ptx::mbar_wait(ptx::smem_u32(&bars.v_full), 0);
+    ptx::tc_fence_after();
+    if (ptx::elect_one()) {
+      for (int k = 0; k < n_kv * (BN / 16); ++k)               // O += P[:, 16k..16k+16) . V[16k..16k+16, :]
+        ptx::mma_ts(tmem + kColO, tmem + k * 8, ptx::make_smem_desc_sw128(sV + k * 2048, 1024, 1024), kIdescPV, k > 0);
+      ptx::mma_commit(ptx::smem_u32(&bars.o_full));
+    }
+    __syncwarp();
+  } else {
+    // ================================ softmax: two threads per row ====================================================
+    const int half = warp >> 2;                                 // chunk parity this thread takes
+    const int r = (warp & 3) * 32 + (tid & 31);                 // row within the tile == TMEM lane
+    const int row = q0 + r;
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int pair_bar = 2 + (warp & 3);                        // named barrier of the two warps of a lane quarter
+
+    const bool softmax1 = (p.kind == OEH_SOFTMAX_1 || p.kind == OEH_SOFTMAX_CLIPPED1);
+    const bool clipped = p.kind >= OEH_SOFTMAX_CLIPPED;
+    const bool has_qs = kGeneric && p.qdq_scores != nullptr;
+    const bool has_qp = kGeneric && p.qdq_probs != nullptr;
+    const bool has_mask = kGeneric && p.mask != nullptr;
+    const bool normalized = clipped || has_qp;
+    Qdq qd_s{1.f, 1.f, 0.f, p.int_max}, qd_p{1.f, 1.f, 0.f, p.int_max};
+    if (has_qs) qd_s = load_qdq(p.qdq_scores, p.int_max);
+    if (has_qp) qd_p = load_qdq(p.qdq_probs, p.int_max);
+    const int64_t mask_row =
+        p.mask ? ((int64_t)b * p.ms0 + (int64_t)h * p.ms1 + (int64_t)(row < p.Tq ? row : 0) * p.ms2) : 0;
+    const int causal_lim = p.causal ? row + (p.Tk - p.Tq) : 0x7fffffff;
+
+    // ---- pass A: e = exp2(s - m_i) over S, running (m, l) ------------------------------------------------------------
+    float m_run = -INFINITY, l_run = 0.f;
+    float mc[kMaxTiles];                                        // frame (running max) of the e values of chunk 2i + half
+#pragma unroll
+    for (int i = 0; i < kMaxTiles; ++i) {
+      mc[i] = 0.f;
+      if (i < n_kv) {
+        const int j = 2 * i + half, k0 = j * CW;
+        ptx::mbar_wait(ptx::smem_u32(&bars.s_full[i]), 0);
+        ptx::tc_fence_after();
+        float s[CW];
+        ptx::tmem_ld32(t_lane + j * CW, reinterpret_cast<uint32_t*>(s));
+        ptx::tmem_ld32(t_lane + j * CW + 32, reinterpret_cast<uint32_t*>(s) + 32);
+        ptx::tmem_wait_ld();
+        if (kGeneric && p.dbg_s && j < 2 && row < p.Tq) {       // raw S of keys [0, 128)
+          float* d = p.dbg_s + (((int64_t)b * p.H + h) * p.Tq + row) * BN + k0;
+#pragma unroll
+          for (int c = 0; c < CW; ++c) d[c] = s[c];
+        }
+        const int valid = min(p.Tk - k0, CW);                   // may be <= 0 in the ragged last tile: vis < 0 hides all
+        const int vis = min(valid - 1, causal_lim - k0);
+        const float mul = transform_scores<CW, kGeneric>(s, p, qd_s, has_qs, has_mask, mask_row, k0, max(valid, 0), vis);
+        const float m_new = fmaxf(m_run, row_max<CW>(s) * mul);
+        const float m_safe = m_new == -INFINITY ? 0.f : m_new;
+        const float alpha = ptx::ex2(m_run - m_safe);           // m_run = -inf -> 0
+        l_run = fmaf(l_run, alpha, exp2_and_sum<CW, !kGeneric>(s, mul, m_safe));
+        m_run = m_new;
+        mc[i] = m_safe;
+        ptx::tmem_st32(t_lane + j * CW, reinterpret_cast<const uint32_t*>(s));
+        ptx::tmem_st32(t_lane + j * CW + 32, reinterpret_cast<const uint32_t*>(s) + 32);
+      }
+    }
+    ptx::tmem_wait_st();
+
+    // ---- the two halves of a row agree on (m, denominator) --------------------------------------------------------------
+    xch_m[half][r] = m_run;
+    xch_l[half][r] = l_run;
+    asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
+    const float m_o = xch_m[half ^ 1][r], l_o = xch_l[half ^ 1][r];
+    const float m_all = fmaxf(m_run, m_o);
+    const float m_fin = m_all == -INFINITY ? 0.f : m_all;
+    float den = l_run * ptx::ex2(m_run - m_fin) + l_o * ptx::ex2(m_o - m_fin);
+    if (softmax1) den += ptx::ex2(-m_fin);
+    const float inv_den = __frcp_rn(den);
+    const float omul = normalized ? 1.f : inv_den;              // one-pass kinds: P stays in the row-max frame (max P = 1)
+
+    // ---- pass B: P ----------------------------------------------------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < kMaxTiles; ++i) {
+      if (i < n_kv) {
+        const int j = 2 * i + half;
+        float s[CW];
+        ptx::tmem_ld32(t_lane + j * CW, reinterpret_cast<uint32_t*>(s));
+        ptx::tmem_ld32(t_lane + j * CW + 32, reinterpret_cast<uint32_t*>(s) + 32);
+        ptx::tmem_wait_ld();
+        // P(2i), P(2i+1) overwrite e-chunk i, read by its owner in iteration i / 2 (this one when i == 0): both halves of the
+        // row must have issued AND completed their reads of this iteration before either writes
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        const float f = ptx::ex2(mc[i] - m_fin);                // chunk frame -> common frame (mc <= m_fin)
+        if (normalized) {
+          normalize_probs<CW, kGeneric, kBF16>(s, p, inv_den * f, clipped, has_qp, qd_p);
+        } else {
+#pragma unroll
+          for (int c = 0; c < CW; ++c) s[c] *= f;
+        }
+        uint32_t pk[CW / 2];
+#pragma unroll
+        for (int c = 0; c < CW / 2; ++c) pk[c] = pack2<kBF16>(s[2 * c], s[2 * c + 1]);
+        ptx::tmem_st32(t_lane + j * (CW / 2), pk);
+      }
+    }
+    ptx::tmem_wait_st();
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (ptx::elect_one()) ptx::mbar_arrive(ptx::smem_u32(&bars.p_full));
+
+    // ---- epilogue: each half finishes 32 head-dim columns of its row ------------------------------------------------------
+    ptx::mbar_wait(ptx::smem_u32(&bars.o_full), 0);
+    ptx::tc_fence_after();
+    float o[32];
+    ptx::tmem_ld32(t_lane + kColO + half * 32, reinterpret_cast<uint32_t*>(o));
+    ptx::tmem_wait_ld();
+    if (row < p.Tq) store_row<kBF16, kGeneric, 32>(o, p, omul, b, h, row, half * 32);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem);
+}
+
+}  // namespace attn_mid
+}  // namespace oeh

@@ -155,7 +155,7 @@ attn_fwd_one_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       uint32_t pk[CH / 2];
       if (c < n_ch) {
         float(&sc)[CH] = *reinterpret_cast<float(*)[CH]>(s + c * CH);
-        if (normalized) normalize_probs<CH, kGeneric>(sc, p, inv_den, clipped, has_qp, qd_p);
+        if (normalized) normalize_probs<CH, kGeneric, kBF16>(sc, p, inv_den, clipped, has_qp, qd_p);
 #pragma unroll
         for (int j = 0; j < CH / 2; ++j) pk[j] = pack2<kBF16>(sc[2 * j], sc[2 * j + 1]);
       } else {
@@ -226,7 +226,7 @@ attn_fwd_one_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
           float s[CH];
           ptx::tmem_ld32(t_lane + c * CH, reinterpret_cast<uint32_t*>(s));
           ptx::tmem_wait_ld();
-          normalize_probs<CH, kGeneric>(s, p, inv_den, clipped, has_qp, qd_p);
+          normalize_probs<CH, kGeneric, kBF16>(s, p, inv_den, clipped, has_qp, qd_p);
           // (columns past Tk inside this chunk may hold clip(gamma) != 0: their V rows are TMA zero fill)
 #pragma unroll
           for (int j = 0; j < CH / 2; ++j) pk[j] = pack2<kBF16>(s[2 * j], s[2 * j + 1]);

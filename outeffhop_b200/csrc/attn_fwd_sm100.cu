@@ -25,6 +25,7 @@
 #include <utility>
 
 #include "attn_common.cuh"
+#include "attn_fwd_mid.cuh"
 #include "attn_fwd_one.cuh"
 #include "attn_fwd_ws.cuh"
 #include "attn_fwd_wsp.cuh"
@@ -228,7 +229,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       for (int j = 0; j < BN; ++j) s[j] = ptx::ex2(fmaf(s[j], mul, -m_safe));
     }
 
-    if (normalized) normalize_probs<BN, kGeneric>(s, p, inv_den, clipped, has_qp, qd_p);
+    if (normalized) normalize_probs<BN, kGeneric, kBF16>(s, p, inv_den, clipped, has_qp, qd_p);
 
     // P -> TMEM (packed 16-bit pairs), aliasing the S columns this thread has already consumed
 #pragma unroll
@@ -418,6 +419,16 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
     if (f == 1) { use_ws = true; use_one = false; }
   }
   if (use_one) use_ws = false;
+  // 128 < Tk <= 512: the whole score row block fits TMEM, so the single-pass kernel of attn_fwd_mid.cuh can replace the
+  // two-pass one.  Measured (profiles/r02_mid_kernel_h.jsonl, B=4 H=12 T=512): causal with the INT8 taps 18.8 vs 22.2 us
+  // (the config-4 shape); clipped without taps 14.6 vs 14.5 us; non-causal with taps 29.7 vs 28.3 us; the one-pass kinds are
+  // faster on the persistent kernel (11.6 vs 14.6 us).  One CTA per SM (512 TMEM columns) costs it the overlap the two-pass
+  // kernel gets from two co-resident CTAs, so it is the default only where it wins.  OEH_MID_KERNEL=0 disables it, =1 sends
+  // every kind with Tk <= 512 there.
+  bool use_mid = norm_mode && a->qdq_probs != nullptr && a->causal && !use_one && a->Tk <= attn_mid::kMaxTiles * BN;
+  if (const long long f = tune(kTuneMidKernel); f >= 0) use_mid = f != 0 && !use_one && a->Tk <= attn_mid::kMaxTiles * BN;
+  if (tune(kTuneAttnKernel) >= 0) use_mid = false;
+  if (use_mid) use_ws = false;
   const int kv_box = use_ws ? attn_ws::BNW : BN;
 
   CUtensorMap tmq, tmk, tmv;
@@ -454,6 +465,16 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
                        !(a->scale > 0.f);
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
   const int ki = (a->dtype == OEH_BF16 ? 2 : 0) + (generic ? 1 : 0);
+  if (use_mid) {
+    static const KernelFn kernels[4] = {attn_mid::attn_fwd_mid_kernel<false, false>, attn_mid::attn_fwd_mid_kernel<false, true>,
+                                        attn_mid::attn_fwd_mid_kernel<true, false>, attn_mid::attn_fwd_mid_kernel<true, true>};
+    if ((rc = ensure_smem(reinterpret_cast<const void*>(kernels[ki]), attn_mid::kSmemBytes))) return rc;
+    dim3 grid((unsigned)((a->Tq + BM - 1) / BM), (unsigned)a->H, (unsigned)a->B);
+    p.n_qt = (int)grid.x;
+    p.hb_chunk = a->H * a->B;                      // causal: ALL heaviest Q tiles first (K / V of a launch fit L2 many times over)
+    kernels[ki]<<<grid, attn_mid::kThreads, attn_mid::kSmemBytes, st>>>(tmq, tmk, tmv, p);
+    return check_launch("attn_fwd_mid_kernel");
+  }
   if (use_ws) {
     const int kw = ki + (norm_mode ? 4 : 0);
     // Q tiles per CTA: 2 = one 640-thread CTA per SM, 1 = two independent 384-thread CTAs per SM (attn_fwd_ws.cuh, Cfg).

@@ -396,7 +396,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         }
 #endif
         exp2_only<BNW, !kGeneric>(s, mul, m_safe);
-        normalize_probs<BNW, kGeneric>(s, p, inv_den, clipped, has_qp, qd_p);
+        normalize_probs<BNW, kGeneric, kBF16>(s, p, inv_den, clipped, has_qp, qd_p);
       } else {
         // online softmax with lazy rescale
         const bool move = tile_max > m_run + kLazyRescale || m_run == -INFINITY;

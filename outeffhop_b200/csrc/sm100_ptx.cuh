@@ -216,6 +216,11 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));

@@ -276,3 +276,55 @@ def test_attention_one_tile_softmax_shapes(regs, kind, gamma, eta, shape, causal
     out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal, out_layout="bhtd")
     ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal)
     np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=TOL, rtol=0)
+
+
+@pytest.mark.parametrize("mid", ["0", "1"])
+@pytest.mark.parametrize("kind,gamma,eta", KINDS)
+@pytest.mark.parametrize("shape,causal", [((2, 3, 512, 512), True), ((2, 3, 512, 512), False), ((1, 2, 130, 130), True),
+                                          ((2, 2, 200, 333), False), ((1, 2, 100, 300), True), ((1, 3, 384, 384), True),
+                                          ((1, 2, 257, 511), True), ((1, 1, 40, 129), False)])
+def test_attention_mid_kernel_single_pass(mid, kind, gamma, eta, shape, causal, override):
+    """128 < Tk <= 512: the single-pass kernel (whole S row block in TMEM, two threads per row; attn_fwd_mid.cuh) forced on
+    for every kind (OEH_MID_KERNEL=1) and off (=0: the two-pass / persistent kernels) -- same oracle, same tolerance; full,
+    ragged, causal with Tq != Tk, one to four K/V tiles per Q tile."""
+    ops = _ops()
+    override("OEH_MID_KERNEL", mid)
+    B, H, Tq, Tk = shape
+    q, k, v = _mk(B, H, Tq, Tk, torch.float16, seed=Tq + Tk + kind, bias=4.0 if kind >= 2 else 0.0)
+    logits = torch.randn(B, H, Tq)
+    out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal,
+                            gate_logits=logits.cuda(), out_layout="bhtd")
+    ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal, gate=O.sigmoid(logits.numpy()))
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=TOL, rtol=0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("kind,gamma,eta", KINDS[:4])
+def test_attention_mid_kernel_taps_and_masks(kind, gamma, eta, dtype, override):
+    """The single-pass kernel with everything on: the three fixed-range taps (OPT order), an additive (B,1,Tq,Tk) mask with
+    the finfo.min clamp, a per-token gate -- against the oracle's chain and against the two-pass kernel on the same inputs."""
+    ops = _ops()
+    B, H, T = 2, 3, 448
+    q, k, v = _mk(B, H, T, T, dtype, seed=4400 + kind)
+    logits = torch.randn(B, H, T)
+    rng = {"s": (-6.0, 7.0), "p": (0.0, 1.0), "c": (-0.9, 1.1)}
+    qs = {n: O.asym_set_quant_range(lo, hi) for n, (lo, hi) in rng.items()}
+    dev = {n: torch.tensor([float(x) for x in O.asym_scale_zero_point(*qs[n])], device="cuda") for n in qs}
+    fq = {n: (lambda x, n=n: O.asym_quantize(x, *qs[n])) for n in qs}
+    fmin = torch.finfo(dtype).min
+    cm = torch.full((T, T), fmin, dtype=dtype).triu(1)[None, None].expand(B, 1, T, T).contiguous()
+    kw = dict(scale=0.125, kind=kind, gamma=gamma, eta=eta, mask=cm.cuda(), clamp_min=True, gate_logits=logits.cuda(),
+              qdq_scores=dev["s"], qdq_probs=dev["p"], qdq_ctx=dev["c"], n_bits=8, ctx_qdq_before_gate=True,
+              out_layout="bhtd")
+    override("OEH_MID_KERNEL", "1")
+    out = ops.attention_fwd(q, k, v, **kw).float().cpu().numpy()
+    override("OEH_MID_KERNEL", "0")
+    two_pass = ops.attention_fwd(q, k, v, **kw).float().cpu().numpy()
+    ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=True, gate=O.sigmoid(logits.numpy()),
+                  qdq_scores=fq["s"], qdq_probs=fq["p"], qdq_ctx=fq["c"], ctx_qdq_before_gate=True)
+    step = float(qs["c"][0])
+    for got in (out, two_pass):
+        diff = np.abs(got - ref)
+        assert diff.max() <= 1.05 * step + (1e-3 if dtype == torch.float16 else 8e-3), (diff.max(), step)
+        assert (diff > 2e-3).mean() < (0.02 if dtype == torch.float16 else 0.2), (diff > 2e-3).mean()
+    assert (np.abs(out - two_pass) > 2e-3).mean() < 0.02
