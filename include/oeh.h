@@ -289,6 +289,40 @@ int oeh_fake_quant_asym_segments(const void* x, void* y, int64_t rows, int32_t s
  * ------------------------------------------------------------------------------------------- */
 int oeh_gelu_erf(const void* x, void* y, int64_t n, int32_t dtype, oeh_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Linear layer with fused epilogue:  y = tap( act( x . w^T + bias ) ),  x (M,K), w (N,K) = nn.Linear.weight, y (M,N),
+ * row strides ldx / ldw / ldy in elements, fp16 / bf16 operands, fp32 accumulation (tcgen05, TMEM accumulators).
+ * Replaces, in one launch:
+ *   - QuantLinear.forward = F.linear -> [fused activation] -> activation_quantizer (quantization/hijacker.py:78-134,
+ *     autoquant_utils.py:18-91; call sites quantized_bert.py:278,300-303,541-606, quantized_opt.py:113-140) with FIXED ranges:
+ *     qparams = HOST array of n_seg (<= 4) device pointers to [scale, zero_point]; n_seg > 1 = equal column segments with their
+ *     own ranges (the fused query|key|value projection, quantized_bert.py:317-330); n_seg = 0 = no tap;
+ *   - HF BertIntermediate: dense -> erf GELU (act = OEH_ACT_GELU_ERF; same evaluation as oeh_gelu_erf), OPT fc1 -> ReLU.
+ * Order of roundings follows the unfused chain: the accumulator + bias is rounded to the tensor dtype (what the GEMM would
+ * have stored), then the activation (rounded again), then the tap.  The tap is tolerance-parity with
+ * `library GEMM -> oeh_fake_quant_asym` (accumulation order moves values across bin edges), like the fused attention taps.
+ * tile_n: 0 = choose (128 / 192 / 256 output columns per CTA tile), else force.  Asynchronous, allocation-free, graph-capturable.
+ * ------------------------------------------------------------------------------------------- */
+enum oeh_activation { OEH_ACT_NONE = 0, OEH_ACT_RELU = 1, OEH_ACT_GELU_ERF = 2 };
+
+typedef struct OehLinearArgs {
+  const void* x;
+  const void* w;
+  const void* bias;            /* (N) of the tensor dtype, 16-byte aligned, or NULL */
+  void* y;
+  int64_t ldx, ldw, ldy;
+  int32_t M, N, K;
+  int32_t dtype;               /* OEH_F16 or OEH_BF16 */
+  int32_t act;                 /* oeh_activation */
+  int32_t n_seg;               /* 0..4 tap segments */
+  int32_t n_bits;
+  int32_t tile_n;
+  const float* qparams[4];     /* device [scale, zero_point] per segment */
+  oeh_stream_t stream;
+} OehLinearArgs;
+
+int oeh_linear_fwd(const OehLinearArgs* args);
+
 #ifdef __cplusplus
 }
 #endif

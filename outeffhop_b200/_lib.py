@@ -35,6 +35,20 @@ class OehAttnArgs(C.Structure):
     ]
 
 
+class OehLinearArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("y", C.c_void_p),
+        ("ldx", C.c_int64), ("ldw", C.c_int64), ("ldy", C.c_int64),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("dtype", C.c_int32), ("act", C.c_int32),
+        ("n_seg", C.c_int32), ("n_bits", C.c_int32), ("tile_n", C.c_int32),
+        ("qparams", C.c_void_p * 4),
+        ("stream", C.c_void_p),
+    ]
+
+
+ACT_NONE, ACT_RELU, ACT_GELU_ERF = 0, 1, 2
+
+
 class OehUnsupported(NotImplementedError):
     """The C layer declined this shape/dtype/branch (OEH_ERR_UNSUPPORTED)."""
 
@@ -94,6 +108,7 @@ SYMBOLS = {
     "oeh_fake_quant_asym_segments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64,
                                                C.c_int64, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "oeh_gelu_erf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "oeh_linear_fwd": (C.c_int, [C.POINTER(OehLinearArgs)]),
 }
 # test-only entry point (not part of the public header)
 _PRIVATE = {

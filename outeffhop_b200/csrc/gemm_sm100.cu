@@ -1,0 +1,435 @@
+// Linear layer with fused epilogue for sm_100a:  Y = tap( act( X . W^T + bias ) )      (X: M x K, W: N x K, both K-major)
+//
+// The reference's QuantLinear quantizes the Linear output inside the same module call (quantization/hijacker.py:78-134,
+// autoquant_utils.py:18-91: F.linear -> [activation] -> activation_quantizer); HF's BertIntermediate applies the erf GELU
+// right behind its dense layer.  As separate kernels each of those is a full extra pass over the (M, N) activation
+// (profiles/r01_launches_int8_opt_step_aa.summary.txt: 24 % of the INT8 OPT step, 12 % GELU in the fp16 BERT step).  Here
+// they run in the TMEM -> register epilogue of a hand-written tcgen05 GEMM:
+//
+//   warp 0       TMA producer: A (128 x 64) and B (BN x 64) k-blocks, SWIZZLE_128B, through a kStages-deep mbarrier ring
+//   warp 1       MMA issuer: tcgen05.mma kind::f16 M128 x N(BN) x K16, fp32 accumulators in TMEM, DOUBLE-BUFFERED
+//                (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1
+//   warps 2..9   epilogue, two warps per TMEM lane quarter (each takes half of the tile's columns): tcgen05.ld 32 columns
+//                -> + bias -> round to the tensor dtype (what the unfused GEMM would have stored) -> ReLU / erf GELU
+//                -> fixed-range fake-quant tap (per-column-segment qparams: the fused q|k|v projection keeps three ranges)
+//                -> 16-bit pack -> swizzled staging tile in shared memory -> TMA store (coalesced, clipped at the edges)
+//   persistent CTAs (one per SM) walk the output tiles with stride gridDim.x.
+//
+// Roofline: tensor pipe, 2 M N K flop per call.  Like the fused attention taps, the epilogue tap is tolerance-parity with
+// `GEMM -> oeh_fake_quant_asym` (accumulation order moves values across bin edges); the standalone quantizer keeps the
+// bit-exact contract.
+#include <cstring>
+#include <mutex>
+#include <set>
+#include <utility>
+
+#include "gelu_math.cuh"
+#include "oeh_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace oeh {
+namespace {
+
+constexpr int BM = 128, BK = 64;
+constexpr int kStageA = BM * BK * 2;                     // 16 KB
+constexpr int kEpiWarps = 8, kThreads = (2 + kEpiWarps) * 32;
+constexpr int kChunk = 32;                               // columns per epilogue step / TMA store box
+constexpr int kOutBuf = BM * kChunk * 2;                 // 8 KB staging tile (128 rows x 64 B, SWIZZLE_64B)
+constexpr int kMaxSeg = 4;
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStageB = BN * BK * 2;
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = BN == 128 ? 6 : 4;
+  static constexpr uint32_t kTmemCols = BN <= 128 ? 256 : 512;          // two accumulators
+  static constexpr int kSmemBytes = kStages * kStage + 4 * kOutBuf + 1024;
+};
+
+struct GemmParams {
+  int M, N, K;
+  int n_mblk, n_nblk, n_kblk;
+  const void* bias;
+  int act;                                               // OEH_ACT_*
+  const float* qp[kMaxSeg];                              // device [scale, zero_point] per column segment (NULL = no tap)
+  int seg_cols;                                          // columns per segment (multiple of the tile width)
+  float int_max;
+};
+
+template <int kStages>
+struct Barriers {
+  uint64_t full[kStages], empty[kStages];
+  uint64_t tmem_full[2], tmem_empty[2];
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <bool kBF16>
+__device__ __forceinline__ uint32_t pack16(float a, float b) {
+  if constexpr (kBF16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+}
+template <bool kBF16>
+__device__ __forceinline__ void unpack16(uint32_t u, float& a, float& b) {
+  if constexpr (kBF16) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+    a = f.x; b = f.y;
+  } else {
+    const float2 f = __half22float2(*reinterpret_cast<__half2*>(&u));
+    a = f.x; b = f.y;
+  }
+}
+
+template <bool kBF16, int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb,
+            const __grid_constant__ CUtensorMap tmy, const __grid_constant__ GemmParams p) {
+  using C = Cfg<BN>;
+  constexpr int kStages = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) Barriers<kStages> bars;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sOut = smem0 + kStages * C::kStage;             // 4 staging tiles of 8 KB (2 per column half)
+  const int n_tiles = p.n_mblk * p.n_nblk;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&bars.full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars.empty[i]), 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&bars.tmem_full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars.tmem_empty[i]), kEpiWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 1) ptx::tmem_alloc<C::kTmemCols>(ptx::smem_u32(&tmem_base_slot));
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ======================================================================
+    if (ptx::elect_one()) {
+      ptx::prefetch_tmap(&tma);
+      ptx::prefetch_tmap(&tmb);
+    }
+    int it = 0;                                                  // k-block counter across tiles -> ring slot / parity
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int m0 = (tile % p.n_mblk) * BM, n0 = (tile / p.n_mblk) * BN;
+      for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
+        const int s = it % kStages, n = it / kStages;
+        if (n > 0) ptx::mbar_wait(ptx::smem_u32(&bars.empty[s]), (uint32_t)(n - 1) & 1u);
+        if (ptx::elect_one()) {
+          const uint32_t bf = ptx::smem_u32(&bars.full[s]);
+          ptx::mbar_expect_tx(bf, C::kStage);
+          tma_load_2d(smem0 + s * C::kStage, &tma, bf, kb * BK, m0);
+          tma_load_2d(smem0 + s * C::kStage + kStageA, &tmb, bf, kb * BK, n0);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ========================================================================
+    constexpr uint32_t kIdesc = ptx::make_idesc_f16(kBF16, BM, BN, false, false);
+    int it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const int acc = ti & 1;
+      if (ti >= 2) ptx::mbar_wait(ptx::smem_u32(&bars.tmem_empty[acc]), (uint32_t)((ti >> 1) - 1) & 1u);
+      ptx::tc_fence_after();
+      for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
+        const int s = it % kStages;
+        ptx::mbar_wait(ptx::smem_u32(&bars.full[s]), (uint32_t)(it / kStages) & 1u);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t a = smem0 + s * C::kStage, b = a + kStageA;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            ptx::mma_ss(tmem + acc * BN, ptx::make_smem_desc_sw128(a + k * 32, 16, 1024),
+                        ptx::make_smem_desc_sw128(b + k * 32, 16, 1024), kIdesc, (kb | k) != 0);
+          ptx::mma_commit(ptx::smem_u32(&bars.empty[s]));          // slot free once these MMAs have read it
+          if (kb + 1 == p.n_kblk) ptx::mma_commit(ptx::smem_u32(&bars.tmem_full[acc]));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================ epilogue: 2 warps per TMEM lane quarter ============================================
+    const int q = warp & 3, part = (warp - 2) >> 2;                // lane quarter; column half
+    const int r = q * 32 + (tid & 31);                             // row within the tile == TMEM lane
+    const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+    const int part_bar = 1 + part;                                 // named barrier of the 4 warps of a column half
+    const bool issuer = (warp == 2 + 4 * part) && (tid & 31) == 0; // the thread that owns this half's TMA stores
+    const uint32_t sBuf = sOut + part * 2 * kOutBuf;
+    const uint32_t row_off = (uint32_t)r * 64u, sw = ((uint32_t)r >> 1) & 3u;   // SWIZZLE_64B: chunk ^= (row / 2) % 4
+    if (warp == 2 && ptx::elect_one()) ptx::prefetch_tmap(&tmy);
+    int ti = 0, chunk_it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const int m0 = (tile % p.n_mblk) * BM, n0 = (tile / p.n_mblk) * BN;
+      const int acc = ti & 1;
+      // per-tile tap parameters (a tile never straddles two column segments: host checks seg_cols % BN == 0)
+      const float* qp = p.seg_cols > 0 ? p.qp[n0 / p.seg_cols] : p.qp[0];
+      float q_scale = 1.f, q_inv = 1.f, q_lo = 0.f, q_hi = 0.f;
+      if (qp) {
+        q_scale = __ldg(qp);
+        const float zp = __ldg(qp + 1);
+        q_inv = __frcp_rn(q_scale);
+        q_lo = -zp;
+        q_hi = p.int_max - zp;
+      }
+      ptx::mbar_wait(ptx::smem_u32(&bars.tmem_full[acc]), (uint32_t)(ti >> 1) & 1u);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 2 / kChunk; ++c, ++chunk_it) {
+        const int col = part * (BN / 2) + c * kChunk;              // column within the tile
+        float v[kChunk];
+        ptx::tmem_ld32(t_lane + acc * BN + col, reinterpret_cast<uint32_t*>(v));
+        ptx::tmem_wait_ld();
+        if (c + 1 == BN / 2 / kChunk) {                            // last read of this accumulator by this warp
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (ptx::elect_one()) ptx::mbar_arrive(ptx::smem_u32(&bars.tmem_empty[acc]));
+        }
+        const int gcol = n0 + col;
+        if (p.bias) {                                              // 32 bias values = 64 B, the same for every lane (broadcast)
+          const uint4* bp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias) + gcol);
+          if (gcol + kChunk <= p.N) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 bv = __ldg(bp + g);
+              const uint32_t w[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float b0, b1;
+                unpack16<kBF16>(w[e], b0, b1);
+                v[g * 8 + 2 * e] += b0;
+                v[g * 8 + 2 * e + 1] += b1;
+              }
+            }
+          } else {                                                 // ragged last column block
+            const uint16_t* bs = reinterpret_cast<const uint16_t*>(p.bias);
+#pragma unroll
+            for (int j = 0; j < kChunk; j += 2) {
+              float b0 = 0.f, b1 = 0.f, d;
+              if (gcol + j < p.N) unpack16<kBF16>((uint32_t)__ldg(bs + gcol + j), b0, d);
+              if (gcol + j + 1 < p.N) unpack16<kBF16>((uint32_t)__ldg(bs + gcol + j + 1), b1, d);
+              v[j] += b0;
+              v[j + 1] += b1;
+            }
+          }
+        }
+        uint32_t pk[kChunk / 2];
+        if (p.act == OEH_ACT_NONE && !qp) {
+#pragma unroll
+          for (int j = 0; j < kChunk / 2; ++j) pk[j] = pack16<kBF16>(v[2 * j], v[2 * j + 1]);
+        } else {
+          // what the unfused path would have stored after the GEMM, then the activation and the tap on that value
+#pragma unroll
+          for (int j = 0; j < kChunk / 2; ++j) unpack16<kBF16>(pack16<kBF16>(v[2 * j], v[2 * j + 1]), v[2 * j], v[2 * j + 1]);
+          if (p.act == OEH_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.act == OEH_ACT_GELU_ERF) {
+#pragma unroll
+            for (int j = 0; j < kChunk; j += 2) {
+              gelu_math::gelu2(v[j], v[j + 1], v[j], v[j + 1]);
+              unpack16<kBF16>(pack16<kBF16>(v[j], v[j + 1]), v[j], v[j + 1]);     // the activation's own 16-bit store
+            }
+          }
+          if (qp) {
+            const uint64_t inv2 = ptx::pack2f(q_inv, q_inv), sc2 = ptx::pack2f(q_scale, q_scale);
+            const uint64_t mg = ptx::pack2f(12582912.f, 12582912.f), nmg = ptx::pack2f(-12582912.f, -12582912.f);
+#pragma unroll
+            for (int j = 0; j < kChunk; j += 2) {
+              float a, b;
+              ptx::unpack2f(ptx::fmul2(ptx::pack2f(v[j], v[j + 1]), inv2), a, b);
+              a = fminf(fmaxf(a, q_lo), q_hi);
+              b = fminf(fmaxf(b, q_lo), q_hi);
+              const uint64_t c2 = ptx::fadd2(ptx::fadd2(ptx::pack2f(a, b), mg), nmg);   // rint, exact for |.| < 2^22
+              ptx::unpack2f(ptx::fmul2(c2, sc2), v[j], v[j + 1]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < kChunk / 2; ++j) pk[j] = pack16<kBF16>(v[2 * j], v[2 * j + 1]);
+        }
+        // staging tile (double-buffered per column half) -> TMA store
+        const uint32_t buf = sBuf + (uint32_t)(chunk_it & 1) * kOutBuf;
+        if (issuer) tma_store_wait_read<1>();                      // the store that last used this buffer has read it
+        asm volatile("bar.sync %0, 128;" ::"r"(part_bar) : "memory");
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          ptx::st_shared_v4(buf + row_off + (((uint32_t)g ^ sw) << 4), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        ptx::fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(part_bar) : "memory");
+        if (issuer) {
+          tma_store_2d(&tmy, buf, gcol, m0);
+          tma_store_commit();
+        }
+      }
+    }
+    if (issuer) tma_store_wait_all();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<C::kTmemCols>(tmem);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      ptr = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(ptr);
+  }();
+  return fn;
+}
+
+// 2-D map over a row-major (rows, cols) 16-bit matrix with row stride ld (elements): dim0 = cols (contiguous)
+int make_map2d(CUtensorMap* tm, const void* base, int dtype, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+               int box_rows, CUtensorMapSwizzle swz, const char* what) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return set_error(OEH_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16 != 0 || ld < cols)
+    return set_error(OEH_ERR_UNSUPPORTED, "oeh_linear_fwd: %s must be 16-byte aligned with a row stride that is a multiple of 8 "
+                     "elements and >= the row length", what);
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult res = enc(tm, dtype == OEH_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                     const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (res != CUDA_SUCCESS)
+    return set_error(OEH_ERR_UNSUPPORTED, "oeh_linear_fwd: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)res);
+  return OEH_OK;
+}
+
+int ensure_smem(const void* fn, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  int dev = 0;
+  OEH_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({dev, fn})) return OEH_OK;
+  OEH_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.insert({dev, fn});
+  return OEH_OK;
+}
+
+template <bool kBF16, int BN>
+int launch(const OehLinearArgs* a, GemmParams& p, int grid_cap) {
+  using C = Cfg<BN>;
+  CUtensorMap tma, tmb, tmy;
+  int rc;
+  if ((rc = make_map2d(&tma, a->x, a->dtype, a->M, a->K, a->ldx, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B, "x"))) return rc;
+  if ((rc = make_map2d(&tmb, a->w, a->dtype, a->N, a->K, a->ldw, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B, "w"))) return rc;
+  if ((rc = make_map2d(&tmy, a->y, a->dtype, a->M, a->N, a->ldy, kChunk, BM, CU_TENSOR_MAP_SWIZZLE_64B, "y"))) return rc;
+  p.n_mblk = (a->M + BM - 1) / BM;
+  p.n_nblk = (a->N + BN - 1) / BN;
+  p.n_kblk = (a->K + BK - 1) / BK;
+  auto fn = gemm_kernel<kBF16, BN>;
+  if ((rc = ensure_smem(reinterpret_cast<const void*>(fn), C::kSmemBytes))) return rc;
+  const long long tiles = (long long)p.n_mblk * p.n_nblk;
+  const int grid = (int)(tiles < grid_cap ? tiles : grid_cap);
+  fn<<<grid, kThreads, C::kSmemBytes, (cudaStream_t)a->stream>>>(tma, tmb, tmy, p);
+  return check_launch("gemm_kernel");
+}
+
+}  // namespace
+}  // namespace oeh
+
+using namespace oeh;
+
+extern "C" int oeh_linear_fwd(const OehLinearArgs* a) {
+  OEH_CHECK_ARG(a, "oeh_linear_fwd: null args");
+  OEH_CHECK_ARG(a->M >= 0 && a->N >= 0 && a->K >= 0, "oeh_linear_fwd: negative dimension");
+  if (a->M == 0 || a->N == 0) return OEH_OK;
+  OEH_CHECK_ARG(a->K > 0, "oeh_linear_fwd: K == 0");
+  OEH_CHECK_ARG(a->x && a->w && a->y, "oeh_linear_fwd: null tensor pointer");
+  if (a->dtype != OEH_F16 && a->dtype != OEH_BF16)
+    return set_error(OEH_ERR_UNSUPPORTED, "oeh_linear_fwd: dtype %d (fp16 / bf16 operands, fp32 accumulate)", a->dtype);
+  OEH_CHECK_ARG(a->act >= OEH_ACT_NONE && a->act <= OEH_ACT_GELU_ERF, "oeh_linear_fwd: unknown activation %d", a->act);
+  OEH_CHECK_ARG(a->n_seg >= 0 && a->n_seg <= kMaxSeg, "oeh_linear_fwd: n_seg=%d outside [0,%d]", a->n_seg, kMaxSeg);
+  if (a->n_seg > 0 && (a->n_bits < 1 || a->n_bits > 16))
+    return set_error(OEH_ERR_BAD_ARG, "oeh_linear_fwd: n_bits=%d outside [1,16]", a->n_bits);
+  if (a->bias && (reinterpret_cast<uintptr_t>(a->bias) & 15))
+    return set_error(OEH_ERR_UNSUPPORTED, "oeh_linear_fwd: bias must be 16-byte aligned");
+  if (a->N % 8 != 0) return set_error(OEH_ERR_UNSUPPORTED, "oeh_linear_fwd: N must be a multiple of 8");
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.bias = a->bias;
+  p.act = a->act;
+  p.int_max = (float)((1 << (a->n_bits > 0 ? a->n_bits : 8)) - 1);
+  for (int i = 0; i < a->n_seg; ++i) {
+    OEH_CHECK_ARG(a->qparams[i], "oeh_linear_fwd: null qparams[%d]", i);
+    p.qp[i] = a->qparams[i];
+  }
+  int seg_cols = 0;
+  if (a->n_seg > 1) {
+    if (a->N % a->n_seg) return set_error(OEH_ERR_BAD_ARG, "oeh_linear_fwd: N=%d is not divisible into %d segments", a->N, a->n_seg);
+    seg_cols = a->N / a->n_seg;
+  }
+  p.seg_cols = seg_cols;
+
+  // tile width: fewest rounds x width over the SMs; a tile must not straddle two tap segments
+  const int sms = num_sms();
+  const int widths[3] = {256, 192, 128};
+  int best = 0;
+  double best_cost = 1e30;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = widths[i];
+    if (seg_cols && seg_cols % bn) continue;
+    const long long tiles = (long long)((a->M + BM - 1) / BM) * ((a->N + bn - 1) / bn);
+    const double cost = (double)((tiles + sms - 1) / sms) * bn;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  if (a->tile_n == 128 || a->tile_n == 192 || a->tile_n == 256) {
+    if (seg_cols && seg_cols % a->tile_n)
+      return set_error(OEH_ERR_BAD_ARG, "oeh_linear_fwd: tile_n=%d does not divide the segment width %d", a->tile_n, seg_cols);
+    best = a->tile_n;
+  }
+  if (!best) return set_error(OEH_ERR_UNSUPPORTED, "oeh_linear_fwd: segment width %d is not a multiple of 128", seg_cols);
+  const bool bf = a->dtype == OEH_BF16;
+  switch (best) {
+    case 256: return bf ? launch<true, 256>(a, p, sms) : launch<false, 256>(a, p, sms);
+    case 192: return bf ? launch<true, 192>(a, p, sms) : launch<false, 192>(a, p, sms);
+    default: return bf ? launch<true, 128>(a, p, sms) : launch<false, 128>(a, p, sms);
+  }
+}

@@ -159,12 +159,37 @@ def _is_erf_gelu(act) -> bool:
     return type(act).__name__ == "GELUActivation" and getattr(act, "act", None) is torch.nn.functional.gelu
 
 
+class BertIntermediateFused(torch.nn.Module):
+    """HF ``BertIntermediate`` (dense -> erf GELU; the pair the reference hands to ``quantize_intermediate``,
+    quantized_bert.py:609-617) as ONE launch: the GELU runs in the epilogue of the library's tcgen05 GEMM (``oeh_linear_fwd``)
+    for 16-bit CUDA tensors in eval; anything else (training graphs, fp32, hooks on either submodule) runs the two modules.
+    Same submodule names (``dense``, ``intermediate_act_fn``)."""
+
+    def __init__(self, org):
+        super().__init__()
+        self.dense, self.intermediate_act_fn = org.dense, org.intermediate_act_fn
+
+    def forward(self, hidden_states):
+        d, act = self.dense, self.intermediate_act_fn
+        if (not self.training and hidden_states.is_cuda and hidden_states.dtype in (torch.float16, torch.bfloat16)
+                and type(d) is torch.nn.Linear and d.weight.dtype == hidden_states.dtype and isinstance(act, GELUFused)
+                and not (torch.is_grad_enabled() and (hidden_states.requires_grad or d.weight.requires_grad))
+                and not any(m._forward_hooks or m._forward_pre_hooks for m in (d, act))
+                and d.out_features % 8 == 0 and d.in_features % 8 == 0):
+            from . import ops
+            return ops.linear_fwd(hidden_states, d.weight, d.bias, act="gelu")
+        return act(d(hidden_states))
+
+
 def fuse_bert_gelu(model):
-    """Swap the erf-GELU activation of every ``layer.intermediate`` for :class:`GELUFused` (other activations stay)."""
+    """Swap the erf-GELU activation of every ``layer.intermediate`` for :class:`GELUFused` (other activations stay) and the
+    ``BertIntermediate`` module itself for :class:`BertIntermediateFused` (dense + GELU in one GEMM launch)."""
     bert = getattr(model, "bert", model)
     for layer in bert.encoder.layer:
         if _is_erf_gelu(layer.intermediate.intermediate_act_fn):
             layer.intermediate.intermediate_act_fn = GELUFused().train(layer.training)
+            if not isinstance(layer.intermediate, BertIntermediateFused):
+                layer.intermediate = BertIntermediateFused(layer.intermediate).train(layer.training)
     return model
 
 

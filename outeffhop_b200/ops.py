@@ -417,3 +417,43 @@ def fake_quant_asym_segments(x: torch.Tensor, qparams, n_bits: int = 8, out: Opt
     L.check(L.lib().oeh_fake_quant_asym_segments(xc.data_ptr(), y.data_ptr(), rows, cols // n_seg, n_seg, cols, cols,
                                                  _dtype_code(xc), ptrs, int(n_bits), _stream()))
     return y
+
+
+def linear_fwd(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: str = "none",
+               qparams=None, n_bits: int = 8, out: Optional[torch.Tensor] = None, tile_n: int = 0) -> torch.Tensor:
+    """``tap(act(x @ weight.T + bias))`` in ONE tcgen05 GEMM launch (oeh_linear_fwd).  x: (..., K) fp16 / bf16 with a contiguous
+    last dim, weight: (N, K) (nn.Linear layout), bias: (N) or None.  ``act``: "none" | "relu" | "gelu" (erf form).
+    ``qparams``: None, one device tensor [scale, zero_point] (a frozen output tap) or a list of up to 4 of them (equal column
+    segments with their own ranges -- the fused q|k|v projection)."""
+    _require_cuda(x, weight, bias)
+    if x.dtype not in (torch.float16, torch.bfloat16) or weight.dtype != x.dtype or (bias is not None and bias.dtype != x.dtype):
+        raise TypeError("linear_fwd: x, weight and bias must share one 16-bit dtype")
+    K = x.shape[-1]
+    N = weight.shape[0]
+    if weight.dim() != 2 or weight.shape[1] != K:
+        raise ValueError(f"linear_fwd: weight {tuple(weight.shape)} does not match x (..., {K})")
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    w = weight if weight.stride(-1) == 1 else weight.contiguous()
+    M = x2.shape[0]
+    y = out if out is not None else torch.empty((M, N), dtype=x.dtype, device=x.device)
+    if y.shape[-1] != N or y.numel() != M * N or y.stride(-1) != 1:
+        raise ValueError("linear_fwd: out must be an (M, N) tensor with a contiguous last dim")
+    y2 = y.view(-1, N) if y.dim() != 2 else y
+    a = L.OehLinearArgs()
+    a.x, a.w, a.y = x2.data_ptr(), w.data_ptr(), y2.data_ptr()
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.ldx, a.ldw, a.ldy = x2.stride(0) if M > 1 else K, w.stride(0), y2.stride(0) if M > 1 else N
+    a.M, a.N, a.K = M, N, K
+    a.dtype = _dtype_code(x)
+    a.act = {"none": L.ACT_NONE, "relu": L.ACT_RELU, "gelu": L.ACT_GELU_ERF}[act]
+    qs = [] if qparams is None else ([qparams] if torch.is_tensor(qparams) else list(qparams))
+    for i, t in enumerate(qs):
+        if t.dtype != torch.float32 or t.numel() < 2 or not t.is_cuda:
+            raise ValueError("linear_fwd: qparams must be CUDA fp32 tensors [scale, zero_point]")
+        a.qparams[i] = t.data_ptr()
+    a.n_seg, a.n_bits, a.tile_n = len(qs), int(n_bits), int(tile_n)
+    a.stream = _stream()
+    L.check(L.lib().oeh_linear_fwd(C.byref(a)))
+    return y if out is not None else y.view(*x.shape[:-1], N)

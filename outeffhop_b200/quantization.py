@@ -910,11 +910,31 @@ class QuantLinear(QuantizedModule, nn.Linear):
             self.cached_params = (weight.detach().clone(), bias.detach().clone() if bias is not None else None)
         return weight, bias
 
+    def _fused_gemm_act(self, x, weight):
+        """The activation name for ``ops.linear_fwd`` when this call can run on the library's own tcgen05 GEMM (16-bit CUDA
+        eval call, no observers on the fused activation), else None."""
+        act = self.activation_function
+        if (self.training or not x.is_cuda or x.dtype not in (torch.float16, torch.bfloat16) or weight.dtype != x.dtype
+                or torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad) or weight.shape[0] % 8
+                or x.shape[-1] % 8):
+            return None
+        if act is None:
+            return "none"
+        if act._forward_hooks or act._forward_pre_hooks:
+            return None
+        if isinstance(act, nn.ReLU):
+            return "relu"
+        if isinstance(act, nn.GELU) and act.approximate == "none":
+            return "gelu"
+        return None
+
     def linear_only(self, x):
         """The layer WITHOUT its output tap (cached fake-quantized weight, optional fused activation): for callers that
         fold the tap into the next kernel (``tap_fusable`` / ``tap_qparams``)."""
         weight, bias = self.get_params()
         act = self.activation_function
+        if isinstance(act, nn.GELU) and self._fused_gemm_act(x, weight) == "gelu":
+            return ops.linear_fwd(x, weight, bias, act="gelu")        # dense -> erf GELU in the GEMM epilogue
         if isinstance(act, nn.ReLU) and bias is not None and x.is_cuda and x.dtype == weight.dtype \
                 and not torch.is_grad_enabled() and not act._forward_hooks and not act._forward_pre_hooks:
             # eval: bias + ReLU in the GEMM epilogue (one cuBLASLt call; max(., 0) of the same accumulator is exact)
@@ -938,6 +958,15 @@ class QuantLinear(QuantizedModule, nn.Linear):
         return self.activation_quantizer.quantizer.qparams if self._qa_host else None
 
     def forward(self, x, offsets=None):
+        if self._qa_host and self.tap_fusable:
+            # frozen output tap: F.linear -> [activation] -> activation_quantizer (hijacker.py:78-134) as ONE GEMM launch with
+            # the tap in its epilogue.  Measured against cuBLASLt + separate kernels (profiles/r02_gemm_*.jsonl): ahead for
+            # wide outputs and whenever an activation is fused; narrow K-heavy layers keep the library GEMM.
+            weight, bias = self.get_params()
+            act = self._fused_gemm_act(x, weight)
+            if act is not None and (act != "none" or weight.shape[0] >= 1536):
+                return ops.linear_fwd(x, weight, bias, act=act, qparams=self.tap_qparams(),
+                                      n_bits=self.activation_quantizer.n_bits)
         res = self.linear_only(x)
         if self._qa_host:
             res = self.activation_quantizer(res)

@@ -114,9 +114,16 @@ def quantized_fused_qkv(owner: nn.Module, mods, hidden_states: torch.Tensor, num
             b = None if params[0][1] is None else torch.cat([b for _, b in params], dim=0)
         cache = (key, w, b, params)                           # `params` keeps the keyed tensors alive
         owner.__dict__["_qkv_cache"] = cache
-    y = nn.functional.linear(hidden_states, cache[1], cache[2])
-    if all(active):
-        y = ops.fake_quant_asym_segments(y, [m.tap_qparams() for m in mods], mods[0].activation_quantizer.n_bits)
+    seg = cache[1].shape[0] // 3
+    if (all(active) and hidden_states.dtype in (torch.float16, torch.bfloat16) and cache[1].dtype == hidden_states.dtype
+            and seg % 128 == 0 and hidden_states.shape[-1] % 8 == 0 and not torch.is_grad_enabled()):
+        # the three projections AND their three taps in one GEMM launch (per-segment ranges in the epilogue)
+        y = ops.linear_fwd(hidden_states, cache[1], cache[2], qparams=[m.tap_qparams() for m in mods],
+                           n_bits=mods[0].activation_quantizer.n_bits)
+    else:
+        y = nn.functional.linear(hidden_states, cache[1], cache[2])
+        if all(active):
+            y = ops.fake_quant_asym_segments(y, [m.tap_qparams() for m in mods], mods[0].activation_quantizer.n_bits)
     B, T = y.shape[0], y.shape[1]
     y = y.view(B, T, 3, num_heads, head_dim)
     return tuple(y[:, :, j].permute(0, 2, 1, 3) for j in range(3))
