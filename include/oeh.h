@@ -301,7 +301,8 @@ int oeh_gelu_erf(const void* x, void* y, int64_t n, int32_t dtype, oeh_stream_t 
  * Order of roundings follows the unfused chain: the accumulator + bias is rounded to the tensor dtype (what the GEMM would
  * have stored), then the activation (rounded again), then the tap.  The tap is tolerance-parity with
  * `library GEMM -> oeh_fake_quant_asym` (accumulation order moves values across bin edges), like the fused attention taps.
- * tile_n: 0 = choose (128 / 192 / 256 output columns per CTA tile), else force.  Asynchronous, allocation-free, graph-capturable.
+ * tile_n: 0 = choose; 128 / 256 = single-CTA tiles of 128 rows x that many columns; 2128 / 2256 = CTA pairs
+ * (tcgen05 cta_group::2) on 256 x 128 / 256 x 256 tiles.  Asynchronous, allocation-free, graph-capturable.
  * ------------------------------------------------------------------------------------------- */
 enum oeh_activation { OEH_ACT_NONE = 0, OEH_ACT_RELU = 1, OEH_ACT_GELU_ERF = 2 };
 

@@ -9,11 +9,18 @@
 //   warp 0       TMA producer: A (128 x 64) and B (BN x 64) k-blocks, SWIZZLE_128B, through a kStages-deep mbarrier ring
 //   warp 1       MMA issuer: tcgen05.mma kind::f16 M128 x N(BN) x K16, fp32 accumulators in TMEM, DOUBLE-BUFFERED
 //                (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1
-//   warps 2..9   epilogue, two warps per TMEM lane quarter (each takes half of the tile's columns): tcgen05.ld 32 columns
+//   warps 2..17  epilogue, FOUR warps per TMEM lane quarter (each takes a quarter of the tile's columns; with two the erf GELU
+//                was latency-bound: 26.8 -> 23.9 us at 4096 x 3072 x 768, profiles/r02_gemm_epilogue_*.txt): tcgen05.ld 32 columns
 //                -> + bias -> round to the tensor dtype (what the unfused GEMM would have stored) -> ReLU / erf GELU
 //                -> fixed-range fake-quant tap (per-column-segment qparams: the fused q|k|v projection keeps three ranges)
 //                -> 16-bit pack -> swizzled staging tile in shared memory -> TMA store (coalesced, clipped at the edges)
 //   persistent CTAs (one per SM) walk the output tiles with stride gridDim.x.
+//
+// kCta2 = true: the CTA-PAIR form (cta_group::2, clusters of two CTAs on one TPC).  The pair computes a 256 x BN tile: each
+// CTA loads its own 128 rows of A and HALF of the B tile (BN/2 rows), the leader CTA issues tcgen05.mma.cta_group::2
+// (M = 256) which reads both halves of B, and every CTA finishes its own 128 accumulator rows.  Per CTA and k-block that is
+// 32 KB through L2 and shared memory instead of 48 KB: the single-CTA form is bound by exactly that traffic (operands
+// written by TMA and read back by the tensor core: 96 + 96 B/clk against a 128 B/clk shared-memory port).
 //
 // Roofline: tensor pipe, 2 M N K flop per call.  Like the fused attention taps, the epilogue tap is tolerance-parity with
 // `GEMM -> oeh_fake_quant_asym` (accumulation order moves values across bin edges); the standalone quantizer keeps the
@@ -32,18 +39,22 @@ namespace {
 
 constexpr int BM = 128, BK = 64;
 constexpr int kStageA = BM * BK * 2;                     // 16 KB
-constexpr int kEpiWarps = 8, kThreads = (2 + kEpiWarps) * 32;
+#ifndef OEH_GEMM_EPI_WARPS
+#define OEH_GEMM_EPI_WARPS 16
+#endif
+constexpr int kEpiWarps = OEH_GEMM_EPI_WARPS, kParts = kEpiWarps / 4, kThreads = (2 + kEpiWarps) * 32;   // kParts column parts x 4 lane quarters
 constexpr int kChunk = 32;                               // columns per epilogue step / TMA store box
 constexpr int kOutBuf = BM * kChunk * 2;                 // 8 KB staging tile (128 rows x 64 B, SWIZZLE_64B)
 constexpr int kMaxSeg = 4;
 
-template <int BN>
+template <int BN, bool kCta2>
 struct Cfg {
-  static constexpr int kStageB = BN * BK * 2;
+  static constexpr int kStageB = (kCta2 ? BN / 2 : BN) * BK * 2;        // rows of B this CTA loads per k-block
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = BN == 128 ? 6 : 4;
+  static constexpr int kRing = 226 * 1024 - 2 * kParts * kOutBuf;       // what the staging tiles leave of 227 KB
+  static constexpr int kStages = kRing / kStage > 8 ? 8 : kRing / kStage;
   static constexpr uint32_t kTmemCols = BN <= 128 ? 256 : 512;          // two accumulators
-  static constexpr int kSmemBytes = kStages * kStage + 4 * kOutBuf + 1024;
+  static constexpr int kSmemBytes = kStages * kStage + 2 * kParts * kOutBuf + 1024;
 };
 
 struct GemmParams {
@@ -54,6 +65,7 @@ struct GemmParams {
   const float* qp[kMaxSeg];                              // device [scale, zero_point] per column segment (NULL = no tap)
   int seg_cols;                                          // columns per segment (multiple of the tile width)
   float int_max;
+  int dbg;                                               // timing experiments (tile_n / 10000): 1 = no output stores
 };
 
 template <int kStages>
@@ -79,6 +91,47 @@ __device__ __forceinline__ void tma_store_wait_read() {
 }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) forms -----------------------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;            // shared::cluster address of the same offset in the EVEN CTA of a pair
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_result) {   // one warp of EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "n"(kCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void mma_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// all MMAs issued so far by this thread arrive (when complete) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+// the bytes land in THIS CTA's shared memory, the transaction count goes to the leader's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {        // arrive on the leader CTA's barrier (own, if leader)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+
 template <bool kBF16>
 __device__ __forceinline__ uint32_t pack16(float a, float b) {
   if constexpr (kBF16) {
@@ -100,11 +153,11 @@ __device__ __forceinline__ void unpack16(uint32_t u, float& a, float& b) {
   }
 }
 
-template <bool kBF16, int BN>
+template <bool kBF16, int BN, bool kCta2>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb,
             const __grid_constant__ CUtensorMap tmy, const __grid_constant__ GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, kCta2>;
   constexpr int kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) Barriers<kStages> bars;
@@ -113,25 +166,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sOut = smem0 + kStages * C::kStage;             // 4 staging tiles of 8 KB (2 per column half)
-  const int n_tiles = p.n_mblk * p.n_nblk;
+  // work items: output tiles (single CTA) or 256-row tile pairs (CTA pair: rank r takes rows [256 i + 128 r, +128))
+  const int rank = kCta2 ? (int)cluster_ctarank() : 0;
+  const int n_mitems = kCta2 ? (p.n_mblk + 1) / 2 : p.n_mblk;
+  const int n_items = n_mitems * p.n_nblk;
+  const int item0 = kCta2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_stride = kCta2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto tile_m0 = [&](int item) { return ((item % n_mitems) * (kCta2 ? 2 : 1) + rank) * BM; };
+  auto tile_n0 = [&](int item) { return (item / n_mitems) * BN; };
 
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < kStages; ++i) {
-      ptx::mbar_init(ptx::smem_u32(&bars.full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars.full[i]), kCta2 ? 2 : 1);      // pair: one arrival from each CTA's producer
       ptx::mbar_init(ptx::smem_u32(&bars.empty[i]), 1);
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(ptx::smem_u32(&bars.tmem_full[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars.tmem_empty[i]), kEpiWarps);
+      ptx::mbar_init(ptx::smem_u32(&bars.tmem_empty[i]), kCta2 ? 2 * kEpiWarps : kEpiWarps);
     }
     ptx::fence_mbar_init();
   }
   __syncwarp();
-  if (warp == 1) ptx::tmem_alloc<C::kTmemCols>(ptx::smem_u32(&tmem_base_slot));
+  if (warp == 1) {
+    if constexpr (kCta2) tmem_alloc_pair<C::kTmemCols>(ptx::smem_u32(&tmem_base_slot));
+    else ptx::tmem_alloc<C::kTmemCols>(ptx::smem_u32(&tmem_base_slot));
+  }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (kCta2) cluster_sync_all();        // the peer's barriers are initialised before anything is sent to them
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
 
@@ -142,47 +206,64 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
       ptx::prefetch_tmap(&tmb);
     }
     int it = 0;                                                  // k-block counter across tiles -> ring slot / parity
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int m0 = (tile % p.n_mblk) * BM, n0 = (tile / p.n_mblk) * BN;
+    for (int item = item0; item < n_items; item += item_stride) {
+      const int m0 = tile_m0(item), n0 = tile_n0(item);
       for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
         const int s = it % kStages, n = it / kStages;
         if (n > 0) ptx::mbar_wait(ptx::smem_u32(&bars.empty[s]), (uint32_t)(n - 1) & 1u);
         if (ptx::elect_one()) {
           const uint32_t bf = ptx::smem_u32(&bars.full[s]);
-          ptx::mbar_expect_tx(bf, C::kStage);
-          tma_load_2d(smem0 + s * C::kStage, &tma, bf, kb * BK, m0);
-          tma_load_2d(smem0 + s * C::kStage + kStageA, &tmb, bf, kb * BK, n0);
+          if constexpr (kCta2) {
+            // both CTAs' bytes are counted on the LEADER's barrier; the leader announces them, the other CTA just arrives
+            if (rank == 0) ptx::mbar_expect_tx(bf, 2 * C::kStage);
+            else mbar_arrive_leader(bf);
+            tma_load_2d_pair(smem0 + s * C::kStage, &tma, bf, kb * BK, m0);
+            tma_load_2d_pair(smem0 + s * C::kStage + kStageA, &tmb, bf, kb * BK, n0 + rank * (BN / 2));
+          } else {
+            ptx::mbar_expect_tx(bf, C::kStage);
+            tma_load_2d(smem0 + s * C::kStage, &tma, bf, kb * BK, m0);
+            tma_load_2d(smem0 + s * C::kStage + kStageA, &tmb, bf, kb * BK, n0);
+          }
         }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ========================================================================
-    constexpr uint32_t kIdesc = ptx::make_idesc_f16(kBF16, BM, BN, false, false);
+    constexpr uint32_t kIdesc = ptx::make_idesc_f16(kBF16, kCta2 ? 2 * BM : BM, BN, false, false);
     int it = 0, ti = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-      const int acc = ti & 1;
-      if (ti >= 2) ptx::mbar_wait(ptx::smem_u32(&bars.tmem_empty[acc]), (uint32_t)((ti >> 1) - 1) & 1u);
-      ptx::tc_fence_after();
-      for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
-        const int s = it % kStages;
-        ptx::mbar_wait(ptx::smem_u32(&bars.full[s]), (uint32_t)(it / kStages) & 1u);
+    if (!kCta2 || rank == 0) {                                   // pair: the leader issues for both CTAs
+      for (int item = item0; item < n_items; item += item_stride, ++ti) {
+        const int acc = ti & 1;
+        if (ti >= 2) ptx::mbar_wait(ptx::smem_u32(&bars.tmem_empty[acc]), (uint32_t)((ti >> 1) - 1) & 1u);
         ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint32_t a = smem0 + s * C::kStage, b = a + kStageA;
+        for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
+          const int s = it % kStages;
+          ptx::mbar_wait(ptx::smem_u32(&bars.full[s]), (uint32_t)(it / kStages) & 1u);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t a = smem0 + s * C::kStage, b = a + kStageA;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            ptx::mma_ss(tmem + acc * BN, ptx::make_smem_desc_sw128(a + k * 32, 16, 1024),
-                        ptx::make_smem_desc_sw128(b + k * 32, 16, 1024), kIdesc, (kb | k) != 0);
-          ptx::mma_commit(ptx::smem_u32(&bars.empty[s]));          // slot free once these MMAs have read it
-          if (kb + 1 == p.n_kblk) ptx::mma_commit(ptx::smem_u32(&bars.tmem_full[acc]));
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = ptx::make_smem_desc_sw128(a + k * 32, 16, 1024), db = ptx::make_smem_desc_sw128(b + k * 32, 16, 1024);
+              if constexpr (kCta2) mma_ss_pair(tmem + acc * BN, da, db, kIdesc, (kb | k) != 0);
+              else ptx::mma_ss(tmem + acc * BN, da, db, kIdesc, (kb | k) != 0);
+            }
+            if constexpr (kCta2) {
+              mma_commit_pair(ptx::smem_u32(&bars.empty[s]));    // frees the slot in BOTH CTAs
+              if (kb + 1 == p.n_kblk) mma_commit_pair(ptx::smem_u32(&bars.tmem_full[acc]));
+            } else {
+              ptx::mma_commit(ptx::smem_u32(&bars.empty[s]));    // slot free once these MMAs have read it
+              if (kb + 1 == p.n_kblk) ptx::mma_commit(ptx::smem_u32(&bars.tmem_full[acc]));
+            }
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else {
     // ================================ epilogue: 2 warps per TMEM lane quarter ============================================
-    const int q = warp & 3, part = (warp - 2) >> 2;                // lane quarter; column half
+    const int q = warp & 3, part = (warp - 2) >> 2;                // lane quarter; column part
     const int r = q * 32 + (tid & 31);                             // row within the tile == TMEM lane
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
     const int part_bar = 1 + part;                                 // named barrier of the 4 warps of a column half
@@ -191,8 +272,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
     const uint32_t row_off = (uint32_t)r * 64u, sw = ((uint32_t)r >> 1) & 3u;   // SWIZZLE_64B: chunk ^= (row / 2) % 4
     if (warp == 2 && ptx::elect_one()) ptx::prefetch_tmap(&tmy);
     int ti = 0, chunk_it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-      const int m0 = (tile % p.n_mblk) * BM, n0 = (tile / p.n_mblk) * BN;
+    for (int item = item0; item < n_items; item += item_stride, ++ti) {
+      const int m0 = tile_m0(item), n0 = tile_n0(item);
       const int acc = ti & 1;
       // per-tile tap parameters (a tile never straddles two column segments: host checks seg_cols % BN == 0)
       const float* qp = p.seg_cols > 0 ? p.qp[n0 / p.seg_cols] : p.qp[0];
@@ -207,15 +288,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
       ptx::mbar_wait(ptx::smem_u32(&bars.tmem_full[acc]), (uint32_t)(ti >> 1) & 1u);
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 2 / kChunk; ++c, ++chunk_it) {
-        const int col = part * (BN / 2) + c * kChunk;              // column within the tile
+      for (int c = 0; c < BN / kParts / kChunk; ++c, ++chunk_it) {
+        const int col = part * (BN / kParts) + c * kChunk;              // column within the tile
         float v[kChunk];
         ptx::tmem_ld32(t_lane + acc * BN + col, reinterpret_cast<uint32_t*>(v));
         ptx::tmem_wait_ld();
-        if (c + 1 == BN / 2 / kChunk) {                            // last read of this accumulator by this warp
+        if (c + 1 == BN / kParts / kChunk) {                            // last read of this accumulator by this warp
           ptx::tc_fence_before();
           __syncwarp();
-          if (ptx::elect_one()) ptx::mbar_arrive(ptx::smem_u32(&bars.tmem_empty[acc]));
+          if (ptx::elect_one()) {
+            if constexpr (kCta2) mbar_arrive_leader(ptx::smem_u32(&bars.tmem_empty[acc]));   // the leader's issuer waits for both CTAs
+            else ptx::mbar_arrive(ptx::smem_u32(&bars.tmem_empty[acc]));
+          }
         }
         const int gcol = n0 + col;
         if (p.bias) {                                              // 32 bias values = 64 B, the same for every lane (broadcast)
@@ -279,6 +363,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
 #pragma unroll
           for (int j = 0; j < kChunk / 2; ++j) pk[j] = pack16<kBF16>(v[2 * j], v[2 * j + 1]);
         }
+        if (p.dbg & 1) continue;
         // staging tile (double-buffered per column half) -> TMA store
         const uint32_t buf = sBuf + (uint32_t)(chunk_it & 1) * kOutBuf;
         if (issuer) tma_store_wait_read<1>();                      // the store that last used this buffer has read it
@@ -299,7 +384,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<C::kTmemCols>(tmem);
+  if constexpr (kCta2) cluster_sync_all();        // nobody leaves while the peer may still signal its barriers / read its TMEM
+  if (warp == 1) {
+    if constexpr (kCta2) tmem_dealloc_pair<C::kTmemCols>(tmem);
+    else ptx::tmem_dealloc<C::kTmemCols>(tmem);
+  }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
@@ -351,22 +440,40 @@ int ensure_smem(const void* fn, int bytes) {
   return OEH_OK;
 }
 
-template <bool kBF16, int BN>
+template <bool kBF16, int BN, bool kCta2>
 int launch(const OehLinearArgs* a, GemmParams& p, int grid_cap) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, kCta2>;
   CUtensorMap tma, tmb, tmy;
   int rc;
   if ((rc = make_map2d(&tma, a->x, a->dtype, a->M, a->K, a->ldx, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B, "x"))) return rc;
-  if ((rc = make_map2d(&tmb, a->w, a->dtype, a->N, a->K, a->ldw, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B, "w"))) return rc;
+  if ((rc = make_map2d(&tmb, a->w, a->dtype, a->N, a->K, a->ldw, BK, kCta2 ? BN / 2 : BN, CU_TENSOR_MAP_SWIZZLE_128B, "w")))
+    return rc;
   if ((rc = make_map2d(&tmy, a->y, a->dtype, a->M, a->N, a->ldy, kChunk, BM, CU_TENSOR_MAP_SWIZZLE_64B, "y"))) return rc;
   p.n_mblk = (a->M + BM - 1) / BM;
   p.n_nblk = (a->N + BN - 1) / BN;
   p.n_kblk = (a->K + BK - 1) / BK;
-  auto fn = gemm_kernel<kBF16, BN>;
+  auto fn = gemm_kernel<kBF16, BN, kCta2>;
   if ((rc = ensure_smem(reinterpret_cast<const void*>(fn), C::kSmemBytes))) return rc;
-  const long long tiles = (long long)p.n_mblk * p.n_nblk;
-  const int grid = (int)(tiles < grid_cap ? tiles : grid_cap);
-  fn<<<grid, kThreads, C::kSmemBytes, (cudaStream_t)a->stream>>>(tma, tmb, tmy, p);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  if (kCta2) {
+    const long long items = (long long)((p.n_mblk + 1) / 2) * p.n_nblk;
+    const long long pairs = items < grid_cap / 2 ? items : grid_cap / 2;
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    const long long tiles = (long long)p.n_mblk * p.n_nblk;
+    cfg.gridDim = dim3((unsigned)(tiles < grid_cap ? tiles : grid_cap));
+  }
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = (cudaStream_t)a->stream;
+  OEH_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, tma, tmb, tmy, p));
   return check_launch("gemm_kernel");
 }
 
@@ -408,28 +515,40 @@ extern "C" int oeh_linear_fwd(const OehLinearArgs* a) {
   }
   p.seg_cols = seg_cols;
 
-  // tile width: fewest rounds x width over the SMs; a tile must not straddle two tap segments
+  // Tile shape: fewest rounds x width over the SMs; a tile must not straddle two tap segments.  The CTA-pair form
+  // (256 x BN per pair) moves a third less data per flop and is preferred whenever it fills the machine as well.
+  // tile_n: 0 = choose; 128 / 256 = single-CTA tiles of that width; 2256 / 2128 = CTA pairs, 256 x 256 / 256 x 128.
   const int sms = num_sms();
-  const int widths[3] = {256, 192, 128};
-  int best = 0;
+  struct Shape { int bn; bool pair; };
+  constexpr int kShapes = 4;
+  const Shape shapes[kShapes] = {{256, true}, {128, true}, {256, false}, {128, false}};
+  int best = -1;
   double best_cost = 1e30;
-  for (int i = 0; i < 3; ++i) {
-    const int bn = widths[i];
+  for (int i = 0; i < kShapes; ++i) {
+    const int bn = shapes[i].bn;
     if (seg_cols && seg_cols % bn) continue;
-    const long long tiles = (long long)((a->M + BM - 1) / BM) * ((a->N + bn - 1) / bn);
-    const double cost = (double)((tiles + sms - 1) / sms) * bn;
-    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+    const long long mi = shapes[i].pair ? ((a->M + 2 * BM - 1) / (2 * BM)) : ((a->M + BM - 1) / BM);
+    const long long items = mi * ((a->N + bn - 1) / bn);
+    const long long slots = shapes[i].pair ? sms / 2 : sms;
+    // time ~ rounds x (work per CTA per item) x (bytes-per-flop penalty of the single-CTA form)
+    const double cost = (double)((items + slots - 1) / slots) * bn * (shapes[i].pair ? 1.0 : 1.3);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = i; }
   }
-  if (a->tile_n == 128 || a->tile_n == 192 || a->tile_n == 256) {
-    if (seg_cols && seg_cols % a->tile_n)
+  p.dbg = a->tile_n / 10000;
+  if (a->tile_n % 10000 != 0) {
+    best = -1;
+    for (int i = 0; i < kShapes; ++i)
+      if (a->tile_n % 10000 == shapes[i].bn + (shapes[i].pair ? 2000 : 0)) best = i;
+    if (best < 0) return set_error(OEH_ERR_BAD_ARG, "oeh_linear_fwd: tile_n=%d (0, 128, 256, 2128, 2256)", a->tile_n);
+    if (seg_cols && seg_cols % shapes[best].bn)
       return set_error(OEH_ERR_BAD_ARG, "oeh_linear_fwd: tile_n=%d does not divide the segment width %d", a->tile_n, seg_cols);
-    best = a->tile_n;
   }
-  if (!best) return set_error(OEH_ERR_UNSUPPORTED, "oeh_linear_fwd: segment width %d is not a multiple of 128", seg_cols);
+  if (best < 0) return set_error(OEH_ERR_UNSUPPORTED, "oeh_linear_fwd: segment width %d is not a multiple of 128", seg_cols);
   const bool bf = a->dtype == OEH_BF16;
   switch (best) {
-    case 256: return bf ? launch<true, 256>(a, p, sms) : launch<false, 256>(a, p, sms);
-    case 192: return bf ? launch<true, 192>(a, p, sms) : launch<false, 192>(a, p, sms);
-    default: return bf ? launch<true, 128>(a, p, sms) : launch<false, 128>(a, p, sms);
+    case 0: return bf ? launch<true, 256, true>(a, p, sms) : launch<false, 256, true>(a, p, sms);
+    case 1: return bf ? launch<true, 128, true>(a, p, sms) : launch<false, 128, true>(a, p, sms);
+    case 2: return bf ? launch<true, 256, false>(a, p, sms) : launch<false, 256, false>(a, p, sms);
+    default: return bf ? launch<true, 128, false>(a, p, sms) : launch<false, 128, false>(a, p, sms);
   }
 }

@@ -47,7 +47,7 @@ def _ulp(ref, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
-@pytest.mark.parametrize("tile_n", [0, 128, 192, 256])
+@pytest.mark.parametrize("tile_n", [0, 128, 256, 2128, 2256])   # 2xxx: CTA pairs (cta_group::2)
 @pytest.mark.parametrize("shape", SHAPES)
 def test_linear_matches_fp64_reference(shape, tile_n, dtype):
     ops = _ops()

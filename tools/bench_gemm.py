@@ -38,7 +38,7 @@ def main():
     torch.manual_seed(0)
     dt = torch.float16
     qp = torch.tensor([0.03, 128.0], device="cuda")
-    tiles = [int(t) for t in os.environ.get("TILES", "0,128,192,256").split(",")]
+    tiles = [int(t) for t in os.environ.get("TILES", "0,128,256,2128,2256").split(",")]
     for (M, N, K, act, tap) in ((4096, 2304, 768, "none", 0), (4096, 2304, 768, "none", 3), (4096, 768, 768, "none", 0),
                                 (4096, 3072, 768, "gelu", 0), (4096, 3072, 768, "gelu", 1), (4096, 768, 3072, "none", 0),
                                 (2048, 2304, 768, "none", 3), (2048, 3072, 768, "relu", 1), (2048, 768, 3072, "none", 1),

@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from outeffhop_b200 import ops
 torch.manual_seed(0)
 for (M, N, K, tile, use_bias) in ((4096, 2304, 768, 256, True), (4096, 2304, 768, 256, False), (4096, 2304, 768, 128, True), (256, 512, 64, 256, False),
-                                  (256, 512, 128, 256, False), (128, 256, 768, 256, False), (4096, 768, 768, 192, True), (4096, 256, 64, 256, False)):
+                                  (256, 512, 128, 256, False), (128, 256, 768, 256, False), (4096, 768, 768, 128, True), (4096, 256, 64, 256, False)):
     x = torch.randn(M, K, device="cuda").half(); w = (torch.randn(N, K, device="cuda") * K ** -0.5).half()
     b = torch.randn(N, device="cuda").half() if use_bias else None
     for rep in range(2):
