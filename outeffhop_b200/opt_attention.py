@@ -196,5 +196,10 @@ class OPTAttentionWithExtras(GateMixin, nn.Module):
         gate_logits = self._gate_logits(hidden_states, self.num_heads, self.head_dim)
         attn_output, attn_weights_reshaped = self._core(q, k, v, attention_mask, gate_logits, layer_head_mask,
                                                         output_attentions, bsz, tgt_len, taps=self._taps())
-        attn_output = self.out_proj(attn_output)                                              # :324
+        if hf_kwargs.get("_out_proj_linear_only"):
+            # quantized decoder layers fold out_proj's frozen output tap into the kernel that consumes it (residual add +
+            # tap + LayerNorm, quantized_models.QuantizedOPTDecoderLayer.forward_chained)
+            attn_output = self.out_proj.linear_only(attn_output)
+        else:
+            attn_output = self.out_proj(attn_output)                                          # :324
         return attn_output, attn_weights_reshaped, past_key_value

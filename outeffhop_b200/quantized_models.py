@@ -28,6 +28,7 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
+from . import ops
 from .bert_attention import BertSelfAttentionWithExtras
 from .quantization import (CurrentMinMaxEstimator, FP32Acts, QMethods, QuantizationManager, QuantizedActivation,
                            QuantizedModule, QuantLinear, RangeEstimators)
@@ -342,6 +343,41 @@ class QuantizedOPTDecoderLayer(QuantizedModel):
         self.self_attn_res_act_quantizer = QuantizedActivation(**qp)
         self.ffn_res_act_quantizer = QuantizedActivation(**qp)
 
+    def _chainable(self, next_ln) -> bool:
+        """``forward_chained`` applies: pre-LayerNorm layer in eval with every tap of the two residual blocks frozen."""
+        if not self.do_layer_norm_before or self.training or not isinstance(next_ln, QuantLayerNorm):
+            return False
+        a = _chain_taps(self.final_layer_norm, (self.self_attn_res_act_quantizer,), (self.self_attn.out_proj,))
+        b = _chain_taps(next_ln, (self.ffn_res_act_quantizer,), (self.fc2,))
+        return a is not None and b is not None and self.final_layer_norm.weight.dtype == next_ln.weight.dtype
+
+    def forward_chained(self, x, residual, next_ln, attention_mask=None):
+        """The same layer for a caller that chains layers (QuantizedOPTDecoder.forward): ``x`` = this layer's LayerNorm-ed,
+        tapped input (written by the previous layer's last kernel), ``residual`` = the tapped residual stream.  Two fused
+        kernels replace 2 x (output tap, residual add + tap, LayerNorm + tap) = 6 launches (quantized_opt.py:338-370):
+            out_proj tap -> + residual -> self_attn_res tap -> final_layer_norm -> its tap
+            fc2 tap      -> + residual -> ffn_res tap       -> NEXT layer's self_attn_layer_norm (or the decoder's final one)
+        Returns (next layer's input, new residual)."""
+        attn = OPTAttentionWithExtras.forward(self.self_attn, hidden_states=x, attention_mask=attention_mask,
+                                              _out_proj_linear_only=True)[0]
+        out_proj, tap, ln = self.self_attn.out_proj, self.self_attn_res_act_quantizer, self.final_layer_norm
+        n_bits = _chain_taps(ln, (tap,), (out_proj,))
+        w, b = ln.get_params()
+        x2, residual = ops.add_layer_norm(attn, residual, w, b, ln.eps, qparams_a=out_proj.tap_qparams(),
+                                          qparams_res=tap.kernel_qparams() if tap.active else None,
+                                          qparams_out=ln.activation_quantizer.quantizer.qparams if ln._qa_host else None,
+                                          n_bits=n_bits, return_sum=True)
+        shape = x2.shape
+        f = self.fc1_act(x2.reshape(-1, shape[-1]))                                               # :360
+        f = self.fc2.linear_only(f).view(shape)
+        tap, ln = self.ffn_res_act_quantizer, next_ln
+        n_bits = _chain_taps(ln, (tap,), (self.fc2,))
+        w, b = ln.get_params()
+        return ops.add_layer_norm(f, residual, w, b, ln.eps, qparams_a=self.fc2.tap_qparams(),
+                                  qparams_res=tap.kernel_qparams() if tap.active else None,
+                                  qparams_out=ln.activation_quantizer.quantizer.qparams if ln._qa_host else None,
+                                  n_bits=n_bits, return_sum=True)
+
     def forward(self, hidden_states, attention_mask=None, layer_head_mask=None, output_attentions=False, use_cache=False,
                 past_key_value=None, **unused):
         residual = hidden_states
@@ -380,6 +416,34 @@ class QuantizedOPTDecoderLayer(QuantizedModel):
         return outputs
 
 
+def _chain_taps(layer_norm: "QuantLayerNorm", taps, linears):
+    """n_bits shared by a fused ``dense tap -> add -> residual tap -> LayerNorm -> output tap`` kernel, or None when the
+    pieces cannot share one launch (a tap still estimating, observers attached, mixed bit widths)."""
+    from .quantization import AsymmetricUniformQuantizer
+    bits = set()
+    for t in taps:
+        if t.active:
+            if not t.fixed or t._forward_hooks or t._forward_pre_hooks:
+                return None
+            bits.add(t.activation_quantizer.n_bits)
+    for lin in linears:
+        if not lin.tap_fusable:
+            return None
+        if lin._qa_host:
+            bits.add(lin.activation_quantizer.n_bits)
+    ln = layer_norm
+    out = ln.activation_quantizer
+    if ln._forward_hooks or ln._forward_pre_hooks or ln.bias is None or len(ln.normalized_shape) != 1:
+        return None
+    if ln._qa_host:
+        if out.estimating or not isinstance(out.quantizer, AsymmetricUniformQuantizer):
+            return None
+        bits.add(out.n_bits)
+    if len(bits) > 1:
+        return None
+    return bits.pop() if bits else 8
+
+
 class QuantizedOPTDecoder(QuantizedModel):
     """quantized_opt.py:387-662 for the eval path (no KV cache, no head masks)."""
 
@@ -409,10 +473,23 @@ class QuantizedOPTDecoder(QuantizedModel):
         if self.project_in is not None:
             inputs_embeds = self.project_in(inputs_embeds)
         hidden_states = self.embed_sum_act_quantizer(inputs_embeds + pos_embeds)                 # :556-559
-        for layer in self.layers:
-            hidden_states = layer(hidden_states, attention_mask=attention_mask)[0]
-        if self.final_layer_norm is not None:
-            hidden_states = self.final_layer_norm(hidden_states)
+        layers = list(self.layers)
+        if (layers and self.final_layer_norm is not None and not self.training and hidden_states.is_cuda
+                and hidden_states.dtype in (torch.float16, torch.bfloat16, torch.float32)
+                and all(l._chainable(nxt) for l, nxt in zip(layers, [l.self_attn_layer_norm for l in layers[1:]]
+                                                            + [self.final_layer_norm]))):
+            # Fixed ranges, pre-LayerNorm layers: every ``residual + x`` with its two taps shares ONE kernel with the
+            # LayerNorm (and output tap) that follows it -- across layer boundaries too; the last one is final_layer_norm.
+            x = layers[0].self_attn_layer_norm(hidden_states)
+            for i, layer in enumerate(layers):
+                nxt = layers[i + 1].self_attn_layer_norm if i + 1 < len(layers) else self.final_layer_norm
+                x, hidden_states = layer.forward_chained(x, hidden_states, nxt, attention_mask)
+            hidden_states = x
+        else:
+            for layer in layers:
+                hidden_states = layer(hidden_states, attention_mask=attention_mask)[0]
+            if self.final_layer_norm is not None:
+                hidden_states = self.final_layer_norm(hidden_states)
         if self.project_out is not None:
             hidden_states = self.project_out(hidden_states)
         return hidden_states
