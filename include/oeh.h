@@ -89,7 +89,10 @@ typedef struct OehAttnArgs {
   int64_t v_strides[3];
   int64_t out_strides[3];
   int32_t B, H, Tq, Tk, d;
-  int32_t dtype;     /* oeh_dtype of q,k,v,out: OEH_F16 or OEH_BF16 (fp32 accumulate) */
+  int32_t dtype;     /* oeh_dtype of q,k,v,out: OEH_F16 or OEH_BF16 (fp32 accumulate), or OEH_F32: the tensors are
+                      * fp32 (the reference's eval precision, accelerate_configs/1gpu_no_mp.yaml:14), Q / K / V are rounded to
+                      * fp16 OPERANDS (saturating) in the workspace, accumulation / softmax / taps stay fp32 and the
+                      * context is widened back: the fp16 path's accuracy (2e-3 max-abs), not an fp32 GEMM's */
   float scale;       /* 1/sqrt(d) for BERT (:265); 1.0 for OPT when q is pre-scaled (:167) */
   int32_t kind;      /* oeh_softmax_kind */
   double gamma, eta; /* clipped variants; (eta-gamma) is rounded to fp32 like the Python scalar */
@@ -111,7 +114,7 @@ typedef struct OehAttnArgs {
   const float* qdq_ctx;
   int32_t n_bits;
   int32_t ctx_qdq_before_gate; /* OPT taps PV before the gate (:210), BERT after it (:434) */
-  void* workspace;             /* oeh_attn_workspace_bytes() bytes, 256-B aligned, may be NULL if 0 */
+  void* workspace;             /* oeh_attn_workspace_bytes() bytes (non-zero for OEH_F32 only), 256-B aligned, may be NULL if 0 */
   size_t workspace_bytes;
   oeh_stream_t stream;
 } OehAttnArgs;

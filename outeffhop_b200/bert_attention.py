@@ -44,6 +44,14 @@ class AttentionGateType(BaseEnumOptions):
 FUSED_HEAD_DIM = 64
 
 
+def _fusable_dtype(module, q: torch.Tensor) -> bool:
+    """16-bit activations always take the fused kernel.  fp32 activations (the reference's eval precision,
+    accelerate_configs/1gpu_no_mp.yaml:14) take it only when the module's ``fused_fp32`` flag is set: the kernel then rounds
+    Q / K / V to fp16 operands (fp32 accumulation and softmax), i.e. it has the fp16 path's 2e-3 accuracy, not an fp32 GEMM's
+    -- the default keeps fp32 on the exact, unfused library path."""
+    return q.dtype in (torch.float16, torch.bfloat16) or (q.dtype == torch.float32 and bool(getattr(module, "fused_fp32", False)))
+
+
 class GateMixin:
     """Gate construction (bert_attention.py:98-162; opt_attention.py:81-144) and evaluation
     (bert_attention.py:294-331; opt_attention.py:276-313) shared by the BERT and OPT modules.
@@ -242,6 +250,7 @@ class BertSelfAttentionWithExtras(GateMixin, nn.Module):
             self.softmax_fn = softmax_fn
         self.skip_attn = skip_attn
         self.materialize_probs = False    # force the unfused path (e.g. to feed the Identity probes)
+        self.fused_fp32 = False           # fp32 activations on the fused kernel with fp16 operands (see _fusable_dtype)
         self._init_gate(self.num_attention_heads, self.attention_head_size, self.all_head_size, attn_gate_type,
                         attn_gate_init, attn_gate_mlp, attn_gate_mlp2, attn_gate_linear_all_features, fine_tuning,
                         fine_tuning_std=0.01)
@@ -271,7 +280,7 @@ class BertSelfAttentionWithExtras(GateMixin, nn.Module):
         training_dropout = self.training and self.dropout.p > 0
         active = [t for t in (taps or ()) if t is not None and t.active]
         fusable_taps = all(t.fixed for t in active)
-        fused = (fn is not None and q.dtype in (torch.float16, torch.bfloat16) and d == FUSED_HEAD_DIM
+        fused = (fn is not None and _fusable_dtype(self, q) and d == FUSED_HEAD_DIM
                  and head_mask is None and not output_attentions and not self.materialize_probs
                  and not self._probes_hooked() and not training_dropout and fusable_taps
                  and self.position_embedding_type not in ("relative_key", "relative_key_query"))

@@ -373,14 +373,55 @@ int ensure_smem(const void* fn, int bytes) {
   return OEH_OK;
 }
 
+// ---- fp32 activations ------------------------------------------------------------------------------------------------
+// The reference evaluates in fp32 (accelerate_configs/1gpu_no_mp.yaml:14).  tcgen05 has no fp32 MMA; the fused path for fp32
+// tensors rounds Q / K / V to fp16 OPERANDS (saturating at +-65504), runs the same kernels -- fp32 accumulation, fp32
+// softmax, taps on fp32 values -- and widens the context back to fp32: the accuracy of the fp16 path (2e-3 max-abs against
+// the fp32 oracle), not of an fp32 GEMM, which is why the Python modules use it only on request (``fused_fp32``).
+__global__ void __launch_bounds__(256) cvt_rows_f32_to_f16(const float* __restrict__ src, __half* __restrict__ dst, int H, int T,
+                                                           int64_t s0, int64_t s1, int64_t s2, int64_t rows) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;      // one 16-byte output vector (8 elements) per thread
+  const int64_t row = i >> 3;
+  if (row >= rows) return;
+  const int c = (int)(i & 7) * 8;
+  const int t = (int)(row % T), h = (int)((row / T) % H);
+  const int64_t b = row / ((int64_t)T * H);
+  const float4* sp = reinterpret_cast<const float4*>(src + b * s0 + h * s1 + t * s2 + c);
+  const float4 x = __ldg(sp), y = __ldg(sp + 1);
+  auto sat = [](float v) { return fminf(fmaxf(v, -65504.f), 65504.f); };
+  __half2 o[4] = {__floats2half2_rn(sat(x.x), sat(x.y)), __floats2half2_rn(sat(x.z), sat(x.w)),
+                  __floats2half2_rn(sat(y.x), sat(y.y)), __floats2half2_rn(sat(y.z), sat(y.w))};
+  *reinterpret_cast<uint4*>(dst + row * HD + c) = *reinterpret_cast<uint4*>(o);
+}
+__global__ void __launch_bounds__(256) cvt_rows_f16_to_f32(const __half* __restrict__ src, float* __restrict__ dst, int H, int T,
+                                                           int64_t s0, int64_t s1, int64_t s2, int64_t rows) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t row = i >> 3;
+  if (row >= rows) return;
+  const int c = (int)(i & 7) * 8;
+  const int t = (int)(row % T), h = (int)((row / T) % H);
+  const int64_t b = row / ((int64_t)T * H);
+  const uint4 v = *reinterpret_cast<const uint4*>(src + row * HD + c);
+  const __half2* hp = reinterpret_cast<const __half2*>(&v);
+  const float2 a = __half22float2(hp[0]), bq = __half22float2(hp[1]), cq = __half22float2(hp[2]), d = __half22float2(hp[3]);
+  float4* dp = reinterpret_cast<float4*>(dst + b * s0 + h * s1 + t * s2 + c);
+  dp[0] = make_float4(a.x, a.y, bq.x, bq.y);
+  dp[1] = make_float4(cq.x, cq.y, d.x, d.y);
+}
+inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+size_t fp32_workspace_bytes(const OehAttnArgs* a) {
+  const size_t q = align256((size_t)a->B * a->H * a->Tq * HD * 2), kv = align256((size_t)a->B * a->H * a->Tk * HD * 2);
+  return 2 * q + 2 * kv;
+}
+
 int validate(const OehAttnArgs* a) {
   OEH_CHECK_ARG(a, "oeh_attn_fwd: null args");
   OEH_CHECK_ARG(a->B >= 0 && a->H >= 0 && a->Tq >= 0 && a->Tk >= 0, "oeh_attn_fwd: negative dimension");
   OEH_CHECK_ARG(a->kind >= OEH_SOFTMAX_VANILLA && a->kind <= OEH_SOFTMAX_CLIPPED1, "oeh_attn_fwd: unknown softmax kind %d",
                 a->kind);
   if (a->d != HD) return set_error(OEH_ERR_UNSUPPORTED, "oeh_attn_fwd: head dim %d (only %d is built)", a->d, HD);
-  if (a->dtype != OEH_F16 && a->dtype != OEH_BF16)
-    return set_error(OEH_ERR_UNSUPPORTED, "oeh_attn_fwd: dtype %d (fp16/bf16 inputs only; fp32 uses the unfused path)", a->dtype);
+  if (a->dtype != OEH_F16 && a->dtype != OEH_BF16 && a->dtype != OEH_F32)
+    return set_error(OEH_ERR_UNSUPPORTED, "oeh_attn_fwd: dtype %d", a->dtype);
   if (a->causal && a->Tk < a->Tq)
     return set_error(OEH_ERR_UNSUPPORTED, "oeh_attn_fwd: causal with Tk < Tq");
   if ((a->qdq_scores || a->qdq_probs || a->qdq_ctx) && (a->n_bits < 1 || a->n_bits > 16))
@@ -394,7 +435,9 @@ int validate(const OehAttnArgs* a) {
 using namespace oeh;
 
 extern "C" size_t oeh_attn_workspace_bytes(const OehAttnArgs* args) {
-  (void)args;   // row statistics of the two-pass modes stay in registers: no workspace
+  // row statistics of the two-pass modes stay in registers: 16-bit tensors need no workspace; fp32 tensors need room for
+  // the fp16 copies of q, k, v and the fp16 context
+  if (args && args->dtype == OEH_F32 && args->B > 0 && args->H > 0 && args->Tq > 0 && args->Tk > 0) return fp32_workspace_bytes(args);
   return 0;
 }
 
@@ -405,8 +448,42 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
   OEH_CHECK_ARG(a->Tk > 0, "oeh_attn_fwd: Tk == 0 (softmax over an empty dimension)");
   OEH_CHECK_ARG(a->q && a->k && a->v && a->out, "oeh_attn_fwd: null tensor pointer");
   OEH_CHECK_ARG(a->H <= 65535 && a->B <= 65535, "oeh_attn_fwd: B and H must be <= 65535");
-  if ((reinterpret_cast<uintptr_t>(a->out) & 15) || a->out_strides[0] % 8 || a->out_strides[1] % 8 || a->out_strides[2] % 8)
-    return set_error(OEH_ERR_UNSUPPORTED, "oeh_attn_fwd: out must be 16-byte aligned with strides that are multiples of 8");
+  const int vec = a->dtype == OEH_F32 ? 4 : 8;                   // elements per 16 bytes
+  if ((reinterpret_cast<uintptr_t>(a->out) & 15) || a->out_strides[0] % vec || a->out_strides[1] % vec || a->out_strides[2] % vec)
+    return set_error(OEH_ERR_UNSUPPORTED, "oeh_attn_fwd: out must be 16-byte aligned with strides that are multiples of %d", vec);
+
+  if (a->dtype == OEH_F32) {
+    for (int i = 0; i < 3; ++i)
+      if (a->q_strides[i] % 4 || a->k_strides[i] % 4 || a->v_strides[i] % 4 || a->out_strides[i] % 4)
+        return set_error(OEH_ERR_UNSUPPORTED, "oeh_attn_fwd: fp32 tensors need strides that are multiples of 4 elements");
+    if ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) | reinterpret_cast<uintptr_t>(a->v)) & 15)
+      return set_error(OEH_ERR_UNSUPPORTED, "oeh_attn_fwd: fp32 tensors must be 16-byte aligned");
+    const size_t need = fp32_workspace_bytes(a);
+    if (!a->workspace || a->workspace_bytes < need || (reinterpret_cast<uintptr_t>(a->workspace) & 255))
+      return set_error(OEH_ERR_WORKSPACE, "oeh_attn_fwd: fp32 tensors need a 256-byte aligned workspace of %zu bytes", need);
+    const size_t qb = align256((size_t)a->B * a->H * a->Tq * HD * 2), kvb = align256((size_t)a->B * a->H * a->Tk * HD * 2);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
+    __half *q16 = reinterpret_cast<__half*>(ws), *k16 = reinterpret_cast<__half*>(ws + qb),
+           *v16 = reinterpret_cast<__half*>(ws + qb + kvb), *o16 = reinterpret_cast<__half*>(ws + qb + 2 * kvb);
+    cudaStream_t st = (cudaStream_t)a->stream;
+    const int64_t rq = (int64_t)a->B * a->H * a->Tq, rk = (int64_t)a->B * a->H * a->Tk;
+    auto blocks = [](int64_t rows) { return (unsigned)((rows * 8 + 255) / 256); };
+    cvt_rows_f32_to_f16<<<blocks(rq), 256, 0, st>>>((const float*)a->q, q16, a->H, a->Tq, a->q_strides[0], a->q_strides[1], a->q_strides[2], rq);
+    cvt_rows_f32_to_f16<<<blocks(rk), 256, 0, st>>>((const float*)a->k, k16, a->H, a->Tk, a->k_strides[0], a->k_strides[1], a->k_strides[2], rk);
+    cvt_rows_f32_to_f16<<<blocks(rk), 256, 0, st>>>((const float*)a->v, v16, a->H, a->Tk, a->v_strides[0], a->v_strides[1], a->v_strides[2], rk);
+    if ((rc = check_launch("cvt_rows_f32_to_f16"))) return rc;
+    OehAttnArgs h = *a;
+    h.dtype = OEH_F16;
+    h.q = q16; h.k = k16; h.v = v16; h.out = o16;
+    const int64_t sq[3] = {(int64_t)a->H * a->Tq * HD, (int64_t)a->Tq * HD, HD}, sk[3] = {(int64_t)a->H * a->Tk * HD, (int64_t)a->Tk * HD, HD};
+    for (int i = 0; i < 3; ++i) { h.q_strides[i] = sq[i]; h.out_strides[i] = sq[i]; h.k_strides[i] = sk[i]; h.v_strides[i] = sk[i]; }
+    h.workspace = nullptr;
+    h.workspace_bytes = 0;
+    h.clamp_min = a->clamp_min ? 2 : 0;           // 2: clamp at finfo(float32).min, the dtype the caller's scores have
+    if ((rc = oeh_attn_fwd_debug(&h, dbg_s, dbg_o))) return rc;
+    cvt_rows_f16_to_f32<<<blocks(rq), 256, 0, st>>>(o16, (float*)a->out, a->H, a->Tq, a->out_strides[0], a->out_strides[1], a->out_strides[2], rq);
+    return check_launch("cvt_rows_f16_to_f32");
+  }
 
   // Kernel choice: sequences longer than one Q tile use the warp-specialised two-tile kernel (64-key sub-tiles);
   // up to 128 query rows there is nothing to ping-pong with, and the single-tile kernel (2 CTAs / SM) has the
@@ -447,7 +524,7 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
   p.mask_dtype = a->mask_dtype;
   if (a->mask) { p.ms0 = a->mask_strides[0]; p.ms1 = a->mask_strides[1]; p.ms2 = a->mask_strides[2]; }
   p.clamp_min = a->clamp_min;
-  p.fmin = a->dtype == OEH_F16 ? -65504.f : -3.3895313892515355e38f;
+  p.fmin = (a->dtype == OEH_F16 && a->clamp_min != 2) ? -65504.f : -3.3895313892515355e38f;   // bf16 and fp32 share the exponent range
   p.gate_logits = a->gate_logits;
   p.gate_scale = a->gate_scale;
   p.qdq_scores = a->qdq_scores;

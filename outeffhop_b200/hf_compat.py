@@ -62,8 +62,9 @@ def swap_bert_attention(model, attn_softmax: str = "vanilla", alpha: Optional[fl
                         max_seq_length: Optional[int] = None, skip_attn: bool = False,
                         attn_gate_type="none", attn_gate_init: Optional[float] = None, attn_gate_mlp: bool = False,
                         attn_gate_mlp2: bool = False, attn_gate_linear_all_features: bool = False,
-                        fine_tuning: bool = False):
-    """validate_mlm_config.py:174-191: replace every ``layer.attention.self`` and copy its weights."""
+                        fine_tuning: bool = False, fused_fp32: bool = False):
+    """validate_mlm_config.py:174-191: replace every ``layer.attention.self`` and copy its weights.  ``fused_fp32``: let fp32
+    activations take the fused kernel with fp16 operands (bert_attention._fusable_dtype; default: exact unfused fp32)."""
     softmax_fn = parse_attn_softmax(attn_softmax)
     bert = getattr(model, "bert", model)
     for layer in bert.encoder.layer:
@@ -75,6 +76,7 @@ def swap_bert_attention(model, attn_softmax: str = "vanilla", alpha: Optional[fl
             fine_tuning=fine_tuning)
         new.load_state_dict(old.state_dict(), strict=False)
         p = next(old.parameters())
+        new.fused_fp32 = bool(fused_fp32)
         layer.attention.self = new.to(device=p.device, dtype=p.dtype).train(old.training)
     return model
 
@@ -83,8 +85,8 @@ def swap_opt_attention(model, attn_softmax: str = "vanilla", alpha: Optional[flo
                        max_seq_length: Optional[int] = None, skip_attn: bool = False, attn_gate_type="none",
                        attn_gate_init: Optional[float] = None, attn_gate_mlp: bool = False,
                        attn_gate_mlp2: bool = False, attn_gate_linear_all_features: bool = False,
-                       fine_tuning: bool = False, causal_hint: bool = False):
-    """validate_clm.py:147-168: replace every ``layer.self_attn`` and copy its weights."""
+                       fine_tuning: bool = False, causal_hint: bool = False, fused_fp32: bool = False):
+    """validate_clm.py:147-168: replace every ``layer.self_attn`` and copy its weights (``fused_fp32``: see swap_bert_attention)."""
     softmax_fn = parse_attn_softmax(attn_softmax)
     cfg = model.config
     for layer in model.model.decoder.layers:
@@ -98,6 +100,7 @@ def swap_opt_attention(model, attn_softmax: str = "vanilla", alpha: Optional[flo
         new.load_state_dict(old.state_dict(), strict=False)
         new.causal_hint = causal_hint
         p = next(old.parameters())
+        new.fused_fp32 = bool(fused_fp32)
         layer.self_attn = new.to(device=p.device, dtype=p.dtype).train(old.training)
     return model
 

@@ -24,7 +24,8 @@ import torch
 from torch import nn
 
 from . import ops
-from .bert_attention import FUSED_HEAD_DIM, AttentionGateType, GateMixin, _check_no_grad, fused_qkv_projection
+from .bert_attention import (FUSED_HEAD_DIM, AttentionGateType, GateMixin, _check_no_grad, _fusable_dtype,
+                             fused_qkv_projection)
 from .softmax import KIND_CLIPPED, KIND_CLIPPED1, SoftmaxFn, as_softmax_fn
 
 
@@ -70,6 +71,7 @@ class OPTAttentionWithExtras(GateMixin, nn.Module):
             self.softmax_fn = softmax_fn
         self.skip_attn = skip_attn
         self.materialize_probs = False
+        self.fused_fp32 = False           # see bert_attention._fusable_dtype
         self.causal_hint = False
         self._init_gate(self.num_heads, self.head_dim, self.embed_dim, attn_gate_type, attn_gate_init, attn_gate_mlp,
                         attn_gate_mlp2, attn_gate_linear_all_features, fine_tuning, fine_tuning_std=0.001)
@@ -90,7 +92,7 @@ class OPTAttentionWithExtras(GateMixin, nn.Module):
         src_len = k.shape[2]
         training_dropout = self.training and self.dropout > 0
         active = [t for t in (taps or ()) if t is not None and t.active]
-        fused = (fn is not None and q.dtype in (torch.float16, torch.bfloat16) and self.head_dim == FUSED_HEAD_DIM
+        fused = (fn is not None and _fusable_dtype(self, q) and self.head_dim == FUSED_HEAD_DIM
                  and layer_head_mask is None and not output_attentions and not self.materialize_probs
                  and not self._probes_hooked() and not training_dropout and all(t.fixed for t in active))
         if attention_mask is not None and attention_mask.size() != (bsz, 1, tgt_len, src_len):

@@ -165,6 +165,7 @@ class QuantizedBertSelfAttentionWithExtras(QuantizedModel, BertSelfAttentionWith
         self.attn_probs_after_dropout = nn.Identity()
         self.skip_attn = False
         self.materialize_probs = False
+        self.fused_fp32 = bool(getattr(org_model, "fused_fp32", False))
         self.gate_scaling_factor = 1.0
         self._gate_pack = None
         self._last_gate_logits = None
@@ -213,6 +214,7 @@ class QuantizedOPTAttentionWithExtras(QuantizedModel, OPTAttentionWithExtras):
         self.attn_probs_after_dropout = nn.Identity()
         self.skip_attn = False
         self.materialize_probs = False
+        self.fused_fp32 = bool(getattr(org_model, "fused_fp32", False))
         self.causal_hint = getattr(org_model, "causal_hint", False)
         self.gate_scaling_factor = 1.0            # ``attn_output *= gate`` (quantized_opt.py:250)
         self._gate_pack = None

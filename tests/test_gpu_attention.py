@@ -328,3 +328,23 @@ def test_attention_mid_kernel_taps_and_masks(kind, gamma, eta, dtype, override):
         assert diff.max() <= 1.05 * step + (1e-3 if dtype == torch.float16 else 8e-3), (diff.max(), step)
         assert (diff > 2e-3).mean() < (0.02 if dtype == torch.float16 else 0.2), (diff > 2e-3).mean()
     assert (np.abs(out - two_pass) > 2e-3).mean() < 0.02
+
+
+@pytest.mark.parametrize("kind,gamma,eta", KINDS[:4])
+@pytest.mark.parametrize("shape,causal,layout", [((2, 3, 128, 128), False, "bthd"), ((1, 2, 300, 300), True, "bhtd"),
+                                                 ((2, 2, 77, 130), False, "bthd"), ((1, 2, 1024, 1024), True, "bhtd")])
+def test_attention_fp32_tensors_fp16_operands(kind, gamma, eta, shape, causal, layout):
+    """fp32 q / k / v / out (the reference's eval precision) through the fused kernels: Q, K, V are rounded to fp16 OPERANDS
+    inside oeh_attn_fwd (fp32 accumulation, fp32 softmax), so the result carries the fp16 path's error against the fp32
+    oracle -- the same 2e-3 max-abs contract -- not an fp32 GEMM's."""
+    ops = _ops()
+    B, H, Tq, Tk = shape
+    q, k, v = _mk(B, H, Tq, Tk, torch.float32, seed=Tq + kind, layout=layout)
+    logits = torch.randn(B, H, Tq)
+    out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal, gate_logits=logits.cuda(),
+                            out_layout=layout)
+    assert out.dtype == torch.float32
+    ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal, gate=O.sigmoid(logits.numpy()))
+    if layout == "bthd":
+        ref = ref.transpose(0, 2, 1, 3).reshape(B, Tq, H * 64)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, atol=TOL, rtol=0)

@@ -58,6 +58,33 @@ def test_bert_module_vs_reference_golden(golden, dtype, tol):
                                    err_msg=f"{tag} {key} {dtype}")
 
 
+def test_bert_module_fp32_on_the_fused_kernel_is_opt_in(golden):
+    """fp32 activations: the default stays on the exact unfused path (2e-4 above); ``fused_fp32`` sends them through the fused
+    kernel with fp16 operands -- the fp16 path's tolerance against the live-reference golden, and no S / P tensor."""
+    o = _mods()
+    from outeffhop_b200 import ops
+    g = golden("attention_modules.npz")
+    calls = []
+    orig = ops.attention_fwd
+    ops.attention_fwd = lambda *a, **k: (calls.append(a[0].dtype), orig(*a, **k))[1]
+    try:
+        for tag, key, gated, masked in g["bert_cases"]:
+            m = _load_sd(_make_bert(o, str(key), int(gated)), g, tag, "bert_base").cuda().eval()
+            hidden = _t(g[f"{tag}::hidden"], torch.float32)
+            mask = _t(g[f"{tag}::mask"], torch.float32) if int(masked) else None
+            with torch.no_grad():
+                n0 = len(calls)
+                exact = m(hidden, attention_mask=mask)[0]
+                assert len(calls) == n0                                  # default: not the fused kernel
+                m.fused_fp32 = True
+                out = m(hidden, attention_mask=mask)[0]
+                assert len(calls) == n0 + 1 and calls[-1] == torch.float32 and out.dtype == torch.float32
+            np.testing.assert_allclose(out.cpu().numpy(), g[f"{tag}::out"], atol=3e-3, rtol=0, err_msg=f"{tag} {key}")
+            np.testing.assert_allclose(exact.cpu().numpy(), g[f"{tag}::out"], atol=2e-4, rtol=0)
+    finally:
+        ops.attention_fwd = orig
+
+
 def test_bert_alpha_override_and_mlp_gates(golden):
     o = _mods()
     g = golden("attention_modules.npz")

@@ -59,6 +59,24 @@ def main():
     ms = timed(step, pool)
     out.append(dict(config="BERT-base INT8 (W8A8, FP32 head) clippedsoftmax1(-.025:1), 32x128, fixed ranges after 4 estimation batches",
                     ms_per_step=ms, tokens_per_s=32 * 128 / ms * 1e3, loss=float(step.loss)))
+    # config 1 shape on the GPU: BERT-base fp32 (the reference's eval precision), softmax1, 32 x 128 -- exact unfused
+    # attention (library GEMMs + oeh_softmax_rows) vs the fused kernel with fp16 operands (fused_fp32)
+    for fused in (False, True):
+        from outeffhop_b200 import hf_compat
+        from transformers import BertConfig, BertForMaskedLM
+        cfg = BertConfig()
+        cfg._attn_implementation = "eager"
+        torch.manual_seed(3000)
+        model = BertForMaskedLM(cfg).to("cuda").eval()
+        model = hf_compat.fuse_bert_gelu(hf_compat.fuse_bert_residual_blocks(
+            hf_compat.swap_bert_attention(model, attn_softmax="softmax1", max_seq_length=128, fused_fp32=fused)))
+        host = [EH.synthetic_mlm_batch(32, 128, seed=3000 + i) for i in range(8)]
+        pool = [{k: v.cuda() for k, v in b.items()} for b in host]
+        step = EH.make_bert_eval_step(model, host[0])
+        ms = timed(step, pool)
+        out.append(dict(config=f"1 (GPU): BERT-base fp32 softmax1 32x128, attention {'fused, fp16 operands' if fused else 'unfused, exact fp32'}",
+                        ms_per_step=ms, tokens_per_s=32 * 128 / ms * 1e3, loss=float(step.loss)))
+        del model, step
     for r in out:
         print(json.dumps(r), flush=True)
 
