@@ -48,11 +48,21 @@ def main():
                          ("clippedsoftmax1", dict(kind=3, gamma=-0.025, eta=1.1)),
                          ("vanilla+gate", dict(kind=0)), ("softmax1", dict(kind=1))):
             row = dict(B=B, H=H, T=T, causal=causal, case=name)
+            run = lambda s: ops.attention_fwd(s[0], s[1], s[2], scale=0.125, causal=causal, gate_logits=s[3], out=s[4], **kw)
             for mid in ("0", "1"):
                 _lib.set_override("OEH_MID_KERNEL", mid)
-                run = lambda s: ops.attention_fwd(s[0], s[1], s[2], scale=0.125, causal=causal, gate_logits=s[3], out=s[4], **kw)
                 row["mid_us" if mid == "1" else "other_us"] = round(time_launch(run, pool), 2)
             _lib.set_override("OEH_MID_KERNEL", None)
+            _lib.set_override("OEH_ATTN_KERNEL", "tile")          # one 128-row Q tile per 128-thread CTA, two CTAs per SM
+            row["tile_us"] = round(time_launch(run, pool), 2)
+            _lib.set_override("OEH_ATTN_KERNEL", None)
+            for pers, tiles in (("0", "1"), ("1", "1"), ("1", "2")):
+                _lib.set_override("OEH_MID_KERNEL", "0")
+                _lib.set_override("OEH_WS_PERSISTENT", pers)
+                _lib.set_override("OEH_WS_TILES", tiles)
+                row[f"ws_p{pers}_t{tiles}_us"] = round(time_launch(run, pool), 2)
+            for k2 in ("OEH_MID_KERNEL", "OEH_WS_PERSISTENT", "OEH_WS_TILES"):
+                _lib.set_override(k2, None)
             flops = (2.0 * B * H * T * (T + 1) * 64) if causal else 4.0 * B * H * T * T * 64
             row["mid_tflops"] = round(flops / row["mid_us"] / 1e6, 1)
             print(json.dumps(row), flush=True)
