@@ -269,6 +269,16 @@ int oeh_add_layer_norm(const void* a, const void* b, const void* weight, const v
                        int64_t cols, double eps, int32_t dtype, const float* qparams_a, const float* qparams_res,
                        const float* qparams_out, int32_t n_bits, void* sum_out, oeh_stream_t stream);
 
+/* oeh_add_layer_norm that ALSO emits the per-token attention-gate logits of the module that consumes y (Linear(64,1) gate
+ * predictors, bert_attention.py:303-320 / opt_attention.py:285-302: out[b,h,t] = w_h . y[b,t,64h:64h+64] + b_h):
+ * gate_w (H,64) fp32, gate_b (H) fp32, gate_out (B,H,T) fp32, rows == B*T, cols == 64*H.  Saves the separate
+ * oeh_gate_logits pass over the hidden states.  gate_out NULL = oeh_add_layer_norm. */
+int oeh_add_layer_norm_gate(const void* a, const void* b, const void* weight, const void* bias, void* y, int64_t rows,
+                            int64_t cols, double eps, int32_t dtype, const float* qparams_a, const float* qparams_res,
+                            const float* qparams_out, int32_t n_bits, void* sum_out, const float* gate_w,
+                            const float* gate_b, float* gate_out, int32_t T, int32_t H, oeh_stream_t stream);
+
+
 /* y = qdq_sum(a + qdq_b(b)): oeh_add_fake_quant with the output tap of the QuantLinear that produced b folded in
  * (QuantizedOPTDecoderLayer: fc2's tap, the residual add and ffn_res_act_quantizer, quantized_opt.py:362-369).
  * qparams_b may be NULL (= oeh_add_fake_quant).  Fixed ranges only. */

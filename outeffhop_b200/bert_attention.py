@@ -155,6 +155,16 @@ class GateMixin:
         self._gate_pack = (key, pack)
         return pack
 
+    def fusable_gate(self, device):
+        """(w (H,64), b (H)) fp32 of Linear per-token gate predictors, for a producer kernel that can emit the gate logits
+        together with the hidden states it writes (``ops.add_layer_norm(..., gate=...)``); None for every other gate flavour."""
+        if (self.attn_gate_type != AttentionGateType.conditional_per_token or self.attn_gate_linear_all_features
+                or not isinstance(self.alpha, nn.ModuleList) or not isinstance(self.alpha[0], nn.Linear)
+                or self.alpha[0].in_features != FUSED_HEAD_DIM):
+            return None
+        w1, b1, _, _ = self._packed_gate_weights(device)
+        return w1, b1
+
     def _gate_logits(self, hidden_states: torch.Tensor, num_heads: int, head_dim: int) -> Optional[torch.Tensor]:
         """(B,H,T) fp32 gate logits, or None when the module has no gate."""
         gt = self.attn_gate_type

@@ -31,14 +31,16 @@ __device__ __forceinline__ int4 ld_row(const int4* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_row(int4* p, const int4& v) { __stcs(p, v); }
 #endif
 
-template <typename T, int kVecs>
+template <typename T, int kVecs, bool kGate>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ gamma,
                       const T* __restrict__ beta, T* __restrict__ y, int64_t rows, int cols, float eps,
                       const float* __restrict__ q_a, const float* __restrict__ q_res, const float* __restrict__ q_out,
-                      float int_max, T* __restrict__ sum_out) {
+                      float int_max, T* __restrict__ sum_out, const float* __restrict__ gate_w,
+                      const float* __restrict__ gate_b, float* __restrict__ gate_out, int T_len, int H) {
   using V = Vec16<T>;
   constexpr int N = V::N;
+  constexpr int LPH = 64 / N;                              // lanes that hold one 64-wide head of the row
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -101,6 +103,11 @@ add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T*
   const V* gv = reinterpret_cast<const V*>(gamma);
   const V* bev = reinterpret_cast<const V*>(beta);
   V* yv = reinterpret_cast<V*>(y + row * cols);
+  float gacc[kGate ? kVecs : 1];
+  if (kGate) {
+#pragma unroll
+    for (int v = 0; v < kVecs; ++v) gacc[v] = 0.f;
+  }
 #pragma unroll
   for (int v = 0; v < kVecs; ++v) {
     const int i = lane + 32 * v;
@@ -116,13 +123,37 @@ add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T*
       }
       if (q_out) qo.apply(out, false);
       st_row(reinterpret_cast<int4*>(yv + i), *reinterpret_cast<const int4*>(&out));
+      if (kGate) {                                         // per-token gate logit of head i / LPH from the row just written
+        const float* wp = gate_w + (int64_t)i * N;         // (H, 64) contiguous == the row's layout
+        float acc = 0.f;
+#pragma unroll
+        for (int e = 0; e < N; ++e) acc = fmaf(DT<T>::to_f(out.v[e]), __ldg(wp + e), acc);
+        gacc[v] = acc;
+      }
+    }
+  }
+  if (kGate) {
+    // out[b,h,t] = fc_h(y[b,t,h*64:(h+1)*64]) (bert_attention.py:303-320; opt_attention.py:285-302) for the attention that
+    // consumes this LayerNorm output: a head is LPH consecutive lanes of one vector round
+    const int64_t bidx = row / T_len, t = row % T_len;
+#pragma unroll
+    for (int v = 0; v < kVecs; ++v) {
+      float acc = gacc[v];
+#pragma unroll
+      for (int o = LPH / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      const int i = lane + 32 * v;
+      if (i < nvec && (lane % LPH) == 0) {
+        const int h = i / LPH;
+        gate_out[(bidx * H + h) * T_len + t] = acc + __ldg(gate_b + h);
+      }
     }
   }
 }
 
 template <typename T>
 int launch(const void* a, const void* b, const void* gamma, const void* beta, void* y, int64_t rows, int64_t cols, float eps,
-           const float* q_a, const float* q_res, const float* q_out, int n_bits, void* sum_out, cudaStream_t st) {
+           const float* q_a, const float* q_res, const float* q_out, int n_bits, void* sum_out, cudaStream_t st,
+           const float* gate_w = nullptr, const float* gate_b = nullptr, float* gate_out = nullptr, int T_len = 1, int H = 0) {
   constexpr int N = Vec16<T>::N;
   if (cols % N != 0 || cols / N > 32 * 8)
     return set_error(OEH_ERR_UNSUPPORTED, "oeh_add_layer_norm: cols=%lld must be a multiple of %d and at most %d",
@@ -135,9 +166,14 @@ int launch(const void* a, const void* b, const void* gamma, const void* beta, vo
   const unsigned grid = (unsigned)((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
 #define OEH_LN_CASE(K)                                                                                               \
   case K:                                                                                                            \
-    add_layer_norm_kernel<T, K><<<grid, kWarpsPerBlock * 32, 0, st>>>((const T*)a, (const T*)b, (const T*)gamma,     \
-                                                                     (const T*)beta, (T*)y, rows, (int)cols, eps,   \
-                                                                     q_a, q_res, q_out, int_max, (T*)sum_out);      \
+    if (gate_out)                                                                                                    \
+      add_layer_norm_kernel<T, K, true><<<grid, kWarpsPerBlock * 32, 0, st>>>(                                       \
+          (const T*)a, (const T*)b, (const T*)gamma, (const T*)beta, (T*)y, rows, (int)cols, eps, q_a, q_res, q_out, \
+          int_max, (T*)sum_out, gate_w, gate_b, gate_out, T_len, H);                                                 \
+    else                                                                                                             \
+      add_layer_norm_kernel<T, K, false><<<grid, kWarpsPerBlock * 32, 0, st>>>(                                      \
+          (const T*)a, (const T*)b, (const T*)gamma, (const T*)beta, (T*)y, rows, (int)cols, eps, q_a, q_res, q_out, \
+          int_max, (T*)sum_out, nullptr, nullptr, nullptr, 1, 0);                                                    \
     break;
   switch (kv) {
     OEH_LN_CASE(1) OEH_LN_CASE(2) OEH_LN_CASE(3) OEH_LN_CASE(4) OEH_LN_CASE(5) OEH_LN_CASE(6) OEH_LN_CASE(7) OEH_LN_CASE(8)
@@ -151,10 +187,31 @@ int launch(const void* a, const void* b, const void* gamma, const void* beta, vo
 
 using namespace oeh;
 
+extern "C" int oeh_add_layer_norm_gate(const void* a, const void* b, const void* weight, const void* bias, void* y,
+                                       int64_t rows, int64_t cols, double eps, int32_t dtype, const float* qparams_a,
+                                       const float* qparams_res, const float* qparams_out, int32_t n_bits, void* sum_out,
+                                       const float* gate_w, const float* gate_b, float* gate_out, int32_t T, int32_t H,
+                                       oeh_stream_t stream);
+
 extern "C" int oeh_add_layer_norm(const void* a, const void* b, const void* weight, const void* bias, void* y, int64_t rows,
                                   int64_t cols, double eps, int32_t dtype, const float* qparams_a,
                                   const float* qparams_res, const float* qparams_out, int32_t n_bits, void* sum_out,
                                   oeh_stream_t stream) {
+  return oeh_add_layer_norm_gate(a, b, weight, bias, y, rows, cols, eps, dtype, qparams_a, qparams_res, qparams_out, n_bits,
+                                 sum_out, nullptr, nullptr, nullptr, 1, 0, stream);
+}
+
+extern "C" int oeh_add_layer_norm_gate(const void* a, const void* b, const void* weight, const void* bias, void* y,
+                                       int64_t rows, int64_t cols, double eps, int32_t dtype, const float* qparams_a,
+                                       const float* qparams_res, const float* qparams_out, int32_t n_bits, void* sum_out,
+                                       const float* gate_w, const float* gate_b, float* gate_out, int32_t T, int32_t H,
+                                       oeh_stream_t stream) {
+  if (gate_out) {
+    OEH_CHECK_ARG(gate_w && gate_b, "oeh_add_layer_norm_gate: null gate weights");
+    OEH_CHECK_ARG(T > 0 && H > 0 && (int64_t)H * 64 == cols && rows % T == 0,
+                  "oeh_add_layer_norm_gate: the gate needs cols == 64 H and rows == B T (cols=%lld H=%d rows=%lld T=%d)",
+                  (long long)cols, H, (long long)rows, T);
+  }
   OEH_CHECK_ARG(rows >= 0 && cols > 0, "oeh_add_layer_norm: bad shape (%lld, %lld)", (long long)rows, (long long)cols);
   if (rows == 0) return OEH_OK;
   OEH_CHECK_ARG(a && weight && y, "oeh_add_layer_norm: null pointer");
@@ -163,10 +220,15 @@ extern "C" int oeh_add_layer_norm(const void* a, const void* b, const void* weig
   if (!(qparams_a || qparams_res || qparams_out)) n_bits = 8;
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case OEH_F32: return launch<float>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_a, qparams_res, qparams_out, n_bits, sum_out, st);
-    case OEH_F16: return launch<__half>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_a, qparams_res, qparams_out, n_bits, sum_out, st);
+    case OEH_F32:
+      return launch<float>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_a, qparams_res, qparams_out, n_bits, sum_out, st,
+                           gate_w, gate_b, gate_out, T, H);
+    case OEH_F16:
+      return launch<__half>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_a, qparams_res, qparams_out, n_bits, sum_out, st,
+                            gate_w, gate_b, gate_out, T, H);
     case OEH_BF16:
-      return launch<__nv_bfloat16>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_a, qparams_res, qparams_out, n_bits, sum_out, st);
+      return launch<__nv_bfloat16>(a, b, weight, bias, y, rows, cols, (float)eps, qparams_a, qparams_res, qparams_out, n_bits,
+                                   sum_out, st, gate_w, gate_b, gate_out, T, H);
   }
   return set_error(OEH_ERR_BAD_ARG, "oeh_add_layer_norm: unknown dtype %d", dtype);
 }

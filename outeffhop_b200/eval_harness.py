@@ -154,10 +154,18 @@ def opt_clm_loss(model, input_ids: torch.Tensor, labels: torch.Tensor, causal_ma
         # boundaries too (the last one is the decoder's final_layer_norm)
         from . import ops
         ln = layers[0].self_attn_layer_norm
-        x = ops.add_layer_norm(h, None, ln.weight, ln.bias, ln.eps)
+        gates = [l.gate_predictors(h.device) if h.dim() == 3 else None for l in layers] + [None]
+        x = ops.add_layer_norm(h, None, ln.weight, ln.bias, ln.eps, gate=gates[0])
+        logits = None
+        if gates[0] is not None:
+            x, logits = x
         for i, layer in enumerate(layers):
             next_ln = layers[i + 1].self_attn_layer_norm if i + 1 < len(layers) else dec.final_layer_norm
-            x, h = layer.forward_chained(x, h, next_ln, attention_mask=causal_mask, position_ids=position_ids)
+            # the kernel that writes the next layer's input also emits that layer's per-token gate logits
+            out = layer.forward_chained(x, h, next_ln, attention_mask=causal_mask, position_ids=position_ids,
+                                        gate_logits=logits, next_gate=gates[i + 1])
+            x, h = out[0], out[1]
+            logits = out[2] if gates[i + 1] is not None else None
         h = x
     else:
         for layer in layers:

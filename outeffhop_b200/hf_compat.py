@@ -47,8 +47,9 @@ class OPTAttentionWithExtrasHF(OPTAttentionWithExtras):
                 layer_head_mask=None, output_attentions=False, **kw):
         if kw.get("past_key_values") is not None:
             raise NotImplementedError("KV caches are not used on the evaluation path (pass use_cache=False)")
+        extra = {k: kw[k] for k in ("_gate_logits", "_out_proj_linear_only") if k in kw}
         out, weights, past = super().forward(hidden_states, key_value_states, past_key_value, attention_mask,
-                                             layer_head_mask, bool(output_attentions))
+                                             layer_head_mask, bool(output_attentions), **extra)
         if not NEW_STYLE:
             return out, weights, past
         return out, weights
@@ -235,20 +236,28 @@ class OPTDecoderLayerFused(torch.nn.Module):
         return (residual.view(-1, shape[-1]) + f).view(shape)
 
 
-    def forward_chained(self, x, residual, next_ln, attention_mask=None, position_ids=None):
+    def gate_predictors(self, device):
+        """Linear per-token gate predictors of this layer's attention (for the kernel that writes its input), or None."""
+        fn = getattr(self.self_attn, "fusable_gate", None)
+        return fn(device) if fn is not None and not self.self_attn.training else None
+
+    def forward_chained(self, x, residual, next_ln, attention_mask=None, position_ids=None, gate_logits=None, next_gate=None):
         """The same layer for a caller that chains layers: ``x`` = this layer's LayerNorm-ed input (computed by the previous
         layer's last kernel), ``residual`` = the un-normalised stream.  Returns (LayerNorm_next(residual'), residual') with
-        the final ``residual + ffn`` and the NEXT layer's first LayerNorm (``next_ln``) fused as well."""
+        the final ``residual + ffn`` and the NEXT layer's first LayerNorm (``next_ln``) fused as well.  ``gate_logits``: this
+        layer's per-token gate logits if the kernel that wrote ``x`` produced them; ``next_gate``: the next layer's gate
+        predictors -- its logits are then emitted by this layer's last kernel and returned third."""
         from . import ops
         ln2 = self.final_layer_norm
+        kw = {} if gate_logits is None else {"_gate_logits": gate_logits}
         attn = self.self_attn(hidden_states=x, past_key_values=None, position_ids=position_ids,
-                              attention_mask=attention_mask)[0]
+                              attention_mask=attention_mask, **kw)[0]
         x2, residual = ops.add_layer_norm(residual, attn, ln2.weight, ln2.bias, ln2.eps, return_sum=True)
         shape = x2.shape
         f = torch._addmm_activation(self.fc1.bias, x2.view(-1, shape[-1]), self.fc1.weight.t()) \
             if self.fc1.bias is not None else torch.relu(self.fc1(x2.view(-1, shape[-1])))
         f = self.fc2(f).view(shape)
-        return ops.add_layer_norm(residual, f, next_ln.weight, next_ln.bias, next_ln.eps, return_sum=True)
+        return ops.add_layer_norm(residual, f, next_ln.weight, next_ln.bias, next_ln.eps, return_sum=True, gate=next_gate)
 
 
 def fuse_opt_decoder_layers(model):

@@ -365,10 +365,12 @@ def add_layer_norm(a: torch.Tensor, b: Optional[torch.Tensor], weight: torch.Ten
                    eps: float = 1e-12, qparams_res: Optional[torch.Tensor] = None,
                    qparams_out: Optional[torch.Tensor] = None, n_bits: int = 8,
                    out: Optional[torch.Tensor] = None, qparams_a: Optional[torch.Tensor] = None,
-                   return_sum: bool = False):
+                   return_sum: bool = False, gate=None):
     """[qdq_out] LayerNorm([qdq_res]([qdq_a] a + b)) over the last dimension in one pass (oeh_add_layer_norm).  ``b``
     None = plain LayerNorm; ``qparams_*`` = device [scale, zero_point] of fixed-range taps; ``return_sum``: also return
-    the (tapped) sum, which pre-LayerNorm blocks carry on as the residual."""
+    the (tapped) sum, which pre-LayerNorm blocks carry on as the residual.  ``gate`` = (w (H,64) fp32, b (H) fp32) of the
+    Linear per-token gate predictors of the attention module that consumes the result: the (B,H,T) fp32 gate logits are
+    produced by the same kernel and returned last (a (B,T,64 H) input is required)."""
     _require_cuda(a, b, weight, bias, qparams_a, qparams_res, qparams_out)
     if b is not None and (b.shape != a.shape or b.dtype != a.dtype):
         raise ValueError("add_layer_norm: a and b must have the same shape and dtype")
@@ -382,13 +384,28 @@ def add_layer_norm(a: torch.Tensor, b: Optional[torch.Tensor], weight: torch.Ten
     y = out if out is not None else torch.empty_like(ac)
     total = torch.empty_like(ac) if return_sum else None
     rows = ac.numel() // max(cols, 1)
-    L.check(L.lib().oeh_add_layer_norm(ac.data_ptr(), bc.data_ptr() if bc is not None else None, wc.data_ptr(),
-                                       bic.data_ptr() if bic is not None else None, y.data_ptr(), rows, cols, float(eps),
-                                       _dtype_code(ac), qparams_a.data_ptr() if qparams_a is not None else None,
-                                       qparams_res.data_ptr() if qparams_res is not None else None,
-                                       qparams_out.data_ptr() if qparams_out is not None else None, int(n_bits),
-                                       total.data_ptr() if total is not None else None, _stream()))
-    return (y, total) if return_sum else y
+    logits = gw = gb = None
+    T_len, H = 1, 0
+    if gate is not None:
+        gw, gb = gate
+        H = gw.shape[0]
+        if ac.dim() != 3 or gw.shape != (H, 64) or gb.shape != (H,) or cols != 64 * H or gw.dtype != torch.float32 \
+                or gb.dtype != torch.float32 or not gw.is_contiguous() or not gb.is_contiguous():
+            raise ValueError("add_layer_norm: gate needs a (B,T,64*H) input and contiguous fp32 (H,64) / (H,) predictors")
+        T_len = ac.shape[1]
+        logits = torch.empty((ac.shape[0], H, T_len), dtype=torch.float32, device=ac.device)
+    L.check(L.lib().oeh_add_layer_norm_gate(ac.data_ptr(), bc.data_ptr() if bc is not None else None, wc.data_ptr(),
+                                            bic.data_ptr() if bic is not None else None, y.data_ptr(), rows, cols, float(eps),
+                                            _dtype_code(ac), qparams_a.data_ptr() if qparams_a is not None else None,
+                                            qparams_res.data_ptr() if qparams_res is not None else None,
+                                            qparams_out.data_ptr() if qparams_out is not None else None, int(n_bits),
+                                            total.data_ptr() if total is not None else None,
+                                            gw.data_ptr() if gw is not None else None, gb.data_ptr() if gb is not None else None,
+                                            logits.data_ptr() if logits is not None else None, int(T_len), int(H), _stream()))
+    res = (y, total) if return_sum else (y,)
+    if gate is not None:
+        res = res + (logits,)
+    return res if len(res) > 1 else res[0]
 
 
 def gelu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

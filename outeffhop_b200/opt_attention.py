@@ -195,7 +195,11 @@ class OPTAttentionWithExtras(GateMixin, nn.Module):
         if self.is_decoder:
             past_key_value = (k, v)                                                           # :196
 
-        gate_logits = self._gate_logits(hidden_states, self.num_heads, self.head_dim)
+        gate_logits = hf_kwargs.get("_gate_logits")            # already produced by the kernel that wrote hidden_states
+        if gate_logits is None:
+            gate_logits = self._gate_logits(hidden_states, self.num_heads, self.head_dim)
+        else:
+            self._last_gate_logits = gate_logits
         attn_output, attn_weights_reshaped = self._core(q, k, v, attention_mask, gate_logits, layer_head_mask,
                                                         output_attentions, bsz, tgt_len, taps=self._taps())
         if hf_kwargs.get("_out_proj_linear_only"):

@@ -181,3 +181,28 @@ def test_fused_opt_decoder_layer_matches_hf_layer():
         got = EH.opt_clm_loss(model, ids, lab, mask, pos).item()
     assert abs(got - want) < 2e-3 * abs(want), (got, want)
     assert "model.decoder.layers.1.final_layer_norm.weight" in model.state_dict()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+def test_add_layer_norm_emits_gate_logits(dtype):
+    """oeh_add_layer_norm_gate: the LayerNorm kernel also produces the per-token gate logits of the attention module that
+    consumes its output (Linear(64,1) predictors, bert_attention.py:303-320 / opt_attention.py:285-302) -- identical y, and
+    logits equal to oeh_gate_logits on that y."""
+    from outeffhop_b200 import ops
+    torch.manual_seed(5)
+    B, T, H = 3, 70, 12
+    a = torch.randn(B, T, 64 * H, device="cuda").to(dtype)
+    b = torch.randn(B, T, 64 * H, device="cuda").to(dtype)
+    w = (1 + 0.1 * torch.randn(64 * H, device="cuda")).to(dtype)
+    bias = (0.1 * torch.randn(64 * H, device="cuda")).to(dtype)
+    gw = torch.randn(H, 64, device="cuda") * 0.2
+    gb = torch.randn(H, device="cuda")
+    y0, s0 = ops.add_layer_norm(a, b, w, bias, 1e-5, return_sum=True)
+    y1, s1, logits = ops.add_layer_norm(a, b, w, bias, 1e-5, return_sum=True, gate=(gw, gb))
+    assert torch.equal(y0, y1) and torch.equal(s0, s1) and logits.shape == (B, H, T)
+    ref = ops.gate_logits(y0, H, gw, gb)
+    assert torch.allclose(logits, ref, atol=2e-5, rtol=1e-5), float((logits - ref).abs().max())
+    y2, logits2 = ops.add_layer_norm(a, None, w, bias, 1e-5, gate=(gw, gb))            # plain LayerNorm + gate
+    assert torch.equal(y2, ops.add_layer_norm(a, None, w, bias, 1e-5))
+    assert torch.allclose(logits2, ops.gate_logits(y2, H, gw, gb), atol=2e-5, rtol=1e-5)
