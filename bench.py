@@ -13,8 +13,8 @@ collective; the eval-loss (sum, count) pair is all-reduced once at the end.
 
 Prints ONE JSON line (rank 0).  ``value`` = whole-job tokens/s with inputs resident in HBM; ``e2e`` = the same
 through the module API with pinned-host inputs (H2D) and a host read of the loss (D2H) every step;
-``roofline`` = the fused attention kernel (the dominant kernel of THIS code; the rest of the step is library
-GEMMs) timed alone with CUDA events on its launch stream on the model's own Q/K/V shapes;
+``roofline`` = the fused attention kernel (the hot path's own kernel; the step's largest single kernel is now this
+repo's FFN1 GEMM with the GELU epilogue, the other GEMMs are library calls) timed alone with CUDA events on its launch stream on the model's own Q/K/V shapes;
 ``cpu_baseline`` = the oracle port of the reference path on the host cores (rank 0, N=1).
 """
 from __future__ import annotations
@@ -452,7 +452,9 @@ def run_ours(args):
                        "l2": "no flush: 220 MB of fp16 weights + activations per step exceed the 126 MB L2"},
             "e2e": {"value": tokens / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": step.h2d_bytes(),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps},
-            "gpu_launches": (4 * LAYERS + 2) * steps,     # per step and layer: fused attention + 2 x fused add+LayerNorm + erf GELU; + the 2 loss kernels
+            # own kernels per step: per layer the fused attention, 2 x fused add+LayerNorm and the tcgen05 FFN1 GEMM with the
+            # erf GELU in its epilogue (oeh_linear_fwd); + the 2 loss kernels (the other GEMMs are cuBLASLt)
+            "gpu_launches": (4 * LAYERS + 2) * steps,
             "clocks": clocks,
             "perplexity": ppl,
             "roofline": {"kernel": "attn_fwd_one_kernel<fp16> (fused QK^T->clippedsoftmax1->PV, one K/V tile), "
