@@ -302,6 +302,14 @@ int oeh_fake_quant_asym_segments(const void* x, void* y, int64_t rows, int32_t s
  * ------------------------------------------------------------------------------------------- */
 int oeh_gelu_erf(const void* x, void* y, int64_t n, int32_t dtype, oeh_stream_t stream);
 
+/* HF BertEmbeddings.forward (transformers modeling_bert; the embedding shell the reference's models keep, quantized at
+ * quantized_bert.py:146-218) in one launch: y[r] = LayerNorm((word[ids[r]] + type[type_ids[r]]) + pos[pos_ids[r]]), sums in
+ * the tensor dtype in that order (each rounded once, as the two ATen adds do).  type_ids NULL = type 0, pos_ids NULL =
+ * r % T; type_table / pos_table may be NULL.  ids are clamped to [0, vocab).  rows = B*T. */
+int oeh_embed_layer_norm(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const void* word,
+                         const void* type_table, const void* pos_table, const void* weight, const void* bias, void* y,
+                         int64_t rows, int64_t cols, int32_t T, int64_t vocab, double eps, int32_t dtype, oeh_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Linear layer with fused epilogue:  y = tap( act( x . w^T + bias ) ),  x (M,K), w (N,K) = nn.Linear.weight, y (M,N),
  * row strides ldx / ldw / ldy in elements, fp16 / bf16 operands, fp32 accumulation (tcgen05, TMEM accumulators).

@@ -112,6 +112,9 @@ SYMBOLS = {
                                                C.c_int64, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "oeh_gelu_erf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "oeh_linear_fwd": (C.c_int, [C.POINTER(OehLinearArgs)]),
+    "oeh_embed_layer_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_double,
+                                       C.c_int32, C.c_void_p]),
 }
 # test-only entry point (not part of the public header)
 _PRIVATE = {

@@ -150,6 +150,106 @@ add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T*
   }
 }
 
+// BertEmbeddings.forward (HF modeling_bert, the shell around the reference's encoder): y = LayerNorm((word[id] + type[tt])
+// + pos[p]) -- three gathers, two adds and a LayerNorm in ATen (6 launches, the sums materialised); here one warp gathers
+// the three rows, adds them in the tensor dtype in the same order (each sum rounded once, like the two ATen adds) and
+// normalises in registers.  token_type_ids / position_ids may be NULL (type 0 / position = token index within its sequence).
+template <typename T, int kVecs>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+embed_layer_norm_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ type_ids,
+                        const int64_t* __restrict__ pos_ids, const T* __restrict__ word, const T* __restrict__ type_tab,
+                        const T* __restrict__ pos_tab, const T* __restrict__ gamma, const T* __restrict__ beta,
+                        T* __restrict__ y, int64_t rows, int cols, int T_len, int64_t vocab, float eps) {
+  using V = Vec16<T>;
+  constexpr int N = V::N;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = cols / N;
+  int64_t id = __ldg(ids + row);
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);        // out-of-range ids raise in torch; never fault here
+  const int64_t tt = type_ids ? __ldg(type_ids + row) : 0;
+  const int64_t pp = pos_ids ? __ldg(pos_ids + row) : row % T_len;
+  const V* wv = reinterpret_cast<const V*>(word + id * cols);
+  const V* tv = type_tab ? reinterpret_cast<const V*>(type_tab + tt * cols) : nullptr;
+  const V* pv = pos_tab ? reinterpret_cast<const V*>(pos_tab + pp * cols) : nullptr;
+  float x[kVecs][N];
+  float sum = 0.f;
+#pragma unroll
+  for (int v = 0; v < kVecs; ++v) {
+    const int i = lane + 32 * v;
+    V a;
+    if (i < nvec) {
+      a = wv[i];
+      if (tv) add_vec<T>(a, tv[i]);
+      if (pv) add_vec<T>(a, pv[i]);
+    }
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+      const float sv = i < nvec ? DT<T>::to_f(a.v[e]) : 0.f;
+      x[v][e] = sv;
+      sum += sv;
+    }
+  }
+  const float mean = warp_sum(sum) / (float)cols;
+  float ssq = 0.f;
+#pragma unroll
+  for (int v = 0; v < kVecs; ++v)
+    if (lane + 32 * v < nvec) {
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        const float d = x[v][e] - mean;
+        ssq = fmaf(d, d, ssq);
+      }
+    }
+  const float rstd = rsqrtf(warp_sum(ssq) / (float)cols + eps);
+  const V* gv = reinterpret_cast<const V*>(gamma);
+  const V* bev = reinterpret_cast<const V*>(beta);
+  V* yv = reinterpret_cast<V*>(y + row * cols);
+#pragma unroll
+  for (int v = 0; v < kVecs; ++v) {
+    const int i = lane + 32 * v;
+    if (i < nvec) {
+      const V g = gv[i];
+      V be, out;
+      if (beta) be = bev[i];
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        float r = DT<T>::to_f(g.v[e]) * (rstd * (x[v][e] - mean));
+        if (beta) r += DT<T>::to_f(be.v[e]);
+        out.v[e] = DT<T>::from_f(r);
+      }
+      yv[i] = out;
+    }
+  }
+}
+
+template <typename T>
+int launch_embed(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const void* word, const void* type_tab,
+                 const void* pos_tab, const void* gamma, const void* beta, void* y, int64_t rows, int64_t cols, int T_len,
+                 int64_t vocab, float eps, cudaStream_t st) {
+  constexpr int N = Vec16<T>::N;
+  if (cols % N != 0 || cols / N > 32 * 8)
+    return set_error(OEH_ERR_UNSUPPORTED, "oeh_embed_layer_norm: cols=%lld must be a multiple of %d and at most %d",
+                     (long long)cols, N, 32 * 8 * N);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(word) | reinterpret_cast<uintptr_t>(type_tab) | reinterpret_cast<uintptr_t>(pos_tab) |
+                       reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(y);
+  if (al & 15) return set_error(OEH_ERR_UNSUPPORTED, "oeh_embed_layer_norm: pointers must be 16-byte aligned");
+  const int kv = (int)((cols / N + 31) / 32);
+  const unsigned grid = (unsigned)((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+#define OEH_EMB_CASE(K)                                                                                                       \
+  case K:                                                                                                                     \
+    embed_layer_norm_kernel<T, K><<<grid, kWarpsPerBlock * 32, 0, st>>>(ids, type_ids, pos_ids, (const T*)word,               \
+                                                                        (const T*)type_tab, (const T*)pos_tab, (const T*)gamma, \
+                                                                        (const T*)beta, (T*)y, rows, (int)cols, T_len, vocab, eps); \
+    break;
+  switch (kv) {
+    OEH_EMB_CASE(1) OEH_EMB_CASE(2) OEH_EMB_CASE(3) OEH_EMB_CASE(4) OEH_EMB_CASE(5) OEH_EMB_CASE(6) OEH_EMB_CASE(7) OEH_EMB_CASE(8)
+  }
+#undef OEH_EMB_CASE
+  return check_launch("embed_layer_norm_kernel");
+}
+
 template <typename T>
 int launch(const void* a, const void* b, const void* gamma, const void* beta, void* y, int64_t rows, int64_t cols, float eps,
            const float* q_a, const float* q_res, const float* q_out, int n_bits, void* sum_out, cudaStream_t st,
@@ -231,4 +331,24 @@ extern "C" int oeh_add_layer_norm_gate(const void* a, const void* b, const void*
                                    sum_out, st, gate_w, gate_b, gate_out, T, H);
   }
   return set_error(OEH_ERR_BAD_ARG, "oeh_add_layer_norm: unknown dtype %d", dtype);
+}
+
+extern "C" int oeh_embed_layer_norm(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const void* word,
+                                    const void* type_table, const void* pos_table, const void* weight, const void* bias, void* y,
+                                    int64_t rows, int64_t cols, int32_t T, int64_t vocab, double eps, int32_t dtype,
+                                    oeh_stream_t stream) {
+  OEH_CHECK_ARG(rows >= 0 && cols > 0 && T > 0 && vocab > 0, "oeh_embed_layer_norm: bad shape");
+  if (rows == 0) return OEH_OK;
+  OEH_CHECK_ARG(ids && word && weight && y, "oeh_embed_layer_norm: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case OEH_F32:
+      return launch_embed<float>(ids, type_ids, pos_ids, word, type_table, pos_table, weight, bias, y, rows, cols, T, vocab, (float)eps, st);
+    case OEH_F16:
+      return launch_embed<__half>(ids, type_ids, pos_ids, word, type_table, pos_table, weight, bias, y, rows, cols, T, vocab, (float)eps, st);
+    case OEH_BF16:
+      return launch_embed<__nv_bfloat16>(ids, type_ids, pos_ids, word, type_table, pos_table, weight, bias, y, rows, cols, T, vocab,
+                                         (float)eps, st);
+  }
+  return set_error(OEH_ERR_BAD_ARG, "oeh_embed_layer_norm: unknown dtype %d", dtype);
 }

@@ -16,8 +16,8 @@ from typing import Callable, Dict, Optional
 
 import torch
 
-from .hf_compat import (fuse_bert_gelu, fuse_bert_residual_blocks, fuse_opt_decoder_layers, swap_bert_attention,
-                        swap_opt_attention)
+from .hf_compat import (fuse_bert_gelu, fuse_bert_residual_blocks, fuse_bert_shell, fuse_opt_decoder_layers,
+                        swap_bert_attention, swap_opt_attention)
 
 
 # ---- model / data builders ---------------------------------------------------------------------------------
@@ -26,7 +26,8 @@ def build_bert_base(seed: int = 3000, dtype=torch.float16, device="cuda", attn_s
                     num_hidden_layers: int = 12, fuse_residual: bool = True, **attn_kw):
     """BertConfig() defaults = BERT-base (12L/768/12H/3072, vocab 30522), random init (Cfg1/Cfg2).
     ``fuse_residual``: also swap BertSelfOutput / BertOutput for the fused add + LayerNorm modules and the FFN
-    activation for the library's erf GELU."""
+    activation for the library's erf GELU (in the FFN1 GEMM epilogue), and the embeddings / MLM-head transform for their
+    one-kernel forms."""
     from transformers import BertConfig, BertForMaskedLM
     cfg = BertConfig(num_hidden_layers=num_hidden_layers)
     cfg._attn_implementation = "eager"
@@ -34,7 +35,7 @@ def build_bert_base(seed: int = 3000, dtype=torch.float16, device="cuda", attn_s
     model = BertForMaskedLM(cfg)
     model = model.to(device=device, dtype=dtype).eval()
     model = swap_bert_attention(model, attn_softmax=attn_softmax, max_seq_length=128, **attn_kw)
-    return fuse_bert_gelu(fuse_bert_residual_blocks(model)) if fuse_residual else model
+    return fuse_bert_shell(fuse_bert_gelu(fuse_bert_residual_blocks(model))) if fuse_residual else model
 
 
 def build_opt_125m(seed: int = 5678, dtype=torch.float16, device="cuda", attn_softmax="vanilla",

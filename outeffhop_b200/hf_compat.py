@@ -197,6 +197,76 @@ def fuse_bert_gelu(model):
     return model
 
 
+class BertEmbeddingsFused(torch.nn.Module):
+    """HF ``BertEmbeddings`` (the embedding shell the reference keeps; quantized at quantized_bert.py:146-218) for eval with
+    absolute positions: three gathers, two adds and the LayerNorm in ONE kernel (``oeh_embed_layer_norm``; the sums are rounded
+    in the tensor dtype in HF's order).  Same submodule / buffer names, so state_dicts and the quantized wrapper keep working;
+    anything else (training, ``inputs_embeds``, hooks on a submodule) runs the original forward."""
+
+    def __init__(self, org):
+        super().__init__()
+        self.__dict__["_org"] = org                     # not a registered submodule: its children are re-registered below
+        for name, mod in org.named_children():
+            self.add_module(name, mod)
+        for name, buf in org.named_buffers(recurse=False):
+            self.register_buffer(name, buf, persistent=name in org.state_dict())
+        self.position_embedding_type = getattr(org, "position_embedding_type", "absolute")
+
+    def forward(self, input_ids=None, token_type_ids=None, position_ids=None, inputs_embeds=None, past_key_values_length=0):
+        mods = (self.word_embeddings, self.position_embeddings, self.token_type_embeddings, self.LayerNorm)
+        w = self.word_embeddings.weight
+        if (self.training or input_ids is None or inputs_embeds is not None or past_key_values_length != 0
+                or self.position_embedding_type != "absolute" or not w.is_cuda or input_ids.dim() != 2
+                or any(m._forward_hooks or m._forward_pre_hooks for m in mods)
+                or (torch.is_grad_enabled() and w.requires_grad) or self.LayerNorm.weight.dtype != w.dtype):
+            return self._org.forward(input_ids=input_ids, token_type_ids=token_type_ids, position_ids=position_ids,
+                                     inputs_embeds=inputs_embeds, past_key_values_length=past_key_values_length)
+        from . import ops
+        ln = self.LayerNorm
+        try:
+            return ops.embed_layer_norm(input_ids, w, self.position_embeddings.weight, self.token_type_embeddings.weight,
+                                        ln.weight, ln.bias, ln.eps, token_type_ids=token_type_ids, position_ids=position_ids)
+        except NotImplementedError:                     # hidden size the register-resident kernel is not built for
+            return self._org.forward(input_ids=input_ids, token_type_ids=token_type_ids, position_ids=position_ids)
+
+
+class BertHeadTransformFused(torch.nn.Module):
+    """HF ``BertPredictionHeadTransform`` (dense -> GELU -> LayerNorm, the FP32/FP16 MLM head the reference leaves
+    unquantized, quantized_bert.py:866-870) with the library's kernels: GELU in the GEMM epilogue, LayerNorm in one pass."""
+
+    def __init__(self, org):
+        super().__init__()
+        self.dense, self.transform_act_fn, self.LayerNorm = org.dense, org.transform_act_fn, org.LayerNorm
+
+    def forward(self, hidden_states):
+        d, ln = self.dense, self.LayerNorm
+        if (self.training or not hidden_states.is_cuda or hidden_states.dtype not in (torch.float16, torch.bfloat16)
+                or type(d) is not torch.nn.Linear or d.weight.dtype != hidden_states.dtype or not _is_erf_gelu(self.transform_act_fn)
+                or (torch.is_grad_enabled() and (hidden_states.requires_grad or d.weight.requires_grad))
+                or any(m._forward_hooks or m._forward_pre_hooks for m in (d, ln))
+                or isinstance(self.transform_act_fn, torch.nn.Module) and (self.transform_act_fn._forward_hooks or self.transform_act_fn._forward_pre_hooks)
+                or d.out_features % 8 or d.in_features % 8 or ln.bias is None):
+            return ln(self.transform_act_fn(d(hidden_states)))
+        from . import ops
+        x = ops.linear_fwd(hidden_states, d.weight, d.bias, act="gelu")
+        try:
+            return ops.add_layer_norm(x, None, ln.weight, ln.bias, ln.eps)
+        except NotImplementedError:
+            return ln(x)
+
+
+def fuse_bert_shell(model):
+    """Swap ``bert.embeddings`` for :class:`BertEmbeddingsFused` and the MLM head's transform for :class:`BertHeadTransformFused`
+    (eval only; other heads / embedding variants are left alone)."""
+    bert = getattr(model, "bert", model)
+    if type(bert.embeddings).__name__ == "BertEmbeddings":
+        bert.embeddings = BertEmbeddingsFused(bert.embeddings).train(bert.embeddings.training)
+    pred = getattr(getattr(model, "cls", None), "predictions", None)
+    if pred is not None and type(pred.transform).__name__ == "BertPredictionHeadTransform":
+        pred.transform = BertHeadTransformFused(pred.transform).train(pred.transform.training)
+    return model
+
+
 class OPTDecoderLayerFused(torch.nn.Module):
     """HF OPTDecoderLayer (pre-LayerNorm variants: 125m, 1.3b, ...; the module the reference wraps at
     quantized_opt.py:277-384) for eval with fewer, fused launches: LayerNorm kernels from liboeh, ``residual + attn`` and

@@ -474,3 +474,27 @@ def linear_fwd(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     a.stream = _stream()
     L.check(L.lib().oeh_linear_fwd(C.byref(a)))
     return y if out is not None else y.view(*x.shape[:-1], N)
+
+
+def embed_layer_norm(input_ids: torch.Tensor, word: torch.Tensor, pos: Optional[torch.Tensor], tok_type: Optional[torch.Tensor],
+                     weight: torch.Tensor, bias: Optional[torch.Tensor], eps: float, token_type_ids: Optional[torch.Tensor] = None,
+                     position_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``LayerNorm((word[ids] + tok_type[token_type_ids]) + pos[position_ids])`` in one launch (oeh_embed_layer_norm): HF
+    BertEmbeddings.forward for (B,T) int64 ids; missing ``token_type_ids`` = type 0, missing ``position_ids`` = 0..T-1."""
+    _require_cuda(input_ids, word, pos, tok_type, weight, bias, token_type_ids, position_ids)
+    B, T = input_ids.shape
+    cols = word.shape[1]
+    for t in (pos, tok_type):
+        if t is not None and (t.dtype != word.dtype or t.shape[1] != cols or not t.is_contiguous()):
+            raise ValueError("embed_layer_norm: tables must be contiguous, of one dtype and one width")
+    ids = input_ids.contiguous()
+    tt = None if token_type_ids is None else token_type_ids.expand(B, T).contiguous()
+    pp = None if position_ids is None else position_ids.expand(B, T).contiguous()
+    y = torch.empty((B, T, cols), dtype=word.dtype, device=word.device)
+    L.check(L.lib().oeh_embed_layer_norm(ids.data_ptr(), tt.data_ptr() if tt is not None else None,
+                                         pp.data_ptr() if pp is not None else None, word.contiguous().data_ptr(),
+                                         tok_type.data_ptr() if tok_type is not None else None,
+                                         pos.data_ptr() if pos is not None else None, weight.contiguous().data_ptr(),
+                                         bias.contiguous().data_ptr() if bias is not None else None, y.data_ptr(), B * T, cols, T,
+                                         word.shape[0], float(eps), _dtype_code(word), _stream()))
+    return y

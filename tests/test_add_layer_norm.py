@@ -206,3 +206,32 @@ def test_add_layer_norm_emits_gate_logits(dtype):
     y2, logits2 = ops.add_layer_norm(a, None, w, bias, 1e-5, gate=(gw, gb))            # plain LayerNorm + gate
     assert torch.equal(y2, ops.add_layer_norm(a, None, w, bias, 1e-5))
     assert torch.allclose(logits2, ops.gate_logits(y2, H, gw, gb), atol=2e-5, rtol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+def test_fused_bert_embeddings_and_head_transform_match_hf(dtype):
+    """hf_compat.fuse_bert_shell: BertEmbeddings (3 gathers + 2 adds + LayerNorm) and BertPredictionHeadTransform
+    (dense + GELU + LayerNorm) as single kernels vs the HF modules they replace."""
+    from transformers import BertConfig, BertForMaskedLM
+    from outeffhop_b200 import hf_compat
+    cfg = BertConfig(num_hidden_layers=1)
+    torch.manual_seed(0)
+    ref = BertForMaskedLM(cfg).cuda().to(dtype).eval()
+    with torch.no_grad():
+        ref.bert.embeddings.LayerNorm.weight.add_(0.1 * torch.randn_like(ref.bert.embeddings.LayerNorm.weight))
+    import copy
+    fused = hf_compat.fuse_bert_shell(copy.deepcopy(ref))
+    assert isinstance(fused.bert.embeddings, hf_compat.BertEmbeddingsFused)
+    assert list(fused.state_dict()) == list(ref.state_dict())
+    ids = torch.randint(0, cfg.vocab_size, (4, 128), device="cuda")
+    tt = torch.randint(0, 2, (4, 128), device="cuda")
+    with torch.no_grad():
+        for kw in ({}, {"token_type_ids": tt}, {"position_ids": torch.arange(127, -1, -1, device="cuda")[None]}):
+            a, b = fused.bert.embeddings(input_ids=ids, **kw), ref.bert.embeddings(input_ids=ids, **kw)
+            tol = 1e-5 if dtype == torch.float32 else (2e-3 if dtype == torch.float16 else 2e-2)
+            assert (a.float() - b.float()).abs().max().item() <= tol, kw      # same sums; LayerNorm rounding differs by <= 1 ulp
+        if dtype != torch.float32:
+            h = torch.randn(4, 128, cfg.hidden_size, device="cuda").to(dtype)
+            a, b = fused.cls.predictions.transform(h), ref.cls.predictions.transform(h)
+            assert (a.float() - b.float()).abs().max().item() <= (6e-3 if dtype == torch.float16 else 5e-2)
