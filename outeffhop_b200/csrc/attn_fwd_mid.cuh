@@ -30,9 +30,14 @@ namespace attn_mid {
 using namespace attn;
 
 constexpr int BM = 128;                          // query rows per CTA
-constexpr int CW = 64;                           // keys per softmax chunk
 constexpr int kMaxTiles = 4;                     // K / V tiles of 128 keys resident at once (Tk <= 512)
-constexpr int kSoftmaxWarps = 8, kThreads = (kSoftmaxWarps + 1) * 32;
+// kParts threads per query row (2 or 4): warps w, w+4, ... share TMEM lane quarter w & 3 and split a 128-key tile into kParts
+// chunks of CW = 128 / kParts keys
+template <int kParts>
+struct Shape {
+  static constexpr int CW = 128 / kParts;
+  static constexpr int kSoftmaxWarps = 4 * kParts, kThreads = (kSoftmaxWarps + 1) * 32;
+};
 constexpr int kSmemBytes = (1 + 2 * kMaxTiles) * kTileBytes + 1024;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColO = 448;
@@ -45,14 +50,15 @@ struct Barriers {
   uint64_t o_full;                               // O complete
 };
 
-template <bool kBF16, bool kGeneric>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool kBF16, bool kGeneric, int kParts>
+__global__ void __launch_bounds__(Shape<kParts>::kThreads, 1)
 attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                     const __grid_constant__ CUtensorMap tmv, const __grid_constant__ AttnParams p) {
+  constexpr int CW = Shape<kParts>::CW, kSoftmaxWarps = Shape<kParts>::kSoftmaxWarps;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) Barriers bars;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float xch_m[2][BM], xch_l[2][BM];
+  __shared__ float xch_m[kParts][BM], xch_l[kParts][BM];
 
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -137,11 +143,11 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     __syncwarp();
   } else {
     // ================================ softmax: two threads per row ====================================================
-    const int half = warp >> 2;                                 // chunk parity this thread takes
+    const int half = warp >> 2;                                 // which of the kParts chunks of a tile this thread takes
     const int r = (warp & 3) * 32 + (tid & 31);                 // row within the tile == TMEM lane
     const int row = q0 + r;
     const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const int pair_bar = 2 + (warp & 3);                        // named barrier of the two warps of a lane quarter
+    const int pair_bar = 2 + (warp & 3);                        // named barrier of the kParts warps of a lane quarter
 
     const bool softmax1 = (p.kind == OEH_SOFTMAX_1 || p.kind == OEH_SOFTMAX_CLIPPED1);
     const bool clipped = p.kind >= OEH_SOFTMAX_CLIPPED;
@@ -163,14 +169,14 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     for (int i = 0; i < kMaxTiles; ++i) {
       mc[i] = 0.f;
       if (i < n_kv) {
-        const int j = 2 * i + half, k0 = j * CW;
+        const int j = kParts * i + half, k0 = j * CW;
         ptx::mbar_wait(ptx::smem_u32(&bars.s_full[i]), 0);
         ptx::tc_fence_after();
         float s[CW];
-        ptx::tmem_ld32(t_lane + j * CW, reinterpret_cast<uint32_t*>(s));
-        ptx::tmem_ld32(t_lane + j * CW + 32, reinterpret_cast<uint32_t*>(s) + 32);
+#pragma unroll
+        for (int c = 0; c < CW / 32; ++c) ptx::tmem_ld32(t_lane + j * CW + 32 * c, reinterpret_cast<uint32_t*>(s) + 32 * c);
         ptx::tmem_wait_ld();
-        if (kGeneric && p.dbg_s && j < 2 && row < p.Tq) {       // raw S of keys [0, 128)
+        if (kGeneric && p.dbg_s && j < kParts && row < p.Tq) {  // raw S of keys [0, 128)
           float* d = p.dbg_s + (((int64_t)b * p.H + h) * p.Tq + row) * BN + k0;
 #pragma unroll
           for (int c = 0; c < CW; ++c) d[c] = s[c];
@@ -184,20 +190,23 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         l_run = fmaf(l_run, alpha, exp2_and_sum<CW, !kGeneric>(s, mul, m_safe));
         m_run = m_new;
         mc[i] = m_safe;
-        ptx::tmem_st32(t_lane + j * CW, reinterpret_cast<const uint32_t*>(s));
-        ptx::tmem_st32(t_lane + j * CW + 32, reinterpret_cast<const uint32_t*>(s) + 32);
+#pragma unroll
+        for (int c = 0; c < CW / 32; ++c) ptx::tmem_st32(t_lane + j * CW + 32 * c, reinterpret_cast<const uint32_t*>(s) + 32 * c);
       }
     }
     ptx::tmem_wait_st();
 
-    // ---- the two halves of a row agree on (m, denominator) --------------------------------------------------------------
+    // ---- the kParts threads of a row agree on (m, denominator) -----------------------------------------------------------
     xch_m[half][r] = m_run;
     xch_l[half][r] = l_run;
     asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
-    const float m_o = xch_m[half ^ 1][r], l_o = xch_l[half ^ 1][r];
-    const float m_all = fmaxf(m_run, m_o);
+    float m_all = m_run;
+#pragma unroll
+    for (int q2 = 0; q2 < kParts; ++q2) m_all = fmaxf(m_all, xch_m[q2][r]);
     const float m_fin = m_all == -INFINITY ? 0.f : m_all;
-    float den = l_run * ptx::ex2(m_run - m_fin) + l_o * ptx::ex2(m_o - m_fin);
+    float den = 0.f;
+#pragma unroll
+    for (int q2 = 0; q2 < kParts; ++q2) den = fmaf(xch_l[q2][r], ptx::ex2(xch_m[q2][r] - m_fin), den);
     if (softmax1) den += ptx::ex2(-m_fin);
     const float inv_den = __frcp_rn(den);
     const float omul = normalized ? 1.f : inv_den;              // one-pass kinds: P stays in the row-max frame (max P = 1)
@@ -206,14 +215,14 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
 #pragma unroll
     for (int i = 0; i < kMaxTiles; ++i) {
       if (i < n_kv) {
-        const int j = 2 * i + half;
+        const int j = kParts * i + half;
         float s[CW];
-        ptx::tmem_ld32(t_lane + j * CW, reinterpret_cast<uint32_t*>(s));
-        ptx::tmem_ld32(t_lane + j * CW + 32, reinterpret_cast<uint32_t*>(s) + 32);
+#pragma unroll
+        for (int c = 0; c < CW / 32; ++c) ptx::tmem_ld32(t_lane + j * CW + 32 * c, reinterpret_cast<uint32_t*>(s) + 32 * c);
         ptx::tmem_wait_ld();
-        // P(2i), P(2i+1) overwrite e-chunk i, read by its owner in iteration i / 2 (this one when i == 0): both halves of the
-        // row must have issued AND completed their reads of this iteration before either writes
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        // The P chunks of iteration i (kParts * CW / 2 = 64 packed columns) overwrite e-chunks read in iteration <= i (in this very
+        // iteration when i == 0): every thread of the row must have COMPLETED its reads of this iteration before any writes
+        asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * kParts) : "memory");
         const float f = ptx::ex2(mc[i] - m_fin);                // chunk frame -> common frame (mc <= m_fin)
         if (normalized) {
           normalize_probs<CW, kGeneric, kBF16>(s, p, inv_den * f, clipped, has_qp, qd_p);
@@ -224,7 +233,8 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         uint32_t pk[CW / 2];
 #pragma unroll
         for (int c = 0; c < CW / 2; ++c) pk[c] = pack2<kBF16>(s[2 * c], s[2 * c + 1]);
-        ptx::tmem_st32(t_lane + j * (CW / 2), pk);
+        if constexpr (CW == 64) ptx::tmem_st32(t_lane + j * (CW / 2), pk);
+        else ptx::tmem_st16(t_lane + j * (CW / 2), pk);
       }
     }
     ptx::tmem_wait_st();
@@ -232,13 +242,15 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     __syncwarp();
     if (ptx::elect_one()) ptx::mbar_arrive(ptx::smem_u32(&bars.p_full));
 
-    // ---- epilogue: each half finishes 32 head-dim columns of its row ------------------------------------------------------
+    // ---- epilogue: each of the row's threads finishes 64 / kParts head-dim columns ---------------------------------------------
     ptx::mbar_wait(ptx::smem_u32(&bars.o_full), 0);
     ptx::tc_fence_after();
-    float o[32];
-    ptx::tmem_ld32(t_lane + kColO + half * 32, reinterpret_cast<uint32_t*>(o));
+    constexpr int ND = HD / kParts;
+    float o[ND];
+    if constexpr (ND == 32) ptx::tmem_ld32(t_lane + kColO + half * ND, reinterpret_cast<uint32_t*>(o));
+    else ptx::tmem_ld16(t_lane + kColO + half * ND, reinterpret_cast<uint32_t*>(o));
     ptx::tmem_wait_ld();
-    if (row < p.Tq) store_row<kBF16, kGeneric, 32>(o, p, omul, b, h, row, half * 32);
+    if (row < p.Tq) store_row<kBF16, kGeneric, ND>(o, p, omul, b, h, row, half * ND);
   }
 
   ptx::tc_fence_before();

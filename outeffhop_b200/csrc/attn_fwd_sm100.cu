@@ -496,13 +496,17 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
     if (f == 1) { use_ws = true; use_one = false; }
   }
   if (use_one) use_ws = false;
-  // 128 < Tk <= 512: the whole score row block fits TMEM, so the single-pass kernel of attn_fwd_mid.cuh can replace the
-  // two-pass one.  Measured (profiles/r02_mid_kernel_h.jsonl, B=4 H=12 T=512): causal with the INT8 taps 18.8 vs 22.2 us
-  // (the config-4 shape); clipped without taps 14.6 vs 14.5 us; non-causal with taps 29.7 vs 28.3 us; the one-pass kinds are
-  // faster on the persistent kernel (11.6 vs 14.6 us).  One CTA per SM (512 TMEM columns) costs it the overlap the two-pass
-  // kernel gets from two co-resident CTAs, so it is the default only where it wins.  OEH_MID_KERNEL=0 disables it, =1 sends
-  // every kind with Tk <= 512 there.
-  bool use_mid = norm_mode && a->qdq_probs != nullptr && a->causal && !use_one && a->Tk <= attn_mid::kMaxTiles * BN;
+  // 256 < Tk <= 512: the whole score row block fits TMEM, so the single-pass kernel of attn_fwd_mid.cuh can replace the
+  // two-pass one.  Measured (profiles/r02_mid_kernel_4perrow.jsonl, H=12, four threads per row), mid vs the default: with
+  // the INT8 taps B=4 T=512 18.3 vs 22.2 us causal (the config-4 shape) and 25.2 vs 28.3 us non-causal, B=16 T=384 43.5 vs
+  // 43.7, but B=8 T=256 16.8 vs 16.1 and B=32 T=512 causal 110 vs 101 us; clipped without taps 15.0 vs 14.8 us; the
+  // one-pass kinds are faster on the persistent kernel (11.6 vs 15.0 us).  One CTA per SM (512 TMEM columns) costs it the
+  // overlap the two-pass kernel gets from two co-resident CTAs, so it is the default only where it wins: tapped softmax,
+  // more than two key tiles, at most four waves of CTAs.  OEH_MID_KERNEL=0 disables it, =1 sends every kind with
+  // Tk <= 512 there (=3: the two-threads-per-row shape).
+  const long long row_blocks = (long long)a->B * a->H * ((a->Tq + BM - 1) / BM);
+  bool use_mid = norm_mode && a->qdq_probs != nullptr && !use_one && a->Tk > 2 * BN && a->Tk <= attn_mid::kMaxTiles * BN &&
+                 row_blocks <= 4LL * num_sms();
   if (const long long f = tune(kTuneMidKernel); f >= 0) use_mid = f != 0 && !use_one && a->Tk <= attn_mid::kMaxTiles * BN;
   if (tune(kTuneAttnKernel) >= 0) use_mid = false;
   if (use_mid) use_ws = false;
@@ -543,13 +547,19 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
   const int ki = (a->dtype == OEH_BF16 ? 2 : 0) + (generic ? 1 : 0);
   if (use_mid) {
-    static const KernelFn kernels[4] = {attn_mid::attn_fwd_mid_kernel<false, false>, attn_mid::attn_fwd_mid_kernel<false, true>,
-                                        attn_mid::attn_fwd_mid_kernel<true, false>, attn_mid::attn_fwd_mid_kernel<true, true>};
-    if ((rc = ensure_smem(reinterpret_cast<const void*>(kernels[ki]), attn_mid::kSmemBytes))) return rc;
+    // threads per query row: 4 (16 softmax warps) halves a row's serial work once more; OEH_MID_KERNEL=3 selects 2
+    static const KernelFn kernels[2][4] = {
+        {attn_mid::attn_fwd_mid_kernel<false, false, 2>, attn_mid::attn_fwd_mid_kernel<false, true, 2>,
+         attn_mid::attn_fwd_mid_kernel<true, false, 2>, attn_mid::attn_fwd_mid_kernel<true, true, 2>},
+        {attn_mid::attn_fwd_mid_kernel<false, false, 4>, attn_mid::attn_fwd_mid_kernel<false, true, 4>,
+         attn_mid::attn_fwd_mid_kernel<true, false, 4>, attn_mid::attn_fwd_mid_kernel<true, true, 4>}};
+    const int four = tune(kTuneMidKernel) == 3 ? 0 : 1;
+    KernelFn fn = kernels[four][ki];
+    if ((rc = ensure_smem(reinterpret_cast<const void*>(fn), attn_mid::kSmemBytes))) return rc;
     dim3 grid((unsigned)((a->Tq + BM - 1) / BM), (unsigned)a->H, (unsigned)a->B);
     p.n_qt = (int)grid.x;
     p.hb_chunk = a->H * a->B;                      // causal: ALL heaviest Q tiles first (K / V of a launch fit L2 many times over)
-    kernels[ki]<<<grid, attn_mid::kThreads, attn_mid::kSmemBytes, st>>>(tmq, tmk, tmv, p);
+    fn<<<grid, four ? attn_mid::Shape<4>::kThreads : attn_mid::Shape<2>::kThreads, attn_mid::kSmemBytes, st>>>(tmq, tmk, tmv, p);
     return check_launch("attn_fwd_mid_kernel");
   }
   if (use_ws) {

@@ -49,9 +49,9 @@ def main():
                          ("vanilla+gate", dict(kind=0)), ("softmax1", dict(kind=1))):
             row = dict(B=B, H=H, T=T, causal=causal, case=name)
             run = lambda s: ops.attention_fwd(s[0], s[1], s[2], scale=0.125, causal=causal, gate_logits=s[3], out=s[4], **kw)
-            for mid in ("0", "1"):
+            for mid in ("0", "1", "3"):
                 _lib.set_override("OEH_MID_KERNEL", mid)
-                row["mid_us" if mid == "1" else "other_us"] = round(time_launch(run, pool), 2)
+                row[{"0": "other_us", "1": "mid_us", "3": "mid_2perrow_us"}[mid]] = round(time_launch(run, pool), 2)
             _lib.set_override("OEH_MID_KERNEL", None)
             _lib.set_override("OEH_ATTN_KERNEL", "tile")          # one 128-row Q tile per 128-thread CTA, two CTAs per SM
             row["tile_us"] = round(time_launch(run, pool), 2)
