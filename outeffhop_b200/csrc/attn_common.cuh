@@ -334,8 +334,8 @@ __device__ __forceinline__ float zero_prob_threshold(const AttnParams& p, bool c
 // o[] holds the PV accumulator; mul = 1/denominator (1 in the normalised modes).
 // ctx -> [qdq before gate] -> * sigmoid(gate logit)*gate_scale -> [qdq after gate] -> ND/8 x 16-byte stores.
 template <bool kBF16, bool kGeneric, int ND = HD>
-__device__ __forceinline__ void store_row(float (&o)[ND], const AttnParams& p, float mul, int b, int h, int row,
-                                          int d0 = 0) {
+__device__ __forceinline__ void finish_row(float (&o)[ND], const AttnParams& p, float mul, int b, int h, int row,
+                                           int d0 = 0) {
   if (kGeneric && p.dbg_o) {
     float* d = p.dbg_o + (((int64_t)b * p.H + h) * p.Tq + row) * HD + d0;
 #pragma unroll
@@ -361,6 +361,12 @@ __device__ __forceinline__ void store_row(float (&o)[ND], const AttnParams& p, f
 #pragma unroll
     for (int j = 0; j < ND; ++j) o[j] *= mul;
   }
+}
+
+template <bool kBF16, bool kGeneric, int ND = HD>
+__device__ __forceinline__ void store_row(float (&o)[ND], const AttnParams& p, float mul, int b, int h, int row,
+                                          int d0 = 0) {
+  finish_row<kBF16, kGeneric, ND>(o, p, mul, b, h, row, d0);
   uint8_t* optr = reinterpret_cast<uint8_t*>(p.out) +
                   2 * ((int64_t)b * p.os0 + (int64_t)h * p.os1 + (int64_t)row * p.os2 + d0);
 #pragma unroll
@@ -371,6 +377,39 @@ __device__ __forceinline__ void store_row(float (&o)[ND], const AttnParams& p, f
     v.z = pack2<kBF16>(o[c * 8 + 4], o[c * 8 + 5]);
     v.w = pack2<kBF16>(o[c * 8 + 6], o[c * 8 + 7]);
     reinterpret_cast<uint4*>(optr)[c] = v;
+  }
+}
+
+// Warp-cooperative store of 32 finished context rows (lane == row, 64 values each; the caller has applied finish_row).
+// A thread storing its own 128-byte row sends 16 bytes to 32 different lines per instruction -- 256 partial-line requests
+// per warp, ~1 us at the end of every one-tile CTA (profiles/r02_timeline_one.txt).  Here the rows pass through the warp's
+// own 4 KB of shared memory (`stage`; 128-byte swizzle, conflict free both ways) and leave as FULL lines: 8 lanes per row,
+// 4 rows per instruction, 8 instructions.  Only __syncwarp() -- no CTA barrier.  row0 = global query row of lane 0.
+template <bool kBF16>
+__device__ __forceinline__ void store_rows_coalesced(const float (&o)[HD], const AttnParams& p, uint32_t stage, int b, int h,
+                                                     int row0) {
+  const uint32_t lane = threadIdx.x & 31u;
+  {
+    const uint32_t dst = stage + lane * 128u, sw = lane & 7u;
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c)
+      ptx::st_shared_v4(dst + (((uint32_t)c ^ sw) << 4), pack2<kBF16>(o[c * 8 + 0], o[c * 8 + 1]),
+                        pack2<kBF16>(o[c * 8 + 2], o[c * 8 + 3]), pack2<kBF16>(o[c * 8 + 4], o[c * 8 + 5]),
+                        pack2<kBF16>(o[c * 8 + 6], o[c * 8 + 7]));
+  }
+  __syncwarp();
+  const uint32_t cc = lane & 7u, rsub = lane >> 3;
+  uint8_t* obase = reinterpret_cast<uint8_t*>(p.out) + 2 * ((int64_t)b * p.os0 + (int64_t)h * p.os1) + cc * 16u;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t rr = (uint32_t)i * 4u + rsub;
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(stage + rr * 128u + ((cc ^ (rr & 7u)) << 4))
+                 : "memory");
+    const int row = row0 + (int)rr;
+    if (row < p.Tq) *reinterpret_cast<uint4*>(obase + 2 * (int64_t)row * p.os2) = v;
   }
 }
 

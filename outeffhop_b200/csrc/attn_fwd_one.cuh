@@ -36,6 +36,22 @@ constexpr int kSmemBytes = 3 * kTileBytes + 1024;
 constexpr uint32_t kTmemCols = 128;
 constexpr uint32_t kColO = 64;
 
+#ifdef OEH_TIMELINE
+__device__ unsigned long long* g_timeline = nullptr;   // experiment builds only (tools/timeline_one.py): 8 stamps per CTA
+__device__ __forceinline__ void stamp(int k) {
+  if (threadIdx.x == 0 && g_timeline) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    g_timeline[cta * 8 + k] = t;
+    if (k == 0) { uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_timeline[cta * 8 + 7] = sm; }
+  }
+}
+#define OEH_STAMP(k) stamp(k)
+#else
+#define OEH_STAMP(k)
+#endif
+
 template <int N>
 __device__ __forceinline__ void hide_invisible(float (&s)[N], int vis) {
   if (vis < N - 1) {
@@ -45,63 +61,11 @@ __device__ __forceinline__ void hide_invisible(float (&s)[N], int vis) {
   }
 }
 
-// kRegS: the whole S row (128 fp32) lives in registers -- ONE TMEM read instead of the 2-3 chunked passes, at 168
-// registers per thread, i.e. THREE CTAs per SM (444 slots still hold the whole C-BERT grid of 384).
-template <bool kBF16, bool kGeneric, bool kRegS = false>
-__global__ void __launch_bounds__(BM, kRegS ? 3 : 4)
-attn_fwd_one_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
-                    const __grid_constant__ CUtensorMap tmv, const __grid_constant__ AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[3];      // q+k, v, mma
-  __shared__ uint32_t tmem_base_slot;
-
-  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from it
-  // (role, TMEM lane base, barrier / descriptor addresses) on the uniform datapath instead of R2UR-ing it at every use
-  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
-  const int row = q0 + tid;
-
-  const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem0, sK = smem0 + kTileBytes, sV = smem0 + 2 * kTileBytes;
-  const uint32_t bar_qk = ptx::smem_u32(&bars[0]), bar_v = ptx::smem_u32(&bars[1]), bar_mma = ptx::smem_u32(&bars[2]);
-
-  constexpr uint32_t kIdescQK = ptx::make_idesc_f16(kBF16, BM, BN, false, false);
-  constexpr uint32_t kIdescPV = ptx::make_idesc_f16(kBF16, BM, HD, false, true);
-
-  if (warp == 0 && ptx::elect_one()) {
-    ptx::prefetch_tmap(&tmq);                    // descriptor fetches overlap the barrier initialisation
-    ptx::prefetch_tmap(&tmk);
-    ptx::prefetch_tmap(&tmv);
-    ptx::mbar_init(bar_qk, 1);
-    ptx::mbar_init(bar_v, 1);
-    ptx::mbar_init(bar_mma, 1);
-    ptx::fence_mbar_init();
-    // loads first: their latency covers the TMEM allocation and the barrier below
-    ptx::mbar_expect_tx(bar_qk, 2 * kTileBytes);
-    tma_tile(sQ, &tmq, bar_qk, p.cq, q0, h, b);
-    tma_tile(sK, &tmk, bar_qk, p.ck, 0, h, b);
-    ptx::mbar_expect_tx(bar_v, kTileBytes);
-    tma_tile(sV, &tmv, bar_v, p.cv, 0, h, b);
-  }
-  __syncwarp();
-  if (warp == 0) ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(&tmem_base_slot));
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem = tmem_base_slot;
-  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
-
-  if (warp == 0 && ptx::elect_one()) {
-    ptx::mbar_wait(bar_qk, 0);
-    ptx::tc_fence_after();
-#pragma unroll
-    for (int k = 0; k < HD / 16; ++k)
-      ptx::mma_ss(tmem, ptx::make_smem_desc_sw128(sQ + k * 32, 16, 1024), ptx::make_smem_desc_sw128(sK + k * 32, 16, 1024),
-                  kIdescQK, k > 0);
-    ptx::mma_commit(bar_mma);
-  }
-  __syncwarp();
-
+// One query row of a one-tile item: S (this thread's TMEM lane, columns 0..127) -> P (16 bit, columns 0..63 of the same lane).
+// `wait_s` blocks until the QK^T MMA has landed; what is set up before it overlaps the loads.  Returns the factor the epilogue
+// applies to the PV accumulator (1 / denominator for the online kinds, 1 for the normalised ones).
+template <bool kBF16, bool kGeneric, bool kRegS, class WaitS>
+__device__ __forceinline__ float softmax_row_to_p(uint32_t t_lane, const AttnParams& p, int b, int h, int row, WaitS&& wait_s) {
   // ---- per-row state (overlaps the loads / QK^T) -------------------------------------------------------------------
   const bool softmax1 = (p.kind == OEH_SOFTMAX_1 || p.kind == OEH_SOFTMAX_CLIPPED1);
   const bool clipped = p.kind >= OEH_SOFTMAX_CLIPPED;
@@ -117,8 +81,7 @@ attn_fwd_one_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   const int causal_lim = p.causal ? row + (p.Tk - p.Tq) : 0x7fffffff;
   const int n_ch = (p.Tk + CH - 1) / CH;          // chunks that hold real keys (1..4)
 
-  ptx::mbar_wait(bar_mma, 0);
-  ptx::tc_fence_after();
+  wait_s();
 
   float omul = 1.f;
   if constexpr (kRegS) {
@@ -241,9 +204,77 @@ attn_fwd_one_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     }
   }
   }   // chunked passes
+  return omul;
+}
+
+// kRegS: the whole S row (128 fp32) lives in registers -- ONE TMEM read instead of the 2-3 chunked passes, at 168
+// registers per thread, i.e. THREE CTAs per SM (444 slots still hold the whole C-BERT grid of 384).
+template <bool kBF16, bool kGeneric, bool kRegS = false>
+__global__ void __launch_bounds__(BM, kRegS ? 3 : 4)
+attn_fwd_one_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
+                    const __grid_constant__ CUtensorMap tmv, const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[3];      // q+k, v, mma
+  __shared__ uint32_t tmem_base_slot;
+
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from it
+  // (role, TMEM lane base, barrier / descriptor addresses) on the uniform datapath instead of R2UR-ing it at every use
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
+  const int row = q0 + tid;
+  OEH_STAMP(0);
+
+  const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem0, sK = smem0 + kTileBytes, sV = smem0 + 2 * kTileBytes;
+  const uint32_t bar_qk = ptx::smem_u32(&bars[0]), bar_v = ptx::smem_u32(&bars[1]), bar_mma = ptx::smem_u32(&bars[2]);
+
+  constexpr uint32_t kIdescQK = ptx::make_idesc_f16(kBF16, BM, BN, false, false);
+  constexpr uint32_t kIdescPV = ptx::make_idesc_f16(kBF16, BM, HD, false, true);
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmq);                    // descriptor fetches overlap the barrier initialisation
+    ptx::prefetch_tmap(&tmk);
+    ptx::prefetch_tmap(&tmv);
+    ptx::mbar_init(bar_qk, 1);
+    ptx::mbar_init(bar_v, 1);
+    ptx::mbar_init(bar_mma, 1);
+    ptx::fence_mbar_init();
+    // loads first: their latency covers the TMEM allocation and the barrier below
+    ptx::mbar_expect_tx(bar_qk, 2 * kTileBytes);
+    tma_tile(sQ, &tmq, bar_qk, p.cq, q0, h, b);
+    tma_tile(sK, &tmk, bar_qk, p.ck, 0, h, b);
+    ptx::mbar_expect_tx(bar_v, kTileBytes);
+    tma_tile(sV, &tmv, bar_v, p.cv, 0, h, b);
+  }
+  __syncwarp();
+  if (warp == 0) ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(&tmem_base_slot));
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  OEH_STAMP(1);
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::mbar_wait(bar_qk, 0);
+    ptx::tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < HD / 16; ++k)
+      ptx::mma_ss(tmem, ptx::make_smem_desc_sw128(sQ + k * 32, 16, 1024), ptx::make_smem_desc_sw128(sK + k * 32, 16, 1024),
+                  kIdescQK, k > 0);
+    ptx::mma_commit(bar_mma);
+  }
+  __syncwarp();
+
+  const float omul = softmax_row_to_p<kBF16, kGeneric, kRegS>(t_lane, p, b, h, row, [&] {
+    ptx::mbar_wait(bar_mma, 0);
+    ptx::tc_fence_after();
+    OEH_STAMP(2);
+  });
   ptx::tmem_wait_st();
   ptx::tc_fence_before();
   __syncthreads();
+  OEH_STAMP(3);
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::tc_fence_after();
@@ -259,6 +290,7 @@ attn_fwd_one_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   // ---- epilogue -----------------------------------------------------------------------------------------------------
   ptx::mbar_wait(bar_mma, 1);
   ptx::tc_fence_after();
+  OEH_STAMP(4);
   float o[HD];
   {
     uint32_t* orr = reinterpret_cast<uint32_t*>(o);
@@ -269,8 +301,10 @@ attn_fwd_one_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem);
-  if (row >= p.Tq) return;
-  store_row<kBF16, kGeneric>(o, p, omul, b, h, row);
+  OEH_STAMP(5);
+  if (row < p.Tq) finish_row<kBF16, kGeneric>(o, p, omul, b, h, row);
+  store_rows_coalesced<kBF16>(o, p, sQ + (uint32_t)warp * 4096u, b, h, q0 + warp * 32);   // Q is dead since the QK^T MMA
+  OEH_STAMP(6);
 }
 
 }  // namespace attn_one

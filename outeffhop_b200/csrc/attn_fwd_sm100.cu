@@ -441,6 +441,12 @@ extern "C" size_t oeh_attn_workspace_bytes(const OehAttnArgs* args) {
   return 0;
 }
 
+#ifdef OEH_TIMELINE
+extern "C" int oeh_set_timeline(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(attn_one::g_timeline, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
+}
+#endif
+
 extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg_o) {
   int rc = validate(a);
   if (rc) return rc;
@@ -642,7 +648,12 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
         {attn_one::attn_fwd_one_kernel<false, false, true>, attn_one::attn_fwd_one_kernel<false, true, true>,
          attn_one::attn_fwd_one_kernel<true, false, true>, attn_one::attn_fwd_one_kernel<true, true, true>}};
     // S row in registers (3 CTAs / SM, one TMEM read) vs chunked TMEM passes (4 CTAs / SM): 9.37 vs 9.88 us per launch at
-    // the C-BERT shape for the clipped kinds, 9.29 vs 9.52 us for softmax1 (profiles/r01_one_tile_regs_y.txt).  The generic
+    // the C-BERT shape for the clipped kinds, 9.29 vs 9.52 us for softmax1 (profiles/r01_one_tile_regs_y.txt; round 2, with the
+    // coalesced context store: 9.09 / 8.55 us).  A persistent form -- one CTA per SM, three 128-thread item slots, one TMEM
+    // allocation, all first-round loads in flight at once -- was built and measured in round 2 and is NOT faster (8.97 vs
+    // 8.55 us, profiles/r02_one_tile_persistent_vs_item.jsonl): the launch is HBM-bound while its ~19 MB land, and the
+    // per-item grid's natural stagger (the three CTAs of an SM enter ~0.9 us apart) lets the first CTA's softmax run under
+    // the others' loads, while simultaneous slots all receive their last byte together (profiles/r02_timeline_one.txt).  The generic
     // instantiation (taps / masks) does not fit 168 registers without spilling and keeps the chunked passes.
     int regs = generic ? 0 : 1;
     if (const long long f = tune(kTuneOneRegs); f >= 0) regs = f != 0;

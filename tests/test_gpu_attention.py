@@ -265,10 +265,11 @@ def test_attention_causal_work_order(persistent, chunk, kind, gamma, eta, overri
 @pytest.mark.parametrize("regs", ["0", "1"])
 @pytest.mark.parametrize("kind,gamma,eta", KINDS)
 @pytest.mark.parametrize("shape,causal", [((2, 3, 128, 128), False), ((2, 2, 50, 77), False), ((1, 2, 100, 100), True),
-                                          ((1, 1, 130, 1), False)])
+                                          ((1, 1, 130, 1), False), ((2, 2, 300, 100), False)])
 def test_attention_one_tile_softmax_shapes(regs, kind, gamma, eta, shape, causal, override):
     """One-tile kernel (Tk <= 128): S row held in registers (one TMEM read, 3 CTAs / SM) and the chunked TMEM passes
-    (4 CTAs / SM) against the oracle, on full, ragged, causal and single-key rows."""
+    (4 CTAs / SM) against the oracle, on full, ragged (rows of the last warp beyond Tq: the coalesced store must clip them),
+    causal and single-key rows."""
     ops = _ops()
     override("OEH_ONE_REGS", regs)
     B, H, Tq, Tk = shape
@@ -276,6 +277,37 @@ def test_attention_one_tile_softmax_shapes(regs, kind, gamma, eta, shape, causal
     out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal, out_layout="bhtd")
     ref = _oracle(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal)
     np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=TOL, rtol=0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("kind,gamma,eta", KINDS)
+def test_attention_one_tile_store_does_not_touch_neighbours(dtype, kind, gamma, eta):
+    """The one-tile kernel writes the context as full 128-byte lines staged per warp (store_rows_coalesced).  With the
+    reference's (B, T, H*d) layout and Tq = 100 the last warp of every tile holds rows beyond Tq, and a head's row is
+    flanked by the other heads' bytes: a canary-filled output must come back with exactly the rows of the result written."""
+    ops = _ops()
+    B, H, T = 3, 5, 100
+    q, k, v = _mk(B, H, T, T, dtype, seed=9 + kind, layout="bthd")
+    full = torch.full((B, T + 4, H * 64), 7.0, device="cuda", dtype=dtype)       # 4 canary rows behind every batch
+    want = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, out_layout="bhtd")
+    args = dict(scale=0.125, kind=kind, gamma=gamma, eta=eta)
+    # write through a strided view: out rows of batch b start at full[b, 0]
+    from outeffhop_b200 import _lib as L
+    import ctypes as C
+    a = L.OehAttnArgs()
+    view = full[:, :T].view(B, T, H, 64).permute(0, 2, 1, 3)
+    a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), view.data_ptr()
+    for name, t in (("q_strides", q), ("k_strides", k), ("v_strides", v), ("out_strides", view)):
+        setattr(a, name, (C.c_int64 * 3)(t.stride(0), t.stride(1), t.stride(2)))
+    a.B, a.H, a.Tq, a.Tk, a.d = B, H, T, T, 64
+    a.dtype = 1 if dtype == torch.float16 else 2
+    a.scale, a.kind, a.gamma, a.eta = args["scale"], kind, gamma, eta
+    a.gate_scale = 1.0
+    a.stream = torch.cuda.current_stream().cuda_stream
+    L.check(L.lib().oeh_attn_fwd(C.byref(a)))
+    torch.cuda.synchronize()
+    assert torch.equal(view.contiguous(), want)
+    assert bool((full[:, T:] == 7.0).all())
 
 
 @pytest.mark.parametrize("mid", ["0", "1", "3"])      # 0: two-pass / persistent kernels; 1: single pass, 4 threads per row; 3: 2 per row
