@@ -187,16 +187,24 @@ def time_attention_kernel(torch, ops, fn, dtype, pool_sets=8, reps=10):
     return sum(ts) / len(ts) * 1e-3     # seconds per launch
 
 
-def _event_time(torch, f, reps=5, warm=3):
+def _event_time(torch, f, reps=5, warm=3, clock=None):
+    """Seconds per call (CUDA events around `reps` back-to-back calls).  clock: optional one-element list that receives the SM
+    clock (MHz) the GPU was running at when the last call ended (outeffhop_b200._lib.sm_clock_probe, queued behind it)."""
     for _ in range(warm):
         f()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mhz = torch.zeros(1, device="cuda") if clock is not None else None
     torch.cuda.synchronize()
     a.record()
     for _ in range(reps):
         f()
     b.record()
+    if clock is not None:
+        from outeffhop_b200 import _lib
+        _lib.sm_clock_probe(mhz, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
+    if clock is not None:
+        clock.append(float(mhz.item()))
     return a.elapsed_time(b) * 1e-3 / reps
 
 
@@ -232,11 +240,19 @@ def attention_sweep(torch, ops, peaks):
                                       ("clippedsoftmax1_peaky", 3, -0.025, qp), ("clippedsoftmax1_dense", 3, 0.0, q),
                                       ("softmax1_causal", 1, 0.0, q)):
             causal = name.endswith("causal")
+            mhz = []
+            # ~10 ms of back-to-back launches per point after ~10 ms of warm-up: the first launches after the allocations
+            # above run up to 10 % slower (777 vs 845 TF/s at T=2048 with 3 + 5 launches, tools/sweep_clock.py)
             t = _event_time(torch, lambda: ops.attention_fwd(qq, k, v, scale=0.125, kind=kind, gamma=gamma, eta=1.1,
-                                                             causal=causal))
+                                                             causal=causal), reps=20 if T <= 2048 else 5,
+                            warm=20 if T <= 2048 else 5, clock=mhz)
             flops = 2.0 * B * HEADS * T * (T + 1) * HEAD_DIM if causal else 4.0 * B * HEADS * T * T * HEAD_DIM
             tf = flops / t / 1e12
-            out[f"{name}_T{T}"] = {"tflops": round(tf, 1), "frac_of_measured_peak": round(tf / peaks["tensor"], 4)}
+            # sm_mhz_at_end: the clock the launches ran at (probe kernel queued right behind them).  The dense-bf16 peak of
+            # MEASURED_PEAKS.json is a burst figure at full clock; under a sustained tensor load this board settles lower
+            # (its own "sustained" figure), so a fraction of the burst peak is only meaningful next to the clock.
+            out[f"{name}_T{T}"] = {"tflops": round(tf, 1), "frac_of_measured_peak": round(tf / peaks["tensor"], 4),
+                                   "sm_mhz_at_end": round(mhz[0])}
             if name.endswith("peaky"):
                 skip, alive = _skip_fraction(torch, qp, k, gamma, 1.1)
                 out[f"{name}_T{T}"].update(skipped_tile_fraction=round(skip, 4), surviving_keys_per_row=round(alive, 2))

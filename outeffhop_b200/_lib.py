@@ -120,6 +120,7 @@ SYMBOLS = {
 _PRIVATE = {
     "oeh_attn_fwd_debug": (C.c_int, [C.POINTER(OehAttnArgs), C.c_void_p, C.c_void_p]),
     "oeh_set_override": (C.c_int, [C.c_char_p, C.c_longlong]),
+    "oeh_sm_clock_probe": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
@@ -147,7 +148,7 @@ def lib():
 
 def set_override(name: str, value) -> None:
     """Dispatch override of the attention entry point (tests / tuning): ``OEH_ATTN_KERNEL`` ("tile" / "ws"),
-    ``OEH_WS_PERSISTENT``, ``OEH_WS_TILES``, ``OEH_CAUSAL_CHUNK``, ``OEH_ONE_REGS``, ``OEH_MID_KERNEL``; ``None`` clears it.  Process wide,
+    ``OEH_WS_PERSISTENT``, ``OEH_WS_TILES``, ``OEH_CAUSAL_CHUNK``, ``OEH_ONE_REGS``, ``OEH_MID_KERNEL``, ``OEH_ONE_SPLIT``; ``None`` clears it.  Process wide,
     thread-safe; the library reads the environment variables of the same names once, at its first call."""
     if value is None:
         v = -1
@@ -156,6 +157,12 @@ def set_override(name: str, value) -> None:
     else:
         v = int(value)
     check(lib().oeh_set_override(name.encode(), v))
+
+
+def sm_clock_probe(out, stream: int) -> None:
+    """Measurement helper: queue a ~20 us single-thread kernel on ``stream`` that writes the SM clock (MHz, clock64 against
+    %globaltimer) to the one-float device tensor ``out`` -- the clock the kernel queued just before it ran at."""
+    check(lib().oeh_sm_clock_probe(out.data_ptr(), stream))
 
 
 def last_error() -> str:

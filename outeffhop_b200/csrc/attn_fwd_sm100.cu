@@ -26,7 +26,7 @@
 
 #include "attn_common.cuh"
 #include "attn_fwd_mid.cuh"
-#include "attn_fwd_one.cuh"
+#include "attn_fwd_one2.cuh"
 #include "attn_fwd_ws.cuh"
 #include "attn_fwd_wsp.cuh"
 
@@ -336,9 +336,9 @@ int make_tmap(CUtensorMap* tm, TmapCoord* coord, const void* base, int dtype, in
 // The kernel-choice rules below are measured defaults.  They can be overridden per process through oeh_set_override()
 // (thread-safe; what the tests use) or, for command-line experiments, through environment variables of the same names --
 // read ONCE, at the first call, never on the launch path.  Value < 0 = no override.
-enum TuneKey { kTuneAttnKernel = 0, kTuneWsPersistent, kTuneWsTiles, kTuneCausalChunk, kTuneOneRegs, kTuneMidKernel, kTuneKeys };
+enum TuneKey { kTuneAttnKernel = 0, kTuneWsPersistent, kTuneWsTiles, kTuneCausalChunk, kTuneOneRegs, kTuneMidKernel, kTuneOneSplit, kTuneKeys };
 const char* const kTuneNames[kTuneKeys] = {"OEH_ATTN_KERNEL", "OEH_WS_PERSISTENT", "OEH_WS_TILES", "OEH_CAUSAL_CHUNK",
-                                           "OEH_ONE_REGS", "OEH_MID_KERNEL"};
+                                           "OEH_ONE_REGS", "OEH_MID_KERNEL", "OEH_ONE_SPLIT"};
 std::atomic<long long> g_tune[kTuneKeys];
 std::once_flag g_tune_once;
 
@@ -641,6 +641,23 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
     return check_launch("attn_fwd_ws_kernel");
   }
   if (use_one) {
+    // Two threads per query row (attn_fwd_one2.cuh): halves the serial softmax of a CTA.  Measured
+    // (profiles/r02_one_tile_two_per_row.jsonl, H=12 T=128): with the three INT8 taps 12.4 vs 13.2 us at B=32 and 7.8 vs 9.0 us
+    // at B=8, but 34.7 vs 33.1 us at B=128; without taps the register-resident one-thread kernel is as fast (8.57 vs 8.58 us
+    // softmax1, 8.97 vs 9.10 us clipped) -- there the launch is bound by the HBM phase, not by the softmax chain.  Default:
+    // tapped / masked launches of at most one wave of CTAs.  OEH_ONE_SPLIT=0 / 1 forces the choice.
+    const long long one_items = (long long)((a->Tq + BM - 1) / BM) * a->H * a->B;
+    int split = generic && one_items <= 3LL * num_sms();
+    if (const long long f = tune(kTuneOneSplit); f >= 0) split = f != 0;
+    if (tune(kTuneOneRegs) >= 0) split = 0;
+    if (split) {
+      static const KernelFn k2[4] = {attn_one2::attn_fwd_one2_kernel<false, false>, attn_one2::attn_fwd_one2_kernel<false, true>,
+                                     attn_one2::attn_fwd_one2_kernel<true, false>, attn_one2::attn_fwd_one2_kernel<true, true>};
+      if ((rc = ensure_smem(reinterpret_cast<const void*>(k2[ki]), attn_one2::kSmemBytes))) return rc;
+      dim3 grid((unsigned)((a->Tq + BM - 1) / BM), (unsigned)a->H, (unsigned)a->B);
+      k2[ki]<<<grid, attn_one2::kThreads, attn_one2::kSmemBytes, st>>>(tmq, tmk, tmv, p);
+      return check_launch("attn_fwd_one2_kernel");
+    }
     // [register-resident S row][bf16 | generic]
     static const KernelFn kernels[2][4] = {
         {attn_one::attn_fwd_one_kernel<false, false, false>, attn_one::attn_fwd_one_kernel<false, true, false>,

@@ -262,16 +262,22 @@ def test_attention_causal_work_order(persistent, chunk, kind, gamma, eta, overri
     np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=TOL, rtol=0)
 
 
-@pytest.mark.parametrize("regs", ["0", "1"])
+@pytest.mark.parametrize("form", ["split", "regs", "chunked"])
 @pytest.mark.parametrize("kind,gamma,eta", KINDS)
 @pytest.mark.parametrize("shape,causal", [((2, 3, 128, 128), False), ((2, 2, 50, 77), False), ((1, 2, 100, 100), True),
-                                          ((1, 1, 130, 1), False), ((2, 2, 300, 100), False)])
-def test_attention_one_tile_softmax_shapes(regs, kind, gamma, eta, shape, causal, override):
-    """One-tile kernel (Tk <= 128): S row held in registers (one TMEM read, 3 CTAs / SM) and the chunked TMEM passes
-    (4 CTAs / SM) against the oracle, on full, ragged (rows of the last warp beyond Tq: the coalesced store must clip them),
-    causal and single-key rows."""
+                                          ((1, 1, 130, 1), False), ((2, 2, 300, 100), False), ((1, 2, 64, 64), True),
+                                          ((1, 2, 97, 97), False), ((1, 1, 33, 65), False)])
+def test_attention_one_tile_softmax_shapes(form, kind, gamma, eta, shape, causal, override):
+    """One-tile kernels (Tk <= 128) against the oracle on full, ragged (rows of the last warp beyond Tq: the coalesced store must
+    clip them), causal and single-key rows, and key counts that leave the upper half of the row with 0, 1 or 2 chunks:
+    two threads per row (attn_fwd_one2.cuh, the default), and the one-thread kernel with the S row held in registers (one TMEM
+    read, 3 CTAs / SM) or walked in chunked TMEM passes (4 CTAs / SM)."""
     ops = _ops()
-    override("OEH_ONE_REGS", regs)
+    if form == "split":
+        override("OEH_ONE_SPLIT", "1")
+    else:
+        override("OEH_ONE_SPLIT", "0")
+        override("OEH_ONE_REGS", "1" if form == "regs" else "0")
     B, H, Tq, Tk = shape
     q, k, v = _mk(B, H, Tq, Tk, torch.float16, seed=Tq + Tk + kind)
     out = ops.attention_fwd(q, k, v, scale=0.125, kind=kind, gamma=gamma, eta=eta, causal=causal, out_layout="bhtd")
