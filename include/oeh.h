@@ -345,6 +345,48 @@ typedef struct OehLinearArgs {
 
 int oeh_linear_fwd(const OehLinearArgs* args);
 
+/* ---------------------------------------------------------------------------------------------
+ * Linear -> (+ residual) -> LayerNorm in one launch:
+ *     v = round(x . w^T + bias);   s = [qdq_res]([qdq_a](v) + residual);   y = [qdq_out](LayerNorm(s) * ln_weight + ln_bias)
+ * x (M,K), w (N,K) = nn.Linear.weight (row strides ldx / ldw in elements), residual / y / sum_out (M,N) contiguous, fp16 / bf16,
+ * fp32 accumulation and statistics.  Replaces
+ *   - HF BertSelfOutput / BertOutput.forward: LayerNorm(dense(hidden_states) + input_tensor) (transformers modeling_bert; the
+ *     modules the reference wraps at quantized_bert.py:541-606), and with q_a (the QuantLinear's output tap, hijacker.py:119-134),
+ *     q_res (res_act_quantizer, quantized_bert.py:566-567, :602-603) and q_out (QuantLayerNorm's tap, autoquant_utils.py:62-70)
+ *     their quantized forms with FIXED ranges (device [scale, zero_point] pointers; NULL = no tap);
+ *   - the residual joints of the OPT decoder layer (quantized_opt.py:338-370; HF OPTDecoderLayer.forward): out_proj / fc2 ->
+ *     + residual -> the next LayerNorm, with sum_out = the (tapped) sum, which the pre-LayerNorm block carries on as its residual.
+ * residual NULL = LayerNorm(dense(x)) (BertPredictionHeadTransform without its activation does not apply: use oeh_linear_fwd).
+ * A row block is computed by a thread-block cluster of N / 192 or N / 256 CTAs that exchange the row statistics through
+ * distributed shared memory: N must be 192 c or 256 c with c <= 8 (768, 1024, 1536, 2048 ...; oeh_linear_add_layer_norm_supported).
+ * Same element arithmetic as `GEMM -> oeh_add_layer_norm` (sum and taps in the tensor dtype, two-pass statistics in fp32); the
+ * fp32 summation orders differ, so the two agree to the rounding of the tensor dtype.  Asynchronous, allocation-free,
+ * graph-capturable.  Measured on B200 it does NOT beat the two launches yet (profiles/r02_gemm_ln_fused.txt): the shipped model
+ * paths keep `GEMM -> oeh_add_layer_norm`; this entry point is for callers that want the single launch.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct OehLinearLnArgs {
+  const void* x;
+  const void* w;
+  const void* bias;            /* (N) of the tensor dtype, 16-byte aligned, or NULL */
+  const void* residual;        /* (M,N) or NULL */
+  const void* ln_weight;       /* (N), 16-byte aligned */
+  const void* ln_bias;         /* (N) or NULL */
+  void* y;                     /* (M,N) */
+  void* sum_out;               /* (M,N) or NULL */
+  int64_t ldx, ldw;
+  int32_t M, N, K;
+  int32_t dtype;               /* OEH_F16 or OEH_BF16 */
+  int32_t n_bits;
+  double eps;
+  const float* q_a;            /* device [scale, zero_point] or NULL */
+  const float* q_res;
+  const float* q_out;
+  oeh_stream_t stream;
+} OehLinearLnArgs;
+
+int oeh_linear_add_layer_norm(const OehLinearLnArgs* args);
+int oeh_linear_add_layer_norm_supported(int32_t N);   /* 1 if N can be normalised by one cluster */
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,18 @@ class OehLinearArgs(C.Structure):
     ]
 
 
+class OehLinearLnArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("residual", C.c_void_p),
+        ("ln_weight", C.c_void_p), ("ln_bias", C.c_void_p), ("y", C.c_void_p), ("sum_out", C.c_void_p),
+        ("ldx", C.c_int64), ("ldw", C.c_int64),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("dtype", C.c_int32), ("n_bits", C.c_int32),
+        ("eps", C.c_double),
+        ("q_a", C.c_void_p), ("q_res", C.c_void_p), ("q_out", C.c_void_p),
+        ("stream", C.c_void_p),
+    ]
+
+
 ACT_NONE, ACT_RELU, ACT_GELU_ERF = 0, 1, 2
 
 
@@ -112,6 +124,8 @@ SYMBOLS = {
                                                C.c_int64, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "oeh_gelu_erf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "oeh_linear_fwd": (C.c_int, [C.POINTER(OehLinearArgs)]),
+    "oeh_linear_add_layer_norm": (C.c_int, [C.POINTER(OehLinearLnArgs)]),
+    "oeh_linear_add_layer_norm_supported": (C.c_int, [C.c_int32]),
     "oeh_embed_layer_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_double,
                                        C.c_int32, C.c_void_p]),

@@ -476,6 +476,68 @@ def linear_fwd(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     return y if out is not None else y.view(*x.shape[:-1], N)
 
 
+def linear_add_layer_norm_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    """True if ``linear_add_layer_norm`` can take this Linear: 16-bit CUDA tensors and an output width one cluster can normalise
+    (oeh_linear_add_layer_norm_supported: 192 c or 256 c columns, c <= 8), K a multiple of 8."""
+    return (x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and weight.dtype == x.dtype and weight.dim() == 2
+            and weight.shape[1] % 8 == 0 and bool(L.lib().oeh_linear_add_layer_norm_supported(int(weight.shape[0]))))
+
+
+def linear_add_layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor],
+                          ln_weight: torch.Tensor, ln_bias: Optional[torch.Tensor], eps: float = 1e-12, *,
+                          qparams_a: Optional[torch.Tensor] = None, qparams_res: Optional[torch.Tensor] = None,
+                          qparams_out: Optional[torch.Tensor] = None, n_bits: int = 8, return_sum: bool = False,
+                          out: Optional[torch.Tensor] = None):
+    """``[qdq_out] LayerNorm([qdq_res]([qdq_a](x @ weight.T + bias) + residual))`` in ONE launch (oeh_linear_add_layer_norm): the
+    GEMM runs on a thread-block cluster that owns whole rows and normalises them in its epilogue.  x: (..., K), weight: (N, K),
+    residual: (..., N) or None; ``return_sum``: also return the (tapped) sum, the residual a pre-LayerNorm block carries on.
+    Same arithmetic as ``linear`` followed by ``add_layer_norm``."""
+    _require_cuda(x, weight, bias, residual, ln_weight, ln_bias, qparams_a, qparams_res, qparams_out)
+    K, N = x.shape[-1], weight.shape[0]
+    if x.dtype not in (torch.float16, torch.bfloat16) or any(t is not None and t.dtype != x.dtype
+                                                             for t in (weight, bias, residual, ln_weight, ln_bias)):
+        raise TypeError("linear_add_layer_norm: every tensor must share one 16-bit dtype")
+    if weight.dim() != 2 or weight.shape[1] != K:
+        raise ValueError(f"linear_add_layer_norm: weight {tuple(weight.shape)} does not match x (..., {K})")
+    if ln_weight.shape != (N,) or (ln_bias is not None and ln_bias.shape != (N,)) or (bias is not None and bias.shape != (N,)):
+        raise ValueError("linear_add_layer_norm: bias / LayerNorm parameters must be (N,)")
+    if return_sum and residual is None:
+        raise ValueError("linear_add_layer_norm: return_sum needs a residual")
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    w = weight if weight.stride(-1) == 1 else weight.contiguous()
+    M = x2.shape[0]
+    res2 = None
+    if residual is not None:
+        if residual.numel() != M * N or residual.shape[-1] != N:
+            raise ValueError("linear_add_layer_norm: residual must be (..., N) with the rows of x")
+        res2 = residual.contiguous()
+    lead = x.shape[:-1]
+    y = out if out is not None else torch.empty((*lead, N), dtype=x.dtype, device=x.device)
+    if y.numel() != M * N or not y.is_contiguous():
+        raise ValueError("linear_add_layer_norm: out must be a contiguous (..., N) tensor")
+    total = torch.empty((*lead, N), dtype=x.dtype, device=x.device) if return_sum else None
+    a = L.OehLinearLnArgs()
+    a.x, a.w, a.y = x2.data_ptr(), w.data_ptr(), y.data_ptr()
+    a.bias = bias.contiguous().data_ptr() if bias is not None else None
+    a.residual = res2.data_ptr() if res2 is not None else None
+    lw, lb = ln_weight.contiguous(), (ln_bias.contiguous() if ln_bias is not None else None)
+    a.ln_weight, a.ln_bias = lw.data_ptr(), (lb.data_ptr() if lb is not None else None)
+    a.sum_out = total.data_ptr() if total is not None else None
+    a.ldx, a.ldw = (x2.stride(0) if M > 1 else K), w.stride(0)
+    a.M, a.N, a.K = M, N, K
+    a.dtype, a.n_bits, a.eps = _dtype_code(x), int(n_bits), float(eps)
+    for name, t in (("q_a", qparams_a), ("q_res", qparams_res), ("q_out", qparams_out)):
+        if t is not None:
+            if t.dtype != torch.float32 or t.numel() < 2:
+                raise ValueError("linear_add_layer_norm: qparams must be CUDA fp32 tensors [scale, zero_point]")
+            setattr(a, name, t.data_ptr())
+    a.stream = _stream()
+    L.check(L.lib().oeh_linear_add_layer_norm(C.byref(a)))
+    return (y, total) if return_sum else y
+
+
 def embed_layer_norm(input_ids: torch.Tensor, word: torch.Tensor, pos: Optional[torch.Tensor], tok_type: Optional[torch.Tensor],
                      weight: torch.Tensor, bias: Optional[torch.Tensor], eps: float, token_type_ids: Optional[torch.Tensor] = None,
                      position_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
