@@ -36,7 +36,7 @@ __device__ __forceinline__ void gelu_vec(Vec16<T>& v) {
 #pragma unroll
   for (int e = 0; e < Vec16<T>::N; e += 2) {
     float y0, y1;
-    gelu2(DT<T>::to_f(v.v[e]), DT<T>::to_f(v.v[e + 1]), y0, y1);
+    gelu2<false>(DT<T>::to_f(v.v[e]), DT<T>::to_f(v.v[e + 1]), y0, y1);
     v.v[e] = DT<T>::from_f(y0);
     v.v[e + 1] = DT<T>::from_f(y1);
   }
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) gelu_erf_kernel(const 
   }
   for (int64_t t = done + tid; t < n; t += stride) {
     float y0, y1;
-    gelu2(DT<T>::to_f(x[t]), 0.f, y0, y1);
+    gelu2<false>(DT<T>::to_f(x[t]), 0.f, y0, y1);
     y[t] = DT<T>::from_f(y0);
   }
 }

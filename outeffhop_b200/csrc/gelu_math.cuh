@@ -21,7 +21,22 @@ __device__ __forceinline__ float rcp_approx(float x) {       // MUFU.RCP (1 ulp)
   return y;
 }
 
-// gelu of two fp32 values
+// 1 / d for two values in [1, 8.1] WITHOUT the MUFU pipe: seed from the bit pattern (relative error <= 12.5 %), three Newton steps
+// y <- y + y (1 - d y) as packed fp32x2 FMAs (error squared per step: ~6e-8, the size of MUFU.RCP's own).  For the GEMM epilogue,
+// where the exponentials and reciprocals of a 128 x 256 tile (2 MUFU ops per element, 16 per clock and SM) were HALF of the
+// epilogue time (profiles/r02_timeline_gemm.txt).
+__device__ __forceinline__ uint64_t rcp2_fma(uint64_t d2) {
+  float d0, d1;
+  ptx::unpack2f(d2, d0, d1);
+  uint64_t y2 = ptx::pack2f(__int_as_float(0x7EF311C7 - __float_as_int(d0)), __int_as_float(0x7EF311C7 - __float_as_int(d1)));
+  const uint64_t nd2 = d2 ^ 0x8000000080000000ull;                       // -d
+#pragma unroll
+  for (int it = 0; it < 3; ++it) y2 = ptx::ffma2(y2, ptx::ffma2(nd2, y2, bc2(1.f)), y2);
+  return y2;
+}
+
+// gelu of two fp32 values.  kFmaRcp: the reciprocal on the FMA pipe (rcp2_fma) instead of MUFU.RCP.
+template <bool kFmaRcp = false>
 __device__ __forceinline__ void gelu2(float x0, float x1, float& y0, float& y1) {
   const float na0 = -fabsf(x0), na1 = -fabsf(x1);                        // -|x|
   // beyond |x| = 20 Phi(-|x|) < 1e-88 is 0 in any format: cap the argument there, so that |x| * Phi stays finite for inf (gelu(+inf) = inf; NaN still propagates through the x^2 term below)
@@ -29,9 +44,14 @@ __device__ __forceinline__ void gelu2(float x0, float x1, float& y0, float& y1) 
   const uint64_t n2 = ptx::pack2f(n0, n1);
   const uint64_t r2 = ptx::pack2f(fmaxf(x0, 0.f), fmaxf(x1, 0.f));       // max(x, 0)
   const uint64_t d2 = ptx::ffma2(n2, bc2(-0.35355339059327373f), bc2(1.f));   // 1 + |x| / (2 sqrt 2)  in [1, 8.1]
-  float d0, d1;
-  ptx::unpack2f(d2, d0, d1);
-  const uint64_t t2 = ptx::pack2f(rcp_approx(d0), rcp_approx(d1));       // every element on its own: a pure function of x
+  uint64_t t2;
+  if constexpr (kFmaRcp) {
+    t2 = rcp2_fma(d2);
+  } else {
+    float d0, d1;
+    ptx::unpack2f(d2, d0, d1);
+    t2 = ptx::pack2f(rcp_approx(d0), rcp_approx(d1));                    // every element on its own: a pure function of x
+  }
   uint64_t p2 = ptx::ffma2(t2, bc2(kC9), bc2(kC8));
   p2 = ptx::ffma2(p2, t2, bc2(kC7));
   p2 = ptx::ffma2(p2, t2, bc2(kC6));

@@ -153,6 +153,20 @@ __device__ __forceinline__ void unpack16(uint32_t u, float& a, float& b) {
   }
 }
 
+#ifdef OEH_TIMELINE
+__device__ unsigned long long* g_gemm_timeline = nullptr;   // experiment builds only (tools/timeline_gemm.py): 16 stamps per CTA
+__device__ __forceinline__ void gemm_stamp(int k) {
+  if (g_gemm_timeline && k < 16) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_gemm_timeline[blockIdx.x * 16 + k] = t;
+  }
+}
+#define GEMM_STAMP(k) gemm_stamp(k)
+#else
+#define GEMM_STAMP(k)
+#endif
+
 template <bool kBF16, int BN, bool kCta2>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb,
@@ -162,6 +176,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) Barriers<kStages> bars;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ uint4 s_bias[2][BN / 8];                             // the tile's bias slice, double-buffered like the accumulators
 
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -237,6 +252,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
         const int acc = ti & 1;
         if (ti >= 2) ptx::mbar_wait(ptx::smem_u32(&bars.tmem_empty[acc]), (uint32_t)((ti >> 1) - 1) & 1u);
         ptx::tc_fence_after();
+        if ((tid & 31) == 0) GEMM_STAMP(4 * ti + 0);
         for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
           const int s = it % kStages;
           ptx::mbar_wait(ptx::smem_u32(&bars.full[s]), (uint32_t)(it / kStages) & 1u);
@@ -259,6 +275,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
           }
           __syncwarp();
         }
+        if ((tid & 31) == 0) GEMM_STAMP(4 * ti + 1);
       }
     }
   } else {
@@ -285,8 +302,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
         q_lo = -zp;
         q_hi = p.int_max - zp;
       }
+      // the tile's bias slice -> shared memory while the main loop is still running (a global load per chunk on the critical
+      // path of the epilogue cost ~0.3 us each); columns beyond N read as 0
+      {
+        const int e = tid - 64;
+        if (e < BN / 8) {
+          uint4 bv = make_uint4(0u, 0u, 0u, 0u);
+          const int gc = n0 + 8 * e;
+          if (p.bias) {
+            if (gc + 8 <= p.N) {
+              bv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias) + gc));
+            } else {
+              uint16_t tmp[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) tmp[j] = gc + j < p.N ? __ldg(reinterpret_cast<const uint16_t*>(p.bias) + gc + j) : (uint16_t)0;
+              bv = *reinterpret_cast<const uint4*>(tmp);
+            }
+          }
+          s_bias[acc][e] = bv;
+        }
+        asm volatile("bar.sync 5, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      }
       ptx::mbar_wait(ptx::smem_u32(&bars.tmem_full[acc]), (uint32_t)(ti >> 1) & 1u);
       ptx::tc_fence_after();
+      if (tid == 64) GEMM_STAMP(4 * ti + 2);
 #pragma unroll 1
       for (int c = 0; c < BN / kParts / kChunk; ++c, ++chunk_it) {
         const int col = part * (BN / kParts) + c * kChunk;              // column within the tile
@@ -303,29 +342,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
         }
         const int gcol = n0 + col;
         if (p.bias) {                                              // 32 bias values = 64 B, the same for every lane (broadcast)
-          const uint4* bp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias) + gcol);
-          if (gcol + kChunk <= p.N) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint4 bv = __ldg(bp + g);
-              const uint32_t w[4] = {bv.x, bv.y, bv.z, bv.w};
+          for (int g = 0; g < 4; ++g) {
+            const uint4 bv = s_bias[acc][col / 8 + g];
+            const uint32_t w[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float b0, b1;
-                unpack16<kBF16>(w[e], b0, b1);
-                v[g * 8 + 2 * e] += b0;
-                v[g * 8 + 2 * e + 1] += b1;
-              }
-            }
-          } else {                                                 // ragged last column block
-            const uint16_t* bs = reinterpret_cast<const uint16_t*>(p.bias);
-#pragma unroll
-            for (int j = 0; j < kChunk; j += 2) {
-              float b0 = 0.f, b1 = 0.f, d;
-              if (gcol + j < p.N) unpack16<kBF16>((uint32_t)__ldg(bs + gcol + j), b0, d);
-              if (gcol + j + 1 < p.N) unpack16<kBF16>((uint32_t)__ldg(bs + gcol + j + 1), b1, d);
-              v[j] += b0;
-              v[j + 1] += b1;
+            for (int e = 0; e < 4; ++e) {
+              float b0, b1;
+              unpack16<kBF16>(w[e], b0, b1);
+              v[g * 8 + 2 * e] += b0;
+              v[g * 8 + 2 * e + 1] += b1;
             }
           }
         }
@@ -343,8 +369,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
           } else if (p.act == OEH_ACT_GELU_ERF) {
 #pragma unroll
             for (int j = 0; j < kChunk; j += 2) {
-              gelu_math::gelu2(v[j], v[j + 1], v[j], v[j + 1]);
-              unpack16<kBF16>(pack16<kBF16>(v[j], v[j + 1]), v[j], v[j + 1]);     // the activation's own 16-bit store
+              gelu_math::gelu2<false>(v[j], v[j + 1], v[j], v[j + 1]);
+              if (qp) unpack16<kBF16>(pack16<kBF16>(v[j], v[j + 1]), v[j], v[j + 1]);   // the activation's own 16-bit store, which the tap reads
             }
           }
           if (qp) {
@@ -365,19 +391,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
         }
         if (p.dbg & 1) continue;
         // staging tile (double-buffered per column half) -> TMA store
+        // ONE barrier per chunk: before it the issuer waits until every store it has committed (the latest one used the OTHER
+        // buffer, a whole chunk ago) has read its tile, so passing the barrier also tells the part that the other buffer is
+        // free for the next chunk; this chunk's buffer was declared free the same way one chunk earlier.
         const uint32_t buf = sBuf + (uint32_t)(chunk_it & 1) * kOutBuf;
-        if (issuer) tma_store_wait_read<1>();                      // the store that last used this buffer has read it
-        asm volatile("bar.sync %0, 128;" ::"r"(part_bar) : "memory");
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           ptx::st_shared_v4(buf + row_off + (((uint32_t)g ^ sw) << 4), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
         ptx::fence_proxy_async_smem();
+        if (issuer) tma_store_wait_read<0>();
         asm volatile("bar.sync %0, 128;" ::"r"(part_bar) : "memory");
         if (issuer) {
           tma_store_2d(&tmy, buf, gcol, m0);
           tma_store_commit();
         }
       }
+      if (tid == 64) GEMM_STAMP(4 * ti + 3);
     }
     if (issuer) tma_store_wait_all();
   }
@@ -481,6 +510,12 @@ int launch(const OehLinearArgs* a, GemmParams& p, int grid_cap) {
 }  // namespace oeh
 
 using namespace oeh;
+
+#ifdef OEH_TIMELINE
+extern "C" int oeh_set_gemm_timeline(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(g_gemm_timeline, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int oeh_linear_fwd(const OehLinearArgs* a) {
   OEH_CHECK_ARG(a, "oeh_linear_fwd: null args");
