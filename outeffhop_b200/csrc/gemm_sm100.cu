@@ -39,16 +39,22 @@ namespace {
 
 constexpr int BM = 128, BK = 64;
 constexpr int kStageA = BM * BK * 2;                     // 16 KB
-#ifndef OEH_GEMM_EPI_WARPS
-#define OEH_GEMM_EPI_WARPS 16
-#endif
-constexpr int kEpiWarps = OEH_GEMM_EPI_WARPS, kParts = kEpiWarps / 4, kThreads = (2 + kEpiWarps) * 32;   // kParts column parts x 4 lane quarters
+// Epilogue warps: kParts column parts x 4 TMEM lane quarters.  128 / 256-column tiles: 4 parts (16 warps); 192-column tiles: SIX
+// parts of one 32-column chunk each (24 warps, <= 72 registers) -- the erf-GELU epilogue of a 128 x 256 tile on 16 warps takes
+// longer (4.3 us) than the tile's main loop (4.0 us), profiles/r02_timeline_gemm.txt.
+template <int BN>
+struct Epi {
+  static constexpr int kParts = BN == 192 ? 6 : 4;
+  static constexpr int kEpiWarps = 4 * kParts;
+  static constexpr int kThreads = (2 + kEpiWarps) * 32;
+};
 constexpr int kChunk = 32;                               // columns per epilogue step / TMA store box
 constexpr int kOutBuf = BM * kChunk * 2;                 // 8 KB staging tile (128 rows x 64 B, SWIZZLE_64B)
 constexpr int kMaxSeg = 4;
 
 template <int BN, bool kCta2>
 struct Cfg {
+  static constexpr int kParts = Epi<BN>::kParts;
   static constexpr int kStageB = (kCta2 ? BN / 2 : BN) * BK * 2;        // rows of B this CTA loads per k-block
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kRing = 226 * 1024 - 2 * kParts * kOutBuf;       // what the staging tiles leave of 227 KB
@@ -168,11 +174,11 @@ __device__ __forceinline__ void gemm_stamp(int k) {
 #endif
 
 template <bool kBF16, int BN, bool kCta2>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(Epi<BN>::kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb,
             const __grid_constant__ CUtensorMap tmy, const __grid_constant__ GemmParams p) {
   using C = Cfg<BN, kCta2>;
-  constexpr int kStages = C::kStages;
+  constexpr int kStages = C::kStages, kParts = Epi<BN>::kParts, kEpiWarps = Epi<BN>::kEpiWarps;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) Barriers<kStages> bars;
   __shared__ uint32_t tmem_base_slot;
@@ -321,7 +327,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
           }
           s_bias[acc][e] = bv;
         }
-        asm volatile("bar.sync 5, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        asm volatile("bar.sync 8, %0;" ::"n"(kEpiWarps * 32) : "memory");
       }
       ptx::mbar_wait(ptx::smem_u32(&bars.tmem_full[acc]), (uint32_t)(ti >> 1) & 1u);
       ptx::tc_fence_after();
@@ -499,7 +505,7 @@ int launch(const OehLinearArgs* a, GemmParams& p, int grid_cap) {
     const long long tiles = (long long)p.n_mblk * p.n_nblk;
     cfg.gridDim = dim3((unsigned)(tiles < grid_cap ? tiles : grid_cap));
   }
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(Epi<BN>::kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = (cudaStream_t)a->stream;
   OEH_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, tma, tmb, tmy, p));
@@ -555,12 +561,13 @@ extern "C" int oeh_linear_fwd(const OehLinearArgs* a) {
   // tile_n: 0 = choose; 128 / 256 = single-CTA tiles of that width; 2256 / 2128 = CTA pairs, 256 x 256 / 256 x 128.
   const int sms = num_sms();
   struct Shape { int bn; bool pair; };
-  constexpr int kShapes = 4;
-  const Shape shapes[kShapes] = {{256, true}, {128, true}, {256, false}, {128, false}};
+  constexpr int kShapes = 6;
+  const Shape shapes[kShapes] = {{256, true}, {128, true}, {256, false}, {128, false}, {192, true}, {192, false}};
   int best = -1;
   double best_cost = 1e30;
   for (int i = 0; i < kShapes; ++i) {
     const int bn = shapes[i].bn;
+    if (bn == 192) continue;                                     // (chosen below, for the activation epilogues only)
     if (seg_cols && seg_cols % bn) continue;
     const long long mi = shapes[i].pair ? ((a->M + 2 * BM - 1) / (2 * BM)) : ((a->M + BM - 1) / BM);
     const long long items = mi * ((a->N + bn - 1) / bn);
@@ -574,7 +581,7 @@ extern "C" int oeh_linear_fwd(const OehLinearArgs* a) {
     best = -1;
     for (int i = 0; i < kShapes; ++i)
       if (a->tile_n % 10000 == shapes[i].bn + (shapes[i].pair ? 2000 : 0)) best = i;
-    if (best < 0) return set_error(OEH_ERR_BAD_ARG, "oeh_linear_fwd: tile_n=%d (0, 128, 256, 2128, 2256)", a->tile_n);
+    if (best < 0) return set_error(OEH_ERR_BAD_ARG, "oeh_linear_fwd: tile_n=%d (0, 128, 192, 256, 2128, 2192, 2256)", a->tile_n);
     if (seg_cols && seg_cols % shapes[best].bn)
       return set_error(OEH_ERR_BAD_ARG, "oeh_linear_fwd: tile_n=%d does not divide the segment width %d", a->tile_n, seg_cols);
   }
@@ -584,6 +591,8 @@ extern "C" int oeh_linear_fwd(const OehLinearArgs* a) {
     case 0: return bf ? launch<true, 256, true>(a, p, sms) : launch<false, 256, true>(a, p, sms);
     case 1: return bf ? launch<true, 128, true>(a, p, sms) : launch<false, 128, true>(a, p, sms);
     case 2: return bf ? launch<true, 256, false>(a, p, sms) : launch<false, 256, false>(a, p, sms);
-    default: return bf ? launch<true, 128, false>(a, p, sms) : launch<false, 128, false>(a, p, sms);
+    case 3: return bf ? launch<true, 128, false>(a, p, sms) : launch<false, 128, false>(a, p, sms);
+    case 4: return bf ? launch<true, 192, true>(a, p, sms) : launch<false, 192, true>(a, p, sms);
+    default: return bf ? launch<true, 192, false>(a, p, sms) : launch<false, 192, false>(a, p, sms);
   }
 }

@@ -21,14 +21,16 @@ namespace {
 #endif
 constexpr int kWarpsPerBlock = OEH_LN_WARPS;
 
-// Cache policy of the row traffic.  Streaming (evict-first) suits the big standalone tensors of the kernel sweep; inside a
-// model step the inputs were just written by a GEMM and the output is read by the next one, all within L2.
-#ifdef OEH_LN_PLAIN
-__device__ __forceinline__ int4 ld_row(const int4* p) { return *p; }
-__device__ __forceinline__ void st_row(int4* p, const int4& v) { *p = v; }
-#else
+// Cache policy of the row traffic.  Inside a model step the inputs were just written by a GEMM and the output is read by the
+// next one, all within the 126 MB L2: plain loads / stores keep it there.  Streaming (evict-first) accesses are ~10 % faster
+// on big standalone tensors that do not fit L2 (5.6 vs 6.2 us cold at 4096 x 768) but push the result out of L2 under the
+// next GEMM: config 2 runs 1.131 ms with plain accesses, 1.151 ms with streaming ones (tools/bench_ln.py, bench.py; round 2).
+#ifdef OEH_LN_STREAM
 __device__ __forceinline__ int4 ld_row(const int4* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_row(int4* p, const int4& v) { __stcs(p, v); }
+#else
+__device__ __forceinline__ int4 ld_row(const int4* p) { return *p; }
+__device__ __forceinline__ void st_row(int4* p, const int4& v) { *p = v; }
 #endif
 
 template <typename T, int kVecs, bool kGate>

@@ -47,7 +47,7 @@ def _ulp(ref, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
-@pytest.mark.parametrize("tile_n", [0, 128, 256, 2128, 2256])   # 2xxx: CTA pairs (cta_group::2)
+@pytest.mark.parametrize("tile_n", [0, 128, 192, 256, 2128, 2192, 2256])   # 2xxx: CTA pairs (cta_group::2)
 @pytest.mark.parametrize("shape", SHAPES)
 def test_linear_matches_fp64_reference(shape, tile_n, dtype):
     ops = _ops()
@@ -67,13 +67,14 @@ def test_linear_matches_fp64_reference(shape, tile_n, dtype):
     assert bool(((y2.float() - ref2.float()).abs() <= _ulp(ref2, dtype) + acc_tol).all())
 
 
+@pytest.mark.parametrize("tile_n", [0, 192, 2192, 2256])
 @pytest.mark.parametrize("act", ["relu", "gelu"])
 @pytest.mark.parametrize("shape", [(4096, 3072, 768), (2048, 3072, 768), (777, 520, 264)])
-def test_linear_fused_activation(shape, act):
+def test_linear_fused_activation(shape, act, tile_n):
     ops = _ops()
     M, N, K = shape
     x, w, b = _mk(M, N, K, torch.float16, seed=7 + M)
-    y = ops.linear_fwd(x, w, b, act=act)
+    y = ops.linear_fwd(x, w, b, act=act, tile_n=tile_n)
     ref = _ref(x, w, b, torch.float16, act)
     lin = _ref(x, w, b, torch.float16)
     err = (y.float() - ref.float()).abs()
@@ -86,8 +87,9 @@ def test_linear_fused_activation(shape, act):
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
 @pytest.mark.parametrize("act", ["none", "relu", "gelu"])
+@pytest.mark.parametrize("tile_n", [0, 2192])
 @pytest.mark.parametrize("n_seg", [1, 3])
-def test_linear_fused_tap_vs_oracle_quantizer(n_seg, act, dtype):
+def test_linear_fused_tap_vs_oracle_quantizer(n_seg, act, dtype, tile_n):
     """Fixed-range output tap(s) in the epilogue vs oracle.asym_quantize of the untapped 16-bit result (the unfused chain)."""
     ops = _ops()
     M, K = 2048, 768
@@ -97,7 +99,7 @@ def test_linear_fused_tap_vs_oracle_quantizer(n_seg, act, dtype):
     ranges = [(-3.0, 4.0), (-1.5, 1.0), (-5.0, 5.5)][:n_seg]
     qs = [O.asym_set_quant_range(lo, hi) for lo, hi in ranges]
     dev = [torch.tensor([float(v) for v in O.asym_scale_zero_point(*q)], device="cuda") for q in qs]
-    y = ops.linear_fwd(x, w, b, act=act, qparams=dev if n_seg > 1 else dev[0]).float().cpu().numpy()
+    y = ops.linear_fwd(x, w, b, act=act, qparams=dev if n_seg > 1 else dev[0], tile_n=tile_n).float().cpu().numpy()
     for s, q in enumerate(qs):
         sl = slice(768 * s, 768 * (s + 1))
         ref = O.asym_quantize(plain[:, sl], *q)
