@@ -13,7 +13,8 @@
 //                was latency-bound: 26.8 -> 23.9 us at 4096 x 3072 x 768, profiles/r02_gemm_epilogue_*.txt): tcgen05.ld 32 columns
 //                -> + bias -> round to the tensor dtype (what the unfused GEMM would have stored) -> ReLU / erf GELU
 //                -> fixed-range fake-quant tap (per-column-segment qparams: the fused q|k|v projection keeps three ranges)
-//                -> 16-bit pack -> swizzled staging tile in shared memory -> TMA store (coalesced, clipped at the edges)
+//                -> 16-bit pack -> the warp's own swizzled staging tile (32 rows x 32 columns) -> TMA store (clipped at the edges);
+//                no barrier between epilogue warps
 //   persistent CTAs (one per SM) walk the output tiles with stride gridDim.x.
 //
 // kCta2 = true: the CTA-PAIR form (cta_group::2, clusters of two CTAs on one TPC).  The pair computes a 256 x BN tile: each
@@ -49,7 +50,7 @@ struct Epi {
   static constexpr int kThreads = (2 + kEpiWarps) * 32;
 };
 constexpr int kChunk = 32;                               // columns per epilogue step / TMA store box
-constexpr int kOutBuf = BM * kChunk * 2;                 // 8 KB staging tile (128 rows x 64 B, SWIZZLE_64B)
+constexpr int kOutBuf = BM * kChunk * 2;                 // staging per column part: 4 warps x 2 KB (32 rows x 64 B, SWIZZLE_64B), x 2 buffers
 constexpr int kMaxSeg = 4;
 
 template <int BN, bool kCta2>
@@ -182,7 +183,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) Barriers<kStages> bars;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ uint4 s_bias[2][BN / 8];                             // the tile's bias slice, double-buffered like the accumulators
+  __shared__ uint4 s_bias[2][Epi<BN>::kParts][BN / Epi<BN>::kParts / 8];   // (tile parity, column part): the part's bias slice
 
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -289,10 +290,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
     const int q = warp & 3, part = (warp - 2) >> 2;                // lane quarter; column part
     const int r = q * 32 + (tid & 31);                             // row within the tile == TMEM lane
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
-    const int part_bar = 1 + part;                                 // named barrier of the 4 warps of a column half
-    const bool issuer = (warp == 2 + 4 * part) && (tid & 31) == 0; // the thread that owns this half's TMA stores
-    const uint32_t sBuf = sOut + part * 2 * kOutBuf;
-    const uint32_t row_off = (uint32_t)r * 64u, sw = ((uint32_t)r >> 1) & 3u;   // SWIZZLE_64B: chunk ^= (row / 2) % 4
+    // Everything below is WARP-PRIVATE -- no barrier between epilogue warps: a warp stages its own 32 rows x 32 columns (2 KB,
+    // double-buffered), its lane 0 issues and tracks the TMA stores of those boxes, and the bias slice of its column part is
+    // read into its own 128 bytes.  (With one staging tile and one named barrier per column part, bar.sync / fence stalls
+    // were ~20 % of the epilogue warps' samples, and the erf-GELU epilogue -- 4.3 us per tile against a 4.0 us main loop --
+    // is what bounds that GEMM: profiles/r02_timeline_gemm.txt.)
+    const int ew = warp - 2;                                       // 0 .. kEpiWarps-1
+    const bool issuer = (tid & 31) == 0;
+    const uint32_t sBuf = sOut + (uint32_t)ew * (2u * 2048u);
+    const uint32_t lane = (uint32_t)tid & 31u;
+    const uint32_t row_off = lane * 64u, sw = (lane >> 1) & 3u;    // SWIZZLE_64B: chunk ^= (row / 2) % 4
     if (warp == 2 && ptx::elect_one()) ptx::prefetch_tmap(&tmy);
     int ti = 0, chunk_it = 0;
     for (int item = item0; item < n_items; item += item_stride, ++ti) {
@@ -308,13 +315,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
         q_lo = -zp;
         q_hi = p.int_max - zp;
       }
-      // the tile's bias slice -> shared memory while the main loop is still running (a global load per chunk on the critical
-      // path of the epilogue cost ~0.3 us each); columns beyond N read as 0
+      // The bias of this warp's column part -> shared memory before the accumulator is waited for (a global load per chunk on the
+      // critical path of the epilogue cost ~0.3 us each); columns beyond N read as 0.  The four warps of a part write the SAME
+      // values into the part's slot of this tile's parity, so only __syncwarp orders a warp's own write and reads.  Reuse two
+      // tiles later is safe: a warp reads its bias BEFORE it releases the accumulator (tmem_empty), and tile i+2's accumulator
+      // -- which the writers of tile i+2 wait for -- cannot complete before every warp has released tile i's.
+      uint4* my_bias = &s_bias[acc][part][0];
       {
-        const int e = tid - 64;
-        if (e < BN / 8) {
+        constexpr int kV = BN / kParts / 8;
+        if ((int)lane < kV) {
           uint4 bv = make_uint4(0u, 0u, 0u, 0u);
-          const int gc = n0 + 8 * e;
+          const int gc = n0 + part * (BN / kParts) + 8 * (int)lane;
           if (p.bias) {
             if (gc + 8 <= p.N) {
               bv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias) + gc));
@@ -325,9 +336,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
               bv = *reinterpret_cast<const uint4*>(tmp);
             }
           }
-          s_bias[acc][e] = bv;
+          my_bias[lane] = bv;
         }
-        asm volatile("bar.sync 8, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        __syncwarp();
       }
       ptx::mbar_wait(ptx::smem_u32(&bars.tmem_full[acc]), (uint32_t)(ti >> 1) & 1u);
       ptx::tc_fence_after();
@@ -337,8 +348,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
         const int col = part * (BN / kParts) + c * kChunk;              // column within the tile
         float v[kChunk];
         ptx::tmem_ld32(t_lane + acc * BN + col, reinterpret_cast<uint32_t*>(v));
+        uint4 bvec[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) bvec[g] = my_bias[c * (kChunk / 8) + g];
         ptx::tmem_wait_ld();
-        if (c + 1 == BN / kParts / kChunk) {                            // last read of this accumulator by this warp
+        if (c + 1 == BN / kParts / kChunk) {                            // last read of this accumulator (and of the bias) by this warp
           ptx::tc_fence_before();
           __syncwarp();
           if (ptx::elect_one()) {
@@ -350,7 +364,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
         if (p.bias) {                                              // 32 bias values = 64 B, the same for every lane (broadcast)
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const uint4 bv = s_bias[acc][col / 8 + g];
+            const uint4 bv = bvec[g];
             const uint32_t w[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -396,19 +410,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
           for (int j = 0; j < kChunk / 2; ++j) pk[j] = pack16<kBF16>(v[2 * j], v[2 * j + 1]);
         }
         if (p.dbg & 1) continue;
-        // staging tile (double-buffered per column half) -> TMA store
-        // ONE barrier per chunk: before it the issuer waits until every store it has committed (the latest one used the OTHER
-        // buffer, a whole chunk ago) has read its tile, so passing the barrier also tells the part that the other buffer is
-        // free for the next chunk; this chunk's buffer was declared free the same way one chunk earlier.
-        const uint32_t buf = sBuf + (uint32_t)(chunk_it & 1) * kOutBuf;
+        // warp-private staging tile (double-buffered) -> TMA store of a 32 x 32 box
+        const uint32_t buf = sBuf + (uint32_t)(chunk_it & 1) * 2048u;
+        if (issuer) tma_store_wait_read<1>();                      // the store that last used this buffer has read it
+        __syncwarp();
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           ptx::st_shared_v4(buf + row_off + (((uint32_t)g ^ sw) << 4), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
         ptx::fence_proxy_async_smem();
-        if (issuer) tma_store_wait_read<0>();
-        asm volatile("bar.sync %0, 128;" ::"r"(part_bar) : "memory");
+        __syncwarp();
         if (issuer) {
-          tma_store_2d(&tmy, buf, gcol, m0);
+          tma_store_2d(&tmy, buf, gcol, m0 + q * 32);
           tma_store_commit();
         }
       }
@@ -483,7 +495,7 @@ int launch(const OehLinearArgs* a, GemmParams& p, int grid_cap) {
   if ((rc = make_map2d(&tma, a->x, a->dtype, a->M, a->K, a->ldx, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B, "x"))) return rc;
   if ((rc = make_map2d(&tmb, a->w, a->dtype, a->N, a->K, a->ldw, BK, kCta2 ? BN / 2 : BN, CU_TENSOR_MAP_SWIZZLE_128B, "w")))
     return rc;
-  if ((rc = make_map2d(&tmy, a->y, a->dtype, a->M, a->N, a->ldy, kChunk, BM, CU_TENSOR_MAP_SWIZZLE_64B, "y"))) return rc;
+  if ((rc = make_map2d(&tmy, a->y, a->dtype, a->M, a->N, a->ldy, kChunk, 32, CU_TENSOR_MAP_SWIZZLE_64B, "y"))) return rc;
   p.n_mblk = (a->M + BM - 1) / BM;
   p.n_nblk = (a->N + BN - 1) / BN;
   p.n_kblk = (a->K + BK - 1) / BK;
