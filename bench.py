@@ -240,23 +240,22 @@ def attention_sweep(torch, ops, peaks):
                                       ("clippedsoftmax1_peaky", 3, -0.025, qp), ("clippedsoftmax1_dense", 3, 0.0, q),
                                       ("softmax1_causal", 1, 0.0, q)):
             causal = name.endswith("causal")
-            # The two peaks of MEASURED_PEAKS.json are a BURST figure (best of 10 single matmuls at full clock) and a SUSTAINED
-            # one (back to back for seconds; this board then settles at a lower SM clock under its power cap).  Both regimes
-            # are measured here the same way: after ~10 ms of warm-up, `reps` launches timed ONE BY ONE -- the best of them
-            # against the burst peak -- and the same launches back to back (~10 ms) against the sustained peak, with the SM
-            # clock the back-to-back run ended at (probe kernel queued right behind it).
+            # ~10 ms of back-to-back launches after ~10 ms of warm-up (the first launches after the allocations above run up to
+            # 10 % slower), from an idle board (0.25 s pause): `tflops`.  The two peaks of MEASURED_PEAKS.json are a BURST figure
+            # (best single matmul at full clock) and a SUSTAINED one (seconds of back-to-back matmuls, lower SM clock under the
+            # power cap); both fractions are given, with the SM clock this point ended at (probe kernel queued right behind it)
+            # and the best single launch timed on its own.
             f = lambda: ops.attention_fwd(qq, k, v, scale=0.125, kind=kind, gamma=gamma, eta=1.1, causal=causal)
             reps = 20 if T <= 2048 else 5
-            time.sleep(0.25)                                       # every point starts from an idle, cool board
-            best = min(_event_time(torch, f, reps=1, warm=(3 if i == 0 else 0)) for i in range(reps))
+            time.sleep(0.25)
             mhz = []
-            t = _event_time(torch, f, reps=reps, warm=0, clock=mhz)
+            t = _event_time(torch, f, reps=reps, warm=reps, clock=mhz)
+            best = min(_event_time(torch, f, reps=1, warm=0) for _ in range(min(reps, 8)))
             flops = 2.0 * B * HEADS * T * (T + 1) * HEAD_DIM if causal else 4.0 * B * HEADS * T * T * HEAD_DIM
             tf, tf_best = flops / t / 1e12, flops / best / 1e12
-            out[f"{name}_T{T}"] = {"tflops": round(tf_best, 1), "frac_of_measured_peak": round(tf_best / peaks["tensor"], 4),
-                                   "tflops_back_to_back": round(tf, 1),
+            out[f"{name}_T{T}"] = {"tflops": round(tf, 1), "frac_of_measured_peak": round(tf / peaks["tensor"], 4),
                                    "frac_of_sustained_peak": round(tf / peaks["tensor_sustained"], 4),
-                                   "sm_mhz_at_end": round(mhz[0])}
+                                   "tflops_single_launch_best": round(tf_best, 1), "sm_mhz_at_end": round(mhz[0])}
             if name.endswith("peaky"):
                 skip, alive = _skip_fraction(torch, qp, k, gamma, 1.1)
                 out[f"{name}_T{T}"].update(skipped_tile_fraction=round(skip, 4), surviving_keys_per_row=round(alive, 2))
