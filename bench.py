@@ -151,7 +151,7 @@ def run_reference(args):
         "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
     return 0
 
 
@@ -499,11 +499,14 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"4 steps of {BATCH}x{SEQ} tokens (+1 warm-up), fp32, HF BERT-base shell "
                                               "+ C oracle attention (oracle/cpu_model.py)", "ms_per_step": ms_cpu}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+_RESULT_OUT = sys.stdout
 
 
 def main():
@@ -519,6 +522,12 @@ def main():
     ap.add_argument("--profile-one-step", action="store_true",
                     help="bracket one warm eval step with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." on rank 0 under
+    # torchrun): keep a private handle on the real stdout for the result line and send everything else to stderr.
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
