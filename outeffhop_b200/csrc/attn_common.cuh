@@ -413,5 +413,35 @@ __device__ __forceinline__ void store_rows_coalesced(const float (&o)[HD], const
   }
 }
 
+// 32 rows x 32 context columns (64 bytes per row) of one warp -> global, as full 64-byte segments: 4 lanes per row, 8 rows per
+// instruction (store_rows_coalesced of attn_common.cuh for half rows).  stage: the warp's own 2 KB of shared memory.
+template <bool kBF16>
+__device__ __forceinline__ void store_half_rows_coalesced(const float (&o)[32], const AttnParams& p, uint32_t stage, int b, int h,
+                                                          int row0, int d0) {
+  const uint32_t lane = threadIdx.x & 31u;
+  {
+    const uint32_t dst = stage + lane * 64u, sw = (lane >> 1) & 3u;     // 16-byte chunk c of row r at ((c ^ (r/2 & 3)) << 4)
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      ptx::st_shared_v4(dst + (((uint32_t)c ^ sw) << 4), pack2<kBF16>(o[c * 8 + 0], o[c * 8 + 1]),
+                        pack2<kBF16>(o[c * 8 + 2], o[c * 8 + 3]), pack2<kBF16>(o[c * 8 + 4], o[c * 8 + 5]),
+                        pack2<kBF16>(o[c * 8 + 6], o[c * 8 + 7]));
+  }
+  __syncwarp();
+  const uint32_t cc = lane & 3u, rsub = lane >> 2;
+  uint8_t* obase = reinterpret_cast<uint8_t*>(p.out) + 2 * ((int64_t)b * p.os0 + (int64_t)h * p.os1 + d0) + cc * 16u;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t rr = (uint32_t)i * 8u + rsub;
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(stage + rr * 64u + ((cc ^ ((rr >> 1) & 3u)) << 4))
+                 : "memory");
+    const int row = row0 + (int)rr;
+    if (row < p.Tq) *reinterpret_cast<uint4*>(obase + 2 * (int64_t)row * p.os2) = v;
+  }
+}
+
 }  // namespace attn
 }  // namespace oeh

@@ -442,6 +442,9 @@ extern "C" size_t oeh_attn_workspace_bytes(const OehAttnArgs* args) {
 }
 
 #ifdef OEH_TIMELINE
+extern "C" int oeh_set_wsp_timeline(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(attn_wsp::g_wsp_timeline, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
+}
 extern "C" int oeh_set_timeline(unsigned long long* buf) {
   return cudaMemcpyToSymbol(attn_one::g_timeline, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
 }

@@ -41,8 +41,12 @@ struct Cfg {
   static constexpr int kSoftmaxRegs = kTiles == 2 ? 112 : 104, kAuxRegs = 24;
   static constexpr int kCtasPerSm = kTiles == 2 ? 1 : 2;
   static constexpr int kQRows = 128 * kTiles;                        // query rows per CTA
-  static constexpr int kStages = kTiles == 2 ? 8 : 4;
-  static constexpr int kSmemBytes = 2 * kTiles * kTileBytes + 2 * kStages * kSubBytes + 1024;   // 2 x Q tiles | K ring | V ring
+  // kTiles == 2: seven K / V stages and a 2 KB staging slot per softmax warp for the context store (the item's epilogue wrote
+  // 16-byte pieces into 32 different lines per instruction; those 2048 partial-line requests per item also held up the MMA
+  // issuer's and the producer's barrier polls behind them in the load / store pipeline: profiles/r02_timeline_wsp.txt)
+  static constexpr int kStages = kTiles == 2 ? 7 : 4;
+  static constexpr int kStageOut = kTiles == 2 ? kSoftmaxWarps * 2048 : 0;
+  static constexpr int kSmemBytes = 2 * kTiles * kTileBytes + 2 * kStages * kSubBytes + kStageOut + 1024;   // 2 x Q tiles | K ring | V ring | store staging
   static constexpr uint32_t kTmemCols = 256 * kTiles;
   static constexpr uint32_t kColO0 = 128 * kTiles;                   // S_t[b] at (2t+b)*64, O_{t,b} at kColO0 + (2t+b)*64
 };
@@ -54,6 +58,22 @@ struct Barriers {
   uint64_t s_full[2][2], p_full[2][2];
   uint64_t o_final[2], epi_done[2];
 };
+
+#ifdef OEH_TIMELINE
+// experiment builds only (tools/timeline_wsp.py): CTA 0, first 8 items, 4 recorders (MMA issuer of tile 0, TMA producer, softmax
+// streams (tile 0, parity 0 / 1)), 8 stamps each
+__device__ unsigned long long* g_wsp_timeline = nullptr;
+__device__ __forceinline__ void wsp_stamp(int it, int who, int k) {
+  if (blockIdx.x == 0 && it < 8 && (threadIdx.x & 31) == 0 && g_wsp_timeline) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_wsp_timeline[(it * 4 + who) * 8 + k] = t;
+  }
+}
+#define WSP_STAMP(it, who, k) wsp_stamp(it, who, k)
+#else
+#define WSP_STAMP(it, who, k)
+#endif
 
 template <bool kBF16, bool kGeneric, bool kNorm, int kTiles>
 __global__ void __launch_bounds__(Cfg<kTiles>::kThreads, Cfg<kTiles>::kCtasPerSm)
@@ -213,55 +233,75 @@ attn_fwd_wsp_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
                     (first && k == 0) ? 0u : 1u);
     };
     int gk = 0, gv = 0;                                          // steps / PV steps of earlier items
+    bool pre_issued = false;                                     // this item's first two QK^T were issued by the previous item
     for (int it = 0, item; (item = item_of(it)) < n_items; ++it) {
       const Plan pl = make_plan(item);
       const int qb = it & 1;
       const uint64_t dqi = dq + (uint64_t)qb * (kTiles * kTileUnits);
-      auto issue_qk_item = [&](int sb, int stage) {              // S_t[sb] = Q_t . K(stage)^T with this item's Q buffer
+      const uint64_t dqn = dq + (uint64_t)(qb ^ 1) * (kTiles * kTileUnits);   // the next item's Q buffer
+      auto issue_qk = [&](uint64_t dqx, int sb, int stage) {     // S_t[sb] = Q_t . K(stage)^T with the Q buffer dqx
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          ptx::mma_ss(tS0 + sb * 64, dqi + k * 2, dk + stage * kSubUnits + k * 2, kIdescQK, k > 0);
+          ptx::mma_ss(tS0 + sb * 64, dqx + k * 2, dk + stage * kSubUnits + k * 2, kIdescQK, k > 0);
       };
-      ptx::mbar_wait(ptx::smem_u32(&bars.q_full[qb]), (uint32_t)(it >> 1) & 1u);
-      for (int i = 0; i < 2 && i < pl.n_iter; ++i) {             // prologue: the item's first two score tiles
-        const int g = gk + i, ks = g % kStages;
-        ptx::mbar_wait(ptx::smem_u32(&bars.k_full[ks]), (uint32_t)(g / kStages) & 1u);
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          issue_qk_item(g & 1, ks);
-          ptx::mma_commit(ptx::smem_u32(&bars.s_full[t][g & 1]));
-          ptx::mma_commit(ptx::smem_u32(&bars.k_empty[ks]));
+      // The score tiles run two steps ahead of the PV steps, and they keep doing so ACROSS items: the last two steps of an item
+      // issue the first two QK^T of the next one (its Q and K are long there: the producer runs a ring ahead), so that the softmax
+      // streams come out of their epilogue into scores that are waiting.  (Issued by the next item's own prologue they were ~0.5 us
+      // late, and held up behind the epilogue's shared-memory / store burst: profiles/r02_timeline_wsp.txt.)
+      const int next_item = item_of(it + 1);
+      const bool cross = next_item < n_items && pl.n_iter >= 2 && make_plan(next_item).n_iter >= 2;
+      if (t == 0) WSP_STAMP(it, 0, 0);
+      if (!pre_issued) {
+        ptx::mbar_wait(ptx::smem_u32(&bars.q_full[qb]), (uint32_t)(it >> 1) & 1u);
+        if (t == 0) WSP_STAMP(it, 0, 1);
+        for (int i = 0; i < 2 && i < pl.n_iter; ++i) {           // prologue: the item's first two score tiles
+          const int g = gk + i, ks = g % kStages;
+          ptx::mbar_wait(ptx::smem_u32(&bars.k_full[ks]), (uint32_t)(g / kStages) & 1u);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            issue_qk(dqi, g & 1, ks);
+            ptx::mma_commit(ptx::smem_u32(&bars.s_full[t][g & 1]));
+            ptx::mma_commit(ptx::smem_u32(&bars.k_empty[ks]));
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
+      if (t == 0) WSP_STAMP(it, 0, 2);
       for (int i = 0; i < pl.n_iter; ++i) {
         const int g = gk + i, sb = g & 1;
         const bool pv = i >= pl.nA;
         const int v = i - pl.nA, gvv = gv + v, vs = pv ? gvv % kStages : 0;
-        const bool more = i + 2 < pl.n_iter;
+        const bool more = i + 2 < pl.n_iter;                     // this item's step i + 2 ...
+        const bool ahead = !more && cross;                       // ... or the next item's step i + 2 - n_iter (0 or 1)
         const bool last = i + 1 == pl.n_iter;
         const int g2 = g + 2, ks = g2 % kStages;
         if (pv) ptx::mbar_wait(ptx::smem_u32(&bars.v_full[vs]), (uint32_t)(gvv / kStages) & 1u);
-        if (more) ptx::mbar_wait(ptx::smem_u32(&bars.k_full[ks]), (uint32_t)(g2 / kStages) & 1u);
+        if (ahead && i + 2 == pl.n_iter) ptx::mbar_wait(ptx::smem_u32(&bars.q_full[qb ^ 1]), (uint32_t)((it + 1) >> 1) & 1u);
+        if (more || ahead) ptx::mbar_wait(ptx::smem_u32(&bars.k_full[ks]), (uint32_t)(g2 / kStages) & 1u);
         ptx::mbar_wait(ptx::smem_u32(&bars.p_full[t][sb]), (uint32_t)(g >> 1) & 1u);
         // the item's first PV overwrites an accumulator: the previous item's epilogue must have read both of them
         if (pv && v == 0 && it > 0) ptx::mbar_wait(ptx::smem_u32(&bars.epi_done[t]), (uint32_t)(it - 1) & 1u);
         ptx::tc_fence_after();
+        if (t == 0 && i == 0) WSP_STAMP(it, 0, 3);
+        if (t == 0 && i == 1) WSP_STAMP(it, 0, 4);
+        if (t == 0 && i + 2 == pl.n_iter) WSP_STAMP(it, 0, 5);
+        if (t == 0 && last) WSP_STAMP(it, 0, 6);
         if (ptx::elect_one()) {
           if (pv) {
             issue_pv(sb, vs, v < 2);                             // the first PV step of each parity starts its accumulator
             if (last) ptx::mma_commit(ptx::smem_u32(&bars.o_final[t]));
             ptx::mma_commit(ptx::smem_u32(&bars.v_empty[vs]));
           }
-          if (more) {
-            issue_qk_item(sb, ks);
+          if (last) ptx::mma_commit(ptx::smem_u32(&bars.q_empty[qb]));   // every QK^T of THIS item has been issued
+          if (more || ahead) {
+            issue_qk(more ? dqi : dqn, sb, ks);
             ptx::mma_commit(ptx::smem_u32(&bars.s_full[t][sb]));
             ptx::mma_commit(ptx::smem_u32(&bars.k_empty[ks]));
           }
-          if (last) ptx::mma_commit(ptx::smem_u32(&bars.q_empty[qb]));   // every QK^T of the item has been issued
         }
         __syncwarp();
       }
+      pre_issued = cross;
       gk += pl.n_iter;
       gv += pl.n_kv;
     }
@@ -319,6 +359,9 @@ attn_fwd_wsp_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       }
       ptx::mbar_wait(bar_s, (uint32_t)(g >> 1) & 1u);
       ptx::tc_fence_after();
+      if (t == 0 && (warp & 3) == 0 && i < 2) WSP_STAMP(it, 2 + par, 0);
+      if (t == 0 && (warp & 3) == 0 && i >= 2 && i < 4) WSP_STAMP(it, 2 + par, 1);
+      if (t == 0 && (warp & 3) == 0 && i + 2 >= n_iter) WSP_STAMP(it, 2 + par, 2);
       float s[BNW];
       ptx::tmem_ld32(tS, reinterpret_cast<uint32_t*>(s));
       ptx::tmem_ld32(tS + 32, reinterpret_cast<uint32_t*>(s) + 32);
@@ -414,6 +457,7 @@ attn_fwd_wsp_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     }
 
     // ---- epilogue: merge the streams, O / denominator -> gate / taps -> global -----------------------------------
+    if (t == 0 && (warp & 3) == 0) WSP_STAMP(it, 2 + par, 3);
     float a_own = 1.f, a_other = 1.f, omul = 1.f;                 // scales of the two accumulators; 1/denominator
     if (!normalized) {
       float l_other;
@@ -430,8 +474,10 @@ attn_fwd_wsp_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     // an accumulator exists iff some PV step had its parity (only n_kv == 1 leaves one of them untouched)
     const bool has0 = n_kv > 1 || ((gk + nA) & 1) == 0, has1 = n_kv > 1 || ((gk + nA) & 1) == 1;
     const float a0 = par ? a_other : a_own, a1 = par ? a_own : a_other;
+    if (t == 0 && (warp & 3) == 0) WSP_STAMP(it, 2 + par, 4);
     ptx::mbar_wait(ptx::smem_u32(&bars.o_final[t]), (uint32_t)it & 1u);
     ptx::tc_fence_after();
+    if (t == 0 && (warp & 3) == 0) WSP_STAMP(it, 2 + par, 5);
     // this thread finishes head-dim columns [32par, 32par+32) of its row from both accumulators
     float o[32];
     {
@@ -440,6 +486,7 @@ attn_fwd_wsp_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       ptx::tmem_ld32(tOt, u0);
       ptx::tmem_ld32(tOt + 64, u1);
       ptx::tmem_wait_ld();
+      if (t == 0 && warp == 0) WSP_STAMP(it, 1, 0);
       ptx::tc_fence_before();                                     // the accumulators are in registers: the next item's
       __syncwarp();                                               // first PV may overwrite them
       if (ptx::elect_one()) ptx::mbar_arrive(ptx::smem_u32(&bars.epi_done[t]));
@@ -447,7 +494,16 @@ attn_fwd_wsp_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       for (int j = 0; j < 32; ++j)
         o[j] = (has0 ? __uint_as_float(u0[j]) * a0 : 0.f) + (has1 ? __uint_as_float(u1[j]) * a1 : 0.f);
     }
-    if (row < p.Tq) store_row<kBF16, kGeneric, 32>(o, p, omul, b, h, row, par * 32);
+    if (t == 0 && warp == 0) WSP_STAMP(it, 1, 1);
+    if constexpr (kTiles == 2) {
+      if (row < p.Tq) finish_row<kBF16, kGeneric, 32>(o, p, omul, b, h, row, par * 32);
+      if (t == 0 && warp == 0) WSP_STAMP(it, 1, 2);
+      store_half_rows_coalesced<kBF16>(o, p, sV + kStages * kSubBytes + (uint32_t)warp * 2048u, b, h, q0 + t * 128 + (warp & 3) * 32,
+                                       par * 32);
+    } else {
+      if (row < p.Tq) store_row<kBF16, kGeneric, 32>(o, p, omul, b, h, row, par * 32);
+    }
+    if (t == 0 && (warp & 3) == 0) WSP_STAMP(it, 2 + par, 6);
     gk += n_iter;
     }   // items
   }
