@@ -322,8 +322,10 @@ attn_fwd_wsp_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     if (has_qs) qd_s = load_qdq(p.qdq_scores, p.int_max);
     if (has_qp) qd_p = load_qdq(p.qdq_probs, p.int_max);
     int gk = 0;                                                   // steps of earlier items
+    // the plan of an item (integer divisions, ~0.4 us) is made while the PREVIOUS item's epilogue waits for its statistics merge
+    Plan pl_next = make_plan(item_of(0) < n_items ? item_of(0) : 0);
     for (int it = 0, item; (item = item_of(it)) < n_items; ++it) {
-    const Plan pl = make_plan(item);
+    const Plan pl = pl_next;
     const int q0 = pl.q0, h = pl.h, b = pl.b, n_kv = pl.n_kv, nA = pl.nA, n_iter = pl.n_iter;
     const int row = q0 + t * 128 + r;                             // this thread's query row
     const int64_t mask_row =
@@ -458,6 +460,10 @@ attn_fwd_wsp_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
 
     // ---- epilogue: merge the streams, O / denominator -> gate / taps -> global -----------------------------------
     if (t == 0 && (warp & 3) == 0) WSP_STAMP(it, 2 + par, 3);
+    {
+      const int nx = item_of(it + 1);
+      if (nx < n_items) pl_next = make_plan(nx);
+    }
     float a_own = 1.f, a_other = 1.f, omul = 1.f;                 // scales of the two accumulators; 1/denominator
     if (!normalized) {
       float l_other;
@@ -490,13 +496,25 @@ attn_fwd_wsp_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       ptx::tc_fence_before();                                     // the accumulators are in registers: the next item's
       __syncwarp();                                               // first PV may overwrite them
       if (ptx::elect_one()) ptx::mbar_arrive(ptx::smem_u32(&bars.epi_done[t]));
+      if (has0 && has1) {                                         // (always, unless the item has a single key step)
+        // plain launches: 1 / denominator folded into the two scales (finish_row then only stores)
+        const float f0 = kGeneric || p.gate_logits ? a0 : a0 * omul, f1 = kGeneric || p.gate_logits ? a1 : a1 * omul;
+        const uint64_t f02 = ptx::pack2f(f0, f0), f12 = ptx::pack2f(f1, f1);
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        o[j] = (has0 ? __uint_as_float(u0[j]) * a0 : 0.f) + (has1 ? __uint_as_float(u1[j]) * a1 : 0.f);
+        for (int j = 0; j < 32; j += 2)
+          ptx::unpack2f(ptx::ffma2(ptx::pack2f(__uint_as_float(u1[j]), __uint_as_float(u1[j + 1])), f12,
+                                   ptx::fmul2(ptx::pack2f(__uint_as_float(u0[j]), __uint_as_float(u0[j + 1])), f02)),
+                        o[j], o[j + 1]);
+        if (!(kGeneric || p.gate_logits)) omul = 1.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          o[j] = (has0 ? __uint_as_float(u0[j]) * a0 : 0.f) + (has1 ? __uint_as_float(u1[j]) * a1 : 0.f);
+      }
     }
     if (t == 0 && warp == 0) WSP_STAMP(it, 1, 1);
     if constexpr (kTiles == 2) {
-      if (row < p.Tq) finish_row<kBF16, kGeneric, 32>(o, p, omul, b, h, row, par * 32);
+      if ((kGeneric || p.gate_logits) && row < p.Tq) finish_row<kBF16, kGeneric, 32>(o, p, omul, b, h, row, par * 32);
       if (t == 0 && warp == 0) WSP_STAMP(it, 1, 2);
       store_half_rows_coalesced<kBF16>(o, p, sV + kStages * kSubBytes + (uint32_t)warp * 2048u, b, h, q0 + t * 128 + (warp & 3) * 32,
                                        par * 32);
