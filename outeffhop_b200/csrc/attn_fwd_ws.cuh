@@ -468,7 +468,14 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       for (int j = 0; j < 32; ++j)
         o[j] = (has0 ? __uint_as_float(u0[j]) * a0 : 0.f) + (has1 ? __uint_as_float(u1[j]) * a1 : 0.f);
     }
-    if (row < p.Tq) store_row<kBF16, kGeneric, 32>(o, p, omul, b, h, row, par * 32);
+    // Context rows leave as full 64-byte segments staged per warp (store_half_rows_coalesced) in the K ring: every K / V stage
+    // has been consumed once the LAST PV of every tile of the CTA is complete (the two tiles share the rings).
+    if (row < p.Tq) finish_row<kBF16, kGeneric, 32>(o, p, omul, b, h, row, par * 32);
+    if constexpr (kTiles == 2) {
+      ptx::mbar_wait(ptx::smem_u32(&bars.o_final[t ^ 1]), 0);
+    }
+    static_assert(kStages * kSubBytes >= C::kSoftmaxWarps * 2048, "the K ring holds one staging slot per softmax warp");
+    store_half_rows_coalesced<kBF16>(o, p, sK + (uint32_t)warp * 2048u, b, h, q0 + t * 128 + (warp & 3) * 32, par * 32);
   }
 
   // ---- teardown ------------------------------------------------------------------------------------------------
