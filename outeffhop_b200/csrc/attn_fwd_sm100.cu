@@ -586,6 +586,10 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
     // long items better than any static walk).  The two-pass modes are faster as two one-tile CTAs per SM launched per
     // item at every length, so those keep the non-persistent kernel.
     int persistent = !norm_mode && (!a->causal || steps <= 32.0);
+    // ... unless the whole launch is ONE wave of one-tile CTAs (two per SM): then a persistent CTA has nothing to hide and the
+    // per-item form is 4 % ahead (B=4, H=12, T=512: 10.4 vs 10.8 us causal, 11.8 vs 12.4 us; profiles/r02_mid_kernel_u.jsonl)
+    const long long one_tile_items = (long long)a->B * a->H * ((a->Tq + BM - 1) / BM);
+    if (one_tile_items <= 2LL * num_sms()) persistent = 0;
 #ifdef OEH_WS_PERSISTENT
     persistent = OEH_WS_PERSISTENT;
 #endif

@@ -41,11 +41,11 @@ struct Cfg {
   static constexpr int kSoftmaxRegs = kTiles == 2 ? 112 : 104, kAuxRegs = 24;
   static constexpr int kCtasPerSm = kTiles == 2 ? 1 : 2;
   static constexpr int kQRows = 128 * kTiles;                        // query rows per CTA
-  // kTiles == 2: seven K / V stages and a 2 KB staging slot per softmax warp for the context store (the item's epilogue wrote
+  // Seven (two tiles) / three (one tile, two CTAs per SM) K / V stages and a 2 KB staging slot per softmax warp for the context store (the item's epilogue wrote
   // 16-byte pieces into 32 different lines per instruction; those 2048 partial-line requests per item also held up the MMA
   // issuer's and the producer's barrier polls behind them in the load / store pipeline: profiles/r02_timeline_wsp.txt)
-  static constexpr int kStages = kTiles == 2 ? 7 : 4;
-  static constexpr int kStageOut = kTiles == 2 ? kSoftmaxWarps * 2048 : 0;
+  static constexpr int kStages = kTiles == 2 ? 7 : 3;
+  static constexpr int kStageOut = kSoftmaxWarps * 2048;
   static constexpr int kSmemBytes = 2 * kTiles * kTileBytes + 2 * kStages * kSubBytes + kStageOut + 1024;   // 2 x Q tiles | K ring | V ring | store staging
   static constexpr uint32_t kTmemCols = 256 * kTiles;
   static constexpr uint32_t kColO0 = 128 * kTiles;                   // S_t[b] at (2t+b)*64, O_{t,b} at kColO0 + (2t+b)*64
@@ -513,14 +513,10 @@ attn_fwd_wsp_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       }
     }
     if (t == 0 && warp == 0) WSP_STAMP(it, 1, 1);
-    if constexpr (kTiles == 2) {
-      if ((kGeneric || p.gate_logits) && row < p.Tq) finish_row<kBF16, kGeneric, 32>(o, p, omul, b, h, row, par * 32);
-      if (t == 0 && warp == 0) WSP_STAMP(it, 1, 2);
-      store_half_rows_coalesced<kBF16>(o, p, sV + kStages * kSubBytes + (uint32_t)warp * 2048u, b, h, q0 + t * 128 + (warp & 3) * 32,
-                                       par * 32);
-    } else {
-      if (row < p.Tq) store_row<kBF16, kGeneric, 32>(o, p, omul, b, h, row, par * 32);
-    }
+    if ((kGeneric || p.gate_logits) && row < p.Tq) finish_row<kBF16, kGeneric, 32>(o, p, omul, b, h, row, par * 32);
+    if (t == 0 && warp == 0) WSP_STAMP(it, 1, 2);
+    store_half_rows_coalesced<kBF16>(o, p, sV + kStages * kSubBytes + (uint32_t)warp * 2048u, b, h, q0 + t * 128 + (warp & 3) * 32,
+                                     par * 32);
     if (t == 0 && (warp & 3) == 0) WSP_STAMP(it, 2 + par, 6);
     gk += n_iter;
     }   // items
