@@ -369,6 +369,19 @@ __device__ __forceinline__ void store_row(float (&o)[ND], const AttnParams& p, f
   finish_row<kBF16, kGeneric, ND>(o, p, mul, b, h, row, d0);
   uint8_t* optr = reinterpret_cast<uint8_t*>(p.out) +
                   2 * ((int64_t)b * p.os0 + (int64_t)h * p.os1 + (int64_t)row * p.os2 + d0);
+  if constexpr (ND == 16) {
+    // a quarter row is one 32-byte sector: written whole by one 256-bit store when it is aligned (sm_100 STG.256), instead of
+    // as two half-sector pieces
+    if ((reinterpret_cast<uintptr_t>(optr) & 31) == 0) {
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = pack2<kBF16>(o[2 * j], o[2 * j + 1]);
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(optr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                   "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                   : "memory");
+      return;
+    }
+  }
 #pragma unroll
   for (int c = 0; c < ND / 8; ++c) {
     uint4 v;
@@ -378,6 +391,18 @@ __device__ __forceinline__ void store_row(float (&o)[ND], const AttnParams& p, f
     v.w = pack2<kBF16>(o[c * 8 + 6], o[c * 8 + 7]);
     reinterpret_cast<uint4*>(optr)[c] = v;
   }
+}
+
+__device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// one whole 32-byte sector per thread (sm_100 STG.256); ptr must be 32-byte aligned
+__device__ __forceinline__ void st_global_256(void* ptr, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
+               "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
 }
 
 // Warp-cooperative store of 32 finished context rows (lane == row, 64 values each; the caller has applied finish_row).
@@ -398,16 +423,25 @@ __device__ __forceinline__ void store_rows_coalesced(const float (&o)[HD], const
                         pack2<kBF16>(o[c * 8 + 6], o[c * 8 + 7]));
   }
   __syncwarp();
+  uint8_t* obase = reinterpret_cast<uint8_t*>(p.out) + 2 * ((int64_t)b * p.os0 + (int64_t)h * p.os1);
+  if (((reinterpret_cast<uintptr_t>(obase) | (uintptr_t)(2 * p.os2)) & 31) == 0) {
+    // 32-byte sectors: 4 lanes per row, 8 rows per instruction, 4 instructions (256-bit stores)
+    const uint32_t cc = lane & 3u, rsub = lane >> 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t rr = (uint32_t)i * 8u + rsub, base = stage + rr * 128u, s7 = rr & 7u;
+      const uint4 lo = ld_shared_u4(base + (((2u * cc) ^ s7) << 4)), hi = ld_shared_u4(base + (((2u * cc + 1u) ^ s7) << 4));
+      const int row = row0 + (int)rr;
+      if (row < p.Tq) st_global_256(obase + 2 * (int64_t)row * p.os2 + cc * 32u, lo, hi);
+    }
+    return;
+  }
   const uint32_t cc = lane & 7u, rsub = lane >> 3;
-  uint8_t* obase = reinterpret_cast<uint8_t*>(p.out) + 2 * ((int64_t)b * p.os0 + (int64_t)h * p.os1) + cc * 16u;
+  obase += cc * 16u;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const uint32_t rr = (uint32_t)i * 4u + rsub;
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "r"(stage + rr * 128u + ((cc ^ (rr & 7u)) << 4))
-                 : "memory");
+    const uint4 v = ld_shared_u4(stage + rr * 128u + ((cc ^ (rr & 7u)) << 4));
     const int row = row0 + (int)rr;
     if (row < p.Tq) *reinterpret_cast<uint4*>(obase + 2 * (int64_t)row * p.os2) = v;
   }
@@ -428,16 +462,25 @@ __device__ __forceinline__ void store_half_rows_coalesced(const float (&o)[32], 
                         pack2<kBF16>(o[c * 8 + 6], o[c * 8 + 7]));
   }
   __syncwarp();
+  uint8_t* obase = reinterpret_cast<uint8_t*>(p.out) + 2 * ((int64_t)b * p.os0 + (int64_t)h * p.os1 + d0);
+  if (((reinterpret_cast<uintptr_t>(obase) | (uintptr_t)(2 * p.os2)) & 31) == 0) {
+    // 32-byte sectors: 2 lanes per half row, 16 rows per instruction, 2 instructions (256-bit stores)
+    const uint32_t cc = lane & 1u, rsub = lane >> 1;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t rr = (uint32_t)i * 16u + rsub, base = stage + rr * 64u, s3 = (rr >> 1) & 3u;
+      const uint4 lo = ld_shared_u4(base + (((2u * cc) ^ s3) << 4)), hi = ld_shared_u4(base + (((2u * cc + 1u) ^ s3) << 4));
+      const int row = row0 + (int)rr;
+      if (row < p.Tq) st_global_256(obase + 2 * (int64_t)row * p.os2 + cc * 32u, lo, hi);
+    }
+    return;
+  }
   const uint32_t cc = lane & 3u, rsub = lane >> 2;
-  uint8_t* obase = reinterpret_cast<uint8_t*>(p.out) + 2 * ((int64_t)b * p.os0 + (int64_t)h * p.os1 + d0) + cc * 16u;
+  obase += cc * 16u;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t rr = (uint32_t)i * 8u + rsub;
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "r"(stage + rr * 64u + ((cc ^ ((rr >> 1) & 3u)) << 4))
-                 : "memory");
+    const uint4 v = ld_shared_u4(stage + rr * 64u + ((cc ^ ((rr >> 1) & 3u)) << 4));
     const int row = row0 + (int)rr;
     if (row < p.Tq) *reinterpret_cast<uint4*>(obase + 2 * (int64_t)row * p.os2) = v;
   }
