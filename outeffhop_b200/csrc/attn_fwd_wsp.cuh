@@ -85,7 +85,9 @@ attn_fwd_wsp_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) Barriers<kStages> bars;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float xch_m[kTiles][2][128], xch_l[kTiles][2][128];  // (tile, parity, row): statistics merged across streams
+  // (item parity, tile, stream parity, row): statistics merged across streams.  Double-buffered by item: the barrier of item i+1's
+  // merge orders item i's reads before item i+2's writes (one buffer relied on the pipeline handshakes in between for that)
+  __shared__ float xch_m[2][kTiles][2][128], xch_l[2][kTiles][2][128];
 
   // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from it
   // (role, TMEM lane base, barrier / descriptor addresses) on the uniform datapath instead of R2UR-ing it at every use
@@ -337,11 +339,11 @@ attn_fwd_wsp_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
 
     // merge (m_b, l_b) of the two streams of a row: afterwards both hold the row's m in the common frame
     auto merge_streams = [&](float& a_own, float& a_other, float& l_other) {
-      xch_m[t][par][r] = m_run;
-      xch_l[t][par][r] = l_run;
+      xch_m[it & 1][t][par][r] = m_run;
+      xch_l[it & 1][t][par][r] = l_run;
       asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
-      const float m_o = xch_m[t][par ^ 1][r];
-      l_other = xch_l[t][par ^ 1][r];
+      const float m_o = xch_m[it & 1][t][par ^ 1][r];
+      l_other = xch_l[it & 1][t][par ^ 1][r];
       const float m = fmaxf(m_run, m_o);
       const float m_safe = m == -INFINITY ? 0.f : m;
       a_own = ptx::ex2(m_run - m_safe);                           // -inf -> 0

@@ -315,15 +315,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
         q_lo = -zp;
         q_hi = p.int_max - zp;
       }
-      // The bias of this warp's column part -> shared memory before the accumulator is waited for (a global load per chunk on the
-      // critical path of the epilogue cost ~0.3 us each); columns beyond N read as 0.  The four warps of a part write the SAME
-      // values into the part's slot of this tile's parity, so only __syncwarp orders a warp's own write and reads.  Reuse two
-      // tiles later is safe: a warp reads its bias BEFORE it releases the accumulator (tmem_empty), and tile i+2's accumulator
-      // -- which the writers of tile i+2 wait for -- cannot complete before every warp has released tile i's.
+      // The bias of this column part -> shared memory before the accumulator is waited for (a global load per chunk on the
+      // critical path of the epilogue cost ~0.3 us each); columns beyond N read as 0.  Written by the part's first warp into
+      // the slot of this tile's parity; ONE named barrier of the part's four warps per tile (off the critical path: the main
+      // loop is still running) publishes it, and the same barrier one tile later orders these reads before the slot's reuse.
       uint4* my_bias = &s_bias[acc][part][0];
       {
         constexpr int kV = BN / kParts / 8;
-        if ((int)lane < kV) {
+        if (q == 0 && (int)lane < kV) {
           uint4 bv = make_uint4(0u, 0u, 0u, 0u);
           const int gc = n0 + part * (BN / kParts) + 8 * (int)lane;
           if (p.bias) {
@@ -338,7 +337,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
           }
           my_bias[lane] = bv;
         }
-        __syncwarp();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + part) : "memory");
       }
       ptx::mbar_wait(ptx::smem_u32(&bars.tmem_full[acc]), (uint32_t)(ti >> 1) & 1u);
       ptx::tc_fence_after();
