@@ -187,6 +187,39 @@ def time_attention_kernel(torch, ops, fn, dtype, pool_sets=8, reps=10):
     return sum(ts) / len(ts) * 1e-3     # seconds per launch
 
 
+def time_ffn1_gemm(torch, ops, dtype, pool_sets=8, reps=5):
+    """Average launch duration of this repo's tcgen05 GEMM with the erf-GELU epilogue at the model's FFN1 shape
+    (M = 32 x 128 tokens, K = 768, N = 3072): the single largest kernel of the headline step (24 % of it,
+    profiles/r02_launches_bert_step_v.summary.txt).  Cold like time_attention_kernel: activations rotate over a pool
+    larger than L2 (8 x 31.5 MB), back to back in one CUDA graph, one CUDA-event pair."""
+    M, K, N = BATCH * SEQ, HEADS * HEAD_DIM, 4 * HEADS * HEAD_DIM
+    g = torch.Generator(device="cuda").manual_seed(2)
+    w = torch.randn(N, K, device="cuda", dtype=dtype, generator=g) * K ** -0.5
+    b = torch.randn(N, device="cuda", dtype=dtype, generator=g)
+    pool = [(torch.randn(M, K, device="cuda", dtype=dtype, generator=g), torch.empty(M, N, device="cuda", dtype=dtype))
+            for _ in range(pool_sets)]
+    run = lambda s: ops.linear_fwd(s[0], w, b, act="gelu", out=s[1])
+    for s in pool:
+        run(s)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(reps):
+            for s in pool:
+                run(s)
+    graph.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        graph.replay()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(e) / (reps * pool_sets))
+    return sum(ts) / len(ts) * 1e-3, 2.0 * M * N * K, 2.0 * (M * K + N * K + N + M * N)
+
+
 def _event_time(torch, f, reps=5, warm=3, clock=None):
     """Seconds per call (CUDA events around `reps` back-to-back calls).  clock: optional one-element list that receives the SM
     clock (MHz) the GPU was running at when the last call ended (outeffhop_b200._lib.sm_clock_probe, queued behind it)."""
@@ -486,6 +519,19 @@ def run_ours(args):
                          "timing": "80 launches back to back in one CUDA graph over 8 input sets (201 MB > L2), CUDA events",
                          "note": "64 flop/B: HBM/latency-bound at T=128; the tensor roofline applies to attn_sweep (T>=2048)"},
         }
+        # The step's largest own kernel by time share is tensor-bound: reported next to the attention line, same timing method
+        t_gemm, gemm_flops, gemm_bytes = time_ffn1_gemm(torch, ops, torch.float16)
+        line["roofline_gemm"] = {
+            "kernel": "gemm_kernel<fp16, 128x256 tiles, cta_group::2> (oeh_linear_fwd: x @ W^T + bias -> erf GELU in the "
+                      "TMEM->register epilogue -> TMA store), M=4096 K=768 N=3072 (BERT-base FFN1)",
+            "bound": "tensor", "achieved": gemm_flops / t_gemm / 1e12, "peak": peaks["tensor"], "unit": "TFLOP/s",
+            "frac": gemm_flops / t_gemm / 1e12 / peaks["tensor"],
+            "frac_of_sustained_peak": gemm_flops / t_gemm / 1e12 / peaks["tensor_sustained"], "traffic": None,
+            "peak_source": peaks["source"] + ", cuBLAS bf16 burst (sustained beside it)", "launch_us": t_gemm * 1e6,
+            "algorithmic_flops_per_launch": gemm_flops, "algorithmic_bytes_per_launch": gemm_bytes,
+            "timing": "40 launches back to back in one CUDA graph over 8 activation sets (252 MB > L2), CUDA events",
+            "note": "share of the step: 24 % (12 FFN1 launches + the MLM-head transform); the erf-GELU epilogue, not the "
+                    "main loop, bounds it (profiles/r02_timeline_gemm.txt)"}
         if extra is not None:
             line["configs"] = extra
         if not args.no_sweep:

@@ -164,10 +164,18 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
 
     // ---- pass A: e = exp2(s - m_i) over S, running (m, l) ------------------------------------------------------------
     float m_run = -INFINITY, l_run = 0.f;
-    float mc[kMaxTiles];                                        // frame (running max) of the e values of chunk 2i + half
+    // frame (running max) of the e values of chunk kParts * i + half.  Four scalars behind selects, not an indexed array: the tile
+    // loops below are NOT unrolled (OEH_MID_UNROLL_TILES restores the old form for A/B runs) -- fully unrolled the tapped
+    // instantiation was 7544 SASS instructions (118 KB) and a fifth of its stall samples were instruction fetch
+    // (stall_no_inst 19.8 %, profiles/r02_ncu_hot_kernels.txt): every launch inside a model step starts with a cold I-cache
+    float mc0 = 0.f, mc1 = 0.f, mc2 = 0.f, mc3 = 0.f;
+    static_assert(kMaxTiles == 4, "mc0..mc3");
+#ifdef OEH_MID_UNROLL_TILES
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
     for (int i = 0; i < kMaxTiles; ++i) {
-      mc[i] = 0.f;
       if (i < n_kv) {
         const int j = kParts * i + half, k0 = j * CW;
         ptx::mbar_wait(ptx::smem_u32(&bars.s_full[i]), 0);
@@ -189,7 +197,10 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         const float alpha = ptx::ex2(m_run - m_safe);           // m_run = -inf -> 0
         l_run = fmaf(l_run, alpha, exp2_and_sum<CW, !kGeneric>(s, mul, m_safe));
         m_run = m_new;
-        mc[i] = m_safe;
+        mc0 = i == 0 ? m_safe : mc0;
+        mc1 = i == 1 ? m_safe : mc1;
+        mc2 = i == 2 ? m_safe : mc2;
+        mc3 = i == 3 ? m_safe : mc3;
 #pragma unroll
         for (int c = 0; c < CW / 32; ++c) ptx::tmem_st32(t_lane + j * CW + 32 * c, reinterpret_cast<const uint32_t*>(s) + 32 * c);
       }
@@ -212,7 +223,11 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     const float omul = normalized ? 1.f : inv_den;              // one-pass kinds: P stays in the row-max frame (max P = 1)
 
     // ---- pass B: P ----------------------------------------------------------------------------------------------------------
+#ifdef OEH_MID_UNROLL_TILES
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
     for (int i = 0; i < kMaxTiles; ++i) {
       if (i < n_kv) {
         const int j = kParts * i + half;
@@ -223,7 +238,8 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         // The P chunks of iteration i (kParts * CW / 2 = 64 packed columns) overwrite e-chunks read in iteration <= i (in this very
         // iteration when i == 0): every thread of the row must have COMPLETED its reads of this iteration before any writes
         asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * kParts) : "memory");
-        const float f = ptx::ex2(mc[i] - m_fin);                // chunk frame -> common frame (mc <= m_fin)
+        const float mci = i == 0 ? mc0 : i == 1 ? mc1 : i == 2 ? mc2 : mc3;
+        const float f = ptx::ex2(mci - m_fin);                  // chunk frame -> common frame (mc <= m_fin)
         if (normalized) {
           normalize_probs<CW, kGeneric, kBF16>(s, p, inv_den * f, clipped, has_qp, qd_p);
         } else {

@@ -33,51 +33,42 @@ __device__ __forceinline__ int4 ld_row(const int4* p) { return *p; }
 __device__ __forceinline__ void st_row(int4* p, const int4& v) { *p = v; }
 #endif
 
-template <typename T, int kVecs, bool kGate>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ gamma,
+// kTaps = false: the launch has no fake-quant tap, and the three tap chains are compiled out (the floating-point model steps: with
+// them the fp16 instantiation is 4920 SASS instructions, without ~1100 -- 25 launches per step, each starting from a cold
+// instruction cache)
+//
+// kFast (16-bit tensors with taps): every active tap is on the quantizer's common path (8-bit codes exact in the tensor dtype, a
+// normal 1 / scale, zero point in range: QdqVec::fast()), and only that path is compiled in -- straight-line code.  With the
+// rare-case chains (IEEE division, rint, the scalar fp32 detour) inlined at each of the nine tap sites, the hot path was a
+// sequence of far jumps over code it never runs, each landing on a cold instruction-cache line.
+template <typename T, int kVecs, bool kGate, bool kTaps, bool kFast>
+__device__ __forceinline__ void add_layer_norm_row(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ gamma,
                       const T* __restrict__ beta, T* __restrict__ y, int64_t rows, int cols, float eps,
-                      const float* __restrict__ q_a, const float* __restrict__ q_res, const float* __restrict__ q_out,
+                      const float* __restrict__ q_a_, const float* __restrict__ q_res_, const float* __restrict__ q_out_,
                       float int_max, T* __restrict__ sum_out, const float* __restrict__ gate_w,
-                      const float* __restrict__ gate_b, float* __restrict__ gate_out, int T_len, int H) {
+                      const float* __restrict__ gate_b, float* __restrict__ gate_out, int T_len, int H,
+                      float as, float az, float rs, float rz, float os, float oz, int64_t row,
+                      Vec16<T> (&va)[kVecs], Vec16<T> (&vb)[kVecs]) {
+  const float* q_a = kTaps ? q_a_ : nullptr;
+  const float* q_res = kTaps ? q_res_ : nullptr;
+  const float* q_out = kTaps ? q_out_ : nullptr;
   using V = Vec16<T>;
   constexpr int N = V::N;
   constexpr int LPH = 64 / N;                              // lanes that hold one 64-wide head of the row
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int nvec = cols / N;
-  const V* av = reinterpret_cast<const V*>(a + row * cols);
-  const V* bv = b ? reinterpret_cast<const V*>(b + row * cols) : nullptr;
-
-  float as = 1.f, az = 0.f, rs = 1.f, rz = 0.f, os = 1.f, oz = 0.f;
-  if (q_a) { as = DT<T>::rnd(__ldg(q_a)); az = DT<T>::rnd(__ldg(q_a + 1)); }
-  if (q_res) { rs = DT<T>::rnd(__ldg(q_res)); rz = DT<T>::rnd(__ldg(q_res + 1)); }
-  if (q_out) { os = DT<T>::rnd(__ldg(q_out)); oz = DT<T>::rnd(__ldg(q_out + 1)); }
+  const bool bv = b != nullptr;
 
   float x[kVecs][N];
-  V va[kVecs], vb[kVecs];
-#pragma unroll
-  for (int v = 0; v < kVecs; ++v) {                        // all loads of the row in flight before the first use
-    const int i = lane + 32 * v;
-    if (i < nvec) {
-      int4 raw = ld_row(reinterpret_cast<const int4*>(av + i));
-      va[v] = *reinterpret_cast<V*>(&raw);
-      if (bv) {
-        raw = ld_row(reinterpret_cast<const int4*>(bv + i));
-        vb[v] = *reinterpret_cast<V*>(&raw);
-      }
-    }
-  }
   const QdqVec<T> qa(as, az, int_max), qr(rs, rz, int_max), qo(os, oz, int_max);
   float sum = 0.f;
 #pragma unroll
   for (int v = 0; v < kVecs; ++v) {
     const int i = lane + 32 * v;
     if (i < nvec) {                                        // taps and the sum in the tensor dtype, 16 bytes at a time
-      if (q_a) qa.apply(va[v], false);
+      if (q_a) qa.template apply_t<kFast>(va[v], false);
       if (bv) add_vec<T>(va[v], vb[v]);
-      if (q_res) qr.apply(va[v], false);
+      if (q_res) qr.template apply_t<kFast>(va[v], false);
       if (sum_out)                                         // pre-LN blocks (OPT) keep the sum as the next residual
         st_row(reinterpret_cast<int4*>(reinterpret_cast<V*>(sum_out + row * cols) + i), *reinterpret_cast<const int4*>(&va[v]));
     }
@@ -123,13 +114,19 @@ add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T*
         if (beta) r += DT<T>::to_f(be.v[e]);
         out.v[e] = DT<T>::from_f(r);                       // one rounding to the tensor dtype
       }
-      if (q_out) qo.apply(out, false);
+      if (q_out) qo.template apply_t<kFast>(out, false);
       st_row(reinterpret_cast<int4*>(yv + i), *reinterpret_cast<const int4*>(&out));
       if (kGate) {                                         // per-token gate logit of head i / LPH from the row just written
-        const float* wp = gate_w + (int64_t)i * N;         // (H, 64) contiguous == the row's layout
+        const float4* wp = reinterpret_cast<const float4*>(gate_w + (int64_t)i * N);   // (H, 64) contiguous == the row's layout
         float acc = 0.f;
 #pragma unroll
-        for (int e = 0; e < N; ++e) acc = fmaf(DT<T>::to_f(out.v[e]), __ldg(wp + e), acc);
+        for (int e = 0; e < N; e += 4) {                   // N fp32 weights as N / 4 16-byte loads (N * 4 bytes per lane, aligned)
+          const float4 w4 = __ldg(wp + e / 4);
+          acc = fmaf(DT<T>::to_f(out.v[e]), w4.x, acc);
+          acc = fmaf(DT<T>::to_f(out.v[e + 1]), w4.y, acc);
+          acc = fmaf(DT<T>::to_f(out.v[e + 2]), w4.z, acc);
+          acc = fmaf(DT<T>::to_f(out.v[e + 3]), w4.w, acc);
+        }
         gacc[v] = acc;
       }
     }
@@ -150,6 +147,51 @@ add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T*
       }
     }
   }
+}
+
+template <typename T, int kVecs, bool kGate, bool kTaps = true>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+add_layer_norm_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ gamma,
+                      const T* __restrict__ beta, T* __restrict__ y, int64_t rows, int cols, float eps,
+                      const float* __restrict__ q_a, const float* __restrict__ q_res, const float* __restrict__ q_out,
+                      float int_max, T* __restrict__ sum_out, const float* __restrict__ gate_w,
+                      const float* __restrict__ gate_b, float* __restrict__ gate_out, int T_len, int H) {
+  using V = Vec16<T>;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = cols / V::N;
+  float as = 1.f, az = 0.f, rs = 1.f, rz = 0.f, os = 1.f, oz = 0.f;
+  if constexpr (kTaps) {
+    if (q_a) { as = DT<T>::rnd(__ldg(q_a)); az = DT<T>::rnd(__ldg(q_a + 1)); }
+    if (q_res) { rs = DT<T>::rnd(__ldg(q_res)); rz = DT<T>::rnd(__ldg(q_res + 1)); }
+    if (q_out) { os = DT<T>::rnd(__ldg(q_out)); oz = DT<T>::rnd(__ldg(q_out + 1)); }
+  }
+  const V* av = reinterpret_cast<const V*>(a + row * cols);
+  const V* bv = b ? reinterpret_cast<const V*>(b + row * cols) : nullptr;
+  V va[kVecs], vb[kVecs];
+#pragma unroll
+  for (int v = 0; v < kVecs; ++v) {                        // all loads of the row in flight before the first use
+    const int i = lane + 32 * v;
+    if (i < nvec) {
+      int4 raw = ld_row(reinterpret_cast<const int4*>(av + i));
+      va[v] = *reinterpret_cast<V*>(&raw);
+      if (bv) {
+        raw = ld_row(reinterpret_cast<const int4*>(bv + i));
+        vb[v] = *reinterpret_cast<V*>(&raw);
+      }
+    }
+  }
+  if constexpr (kTaps && P2<T>::kPacked) {
+    const bool fast = QdqVec<T>(as, az, int_max).fast() && QdqVec<T>(rs, rz, int_max).fast() && QdqVec<T>(os, oz, int_max).fast();
+    if (fast) {                                              // (an inactive tap has scale 1, zero point 0: fast)
+      add_layer_norm_row<T, kVecs, kGate, true, true>(a, b, gamma, beta, y, rows, cols, eps, q_a, q_res, q_out, int_max, sum_out,
+                                                      gate_w, gate_b, gate_out, T_len, H, as, az, rs, rz, os, oz, row, va, vb);
+      return;
+    }
+  }
+  add_layer_norm_row<T, kVecs, kGate, kTaps, false>(a, b, gamma, beta, y, rows, cols, eps, q_a, q_res, q_out, int_max, sum_out,
+                                                    gate_w, gate_b, gate_out, T_len, H, as, az, rs, rz, os, oz, row, va, vb);
 }
 
 // BertEmbeddings.forward (HF modeling_bert, the shell around the reference's encoder): y = LayerNorm((word[id] + type[tt])
@@ -266,21 +308,26 @@ int launch(const void* a, const void* b, const void* gamma, const void* beta, vo
   const int kv = (int)((cols / N + 31) / 32);
   const float int_max = (float)((1 << n_bits) - 1);
   const unsigned grid = (unsigned)((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const bool taps = q_a || q_res || q_out;
+#define OEH_LN_LAUNCH(K, G, Q)                                                                                       \
+  add_layer_norm_kernel<T, K, G, Q><<<grid, kWarpsPerBlock * 32, 0, st>>>(                                           \
+      (const T*)a, (const T*)b, (const T*)gamma, (const T*)beta, (T*)y, rows, (int)cols, eps, q_a, q_res, q_out,     \
+      int_max, (T*)sum_out, gate_w, gate_b, gate_out, T_len, H)
 #define OEH_LN_CASE(K)                                                                                               \
   case K:                                                                                                            \
-    if (gate_out)                                                                                                    \
-      add_layer_norm_kernel<T, K, true><<<grid, kWarpsPerBlock * 32, 0, st>>>(                                       \
-          (const T*)a, (const T*)b, (const T*)gamma, (const T*)beta, (T*)y, rows, (int)cols, eps, q_a, q_res, q_out, \
-          int_max, (T*)sum_out, gate_w, gate_b, gate_out, T_len, H);                                                 \
-    else                                                                                                             \
-      add_layer_norm_kernel<T, K, false><<<grid, kWarpsPerBlock * 32, 0, st>>>(                                      \
-          (const T*)a, (const T*)b, (const T*)gamma, (const T*)beta, (T*)y, rows, (int)cols, eps, q_a, q_res, q_out, \
-          int_max, (T*)sum_out, nullptr, nullptr, nullptr, 1, 0);                                                    \
+    if (gate_out) {                                                                                                  \
+      if (taps) OEH_LN_LAUNCH(K, true, true);                                                                        \
+      else OEH_LN_LAUNCH(K, true, false);                                                                            \
+    } else {                                                                                                         \
+      if (taps) OEH_LN_LAUNCH(K, false, true);                                                                       \
+      else OEH_LN_LAUNCH(K, false, false);                                                                           \
+    }                                                                                                                \
     break;
   switch (kv) {
     OEH_LN_CASE(1) OEH_LN_CASE(2) OEH_LN_CASE(3) OEH_LN_CASE(4) OEH_LN_CASE(5) OEH_LN_CASE(6) OEH_LN_CASE(7) OEH_LN_CASE(8)
   }
 #undef OEH_LN_CASE
+#undef OEH_LN_LAUNCH
   return check_launch("add_layer_norm_kernel");
 }
 
@@ -310,6 +357,7 @@ extern "C" int oeh_add_layer_norm_gate(const void* a, const void* b, const void*
                                        oeh_stream_t stream) {
   if (gate_out) {
     OEH_CHECK_ARG(gate_w && gate_b, "oeh_add_layer_norm_gate: null gate weights");
+    OEH_CHECK_ARG((reinterpret_cast<uintptr_t>(gate_w) & 15) == 0, "oeh_add_layer_norm_gate: gate weights must be 16-byte aligned");
     OEH_CHECK_ARG(T > 0 && H > 0 && (int64_t)H * 64 == cols && rows % T == 0,
                   "oeh_add_layer_norm_gate: the gate needs cols == 64 H and rows == B T (cols=%lld H=%d rows=%lld T=%d)",
                   (long long)cols, H, (long long)rows, T);

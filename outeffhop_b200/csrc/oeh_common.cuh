@@ -158,6 +158,9 @@ struct QdqVec<T, false> {                         // fp32 tensors: the scalar ch
 #pragma unroll
     for (int e = 0; e < Vec16<T>::N; ++e) v.v[e] = DT<T>::from_f(qdq_one<T>(DT<T>::to_f(v.v[e]), scale, zp, int_max, codes));
   }
+  __device__ __forceinline__ bool fast() const { return false; }
+  template <bool kFast>
+  __device__ __forceinline__ void apply_t(Vec16<T>& v, bool codes) const { apply(v, codes); }
 };
 
 template <typename T>
@@ -199,6 +202,26 @@ struct QdqVec<T, true> {
     if (codes) return q;
     q = __hsub2_rn(q, z2);                        // x_int - zero_point
     return __hmul2_rn(s2, q);                     // scale * (...)
+  }
+  // the common case: packed 16-bit codes, reciprocal quotient, magic-number rounding -- exactly the first branches of one2()
+  __device__ __forceinline__ bool fast() const { return packed && magic && rinv != 0.f; }
+  // kFast: the caller has checked fast(); only that chain is compiled in (same instructions, same results as apply())
+  template <bool kFast>
+  __device__ __forceinline__ void apply_t(Vec16<T>& v, bool codes) const {
+    if constexpr (kFast) {
+      V2* p = reinterpret_cast<V2*>(v.v);
+      const V2 k2 = P2<T>::bcast(P2<T>::kMagic);
+#pragma unroll
+      for (int k = 0; k < Vec16<T>::N / 2; ++k) {
+        const float2 xf = P2<T>::to_f2(p[k]);
+        V2 q = P2<T>::from_f2(__fmul_rn(xf.x, rinv), __fmul_rn(xf.y, rinv));
+        q = __hmin2_nan(__hmax2_nan(q, a2), b2);
+        q = __hsub2_rn(__hadd2_rn(q, k2), k2);
+        p[k] = codes ? __hadd2_rn(q, z2) : __hmul2_rn(s2, q);
+      }
+    } else {
+      apply(v, codes);
+    }
   }
   __device__ __forceinline__ void apply(Vec16<T>& v, bool codes) const {
     if (packed) {

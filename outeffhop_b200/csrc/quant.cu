@@ -8,6 +8,8 @@
 // multiple of the SM count and grid-stride over the tensor with 4 independent 16-byte loads in
 // flight per thread.  No fast-math: the fp32 path must be bit-exact with ATen (IEEE div, rintf =
 // round-half-even, no FMA contraction -- every op below is a single rounding by construction).
+#include <type_traits>
+
 #include "oeh_common.cuh"
 
 namespace oeh {
@@ -44,16 +46,24 @@ __global__ void __launch_bounds__(kThreads) fake_quant_kernel(const T* __restric
   V* yv = reinterpret_cast<V*>(y);
   const int64_t stride = (int64_t)gridDim.x * kThreads;
   int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  for (; i + (kUnroll - 1) * stride < nvec; i += kUnroll * stride) {
-    V in[kUnroll];
+  // The main loop exists twice: with only the quantizer's common chain compiled in (QdqVec::fast(): straight-line code), and
+  // with every rare-case chain.  Interleaved in one loop body the hot path was a string of jumps over code it never runs --
+  // instruction-cache misses at every landing (measured on the LayerNorm taps: profiles/r02_ln_code_size.txt)
+  auto main_loop = [&](auto fast_tag) {
+    constexpr bool kFast = decltype(fast_tag)::value;
+    for (; i + (kUnroll - 1) * stride < nvec; i += kUnroll * stride) {
+      V in[kUnroll];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) in[u] = ld_stream(xv + i + u * stride);
+      for (int u = 0; u < kUnroll; ++u) in[u] = ld_stream(xv + i + u * stride);
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      qv.apply(in[u], codes);
-      st_stream(yv + i + u * stride, in[u]);
+      for (int u = 0; u < kUnroll; ++u) {
+        qv.template apply_t<kFast>(in[u], codes);
+        st_stream(yv + i + u * stride, in[u]);
+      }
     }
-  }
+  };
+  if (qv.fast()) main_loop(std::true_type{});
+  else main_loop(std::false_type{});
   for (; i < nvec; i += stride) {
     V in = xv[i];
     qv.apply(in, codes);
