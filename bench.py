@@ -37,7 +37,8 @@ ATTN_SOFTMAX = "clippedsoftmax1(-.025:1)"
 BATCH, SEQ, HEADS, HEAD_DIM, LAYERS = 32, 128, 12, 64, 12
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel (ncu --set full capture under
 # profiles/); None until a capture of the current kernel is committed
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 18895872   # profiles/r01_ncu_one_clip1_T128.txt: 18.90 MB read + 0 written (ctx still in L2)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 18911744   # profiles/r02_ncu_hot_kernels.txt, launch 5: 18.909 MB read + 0.002 MB written (ctx still in L2)
+NCU_GEMM_TRAFFIC_BYTES_PER_LAUNCH = 11045632   # same capture, launch 6: 11.045 MB read (x + part of W; W and y mostly stay in L2) + 256 B written
 WORKLOAD = "BERT-base fp16 eval, --attn_softmax clippedsoftmax1(-.025:1), seq 128, batch 32 per GPU (BASELINE config 2)"
 
 
@@ -526,7 +527,8 @@ def run_ours(args):
                       "TMEM->register epilogue -> TMA store), M=4096 K=768 N=3072 (BERT-base FFN1)",
             "bound": "tensor", "achieved": gemm_flops / t_gemm / 1e12, "peak": peaks["tensor"], "unit": "TFLOP/s",
             "frac": gemm_flops / t_gemm / 1e12 / peaks["tensor"],
-            "frac_of_sustained_peak": gemm_flops / t_gemm / 1e12 / peaks["tensor_sustained"], "traffic": None,
+            "frac_of_sustained_peak": gemm_flops / t_gemm / 1e12 / peaks["tensor_sustained"],
+            "traffic": NCU_GEMM_TRAFFIC_BYTES_PER_LAUNCH,
             "peak_source": peaks["source"] + ", cuBLAS bf16 burst (sustained beside it)", "launch_us": t_gemm * 1e6,
             "algorithmic_flops_per_launch": gemm_flops, "algorithmic_bytes_per_launch": gemm_bytes,
             "timing": "40 launches back to back in one CUDA graph over 8 activation sets (252 MB > L2), CUDA events",
