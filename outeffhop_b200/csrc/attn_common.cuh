@@ -333,22 +333,37 @@ __device__ __forceinline__ float zero_prob_threshold(const AttnParams& p, bool c
 // Epilogue of one query row (ND = 64: the whole row; ND = 32: the half starting at head-dim column d0):
 // o[] holds the PV accumulator; mul = 1/denominator (1 in the normalised modes).
 // ctx -> [qdq before gate] -> * sigmoid(gate logit)*gate_scale -> [qdq after gate] -> ND/8 x 16-byte stores.
+// What a row's epilogue reads from global memory -- the probs tap's scale, the gate logit, the context tap's parameters --
+// fetched BEFORE the wait for the last PV (epi_prefetch), so that these L2 round trips (~0.4 us, serialised behind the
+// accumulator in profiles/r02_ncu_hot_kernels.txt: 4 % of the mid kernel's samples sat on the gate's sigmoid) overlap it.
+struct EpiPre {
+  float pscale, gate;
+  Qdq qd_c;
+};
+template <bool kBF16, bool kGeneric>
+__device__ __forceinline__ EpiPre epi_prefetch(const AttnParams& p, int b, int h, int row) {
+  EpiPre e{1.f, 1.f, Qdq{1.f, 1.f, 0.f, p.int_max}};
+  if (kGeneric && probs_as_codes<kBF16>(p)) e.pscale = __ldg(p.qdq_probs);   // P was (code - zp): see normalize_probs
+  if (p.gate_logits && row < p.Tq) {
+    const float z = __ldg(p.gate_logits + ((int64_t)b * p.H + h) * p.Tq + row);
+    e.gate = __frcp_rn(1.f + expf(-z)) * p.gate_scale;
+  }
+  if (kGeneric && p.qdq_ctx) e.qd_c = load_qdq(p.qdq_ctx, p.int_max);
+  return e;
+}
+
 template <bool kBF16, bool kGeneric, int ND = HD>
-__device__ __forceinline__ void finish_row(float (&o)[ND], const AttnParams& p, float mul, int b, int h, int row,
-                                           int d0 = 0) {
+__device__ __forceinline__ void finish_row(float (&o)[ND], const AttnParams& p, float mul, int b, int h, int row, int d0,
+                                           const EpiPre& pre) {
   if (kGeneric && p.dbg_o) {
     float* d = p.dbg_o + (((int64_t)b * p.H + h) * p.Tq + row) * HD + d0;
 #pragma unroll
     for (int j = 0; j < ND; ++j) d[j] = o[j];
   }
-  if (kGeneric && probs_as_codes<kBF16>(p)) mul *= __ldg(p.qdq_probs);   // P was (code - zp): see normalize_probs
-  float gate = 1.f;
-  if (p.gate_logits) {
-    const float z = __ldg(p.gate_logits + ((int64_t)b * p.H + h) * p.Tq + row);
-    gate = __frcp_rn(1.f + expf(-z)) * p.gate_scale;
-  }
+  mul *= pre.pscale;
+  const float gate = pre.gate;
   if (kGeneric && p.qdq_ctx) {
-    const Qdq qd_c = load_qdq(p.qdq_ctx, p.int_max);
+    const Qdq qd_c = pre.qd_c;
     if (p.ctx_qdq_before_gate) {                       // OPT: tap on PV, then gate (quantized_opt.py:210)
 #pragma unroll
       for (int j = 0; j < ND; ++j) o[j] = qd_c(o[j] * mul) * gate;
@@ -364,9 +379,15 @@ __device__ __forceinline__ void finish_row(float (&o)[ND], const AttnParams& p, 
 }
 
 template <bool kBF16, bool kGeneric, int ND = HD>
-__device__ __forceinline__ void store_row(float (&o)[ND], const AttnParams& p, float mul, int b, int h, int row,
-                                          int d0 = 0) {
-  finish_row<kBF16, kGeneric, ND>(o, p, mul, b, h, row, d0);
+__device__ __forceinline__ void finish_row(float (&o)[ND], const AttnParams& p, float mul, int b, int h, int row,
+                                           int d0 = 0) {
+  finish_row<kBF16, kGeneric, ND>(o, p, mul, b, h, row, d0, epi_prefetch<kBF16, kGeneric>(p, b, h, row));
+}
+
+template <bool kBF16, bool kGeneric, int ND = HD>
+__device__ __forceinline__ void store_row(float (&o)[ND], const AttnParams& p, float mul, int b, int h, int row, int d0,
+                                          const EpiPre& pre) {
+  finish_row<kBF16, kGeneric, ND>(o, p, mul, b, h, row, d0, pre);
   uint8_t* optr = reinterpret_cast<uint8_t*>(p.out) +
                   2 * ((int64_t)b * p.os0 + (int64_t)h * p.os1 + (int64_t)row * p.os2 + d0);
   if constexpr (ND == 16) {
@@ -391,6 +412,12 @@ __device__ __forceinline__ void store_row(float (&o)[ND], const AttnParams& p, f
     v.w = pack2<kBF16>(o[c * 8 + 6], o[c * 8 + 7]);
     reinterpret_cast<uint4*>(optr)[c] = v;
   }
+}
+
+template <bool kBF16, bool kGeneric, int ND = HD>
+__device__ __forceinline__ void store_row(float (&o)[ND], const AttnParams& p, float mul, int b, int h, int row,
+                                          int d0 = 0) {
+  store_row<kBF16, kGeneric, ND>(o, p, mul, b, h, row, d0, epi_prefetch<kBF16, kGeneric>(p, b, h, row));
 }
 
 __device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {

@@ -259,6 +259,7 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     if (ptx::elect_one()) ptx::mbar_arrive(ptx::smem_u32(&bars.p_full));
 
     // ---- epilogue: each of the row's threads finishes 64 / kParts head-dim columns ---------------------------------------------
+    const EpiPre pre = epi_prefetch<kBF16, kGeneric>(p, b, h, row);   // global reads of the epilogue, under the PV MMAs
     ptx::mbar_wait(ptx::smem_u32(&bars.o_full), 0);
     ptx::tc_fence_after();
     constexpr int ND = HD / kParts;
@@ -266,7 +267,7 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     if constexpr (ND == 32) ptx::tmem_ld32(t_lane + kColO + half * ND, reinterpret_cast<uint32_t*>(o));
     else ptx::tmem_ld16(t_lane + kColO + half * ND, reinterpret_cast<uint32_t*>(o));
     ptx::tmem_wait_ld();
-    if (row < p.Tq) store_row<kBF16, kGeneric, ND>(o, p, omul, b, h, row, half * ND);
+    if (row < p.Tq) store_row<kBF16, kGeneric, ND>(o, p, omul, b, h, row, half * ND, pre);
   }
 
   ptx::tc_fence_before();

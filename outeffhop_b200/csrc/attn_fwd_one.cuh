@@ -288,6 +288,7 @@ attn_fwd_one_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   __syncwarp();
 
   // ---- epilogue -----------------------------------------------------------------------------------------------------
+  const EpiPre pre = epi_prefetch<kBF16, kGeneric>(p, b, h, row);     // global reads of the epilogue, under the PV MMA
   ptx::mbar_wait(bar_mma, 1);
   ptx::tc_fence_after();
   OEH_STAMP(4);
@@ -302,7 +303,7 @@ attn_fwd_one_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem);
   OEH_STAMP(5);
-  if (row < p.Tq) finish_row<kBF16, kGeneric>(o, p, omul, b, h, row);
+  if (row < p.Tq) finish_row<kBF16, kGeneric>(o, p, omul, b, h, row, 0, pre);
   store_rows_coalesced<kBF16>(o, p, sQ + (uint32_t)warp * 4096u, b, h, q0 + warp * 32);   // Q is dead since the QK^T MMA
   OEH_STAMP(6);
 }

@@ -226,6 +226,7 @@ attn_fwd_one2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
   __syncwarp();
 
   // ---- epilogue: each of the row's threads finishes 32 context columns --------------------------------------------------
+  const EpiPre pre = epi_prefetch<kBF16, kGeneric>(p, b, h, row);     // global reads of the epilogue, under the PV MMA
   ptx::mbar_wait(bar_mma, 1);
   ptx::tc_fence_after();
   float o[32];
@@ -234,7 +235,7 @@ attn_fwd_one2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem);
-  if (row < p.Tq) finish_row<kBF16, kGeneric, 32>(o, p, omul, b, h, row, half * 32);
+  if (row < p.Tq) finish_row<kBF16, kGeneric, 32>(o, p, omul, b, h, row, half * 32, pre);
   store_half_rows_coalesced<kBF16>(o, p, sQ + (uint32_t)warp * 2048u, b, h, q0 + wq * 32, half * 32);   // Q is dead since QK^T
 }
 

@@ -454,6 +454,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     // an accumulator exists iff some PV step had its parity (only n_kv == 1 leaves one of them untouched)
     const bool has0 = n_kv > 1 || (nA & 1) == 0, has1 = n_kv > 1 || (nA & 1) == 1;
     const float a0 = par ? a_other : a_own, a1 = par ? a_own : a_other;
+    const EpiPre pre = epi_prefetch<kBF16, kGeneric>(p, b, h, row);   // global reads of the epilogue, under the last PV
     ptx::mbar_wait(ptx::smem_u32(&bars.o_final[t]), 0);
     ptx::tc_fence_after();
     // this thread finishes head-dim columns [32par, 32par+32) of its row from both accumulators
@@ -470,7 +471,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     }
     // Context rows leave as full 64-byte segments staged per warp (store_half_rows_coalesced) in the K ring: every K / V stage
     // has been consumed once the LAST PV of every tile of the CTA is complete (the two tiles share the rings).
-    if (row < p.Tq) finish_row<kBF16, kGeneric, 32>(o, p, omul, b, h, row, par * 32);
+    if (row < p.Tq) finish_row<kBF16, kGeneric, 32>(o, p, omul, b, h, row, par * 32, pre);
     if constexpr (kTiles == 2) {
       ptx::mbar_wait(ptx::smem_u32(&bars.o_final[t ^ 1]), 0);
     }
