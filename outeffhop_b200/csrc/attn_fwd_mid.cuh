@@ -169,6 +169,7 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     // instantiation was 7544 SASS instructions (118 KB) and a fifth of its stall samples were instruction fetch
     // (stall_no_inst 19.8 %, profiles/r02_ncu_hot_kernels.txt): every launch inside a model step starts with a cold I-cache
     float mc0 = 0.f, mc1 = 0.f, mc2 = 0.f, mc3 = 0.f;
+    uint32_t hidden = 0;                                        // bit i: chunk i of this warp is invisible to all of its rows
     static_assert(kMaxTiles == 4, "mc0..mc3");
 #ifdef OEH_MID_UNROLL_TILES
 #pragma unroll
@@ -180,6 +181,16 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         const int j = kParts * i + half, k0 = j * CW;
         ptx::mbar_wait(ptx::smem_u32(&bars.s_full[i]), 0);
         ptx::tc_fence_after();
+        {
+          // A chunk none of this warp's 32 rows can see (above the causal diagonal: 6 of the 16 (lane quarter, chunk) pairs of the
+          // diagonal tile with four parts; or past Tk in the ragged last tile) contributes nothing to (m, l) and its P is 0:
+          // no load, no exponentials -- pass B writes the zeros.
+          const int valid_ = min(p.Tk - k0, CW), vis_ = min(valid_ - 1, causal_lim - k0);
+          if (!(kGeneric && p.dbg_s) && __all_sync(0xffffffffu, vis_ < 0)) {
+            hidden |= 1u << i;
+            continue;
+          }
+        }
         float s[CW];
 #pragma unroll
         for (int c = 0; c < CW / 32; ++c) ptx::tmem_ld32(t_lane + j * CW + 32 * c, reinterpret_cast<uint32_t*>(s) + 32 * c);
@@ -210,7 +221,8 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     // ---- the kParts threads of a row agree on (m, denominator) -----------------------------------------------------------
     xch_m[half][r] = m_run;
     xch_l[half][r] = l_run;
-    asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
+    // (only the kParts warps of this lane quarter exchange rows with each other: a 32 * kParts-thread barrier, not the CTA's)
+    asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * kParts) : "memory");
     float m_all = m_run;
 #pragma unroll
     for (int q2 = 0; q2 < kParts; ++q2) m_all = fmaxf(m_all, xch_m[q2][r]);
@@ -231,6 +243,15 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     for (int i = 0; i < kMaxTiles; ++i) {
       if (i < n_kv) {
         const int j = kParts * i + half;
+        if (hidden >> i & 1u) {                                 // (warp-uniform) P = 0, nothing to read
+          asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * kParts) : "memory");
+          uint32_t z[CW / 2];
+#pragma unroll
+          for (int c = 0; c < CW / 2; ++c) z[c] = 0u;
+          if constexpr (CW == 64) ptx::tmem_st32(t_lane + j * (CW / 2), z);
+          else ptx::tmem_st16(t_lane + j * (CW / 2), z);
+          continue;
+        }
         float s[CW];
 #pragma unroll
         for (int c = 0; c < CW / 32; ++c) ptx::tmem_ld32(t_lane + j * CW + 32 * c, reinterpret_cast<uint32_t*>(s) + 32 * c);

@@ -338,6 +338,26 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       ptx::mbar_wait(bar_s, (uint32_t)(i >> 1) & 1u);
       ptx::tc_fence_after();
       OEH_T(1);
+      if (p.causal && !(kGeneric && p.dbg_s)) {
+        // Causal diagonal: a 64-key step none of this warp's 32 rows can see (12 of the 32 warp-steps of a 256-row item's
+        // diagonal region) adds nothing to (m, l) and its P is 0 -- no tcgen05.ld, no exponentials; the PV MMA of the step
+        // (issued regardless) accumulates zeros.  Once hidden, every later step of the item is hidden for this warp too.
+        const int vis0 = min(min(p.Tk - k0, BNW) - 1, causal_lim - k0);
+        if (__all_sync(0xffffffffu, vis0 < 0)) {
+          if (pv_iter) {
+            uint32_t z[BNW / 2];
+#pragma unroll
+            for (int j = 0; j < BNW / 2; ++j) z[j] = 0u;
+            ptx::tmem_st32(tS, z);
+            ptx::tmem_wait_st();
+            if (!normalized) started = true;                       // the accumulator holds a (zero) PV result
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (ptx::elect_one()) ptx::mbar_arrive(bar_p);
+          continue;
+        }
+      }
       float s[BNW];
       ptx::tmem_ld32(tS, reinterpret_cast<uint32_t*>(s));
       ptx::tmem_ld32(tS + 32, reinterpret_cast<uint32_t*>(s) + 32);
