@@ -271,7 +271,7 @@ int oeh_add_layer_norm(const void* a, const void* b, const void* weight, const v
 
 /* oeh_add_layer_norm that ALSO emits the per-token attention-gate logits of the module that consumes y (Linear(64,1) gate
  * predictors, bert_attention.py:303-320 / opt_attention.py:285-302: out[b,h,t] = w_h . y[b,t,64h:64h+64] + b_h):
- * gate_w (H,64) fp32, gate_b (H) fp32, gate_out (B,H,T) fp32, rows == B*T, cols == 64*H.  Saves the separate
+ * gate_w (H,64) fp32 contiguous and 16-byte aligned, gate_b (H) fp32, gate_out (B,H,T) fp32, rows == B*T, cols == 64*H.  Saves the separate
  * oeh_gate_logits pass over the hidden states.  gate_out NULL = oeh_add_layer_norm. */
 int oeh_add_layer_norm_gate(const void* a, const void* b, const void* weight, const void* bias, void* y, int64_t rows,
                             int64_t cols, double eps, int32_t dtype, const float* qparams_a, const float* qparams_res,

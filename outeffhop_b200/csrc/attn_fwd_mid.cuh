@@ -243,8 +243,18 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     for (int i = 0; i < kMaxTiles; ++i) {
       if (i < n_kv) {
         const int j = kParts * i + half;
-        if (hidden >> i & 1u) {                                 // (warp-uniform) P = 0, nothing to read
-          asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * kParts) : "memory");
+        const bool hid = (hidden >> i & 1u) != 0;               // (warp-uniform) P = 0, nothing to read
+        float s[CW];
+        if (!hid) {
+#pragma unroll
+          for (int c = 0; c < CW / 32; ++c) ptx::tmem_ld32(t_lane + j * CW + 32 * c, reinterpret_cast<uint32_t*>(s) + 32 * c);
+          ptx::tmem_wait_ld();
+        }
+        // The P chunks of iteration i (kParts * CW / 2 = 64 packed columns) overwrite e-chunks read in iteration <= i (in this very
+        // iteration when i == 0): every thread of the row must have COMPLETED its reads of this iteration before any writes
+        // (ONE barrier instruction for both kinds of warp: compute-sanitizer's synccheck wants a barrier's arrivals at one PC)
+        asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * kParts) : "memory");
+        if (hid) {
           uint32_t z[CW / 2];
 #pragma unroll
           for (int c = 0; c < CW / 2; ++c) z[c] = 0u;
@@ -252,13 +262,6 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
           else ptx::tmem_st16(t_lane + j * (CW / 2), z);
           continue;
         }
-        float s[CW];
-#pragma unroll
-        for (int c = 0; c < CW / 32; ++c) ptx::tmem_ld32(t_lane + j * CW + 32 * c, reinterpret_cast<uint32_t*>(s) + 32 * c);
-        ptx::tmem_wait_ld();
-        // The P chunks of iteration i (kParts * CW / 2 = 64 packed columns) overwrite e-chunks read in iteration <= i (in this very
-        // iteration when i == 0): every thread of the row must have COMPLETED its reads of this iteration before any writes
-        asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * kParts) : "memory");
         const float mci = i == 0 ? mc0 : i == 1 ? mc1 : i == 2 ? mc2 : mc3;
         const float f = ptx::ex2(mci - m_fin);                  // chunk frame -> common frame (mc <= m_fin)
         if (normalized) {

@@ -366,7 +366,8 @@ attn_fwd_wsp_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       if (t == 0 && (warp & 3) == 0 && i < 2) WSP_STAMP(it, 2 + par, 0);
       if (t == 0 && (warp & 3) == 0 && i >= 2 && i < 4) WSP_STAMP(it, 2 + par, 1);
       if (t == 0 && (warp & 3) == 0 && i + 2 >= n_iter) WSP_STAMP(it, 2 + par, 2);
-      if (p.causal && !(kGeneric && p.dbg_s)) {
+      // (two-tile CTAs only: the one-tile shapes -- T <= 512 -- have two hidden warp-steps per item and the test costs them more)
+      if (kTiles == 2 && p.causal && !(kGeneric && p.dbg_s)) {
         // Causal diagonal: a 64-key step none of this warp's 32 rows can see (12 of the 32 warp-steps of a 256-row item's
         // diagonal region) adds nothing to (m, l) and its P is 0 -- no tcgen05.ld, no exponentials; the PV MMA of the step
         // (issued regardless) accumulates zeros.  Once hidden, every later step of the item is hidden for this warp too.

@@ -25,6 +25,9 @@ ops.linear_fwd(x, w, None, qparams=[qp, pp, cp])
 # LayerNorm + gate, embeddings
 a = torch.randn(2, 70, 768, device="cuda").half(); g = torch.ones(768, device="cuda").half(); be = torch.zeros(768, device="cuda").half()
 ops.add_layer_norm(a, a, g, be, 1e-5, return_sum=True, gate=(torch.randn(12, 64, device="cuda"), torch.randn(12, device="cuda")))
+ops.add_layer_norm(a, a, g, be, 1e-5, qparams_a=qp, qparams_res=cp, qparams_out=qp, return_sum=True)   # taps: the common-chain body
+ops.add_layer_norm(a, a, g, be, 1e-5, qparams_res=torch.tensor([1e-38, 3.0], device="cuda"), n_bits=12)     # taps: the general body
+ops.fake_quant_asym(a, qp, 8)
 ids = torch.randint(0, 1000, (2, 70), device="cuda")
 ops.embed_layer_norm(ids, torch.randn(1000, 768, device="cuda").half(), torch.randn(128, 768, device="cuda").half(), torch.randn(2, 768, device="cuda").half(), g, be, 1e-12)
 # one-tile kernels (one / two threads per row, coalesced stores), (B, T, H*d) layout with ragged rows
