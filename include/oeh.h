@@ -246,6 +246,13 @@ int oeh_outlier_stats(const void* x, int64_t rows, int64_t cols, int32_t dtype, 
  * in the workspace (rows fp32; 0 for ignored rows).  One pass over the labelled rows, no fp32 copy of the logits.
  * ------------------------------------------------------------------------------------------- */
 size_t oeh_ce_loss_workspace_bytes(int64_t rows);
+/* oeh_ce_loss with HF's causal-LM shift (validate_clm.py:555-561: shift_logits = logits[..., :-1, :], shift_labels =
+ * labels[..., 1:]) applied to the LABEL INDEX instead of to copies of the tensors: with shift_T > 0 the rows are blocks of
+ * shift_T tokens, row (b, t) is scored against labels[b, t + 1] and the last row of every block is ignored -- the same
+ * B * (T - 1) terms.  shift_T == 0 is oeh_ce_loss. */
+int oeh_ce_loss_shifted(const void* logits, int64_t rows, int64_t vocab, int64_t row_stride, int32_t dtype,
+                        const int64_t* labels, int64_t ignore_index, int64_t shift_T, float* out_loss, float* out_count,
+                        void* workspace, size_t workspace_bytes, oeh_stream_t stream);
 int oeh_ce_loss(const void* logits, int64_t rows, int64_t vocab, int64_t row_stride, int32_t dtype,
                 const int64_t* labels, int64_t ignore_index, float* out_loss, float* out_count, void* workspace,
                 size_t workspace_bytes, oeh_stream_t stream);
@@ -301,6 +308,13 @@ int oeh_fake_quant_asym_segments(const void* x, void* y, int64_t rows, int32_t s
  * both tails): correctly rounded for all but 5 of the 63488 finite fp16 inputs (1 ulp) and for every bf16 input.  fp32 tensors: OEH_ERR_UNSUPPORTED.
  * ------------------------------------------------------------------------------------------- */
 int oeh_gelu_erf(const void* x, void* y, int64_t n, int32_t dtype, oeh_stream_t stream);
+
+/* The OPT decoder's input (HF modeling_opt, the shell around the reference's OPTAttentionWithExtras; quantized_opt.py:432-457
+ * builds the same sum): y[r] = word[ids[r]] + pos_table[pos_ids[r] + pos_offset] (OPTLearnedPositionalEmbedding adds its offset
+ * of 2 inside forward), rounded once to the tensor dtype like the ATen add.  pos_ids NULL = r % T.  ids / positions are
+ * clamped into their tables.  rows = B*T; cols a multiple of 16 / sizeof(dtype); tables and y 16-byte aligned. */
+int oeh_embed_sum(const int64_t* ids, const int64_t* pos_ids, const void* word, const void* pos_table, void* y, int64_t rows,
+                  int64_t cols, int32_t T, int64_t vocab, int64_t n_pos, int64_t pos_offset, int32_t dtype, oeh_stream_t stream);
 
 /* HF BertEmbeddings.forward (transformers modeling_bert; the embedding shell the reference's models keep, quantized at
  * quantized_bert.py:146-218) in one launch: y[r] = LayerNorm((word[ids[r]] + type[type_ids[r]]) + pos[pos_ids[r]]), sums in

@@ -51,12 +51,21 @@ __device__ __forceinline__ ML ml_merge(ML a, ML b) {
   return ML{m, a.l * ex2f((a.m - m) * kLog2e) + b.l * ex2f((b.m - m) * kLog2e)};
 }
 
+// Label of logits row r.  shift_T > 0: causal-LM scoring of blocks of shift_T tokens -- row (b, t) is scored against
+// labels[b, t + 1] and the last row of every block is ignored (HF's shift_logits / shift_labels, validate_clm.py:555-561)
+// without a shifted copy of the labels (a fill + a strided copy per step in ATen).
+__device__ __forceinline__ int64_t label_of(const int64_t* __restrict__ labels, int64_t r, int64_t rows, int64_t shift_T,
+                                            int64_t ignore_index) {
+  if (shift_T <= 0) return labels[r];
+  return (r % shift_T == shift_T - 1 || r + 1 >= rows) ? ignore_index : labels[r + 1];
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 ce_rows_kernel(const T* __restrict__ x, int64_t vocab, int64_t row_stride, const int64_t* __restrict__ labels,
-               int64_t ignore_index, int aligned, float* __restrict__ row_loss) {
+               int64_t ignore_index, int aligned, float* __restrict__ row_loss, int64_t shift_T) {
   const int64_t r = blockIdx.x;
-  const int64_t label = labels[r];
+  const int64_t label = label_of(labels, r, (int64_t)gridDim.x, shift_T, ignore_index);
   if (label == ignore_index) {        // not part of the mean: the row is never read
     if (threadIdx.x == 0) row_loss[r] = 0.f;
     return;
@@ -121,11 +130,11 @@ ce_rows_kernel(const T* __restrict__ x, int64_t vocab, int64_t row_stride, const
 
 __global__ void __launch_bounds__(1024)
 ce_mean_kernel(const float* __restrict__ row_loss, const int64_t* __restrict__ labels, int64_t rows,
-               int64_t ignore_index, float* __restrict__ out_loss, float* __restrict__ out_count) {
+               int64_t ignore_index, float* __restrict__ out_loss, float* __restrict__ out_count, int64_t shift_T) {
   double s = 0.0;
   long long c = 0;
   for (int64_t r = threadIdx.x; r < rows; r += blockDim.x) {
-    if (labels[r] != ignore_index) {
+    if (label_of(labels, r, rows, shift_T, ignore_index) != ignore_index) {
       s += (double)row_loss[r];
       ++c;
     }
@@ -150,13 +159,13 @@ ce_mean_kernel(const float* __restrict__ row_loss, const int64_t* __restrict__ l
 
 template <typename T>
 int launch(const void* x, int64_t rows, int64_t vocab, int64_t row_stride, const int64_t* labels, int64_t ignore_index,
-           float* out_loss, float* out_count, float* row_loss, cudaStream_t st) {
+           float* out_loss, float* out_count, float* row_loss, cudaStream_t st, int64_t shift_T) {
   const int aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (row_stride * (int64_t)sizeof(T)) % 16 == 0;
   ce_rows_kernel<T><<<(unsigned)rows, kThreads, 0, st>>>((const T*)x, vocab, row_stride, labels, ignore_index, aligned,
-                                                         row_loss);
+                                                         row_loss, shift_T);
   int rc = check_launch("ce_rows_kernel");
   if (rc) return rc;
-  ce_mean_kernel<<<1, 1024, 0, st>>>(row_loss, labels, rows, ignore_index, out_loss, out_count);
+  ce_mean_kernel<<<1, 1024, 0, st>>>(row_loss, labels, rows, ignore_index, out_loss, out_count, shift_T);
   return check_launch("ce_mean_kernel");
 }
 
@@ -167,10 +176,23 @@ using namespace oeh;
 
 extern "C" size_t oeh_ce_loss_workspace_bytes(int64_t rows) { return rows > 0 ? (size_t)rows * sizeof(float) : 0; }
 
+extern "C" int oeh_ce_loss_shifted(const void* logits, int64_t rows, int64_t vocab, int64_t row_stride, int32_t dtype,
+                                   const int64_t* labels, int64_t ignore_index, int64_t shift_T, float* out_loss,
+                                   float* out_count, void* workspace, size_t workspace_bytes, oeh_stream_t stream);
+
 extern "C" int oeh_ce_loss(const void* logits, int64_t rows, int64_t vocab, int64_t row_stride, int32_t dtype,
                            const int64_t* labels, int64_t ignore_index, float* out_loss, float* out_count,
                            void* workspace, size_t workspace_bytes, oeh_stream_t stream) {
+  return oeh_ce_loss_shifted(logits, rows, vocab, row_stride, dtype, labels, ignore_index, 0, out_loss, out_count, workspace,
+                             workspace_bytes, stream);
+}
+
+extern "C" int oeh_ce_loss_shifted(const void* logits, int64_t rows, int64_t vocab, int64_t row_stride, int32_t dtype,
+                                   const int64_t* labels, int64_t ignore_index, int64_t shift_T, float* out_loss,
+                                   float* out_count, void* workspace, size_t workspace_bytes, oeh_stream_t stream) {
   OEH_CHECK_ARG(rows > 0 && vocab > 0, "oeh_ce_loss: empty batch");
+  OEH_CHECK_ARG(shift_T >= 0 && (shift_T == 0 || rows % shift_T == 0),
+                "oeh_ce_loss_shifted: rows=%lld is not a whole number of blocks of %lld tokens", (long long)rows, (long long)shift_T);
   OEH_CHECK_ARG(rows <= 0x7fffffffLL, "oeh_ce_loss: at most 2^31-1 rows per call");
   OEH_CHECK_ARG(row_stride >= vocab, "oeh_ce_loss: row_stride %lld < vocab %lld", (long long)row_stride, (long long)vocab);
   OEH_CHECK_ARG(logits && labels && out_loss, "oeh_ce_loss: null pointer");
@@ -181,10 +203,10 @@ extern "C" int oeh_ce_loss(const void* logits, int64_t rows, int64_t vocab, int6
   cudaStream_t st = (cudaStream_t)stream;
   float* row_loss = (float*)workspace;
   switch (dtype) {
-    case OEH_F32: return launch<float>(logits, rows, vocab, row_stride, labels, ignore_index, out_loss, out_count, row_loss, st);
-    case OEH_F16: return launch<__half>(logits, rows, vocab, row_stride, labels, ignore_index, out_loss, out_count, row_loss, st);
+    case OEH_F32: return launch<float>(logits, rows, vocab, row_stride, labels, ignore_index, out_loss, out_count, row_loss, st, shift_T);
+    case OEH_F16: return launch<__half>(logits, rows, vocab, row_stride, labels, ignore_index, out_loss, out_count, row_loss, st, shift_T);
     case OEH_BF16:
-      return launch<__nv_bfloat16>(logits, rows, vocab, row_stride, labels, ignore_index, out_loss, out_count, row_loss, st);
+      return launch<__nv_bfloat16>(logits, rows, vocab, row_stride, labels, ignore_index, out_loss, out_count, row_loss, st, shift_T);
   }
   return set_error(OEH_ERR_BAD_ARG, "oeh_ce_loss: unknown dtype %d", dtype);
 }

@@ -294,6 +294,32 @@ int launch_embed(const int64_t* ids, const int64_t* type_ids, const int64_t* pos
   return check_launch("embed_layer_norm_kernel");
 }
 
+// OPTDecoder's input (HF modeling_opt: inputs_embeds + OPTLearnedPositionalEmbedding(position_ids), whose forward adds its
+// offset of 2 to the positions): out[r] = word[ids[r]] + pos[pos_ids[r] + pos_offset], one rounding to the tensor dtype like the
+// ATen add -- two gathers, the int64 offset add and the sum in ATen (4 launches); one warp per row here.
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+embed_sum_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ pos_ids, const T* __restrict__ word,
+                 const T* __restrict__ pos_tab, T* __restrict__ y, int64_t rows, int cols, int T_len, int64_t vocab,
+                 int64_t n_pos, int64_t pos_offset) {
+  using V = Vec16<T>;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  int64_t id = __ldg(ids + row);
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);        // out-of-range ids raise in torch; never fault here
+  int64_t pp = (pos_ids ? __ldg(pos_ids + row) : row % T_len) + pos_offset;
+  pp = pp < 0 ? 0 : (pp >= n_pos ? n_pos - 1 : pp);
+  const V* wv = reinterpret_cast<const V*>(word + id * cols);
+  const V* pv = reinterpret_cast<const V*>(pos_tab + pp * cols);
+  V* yv = reinterpret_cast<V*>(y + row * cols);
+  for (int i = lane; i < cols / V::N; i += 32) {
+    V a = wv[i];
+    add_vec<T>(a, pv[i]);
+    yv[i] = a;
+  }
+}
+
 template <typename T>
 int launch(const void* a, const void* b, const void* gamma, const void* beta, void* y, int64_t rows, int64_t cols, float eps,
            const float* q_a, const float* q_res, const float* q_out, int n_bits, void* sum_out, cudaStream_t st,
@@ -381,6 +407,38 @@ extern "C" int oeh_add_layer_norm_gate(const void* a, const void* b, const void*
                                    sum_out, st, gate_w, gate_b, gate_out, T, H);
   }
   return set_error(OEH_ERR_BAD_ARG, "oeh_add_layer_norm: unknown dtype %d", dtype);
+}
+
+extern "C" int oeh_embed_sum(const int64_t* ids, const int64_t* pos_ids, const void* word, const void* pos_table, void* y,
+                             int64_t rows, int64_t cols, int32_t T, int64_t vocab, int64_t n_pos, int64_t pos_offset,
+                             int32_t dtype, oeh_stream_t stream) {
+  OEH_CHECK_ARG(rows >= 0 && cols > 0 && T > 0 && vocab > 0 && n_pos > 0, "oeh_embed_sum: bad shape");
+  if (rows == 0) return OEH_OK;
+  OEH_CHECK_ARG(ids && word && pos_table && y, "oeh_embed_sum: null pointer");
+  const int vec = dtype == OEH_F32 ? 4 : 8;
+  if (cols % vec != 0) return set_error(OEH_ERR_UNSUPPORTED, "oeh_embed_sum: cols=%lld must be a multiple of %d", (long long)cols, vec);
+  if ((reinterpret_cast<uintptr_t>(word) | reinterpret_cast<uintptr_t>(pos_table) | reinterpret_cast<uintptr_t>(y)) & 15)
+    return set_error(OEH_ERR_UNSUPPORTED, "oeh_embed_sum: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  switch (dtype) {
+    case OEH_F32:
+      embed_sum_kernel<float><<<grid, kWarpsPerBlock * 32, 0, st>>>(ids, pos_ids, (const float*)word, (const float*)pos_table,
+                                                                    (float*)y, rows, (int)cols, T, vocab, n_pos, pos_offset);
+      break;
+    case OEH_F16:
+      embed_sum_kernel<__half><<<grid, kWarpsPerBlock * 32, 0, st>>>(ids, pos_ids, (const __half*)word, (const __half*)pos_table,
+                                                                     (__half*)y, rows, (int)cols, T, vocab, n_pos, pos_offset);
+      break;
+    case OEH_BF16:
+      embed_sum_kernel<__nv_bfloat16><<<grid, kWarpsPerBlock * 32, 0, st>>>(ids, pos_ids, (const __nv_bfloat16*)word,
+                                                                            (const __nv_bfloat16*)pos_table, (__nv_bfloat16*)y, rows,
+                                                                            (int)cols, T, vocab, n_pos, pos_offset);
+      break;
+    default:
+      return set_error(OEH_ERR_BAD_ARG, "oeh_embed_sum: unknown dtype %d", dtype);
+  }
+  return check_launch("embed_sum_kernel");
 }
 
 extern "C" int oeh_embed_layer_norm(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const void* word,

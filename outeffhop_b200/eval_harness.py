@@ -142,11 +142,19 @@ def opt_clm_loss(model, input_ids: torch.Tensor, labels: torch.Tensor, causal_ma
     """OPTForCausalLM.forward for un-padded blocks: token + learned position embeddings -> 12 x OPTDecoderLayer with the
     (B,1,T,T) causal mask -> final LayerNorm -> lm_head -> shifted mean CE in fp32."""
     dec = model.model.decoder
-    h = dec.embed_tokens(input_ids)
-    pos = dec.embed_positions(None, 0, position_ids=position_ids)
-    if dec.project_in is not None:
-        h = dec.project_in(h)
-    h = h + pos
+    tok, posm = dec.embed_tokens, dec.embed_positions
+    if (type(tok) is torch.nn.Embedding and tok.max_norm is None and dec.project_in is None and position_ids is not None
+            and tok.weight.is_cuda and tok.weight.dtype == posm.weight.dtype and not model.training
+            and not tok._forward_hooks and not posm._forward_hooks and input_ids.dim() == 2):
+        # token + learned position embeddings in ONE launch (two gathers, the int64 offset add and the sum in ATen)
+        from . import ops
+        h = ops.embed_sum(input_ids, tok.weight, posm.weight, position_ids, getattr(posm, "offset", 2))
+    else:
+        h = tok(input_ids)
+        pos = posm(None, 0, position_ids=position_ids)
+        if dec.project_in is not None:
+            h = dec.project_in(h)
+        h = h + pos
     from .hf_compat import OPTDecoderLayerFused
     layers = list(dec.layers)
     if (layers and dec.final_layer_norm is not None and dec.final_layer_norm.bias is not None
@@ -182,10 +190,9 @@ def opt_clm_loss(model, input_ids: torch.Tensor, labels: torch.Tensor, causal_ma
         return torch.nn.functional.cross_entropy(logits[:, :-1, :V].reshape(-1, V).float(), labels[:, 1:].reshape(-1))
     # shifted CE without slicing / copying the logits: row (b, t) is scored against labels[b, t+1], the last row
     # of every block is ignored (same set of B*(T-1) terms as HF's shift, validate_clm.py:555-561)
+    # (the shift is applied to the label index inside the kernel: no shifted copy of the labels either)
     from . import ops
-    shifted = torch.full_like(labels, -100)
-    shifted[:, :-1] = labels[:, 1:]
-    return ops.ce_loss(logits.view(-1, logits.shape[-1]), shifted.view(-1), vocab=V)
+    return ops.ce_loss(logits.view(-1, logits.shape[-1]), labels.reshape(-1), vocab=V, shift_block=labels.shape[-1])
 
 
 def make_causal_mask(batch: int, seq: int, dtype, device) -> torch.Tensor:

@@ -333,11 +333,12 @@ def outlier_stats(x: torch.Tensor, eps: float = 1e-6, meter: Optional[torch.Tens
 
 
 def ce_loss(logits: torch.Tensor, labels: torch.Tensor, vocab: Optional[int] = None, ignore_index: int = -100,
-            return_row_losses: bool = False):
+            return_row_losses: bool = False, shift_block: int = 0):
     """Mean cross-entropy in fp32 straight from (rows, >=vocab) logits (oeh_ce_loss): F.cross_entropy(
     logits[:, :vocab].float(), labels) without the fp32 copy or a materialised log-softmax.  ``logits`` may be a
     column-padded 2-D view (last dimension contiguous, any row stride); ``labels`` int64 (rows).  Returns a 0-dim
-    fp32 device tensor (and the per-row fp32 losses when asked)."""
+    fp32 device tensor (and the per-row fp32 losses when asked).  ``shift_block`` = T > 0: HF's causal-LM shift over blocks of T
+    rows -- row (b, t) is scored against labels[b, t + 1], the last row of each block is ignored (oeh_ce_loss_shifted)."""
     _require_cuda(logits, labels)
     if logits.dim() != 2 or logits.stride(1) != 1:
         raise ValueError("ce_loss: expected 2-D logits whose last dimension is contiguous")
@@ -356,8 +357,10 @@ def ce_loss(logits: torch.Tensor, labels: torch.Tensor, vocab: Optional[int] = N
     else:
         ws = _workspace(logits.device, lib.oeh_ce_loss_workspace_bytes(rows))
         ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
-    L.check(lib.oeh_ce_loss(logits.data_ptr(), rows, vocab, logits.stride(0), _dtype_code(logits), lab.data_ptr(),
-                            int(ignore_index), out.data_ptr(), None, ws_ptr, ws_bytes, _stream()))
+    if shift_block < 0 or (shift_block and rows % shift_block):
+        raise ValueError("ce_loss: rows must be a whole number of blocks of shift_block tokens")
+    L.check(lib.oeh_ce_loss_shifted(logits.data_ptr(), rows, vocab, logits.stride(0), _dtype_code(logits), lab.data_ptr(),
+                                    int(ignore_index), int(shift_block), out.data_ptr(), None, ws_ptr, ws_bytes, _stream()))
     return (out, ws) if return_row_losses else out
 
 
@@ -536,6 +539,25 @@ def linear_add_layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[
     a.stream = _stream()
     L.check(L.lib().oeh_linear_add_layer_norm(C.byref(a)))
     return (y, total) if return_sum else y
+
+
+def embed_sum(input_ids: torch.Tensor, word: torch.Tensor, pos: torch.Tensor, position_ids: Optional[torch.Tensor] = None,
+              pos_offset: int = 0) -> torch.Tensor:
+    """``word[ids] + pos[position_ids + pos_offset]`` in one launch (oeh_embed_sum): the OPT decoder's input, HF
+    ``embed_tokens(ids) + embed_positions(position_ids)`` (whose forward adds its offset of 2).  (B,T) int64 ids; missing
+    ``position_ids`` = 0..T-1.  One rounding to the tensor dtype, like the ATen add."""
+    _require_cuda(input_ids, word, pos, position_ids)
+    B, T = input_ids.shape
+    cols = word.shape[1]
+    if pos.dtype != word.dtype or pos.shape[1] != cols or not pos.is_contiguous() or not word.is_contiguous():
+        raise ValueError("embed_sum: tables must be contiguous, of one dtype and one width")
+    ids = input_ids.contiguous()
+    pp = None if position_ids is None else position_ids.expand(B, T).contiguous()
+    y = torch.empty((B, T, cols), dtype=word.dtype, device=word.device)
+    L.check(L.lib().oeh_embed_sum(ids.data_ptr(), pp.data_ptr() if pp is not None else None, word.data_ptr(), pos.data_ptr(),
+                                  y.data_ptr(), B * T, cols, T, word.shape[0], pos.shape[0], int(pos_offset), _dtype_code(word),
+                                  _stream()))
+    return y
 
 
 def embed_layer_norm(input_ids: torch.Tensor, word: torch.Tensor, pos: Optional[torch.Tensor], tok_type: Optional[torch.Tensor],

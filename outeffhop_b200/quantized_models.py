@@ -464,15 +464,25 @@ class QuantizedOPTDecoder(QuantizedModel):
     def forward(self, input_ids, attention_mask: Optional[torch.Tensor] = None, position_ids: Optional[torch.Tensor] = None):
         """``attention_mask``: the (B,1,T,T) additive causal mask of HF-4.31's ``_prepare_decoder_attention_mask``
         (``eval_harness.make_causal_mask``) -- the eval data is un-padded -- or None for a single token."""
-        inputs_embeds = self.embed_tokens(input_ids)
-        if position_ids is None:
-            ones = torch.ones(inputs_embeds.shape[:2], dtype=torch.bool, device=inputs_embeds.device)
-            pos_embeds = self.embed_positions(ones, 0)
+        tok, posq = self.embed_tokens, self.embed_positions.quant_embedding
+        if (position_ids is not None and self.project_in is None and not self.training and input_ids.is_cuda
+                and input_ids.dim() == 2 and tok.max_norm is None and posq.max_norm is None
+                and not (tok._forward_hooks or posq._forward_hooks or self.embed_positions._forward_hooks)):
+            # the two (weight-quantized, cached) tables gathered and summed in ONE launch (oeh_embed_sum)
+            from . import ops
+            w_tok, w_pos = tok.get_params()[0], posq.get_params()[0]
+            emb_sum = ops.embed_sum(input_ids, w_tok.contiguous(), w_pos.contiguous(), position_ids, self.embed_positions.offset)
         else:
-            pos_embeds = self.embed_positions(position_ids=position_ids)
-        if self.project_in is not None:
-            inputs_embeds = self.project_in(inputs_embeds)
-        hidden_states = self.embed_sum_act_quantizer(inputs_embeds + pos_embeds)                 # :556-559
+            inputs_embeds = tok(input_ids)
+            if position_ids is None:
+                ones = torch.ones(inputs_embeds.shape[:2], dtype=torch.bool, device=inputs_embeds.device)
+                pos_embeds = self.embed_positions(ones, 0)
+            else:
+                pos_embeds = self.embed_positions(position_ids=position_ids)
+            if self.project_in is not None:
+                inputs_embeds = self.project_in(inputs_embeds)
+            emb_sum = inputs_embeds + pos_embeds
+        hidden_states = self.embed_sum_act_quantizer(emb_sum)                                    # :556-559
         layers = list(self.layers)
         if (layers and self.final_layer_norm is not None and not self.training and hidden_states.is_cuda
                 and hidden_states.dtype in (torch.float16, torch.bfloat16, torch.float32)
@@ -540,9 +550,8 @@ class QuantizedOPTForCausalLM(QuantizedModel):
             logits = F.linear(h, w, b)
         loss = None
         if labels is not None:
-            shifted = torch.full_like(labels, -100)
-            shifted[:, :-1] = labels[:, 1:]
-            loss = ops.ce_loss(logits.view(-1, logits.shape[-1]), shifted.view(-1), vocab=V)
+            # HF's shift of logits / labels, applied to the label index inside the kernel
+            loss = ops.ce_loss(logits.view(-1, logits.shape[-1]), labels.reshape(-1), vocab=V, shift_block=labels.shape[-1])
         return CausalLMOutputWithPast(loss=loss, logits=logits[..., :V])
 
 

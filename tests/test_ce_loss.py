@@ -39,7 +39,7 @@ def test_symbols_declared():
     import os
     from outeffhop_b200 import _lib
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "oeh.h")).read()
-    for name in ("oeh_ce_loss", "oeh_ce_loss_workspace_bytes"):
+    for name in ("oeh_ce_loss", "oeh_ce_loss_workspace_bytes", "oeh_ce_loss_shifted", "oeh_embed_sum"):
         assert name + "(" in hdr and name in _lib.SYMBOLS
         getattr(_lib.lib(), name)
 
@@ -123,3 +123,49 @@ def test_bert_step_fused_loss_equals_aten_loss():
         ours = EH.bert_mlm_loss(model, ids, lab).item()
         aten = EH.bert_mlm_loss_aten(model, ids, lab).item()
     assert abs(ours - aten) < 2e-3 * abs(aten)          # two different GEMM kernels produce the fp16 logits
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float32", "float16"])
+@pytest.mark.parametrize("B,T,vocab", [(1, 2, 5), (4, 512, 1000), (3, 7, 50272)])
+def test_ce_loss_shifted_equals_hf_shift(dtype, B, T, vocab):
+    """HF's causal-LM loss (validate_clm.py:555-561): CrossEntropyLoss(logits[:, :-1], labels[:, 1:]); the kernel applies the
+    shift to the label index.  Same B*(T-1) terms: bit-identical to oeh_ce_loss on a shifted copy of the labels, and equal to
+    ATen within the fp32 tolerance of this file."""
+    from outeffhop_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    logits = (torch.randn(B, T, vocab, generator=g) * 3).to(_T[dtype]).cuda()
+    labels = torch.randint(0, vocab, (B, T), generator=g).cuda()
+    labels[0, -1] = -100                                         # an ignored label that the shift moves onto row T-2
+    loss, rows = ops.ce_loss(logits.view(-1, vocab), labels.view(-1), vocab=vocab, shift_block=T, return_row_losses=True)
+    shifted = torch.full_like(labels, -100)
+    shifted[:, :-1] = labels[:, 1:]
+    loss2, rows2 = ops.ce_loss(logits.view(-1, vocab), shifted.view(-1), vocab=vocab, return_row_losses=True)
+    assert torch.equal(torch.nan_to_num(loss, nan=-1.0), torch.nan_to_num(loss2, nan=-1.0)) and torch.equal(rows, rows2)   # (B=1, T=2: no labelled row, NaN like ATen)
+    aten = torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, vocab).float(), labels[:, 1:].reshape(-1))
+    if T > 1 and bool((labels[:, 1:] != -100).any()):
+        assert abs(loss.item() - aten.item()) <= 2e-6 * max(1.0, abs(aten.item()))
+    with pytest.raises(ValueError):
+        ops.ce_loss(logits.view(-1, vocab), labels.view(-1), vocab=vocab, shift_block=T + 1 if (B * T) % (T + 1) else B * T + 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float32", "float16", "bfloat16"])
+def test_embed_sum_bit_exact_vs_aten(dtype):
+    """oeh_embed_sum == embed_tokens(ids) + embed_positions(position_ids) of HF's OPT decoder (offset 2 added inside the
+    positional module): gathers and one add in the tensor dtype -- bit-identical."""
+    from outeffhop_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    dt = _T[dtype]
+    word = torch.randn(1000, 768, generator=g).to(dt).cuda()
+    pos = torch.randn(130, 768, generator=g).to(dt).cuda()
+    ids = torch.randint(0, 1000, (3, 128), generator=g).cuda()
+    pids = torch.arange(128).expand(3, 128).cuda()
+    want = torch.nn.functional.embedding(ids, word) + torch.nn.functional.embedding(pids + 2, pos)
+    assert torch.equal(ops.embed_sum(ids, word, pos, pids, 2), want)
+    assert torch.equal(ops.embed_sum(ids, word, pos, None, 2), want)          # default positions 0..T-1
+    pids2 = torch.randint(0, 128, (3, 128), generator=g).cuda()
+    want2 = torch.nn.functional.embedding(ids, word) + torch.nn.functional.embedding(pids2 + 2, pos)
+    assert torch.equal(ops.embed_sum(ids, word, pos, pids2, 2), want2)
+    with pytest.raises(ValueError):
+        ops.embed_sum(ids, word, pos[:, :64].contiguous(), pids, 2)
