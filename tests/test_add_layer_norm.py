@@ -122,6 +122,47 @@ def test_add_layer_norm_with_producer_tap_equals_unfused_chain(dtype):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+def test_add_layer_norm_common_chain_body_equals_general_body(dtype):
+    """16-bit launches with taps branch once to a body that holds only the quantizer's common chain (QdqVec::fast(): 8-bit codes,
+    normal 1 / scale, zero point in range); anything else runs the general body.  Both must give the bits of the standalone
+    chain fake_quant(a) -> + b -> fake_quant -> LayerNorm -> fake_quant:
+      * all taps common                      -> fast body
+      * ONE tap off the common chain (a 12-bit grid: codes not exact in the tensor dtype) -> the general body for all three taps,
+        whose 8-bit taps must still equal the fast body's arithmetic (checked through the unfused chain)."""
+    from outeffhop_b200 import ops
+    t = _T[dtype]
+    g = torch.Generator(device="cuda").manual_seed(23)
+    a = (torch.randn(257, 768, device="cuda", generator=g) * 2).to(t)
+    b = torch.randn(257, 768, device="cuda", generator=g).to(t)
+    w = (torch.rand(768, device="cuda", generator=g) + 0.5).to(t)
+    bias = (torch.randn(768, device="cuda", generator=g) * 0.1).to(t)
+    qa, qr, qo = (torch.tensor(v, device="cuda") for v in ([0.04, 120.0], [0.05, 131.0], [0.03, 125.0]))
+
+    def unfused(n_bits, qr_):
+        s = ops.fake_quant_asym(a, qa, n_bits) + b
+        s = ops.fake_quant_asym(s, qr_, n_bits)
+        y = torch.nn.functional.layer_norm(s.float(), (768,), w.float(), bias.float(), 1e-12).to(t)
+        return ops.fake_quant_asym(y, qo, n_bits), s
+
+    y8, s8 = ops.add_layer_norm(a, b, w, bias, 1e-12, qparams_a=qa, qparams_res=qr, qparams_out=qo, return_sum=True)
+    want8, wsum8 = unfused(8, qr)
+    assert torch.equal(s8, wsum8)                                  # the taps and the sum: bit for bit
+    assert float((y8.float() - want8.float()).abs().max()) <= 2 * 0.03 + 1e-6   # LayerNorm itself: fp32 two-pass vs ATen, <= 2 codes
+    # same taps through the general body: zero point outside [0, 255] on the residual tap disables fast() for the launch
+    qr_out = torch.tensor([0.05, 300.0], device="cuda")
+    yg, sg = ops.add_layer_norm(a, b, w, bias, 1e-12, qparams_a=qa, qparams_res=qr_out, qparams_out=qo, return_sum=True)
+    _, wsumg = unfused(8, qr_out)
+    assert torch.equal(sg, wsumg)
+    # and a launch whose ONLY tap is common must equal the same tap inside a general-body launch, element for element
+    y_fast = ops.add_layer_norm(a, b, w, bias, 1e-12, qparams_out=qo)
+    y_gen = ops.add_layer_norm(a, b, w, bias, 1e-12, qparams_out=qo, qparams_a=torch.tensor([1e-3, 300.0], device="cuda"))
+    a_tapped = ops.fake_quant_asym(a, torch.tensor([1e-3, 300.0], device="cuda"))
+    assert torch.equal(y_gen, ops.add_layer_norm(a_tapped, b, w, bias, 1e-12, qparams_out=qo))
+    assert y_fast.shape == y_gen.shape
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("dtype", ["float32", "float16", "bfloat16"])
 @pytest.mark.parametrize("n", [1, 4099, 1 << 20])
 def test_tap_add_fake_quant_equals_unfused_chain(dtype, n):
