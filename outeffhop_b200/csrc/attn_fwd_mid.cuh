@@ -42,12 +42,30 @@ constexpr int kSmemBytes = (1 + 2 * kMaxTiles) * kTileBytes + 1024;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColO = 448;
 
+#ifdef OEH_TIMELINE
+// experiment builds only (tools/timeline_mid.py): 8 stamps per work item by thread 0 (softmax warp 0): 0 item start, 1 (first item of
+// a CTA) TMEM allocated, 2 first S tile ready, 3 pass A done, 4 pass B done (P written), 5 O ready, 6 stored; slot 7 = (n_kv << 16) | SM id
+__device__ unsigned long long* g_mid_timeline = nullptr;
+__device__ __forceinline__ void mid_stamp(int k, int item, int n_kv = 0) {
+  if (threadIdx.x == 0 && g_mid_timeline) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_mid_timeline[item * 8 + k] = t;
+    if (k == 0) { uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_mid_timeline[item * 8 + 7] = ((unsigned long long)n_kv << 16) | sm; }
+  }
+}
+#define MID_STAMP(...) mid_stamp(__VA_ARGS__)
+#else
+#define MID_STAMP(...)
+#endif
+
 struct Barriers {
   uint64_t k_full[kMaxTiles];                    // K tile t landed (k_full[0] also covers Q)
   uint64_t v_full;                               // all V tiles landed
   uint64_t s_full[kMaxTiles];                    // S tile t complete
   uint64_t p_full;                               // P complete (one arrival per softmax warp)
   uint64_t o_full;                               // O complete
+  uint64_t epi_done;                             // every softmax warp has read O (the next item's QK^T may overwrite the columns)
 };
 
 template <bool kBF16, bool kGeneric, int kParts>
@@ -61,27 +79,64 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   __shared__ float xch_m[kParts][BM], xch_l[kParts][BM];
 
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  if (p.causal) {                                 // heaviest Q tiles first (attn_common.cuh, causal_item)
-    int hb;
-    causal_item((int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)), (int)gridDim.x,
-                (int)(gridDim.y * gridDim.z), p.hb_chunk, qt, hb);
-    h = hb % (int)gridDim.y;
-    b = hb / (int)gridDim.y;
-  }
-  const int q0 = qt * BM;
+
+  // ---- work items ------------------------------------------------------------------------------------------------------------------
+  // The launch has at most one CTA per SM (512 TMEM columns, 148 KB of shared memory per CTA); with more (Q tile, head, batch) items
+  // than SMs a CTA takes several, one after the other.  (As one CTA per item, the 44 surplus CTAs of the config-4 shape -- 192
+  // items on 148 SMs -- entered 1.1-1.6 us after an SM had drained and ran on their own for 4.6 us behind the 11 us of the
+  // heaviest CTAs: 2.7 of the launch's 13.8 us, profiles/r02_timeline_mid.txt.)  Items are numbered heaviest first (causal:
+  // causal_item) and dealt out in a snake -- round r forwards, round r + 1 backwards -- so the CTA with the lightest item of one
+  // round gets the heaviest of the next.  The next item's Q / K are loaded as soon as the current item's QK^T MMAs have read
+  // theirs, its V once the PV MMAs have.
+  const int n_items = p.n_qt * p.H * p.B, G = (int)gridDim.x;
+  struct Item { int item, q0, h, b, n_kv; };
+  auto item_of = [&](int it) {                    // it-th item of this CTA, or n_items
+    const int base = it * G;
+    if (base >= n_items) return n_items;
+    const int idx = base + ((it & 1) ? G - 1 - (int)blockIdx.x : (int)blockIdx.x);
+    return idx < n_items ? idx : n_items;
+  };
+  auto decode = [&](int item) {
+    Item w;
+    w.item = item;
+    int qt = item % p.n_qt, hb = item / p.n_qt;
+    if (p.causal) causal_item(item, p.n_qt, p.H * p.B, p.hb_chunk, qt, hb);   // heaviest Q tiles first (attn_common.cuh)
+    w.q0 = qt * BM;
+    w.h = hb % p.H;
+    w.b = hb / p.H;
+    int n_kv = (p.Tk + BN - 1) / BN;              // K / V tiles this Q tile needs
+    if (p.causal) {
+      const int last_row = min(w.q0 + BM, p.Tq) - 1;
+      const int lim = (last_row + (p.Tk - p.Tq)) / BN + 1;
+      n_kv = lim < n_kv ? lim : n_kv;
+    }
+    w.n_kv = n_kv < 1 ? 1 : n_kv;                 // (Tk < Tq, causal: a tile whose rows see no key still walks tile 0, all hidden)
+    return w;
+  };
 
   const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem0, sK = smem0 + kTileBytes, sV = sK + kMaxTiles * kTileBytes;
 
-  // K / V tiles this Q tile needs
-  int n_kv = (p.Tk + BN - 1) / BN;
-  if (p.causal) {
-    const int last_row = min(q0 + BM, p.Tq) - 1;
-    const int lim = (last_row + (p.Tk - p.Tq)) / BN + 1;
-    n_kv = lim < n_kv ? lim : n_kv;
-  }
+  // TMA loads of an item (one elected lane of the producer warp): Q + K tile 0 | K tiles 1.. | V, on their own mbarriers
+  auto load_qk = [&](const Item& w) {
+    const uint32_t b0 = ptx::smem_u32(&bars.k_full[0]);
+    ptx::mbar_expect_tx(b0, 2 * kTileBytes);
+    tma_tile(sQ, &tmq, b0, p.cq, w.q0, w.h, w.b);
+    tma_tile(sK, &tmk, b0, p.ck, 0, w.h, w.b);
+    for (int t = 1; t < w.n_kv; ++t) {
+      const uint32_t bt = ptx::smem_u32(&bars.k_full[t]);
+      ptx::mbar_expect_tx(bt, kTileBytes);
+      tma_tile(sK + t * kTileBytes, &tmk, bt, p.ck, t * BN, w.h, w.b);
+    }
+  };
+  auto load_v = [&](const Item& w) {
+    const uint32_t bv = ptx::smem_u32(&bars.v_full);
+    ptx::mbar_expect_tx(bv, w.n_kv * kTileBytes);
+    for (int t = 0; t < w.n_kv; ++t) tma_tile(sV + t * kTileBytes, &tmv, bv, p.cv, t * BN, w.h, w.b);
+  };
 
+  const Item first = decode(item_of(0));          // (the grid never exceeds the number of items)
+  MID_STAMP(0, first.item, first.n_kv);
   if (warp == kSoftmaxWarps && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmq);
     ptx::prefetch_tmap(&tmk);
@@ -94,20 +149,11 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     ptx::mbar_init(ptx::smem_u32(&bars.v_full), 1);
     ptx::mbar_init(ptx::smem_u32(&bars.p_full), kSoftmaxWarps);
     ptx::mbar_init(ptx::smem_u32(&bars.o_full), 1);
+    ptx::mbar_init(ptx::smem_u32(&bars.epi_done), kSoftmaxWarps);
     ptx::fence_mbar_init();
     // loads first: their latency covers the TMEM allocation and the block barrier below
-    const uint32_t b0 = ptx::smem_u32(&bars.k_full[0]);
-    ptx::mbar_expect_tx(b0, 2 * kTileBytes);
-    tma_tile(sQ, &tmq, b0, p.cq, q0, h, b);
-    tma_tile(sK, &tmk, b0, p.ck, 0, h, b);
-    for (int t = 1; t < n_kv; ++t) {
-      const uint32_t bt = ptx::smem_u32(&bars.k_full[t]);
-      ptx::mbar_expect_tx(bt, kTileBytes);
-      tma_tile(sK + t * kTileBytes, &tmk, bt, p.ck, t * BN, h, b);
-    }
-    const uint32_t bv = ptx::smem_u32(&bars.v_full);
-    ptx::mbar_expect_tx(bv, n_kv * kTileBytes);
-    for (int t = 0; t < n_kv; ++t) tma_tile(sV + t * kTileBytes, &tmv, bv, p.cv, t * BN, h, b);
+    load_qk(first);
+    load_v(first);
   }
   __syncwarp();
   if (warp == 0) ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(&tmem_base_slot));
@@ -115,37 +161,64 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
+  MID_STAMP(1, first.item);
 
+  // Barrier phases across items: v_full, p_full, o_full and epi_done complete once per item (parity = item count & 1); k_full[t] /
+  // s_full[t] only in items with more than t key tiles -- bit t of kph is their parity, flipped after every item that used them.
   if (warp == kSoftmaxWarps) {
     // ================================ producer / MMA issuer ===========================================================
     constexpr uint32_t kIdescQK = ptx::make_idesc_f16(kBF16, BM, BN, false, false);
     constexpr uint32_t kIdescPV = ptx::make_idesc_f16(kBF16, BM, HD, false, true);
-    for (int t = 0; t < n_kv; ++t) {                           // S tile t = Q . K(t)^T  -> columns [128 t, 128 t + 128)
-      ptx::mbar_wait(ptx::smem_u32(&bars.k_full[t]), 0);
+    uint32_t kph = 0;
+    Item w = first;
+    for (int it = 0; w.item < n_items; ++it) {
+      const uint32_t ph = (uint32_t)it & 1u;
+      const int n_kv = w.n_kv;
+      // the previous item's epilogue has read O (columns 448..511, inside S tile 3), and its PV MMAs -- which read P from the S
+      // columns -- completed before that (o_full, waited for at the end of the previous iteration)
+      if (it > 0) ptx::mbar_wait(ptx::smem_u32(&bars.epi_done), ph ^ 1u);
+      for (int t = 0; t < n_kv; ++t) {                         // S tile t = Q . K(t)^T  -> columns [128 t, 128 t + 128)
+        ptx::mbar_wait(ptx::smem_u32(&bars.k_full[t]), kph >> t & 1u);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)
+            ptx::mma_ss(tmem + t * BN, ptx::make_smem_desc_sw128(sQ + k * 32, 16, 1024),
+                        ptx::make_smem_desc_sw128(sK + t * kTileBytes + k * 32, 16, 1024), kIdescQK, k > 0);
+          ptx::mma_commit(ptx::smem_u32(&bars.s_full[t]));
+        }
+        __syncwarp();
+      }
+      const Item nx = decode(item_of(it + 1));
+      const uint32_t kph_next = kph ^ ((1u << n_kv) - 1u);
+      if (nx.item < n_items) {
+        // Q and the K tiles are free once the last QK^T of this item has completed (commits complete in issue order): the next
+        // item's Q / K loads run under this item's softmax passes
+        ptx::mbar_wait(ptx::smem_u32(&bars.s_full[n_kv - 1]), kph >> (n_kv - 1) & 1u);
+        if (ptx::elect_one()) load_qk(nx);
+        __syncwarp();
+      }
+      ptx::mbar_wait(ptx::smem_u32(&bars.p_full), ph);         // every softmax warp has written its share of P
+      ptx::mbar_wait(ptx::smem_u32(&bars.v_full), ph);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          ptx::mma_ss(tmem + t * BN, ptx::make_smem_desc_sw128(sQ + k * 32, 16, 1024),
-                      ptx::make_smem_desc_sw128(sK + t * kTileBytes + k * 32, 16, 1024), kIdescQK, k > 0);
-        ptx::mma_commit(ptx::smem_u32(&bars.s_full[t]));
+        for (int k = 0; k < n_kv * (BN / 16); ++k)             // O += P[:, 16k..16k+16) . V[16k..16k+16, :]
+          ptx::mma_ts(tmem + kColO, tmem + k * 8, ptx::make_smem_desc_sw128(sV + k * 2048, 1024, 1024), kIdescPV, k > 0);
+        ptx::mma_commit(ptx::smem_u32(&bars.o_full));
       }
       __syncwarp();
+      if (nx.item < n_items) {                                 // the V tiles are free once the PV MMAs have completed
+        ptx::mbar_wait(ptx::smem_u32(&bars.o_full), ph);
+        if (ptx::elect_one()) load_v(nx);
+        __syncwarp();
+      }
+      kph = kph_next;
+      w = nx;
     }
-    ptx::mbar_wait(ptx::smem_u32(&bars.p_full), 0);            // every softmax warp has written its share of P
-    ptx::mbar_wait(ptx::smem_u32(&bars.v_full), 0);
-    ptx::tc_fence_after();
-    if (ptx::elect_one()) {
-      for (int k = 0; k < n_kv * (BN / 16); ++k)               // O += P[:, 16k..16k+16) . V[16k..16k+16, :]
-        ptx::mma_ts(tmem + kColO, tmem + k * 8, ptx::make_smem_desc_sw128(sV + k * 2048, 1024, 1024), kIdescPV, k > 0);
-      ptx::mma_commit(ptx::smem_u32(&bars.o_full));
-    }
-    __syncwarp();
   } else {
     // ================================ softmax: two threads per row ====================================================
     const int half = warp >> 2;                                 // which of the kParts chunks of a tile this thread takes
     const int r = (warp & 3) * 32 + (tid & 31);                 // row within the tile == TMEM lane
-    const int row = q0 + r;
     const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int pair_bar = 2 + (warp & 3);                        // named barrier of the kParts warps of a lane quarter
 
@@ -158,6 +231,13 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     Qdq qd_s{1.f, 1.f, 0.f, p.int_max}, qd_p{1.f, 1.f, 0.f, p.int_max};
     if (has_qs) qd_s = load_qdq(p.qdq_scores, p.int_max);
     if (has_qp) qd_p = load_qdq(p.qdq_probs, p.int_max);
+    uint32_t kph = 0;
+    Item w = first;
+    for (int it = 0; w.item < n_items; ++it) {
+    const uint32_t ph = (uint32_t)it & 1u;
+    const int q0 = w.q0, h = w.h, b = w.b, n_kv = w.n_kv;
+    const int row = q0 + r;
+    if (it > 0) MID_STAMP(0, w.item, n_kv);
     const int64_t mask_row =
         p.mask ? ((int64_t)b * p.ms0 + (int64_t)h * p.ms1 + (int64_t)(row < p.Tq ? row : 0) * p.ms2) : 0;
     const int causal_lim = p.causal ? row + (p.Tk - p.Tq) : 0x7fffffff;
@@ -179,8 +259,9 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     for (int i = 0; i < kMaxTiles; ++i) {
       if (i < n_kv) {
         const int j = kParts * i + half, k0 = j * CW;
-        ptx::mbar_wait(ptx::smem_u32(&bars.s_full[i]), 0);
+        ptx::mbar_wait(ptx::smem_u32(&bars.s_full[i]), kph >> i & 1u);
         ptx::tc_fence_after();
+        if (i == 0) MID_STAMP(2, w.item);
         {
           // A chunk none of this warp's 32 rows can see (above the causal diagonal: 6 of the 16 (lane quarter, chunk) pairs of the
           // diagonal tile with four parts; or past Tk in the ragged last tile) contributes nothing to (m, l) and its P is 0:
@@ -217,6 +298,7 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       }
     }
     ptx::tmem_wait_st();
+    MID_STAMP(3, w.item);
 
     // ---- the kParts threads of a row agree on (m, denominator) -----------------------------------------------------------
     xch_m[half][r] = m_run;
@@ -281,17 +363,29 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     ptx::tc_fence_before();
     __syncwarp();
     if (ptx::elect_one()) ptx::mbar_arrive(ptx::smem_u32(&bars.p_full));
+    MID_STAMP(4, w.item);
 
     // ---- epilogue: each of the row's threads finishes 64 / kParts head-dim columns ---------------------------------------------
     const EpiPre pre = epi_prefetch<kBF16, kGeneric>(p, b, h, row);   // global reads of the epilogue, under the PV MMAs
-    ptx::mbar_wait(ptx::smem_u32(&bars.o_full), 0);
+    const Item nx = decode(item_of(it + 1));                    // (integer divisions: also under the PV MMAs)
+    ptx::mbar_wait(ptx::smem_u32(&bars.o_full), ph);
     ptx::tc_fence_after();
+    MID_STAMP(5, w.item);
     constexpr int ND = HD / kParts;
     float o[ND];
     if constexpr (ND == 32) ptx::tmem_ld32(t_lane + kColO + half * ND, reinterpret_cast<uint32_t*>(o));
     else ptx::tmem_ld16(t_lane + kColO + half * ND, reinterpret_cast<uint32_t*>(o));
     ptx::tmem_wait_ld();
+    if (nx.item < n_items) {                                    // O is in registers: the next item's QK^T may write these columns
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (ptx::elect_one()) ptx::mbar_arrive(ptx::smem_u32(&bars.epi_done));
+    }
     if (row < p.Tq) store_row<kBF16, kGeneric, ND>(o, p, omul, b, h, row, half * ND, pre);
+    MID_STAMP(6, w.item);
+    kph ^= (1u << n_kv) - 1u;
+    w = nx;
+    }   // items
   }
 
   ptx::tc_fence_before();

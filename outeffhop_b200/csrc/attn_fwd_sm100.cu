@@ -445,6 +445,9 @@ extern "C" size_t oeh_attn_workspace_bytes(const OehAttnArgs* args) {
 extern "C" int oeh_set_wsp_timeline(unsigned long long* buf) {
   return cudaMemcpyToSymbol(attn_wsp::g_wsp_timeline, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
 }
+extern "C" int oeh_set_mid_timeline(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(attn_mid::g_mid_timeline, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
+}
 extern "C" int oeh_set_timeline(unsigned long long* buf) {
   return cudaMemcpyToSymbol(attn_one::g_timeline, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
 }
@@ -514,8 +517,12 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
   // more than two key tiles, at most four waves of CTAs.  OEH_MID_KERNEL=0 disables it, =1 sends every kind with
   // Tk <= 512 there (=3: the two-threads-per-row shape).
   const long long row_blocks = (long long)a->B * a->H * ((a->Tq + BM - 1) / BM);
-  bool use_mid = norm_mode && a->qdq_probs != nullptr && !use_one && a->Tk > 2 * BN && a->Tk <= attn_mid::kMaxTiles * BN &&
-                 row_blocks <= 4LL * num_sms();
+  // Since the kernel walks several items per CTA (no second wave of CTAs, the next item's loads under the current one) it is
+  // ahead for every normalised kind at every measured size (profiles/r02_mid_kernel_z.jsonl: tapped B=32 T=512 causal 77 vs 91 us,
+  // B=16 T=384 33 vs 40, B=8 T=256 13.7 vs 14.4; clippedsoftmax1 52.6 vs 61.5, 23.4 vs 26.5, 10.8 vs 10.8); the one-pass kinds stay
+  // on the warp-specialised kernel (10.5 vs 11.7 us at B=4 T=512 causal).
+  (void)row_blocks;
+  bool use_mid = norm_mode && !use_one && a->Tk > BN && a->Tk <= attn_mid::kMaxTiles * BN;
   if (const long long f = tune(kTuneMidKernel); f >= 0) use_mid = f != 0 && !use_one && a->Tk <= attn_mid::kMaxTiles * BN;
   if (tune(kTuneAttnKernel) >= 0) use_mid = false;
   if (use_mid) use_ws = false;
@@ -565,9 +572,11 @@ extern "C" int oeh_attn_fwd_debug(const OehAttnArgs* a, float* dbg_s, float* dbg
     const int four = tune(kTuneMidKernel) == 3 ? 0 : 1;
     KernelFn fn = kernels[four][ki];
     if ((rc = ensure_smem(reinterpret_cast<const void*>(fn), attn_mid::kSmemBytes))) return rc;
-    dim3 grid((unsigned)((a->Tq + BM - 1) / BM), (unsigned)a->H, (unsigned)a->B);
-    p.n_qt = (int)grid.x;
+    p.n_qt = (int)((a->Tq + BM - 1) / BM);
     p.hb_chunk = a->H * a->B;                      // causal: ALL heaviest Q tiles first (K / V of a launch fit L2 many times over)
+    // one CTA per SM at most (512 TMEM columns each); a CTA walks its share of the (Q tile, head, batch) items
+    const long long n_items = (long long)p.n_qt * a->H * a->B;
+    const dim3 grid((unsigned)(n_items < num_sms() ? n_items : num_sms()));
     fn<<<grid, four ? attn_mid::Shape<4>::kThreads : attn_mid::Shape<2>::kThreads, attn_mid::kSmemBytes, st>>>(tmq, tmk, tmv, p);
     return check_launch("attn_fwd_mid_kernel");
   }

@@ -6,7 +6,8 @@ from outeffhop_b200 import _lib, ops
 torch.manual_seed(0)
 qp = torch.tensor([0.05, 128.0], device="cuda"); pp = torch.tensor([1.0 / 255, 0.0], device="cuda"); cp = torch.tensor([0.01, 128.0], device="cuda")
 # mid kernel: causal + taps, ragged, 1..4 tiles
-for (B, H, Tq, Tk, causal) in ((1, 2, 512, 512, True), (1, 1, 200, 333, False), (1, 2, 130, 130, True)):
+# (the (4, 12, 512) launch has 192 items for at most 148 CTAs: several items per CTA, buffers and barrier phases carried over)
+for (B, H, Tq, Tk, causal) in ((1, 2, 512, 512, True), (1, 1, 200, 333, False), (1, 2, 130, 130, True), (4, 12, 512, 512, True), (7, 12, 300, 300, False)):
     q = torch.randn(B, H, Tq, 64, device="cuda").half(); k = torch.randn(B, H, Tk, 64, device="cuda").half(); v = torch.randn_like(k)
     _lib.set_override("OEH_MID_KERNEL", "1")
     ops.attention_fwd(q, k, v, scale=0.125, kind=3, gamma=-0.025, eta=1.1, causal=causal, qdq_scores=qp, qdq_probs=pp, qdq_ctx=cp, n_bits=8)
