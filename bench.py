@@ -15,6 +15,7 @@ Prints ONE JSON line (rank 0).  ``value`` = whole-job tokens/s with inputs resid
 through the module API with pinned-host inputs (H2D) and a host read of the loss (D2H) every step;
 ``roofline`` = the fused attention kernel (the hot path's own kernel; the step's largest single kernel is now this
 repo's FFN1 GEMM with the GELU epilogue, the other GEMMs are library calls) timed alone with CUDA events on its launch stream on the model's own Q/K/V shapes;
+``roofline_gemm`` = the step's largest own kernel (FFN1 GEMM + erf GELU) against the dense tensor peak, timed the same way;
 ``cpu_baseline`` = the oracle port of the reference path on the host cores (rank 0, N=1).
 """
 from __future__ import annotations

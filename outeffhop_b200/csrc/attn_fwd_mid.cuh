@@ -7,7 +7,8 @@
 //   Tk <= 128, stretched over four K/V tiles.  At B=4, H=12, T=512 causal with the three INT8 taps the two-pass kernel
 //   needs 30.7 us per launch (1.6 GFLOP: prologue / epilogue bound, profiles/r01_launches_int8_opt_step_aa.summary.txt).
 //
-// One CTA = one 128-row Q tile of one (batch, head); Q, all K tiles and all V tiles resident in shared memory (144 KB).
+// One work item = one 128-row Q tile of one (batch, head); Q, all K tiles and all V tiles resident in shared memory (144 KB).
+// At most one CTA per SM (all 512 TMEM columns); with more items than SMs a CTA walks several (see "work items" below).
 //   warp 8      producer / issuer: TMA loads (Q + K tile 0 | K tiles 1..3 | V, separate mbarriers), QK^T of tile t as soon
 //               as K(t) lands (one commit per tile), P.V after the softmax warps have written all of P
 //   warps 0-7   softmax, TWO threads per query row: warp w and warp w+4 share TMEM lane quarter w & 3 and split the
