@@ -144,6 +144,19 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   const uint32_t sK = smem0 + kTiles * kTileBytes;              // kStages steps of 64 keys
   const uint32_t sV = sK + kStages * kSubBytes;
 
+  // ---- step plan (shared by all roles) ---------------------------------------------------------------------------
+  int n_kv = (p.Tk + BNW - 1) / BNW;
+  if (p.causal) {
+    const int last_row = min(q0 + kQRows, p.Tq) - 1;            // last real query row of this CTA
+    const int lim = (last_row + (p.Tk - p.Tq)) / BNW + 1;
+    n_kv = lim < n_kv ? lim : n_kv;
+  }
+  const bool softmax1 = (p.kind == OEH_SOFTMAX_1 || p.kind == OEH_SOFTMAX_CLIPPED1);
+  const bool clipped = p.kind >= OEH_SOFTMAX_CLIPPED;
+  constexpr bool normalized = kNorm;                              // host: clipped || qdq_probs
+  const int nA = normalized ? n_kv : 0;                          // stats-pass steps (QK^T only)
+  const int n_iter = nA + n_kv;
+
   if (tid == 0) {
     ptx::mbar_init(ptx::smem_u32(&bars.q_full), 1);
 #pragma unroll
@@ -163,6 +176,21 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       ptx::mbar_init(ptx::smem_u32(&bars.o_final[t]), 1);
     }
     ptx::fence_mbar_init();
+    // The first loads (Q, K of steps 0 and 1) go out HERE, before the TMEM allocation and the block barrier: their latency
+    // (~1.2 us cold) covers both instead of following them (the allocations of two co-resident CTAs serialise: ~0.5 us each,
+    // profiles/r02_micro_tmem_alloc.txt).  The producer warp takes over from step 2.
+    ptx::prefetch_tmap(&tmq);
+    ptx::prefetch_tmap(&tmk);
+    ptx::prefetch_tmap(&tmv);
+    const uint32_t bq = ptx::smem_u32(&bars.q_full);
+    ptx::mbar_expect_tx(bq, kTiles * kTileBytes);
+    tma_tile(sQ, &tmq, bq, p.cq, q0, h, b);
+    if (kTiles == 2) tma_tile(sQ + kTileBytes, &tmq, bq, p.cq, q0 + 128, h, b);
+    for (int i = 0; i < 2 && i < n_iter; ++i) {
+      const uint32_t bf = ptx::smem_u32(&bars.k_full[i]);
+      ptx::mbar_expect_tx(bf, kSubBytes);
+      tma_tile(sK + i * kSubBytes, &tmk, bf, p.ck, (i < nA ? i : i - nA) * BNW, h, b);
+    }
   }
   __syncwarp();
   if (warp == C::kWarpMma0) ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(&tmem_base_slot));
@@ -171,32 +199,9 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
 
-  // ---- step plan (shared by all roles) ---------------------------------------------------------------------------
-  int n_kv = (p.Tk + BNW - 1) / BNW;
-  if (p.causal) {
-    const int last_row = min(q0 + kQRows, p.Tq) - 1;            // last real query row of this CTA
-    const int lim = (last_row + (p.Tk - p.Tq)) / BNW + 1;
-    n_kv = lim < n_kv ? lim : n_kv;
-  }
-  const bool softmax1 = (p.kind == OEH_SOFTMAX_1 || p.kind == OEH_SOFTMAX_CLIPPED1);
-  const bool clipped = p.kind >= OEH_SOFTMAX_CLIPPED;
-  constexpr bool normalized = kNorm;                              // host: clipped || qdq_probs
-  const int nA = normalized ? n_kv : 0;                          // stats-pass steps (QK^T only)
-  const int n_iter = nA + n_kv;
-
   if (warp >= C::kSoftmaxWarps) reg_dealloc<C::kAuxRegs>();
   if (warp == C::kWarpTma) {
     // ================================ TMA producer (whole warp waits, one elected lane issues) ============
-    if (ptx::elect_one()) {
-      ptx::prefetch_tmap(&tmq);
-      ptx::prefetch_tmap(&tmk);
-      ptx::prefetch_tmap(&tmv);
-      const uint32_t bq = ptx::smem_u32(&bars.q_full);
-      ptx::mbar_expect_tx(bq, kTiles * kTileBytes);
-      tma_tile(sQ, &tmq, bq, p.cq, q0, h, b);
-      if (kTiles == 2) tma_tile(sQ + kTileBytes, &tmq, bq, p.cq, q0 + 128, h, b);
-    }
-    __syncwarp();
     auto load_k = [&](int i) {                                  // K of step i -> ring slot i % kStages
       const int s = i % kStages, n = i / kStages;
       if (n > 0) ptx::mbar_wait(ptx::smem_u32(&bars.k_empty[s]), (uint32_t)(n - 1) & 1u);
@@ -207,9 +212,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       }
       __syncwarp();
     };
-    load_k(0);
-    if (n_iter > 1) load_k(1);
-    for (int i = 0; i < n_iter; ++i) {                          // K runs two steps ahead of V, like the MMA issuers
+    for (int i = 0; i < n_iter; ++i) {                          // K runs two steps ahead of V, like the MMA issuers (steps 0, 1: above)
       if (i + 2 < n_iter) load_k(i + 2);
       if (i >= nA) {
         const int v = i - nA, s = v % kStages, n = v / kStages;
