@@ -445,6 +445,9 @@ extern "C" size_t oeh_attn_workspace_bytes(const OehAttnArgs* args) {
 extern "C" int oeh_set_wsp_timeline(unsigned long long* buf) {
   return cudaMemcpyToSymbol(attn_wsp::g_wsp_timeline, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
 }
+extern "C" int oeh_set_ws_timeline(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(attn_ws::g_ws_timeline, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
+}
 extern "C" int oeh_set_mid_timeline(unsigned long long* buf) {
   return cudaMemcpyToSymbol(attn_mid::g_mid_timeline, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
 }

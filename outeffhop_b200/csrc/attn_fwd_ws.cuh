@@ -70,6 +70,25 @@ namespace attn_ws {
 
 using namespace attn;
 
+#ifdef OEH_TIMELINE
+// experiment builds only (tools/timeline_ws.py): 8 stamps per CTA by thread 0 (softmax warp 0 = stream (tile 0, parity 0)):
+// 0 entry, 1 TMEM allocated + block barrier, 2 first S of the stream ready, 3 its last P written, 4 statistics merged,
+// 5 last PV complete, 6 stored; slot 7 = (n_kv << 16) | SM id
+__device__ unsigned long long* g_ws_timeline = nullptr;
+__device__ __forceinline__ void ws_stamp(int k, int n_kv = 0) {
+  if (threadIdx.x == 0 && g_ws_timeline) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    g_ws_timeline[cta * 8 + k] = t;
+    if (k == 0) { uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_ws_timeline[cta * 8 + 7] = ((unsigned long long)n_kv << 16) | sm; }
+  }
+}
+#define WS_STAMP(...) ws_stamp(__VA_ARGS__)
+#else
+#define WS_STAMP(...)
+#endif
+
 constexpr int BNW = 64;                                            // keys per step
 constexpr int kSubBytes = BNW * HD * 2;                            // 8 KB
 // kTiles = Q tiles (of 128 rows) per CTA.  2: one CTA per SM (640 threads, 512 TMEM columns), K / V steps shared by the two
@@ -157,6 +176,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   const int nA = normalized ? n_kv : 0;                          // stats-pass steps (QK^T only)
   const int n_iter = nA + n_kv;
 
+  WS_STAMP(0, n_kv);
   if (tid == 0) {
     ptx::mbar_init(ptx::smem_u32(&bars.q_full), 1);
 #pragma unroll
@@ -198,6 +218,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
+  WS_STAMP(1);
 
   if (warp >= C::kSoftmaxWarps) reg_dealloc<C::kAuxRegs>();
   if (warp == C::kWarpTma) {
@@ -340,6 +361,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       OEH_T(0);
       ptx::mbar_wait(bar_s, (uint32_t)(i >> 1) & 1u);
       ptx::tc_fence_after();
+      if (i == par) WS_STAMP(2);
       OEH_T(1);
       // (two-tile CTAs only: the one-tile shapes -- T <= 512 -- have two hidden warp-steps per item and the test costs them more)
       if (kTiles == 2 && p.causal && !(kGeneric && p.dbg_s)) {
@@ -462,6 +484,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     OEH_T_PRINT("softmax: top s_full ld max exp pack+arrive", n_iter);
 
     // ---- epilogue: merge the streams, O / denominator -> gate / taps -> global -----------------------------------
+    WS_STAMP(3);
     float a_own = 1.f, a_other = 1.f, omul = 1.f;                 // scales of the two accumulators; 1/denominator
     if (!normalized) {
       float l_other;
@@ -479,8 +502,10 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     const bool has0 = n_kv > 1 || (nA & 1) == 0, has1 = n_kv > 1 || (nA & 1) == 1;
     const float a0 = par ? a_other : a_own, a1 = par ? a_own : a_other;
     const EpiPre pre = epi_prefetch<kBF16, kGeneric>(p, b, h, row);   // global reads of the epilogue, under the last PV
+    WS_STAMP(4);
     ptx::mbar_wait(ptx::smem_u32(&bars.o_final[t]), 0);
     ptx::tc_fence_after();
+    WS_STAMP(5);
     // this thread finishes head-dim columns [32par, 32par+32) of its row from both accumulators
     float o[32];
     {
@@ -501,6 +526,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     }
     static_assert(kStages * kSubBytes >= C::kSoftmaxWarps * 2048, "the K ring holds one staging slot per softmax warp");
     store_half_rows_coalesced<kBF16>(o, p, sK + (uint32_t)warp * 2048u, b, h, q0 + t * 128 + (warp & 3) * 32, par * 32);
+    WS_STAMP(6);
   }
 
   // ---- teardown ------------------------------------------------------------------------------------------------
