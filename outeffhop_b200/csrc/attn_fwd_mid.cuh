@@ -247,8 +247,8 @@ attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     float m_run = -INFINITY, l_run = 0.f;
     // frame (running max) of the e values of chunk kParts * i + half.  Four scalars behind selects, not an indexed array: the tile
     // loops below are NOT unrolled (OEH_MID_UNROLL_TILES restores the old form for A/B runs) -- fully unrolled the tapped
-    // instantiation was 7544 SASS instructions (118 KB) and a fifth of its stall samples were instruction fetch
-    // (stall_no_inst 19.8 %, profiles/r02_ncu_hot_kernels.txt): every launch inside a model step starts with a cold I-cache
+    // instantiation was 7544 SASS instructions (118 KB) and a fifth of its stall samples under ncu were instruction fetch
+    // (stall_no_inst 19.8 %, profiles/r02_ncu_hot_kernels.txt); rolled up it is 3048 and times the same back to back
     float mc0 = 0.f, mc1 = 0.f, mc2 = 0.f, mc3 = 0.f;
     uint32_t hidden = 0;                                        // bit i: chunk i of this warp is invisible to all of its rows
     static_assert(kMaxTiles == 4, "mc0..mc3");
