@@ -20,7 +20,7 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "lib", "liboeh.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["api.cu", "quant.cu", "softmax_rows.cu", "gate.cu", "attn_fwd_sm100.cu", "percentile.cu", "outlier_stats.cu", "ce_loss.cu", "layernorm.cu", "gelu.cu", "gemm_sm100.cu", "gemm_ln_sm100.cu"]
+SOURCES = ["api.cu", "quant.cu", "softmax_rows.cu", "gate.cu", "attn_fwd_sm100.cu", "percentile.cu", "outlier_stats.cu", "ce_loss.cu", "layernorm.cu", "layernorm_f32.cu", "layernorm_f16.cu", "layernorm_bf16.cu", "gelu.cu", "gemm_sm100.cu", "gemm_ln_sm100.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

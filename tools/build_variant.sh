@@ -8,7 +8,7 @@ OBJ=/tmp/oeh_variant_$NAME
 mkdir -p $OBJ $ROOT/outeffhop_b200/lib
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC,-O2 -I $ROOT/include"
 pids=()
-for s in api quant softmax_rows gate attn_fwd_sm100 percentile outlier_stats ce_loss layernorm gelu gemm_sm100 gemm_ln_sm100; do
+for s in api quant softmax_rows gate attn_fwd_sm100 percentile outlier_stats ce_loss layernorm layernorm_f32 layernorm_f16 layernorm_bf16 gelu gemm_sm100 gemm_ln_sm100; do
   [ -f $ROOT/outeffhop_b200/csrc/$s.cu ] || continue
   nvcc -c $ROOT/outeffhop_b200/csrc/$s.cu -o $OBJ/$s.o $FLAGS "$@" &
   pids+=($!)
